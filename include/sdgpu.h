@@ -1,0 +1,196 @@
+/*
+ * sdgpu.h — C ABI of the B200-native qluster hot path (k-mer prefilter -> affine-gap global
+ * alignment with traceback -> errorProfile/`comparison`).
+ *
+ * This is the drop-in boundary for SeekDeep's data-parallel hot path.  The reference has no
+ * FFI: the seam is the C++ class API of njhseq's `aligner` / `kmerInfo` / `indexKmers`, as
+ * called from the reference at (paths relative to the SeekDeep repo root):
+ *
+ *   aligner ctor (maxSize, gapInfo, scoring, kMaps, qScorePars, countEndGaps, weighHomopolymers)
+ *       src/SeekDeepPrograms/SeekDeepProgram/clusterDown/clusterDown.cpp:420-426
+ *   aligner::alignCacheGlobal(ref, read)                  clusterDown.cpp:694,739
+ *                                                          src/SeekDeep/objects/ControlBenchmarking/ControlBencher.hpp:117
+ *   aligner::profileAlignment(ref, read, checkKmer, usingQuality, doingMatchQuality)
+ *                                                          clusterDown.cpp:696,741; ControlBencher.hpp:118
+ *   comparison fields (alnScore_, hq/lq/lowKmer mismatches, 1/2/large indels, identities)
+ *                                                          clusterDown.cpp:745-753
+ *   indexKmers(clusters, kLen, runCutOff, kmersByPosition, expandKmerPos, expandKmerSize)
+ *                                                          clusterDown.cpp:412-417, 505-510
+ *   kmerInfo(seq, kLen, revComp) / compareKmers            src/SeekDeepPrograms/SeekDeepProgram/extractor/extractorPairedEnd.cpp:819-824
+ *   collapser::runFullClustering(clusters, iters, ...)     clusterDown.cpp:488-518
+ *
+ * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the
+ * C++ shim (`GpuAligner`) a SeekDeep maintainer would add on the reference side.
+ *
+ * Rules: plain pointers and sizes only; caller-allocated outputs; the library never frees
+ * caller memory; all calls on one ctx are ordered on that ctx's CUDA stream; ctxs are
+ * independent (one per host thread, mirroring njhseq's one-aligner-per-thread AlignerPool,
+ * src/SeekDeepPrograms/SeekDeepProgram/processClusters/processClusters.cpp:145-155).
+ * Errors are int return codes (0 = ok); no exceptions cross the ABI.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with SDGPU_E_CUDA.
+ */
+#ifndef SDGPU_H_
+#define SDGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDGPU_ABI_VERSION 1
+#define SDGPU_MAT_DIM 128 /* substitution matrix is indexed by 7-bit ASCII, like njhseq's mat_[127][127] */
+
+/* return codes */
+enum {
+  SDGPU_OK = 0,
+  SDGPU_E_ARG = 1,         /* bad argument (null pointer, index out of range, ...) */
+  SDGPU_E_CUDA = 2,        /* CUDA runtime error or no device */
+  SDGPU_E_UNSUPPORTED = 3, /* input outside what the kernels implement (e.g. sequence too long) */
+  SDGPU_E_ALPHABET = 4,    /* a base outside the IUPAC nucleotide alphabet */
+  SDGPU_E_OVERFLOW = 5,    /* caller buffer too small (e.g. gap list capacity) */
+  SDGPU_E_STATE = 6        /* call order violation (e.g. checkKmer without an index) */
+};
+
+/* The ten gap penalties of njhseq's gapScoringParameters (positive numbers are penalties).
+ * Reference: extractorSetUp.cpp:138-150 names all ten; qluster sets gap=5,1 gapLeft=5,1
+ * gapRight=0,0 (clusterDownSetUp.cpp:402-404).  "Query" gaps are gaps placed in the read
+ * (second argument, DP columns); "Ref" gaps are gaps placed in the ref (first argument, rows). */
+typedef struct sdgpu_gap_pars {
+  int32_t gapOpen, gapExtend;
+  int32_t gapLeftQueryOpen, gapLeftQueryExtend;
+  int32_t gapRightQueryOpen, gapRightQueryExtend;
+  int32_t gapLeftRefOpen, gapLeftRefExtend;
+  int32_t gapRightRefOpen, gapRightRefExtend;
+} sdgpu_gap_pars;
+
+/* Everything the 7-argument aligner constructor takes (clusterDown.cpp:420-426) except
+ * maxSize (the library sizes its own scratch) and kMaps (built by sdgpu_build_kmer_index). */
+typedef struct sdgpu_params {
+  sdgpu_gap_pars gaps;
+  int32_t scoreMat[SDGPU_MAT_DIM * SDGPU_MAT_DIM]; /* [refChar * 128 + readChar], parts_.scoring_.mat_ */
+  uint32_t primaryQual;      /* qScorePars_.primaryQual_   (25 for --illumina, clusterDownSetUp.cpp:285) */
+  uint32_t secondaryQual;    /* qScorePars_.secondaryQual_ (20) */
+  uint32_t qualThresWindow;  /* qScorePars_.qualThresWindow_ (2) */
+  uint32_t countEndGaps;     /* colOpts_.alignOpts_.countEndGaps_ */
+  uint32_t weighHomopolymers;/* colOpts_.iTOpts_.weighHomopolyer_ */
+  uint32_t reserved;
+} sdgpu_params;
+
+/* One gap run of the global alignment, exactly njhseq's gapInfo(pos_, size_, gapInA_), listed
+ * in traceback order (from the alignment's end towards its start). */
+typedef struct sdgpu_gap {
+  uint32_t pos;    /* position in the gapped sequence's ungapped coordinates where '-' go */
+  uint32_t size;
+  uint32_t gapInA; /* 1: '-' inserted into the ref (A); 0: into the read (B) */
+} sdgpu_gap;
+
+/* njhseq `comparison` + the scalar part of `DistanceComp` (clusterDown.cpp:745-753). */
+typedef struct sdgpu_comparison {
+  int32_t alnScore;
+  uint32_t hqMismatches;
+  uint32_t lqMismatches;
+  uint32_t lowKmerMismatches;
+  uint32_t highQualityMatches;
+  uint32_t lowQualityMatches;
+  uint32_t numGaps;           /* distances_.alignmentGaps_.size(): counted (non-end unless countEndGaps) gap runs */
+  uint32_t basesInAln;        /* distances_.basesInAln_ */
+  uint32_t overLappingEvents; /* distances_.overLappingEvents_ */
+  uint32_t alnLen;            /* columns of the gapped alignment */
+  uint32_t nGapRuns;          /* all gap runs of the traceback, end gaps included */
+  uint32_t status;            /* 0 = ok; SDGPU_ST_* bits */
+  double oneBaseIndel;
+  double twoBaseIndel;
+  double largeBaseIndel;
+  double eventBasedIdentity;
+  double eventBasedIdentityHq;
+  double refCoverage;         /* distances_.ref_.coverage_ */
+  double queryCoverage;       /* distances_.query_.coverage_ */
+} sdgpu_comparison;
+
+#define SDGPU_ST_GAPLIST_TRUNCATED 1u /* more gap runs than the caller's per-pair capacity */
+
+/* flags of sdgpu_align_profile == the three bools of aligner::profileAlignment */
+#define SDGPU_CHECK_KMER 1u
+#define SDGPU_USING_QUALITY 2u
+#define SDGPU_MATCH_QUALITY 4u
+
+typedef struct sdgpu_ctx sdgpu_ctx; /* opaque; one per host thread; owns one device + one stream */
+
+/* Library / device probing (no reference counterpart). */
+int sdgpu_abi_version(void);
+int sdgpu_device_count(void);
+
+/* Replaces: aligner::aligner(maxSize, gapInfo_, scoring_, kMaps, qScorePars_, countEndGaps_,
+ * weighHomopolyer_), clusterDown.cpp:420-426. */
+int sdgpu_create(int device, const sdgpu_params* params, sdgpu_ctx** out);
+void sdgpu_destroy(sdgpu_ctx* ctx);
+const char* sdgpu_last_error(sdgpu_ctx* ctx); /* ctx may be NULL: last create() error of this thread */
+int sdgpu_set_params(sdgpu_ctx* ctx, const sdgpu_params* params); /* e.g. `alignerObj.weighHomopolymers_ = x` */
+
+/* Sequence store.  Replaces the caller-owned std::vector<cluster>/seqInfo the aligner reads
+ * (seqBase_.seq_, seqBase_.qual_, seqBase_.cnt_; clusterDown.cpp:274-285).  `bases` is ASCII
+ * (case-insensitive IUPAC), `quals` phred values (may be NULL: all 0), `offsets` has n+1
+ * entries, `cnts` may be NULL (all 1).  upload replaces the store; append adds to it and
+ * returns the index of the first appended sequence in *firstIndex. */
+int sdgpu_upload_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals,
+                      const uint64_t* offsets, const double* cnts, uint32_t n);
+int sdgpu_append_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals,
+                      const uint64_t* offsets, const double* cnts, uint32_t n,
+                      uint32_t* firstIndex);
+int sdgpu_num_seqs(sdgpu_ctx* ctx, uint32_t* n);
+
+/* Replaces: indexKmers(clusters, kLength_, runCutOff_, kmersByPosition_, expandKmerPos_,
+ * expandKmerSize_) -> KmerMaps, clusterDown.cpp:412-417 and 505-510, followed by
+ * `alignerObj.kMaps_ = recalcKmaps` (clusterDown.cpp:511).  Indexes the sequences listed in
+ * seqIdx (NULL: the whole store), weighting each k-mer by round(cnt). */
+int sdgpu_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* seqIdx, uint32_t nIdx, uint32_t kLen,
+                           uint32_t runCutOff, int kmersByPosition, int expandKmerPos,
+                           uint32_t expandKmerSize);
+/* Look up KmerMaps counts (test/debug hook; ≙ kMaps.kmersByPos_[pos][kmer].count_). */
+int sdgpu_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers /* n*kLen ASCII */,
+                            const uint32_t* positions, uint32_t n, uint32_t* countsOut);
+
+/* Replaces: kmerInfo(seq, kLen, false) for every stored sequence (extractorPairedEnd.cpp:819,
+ * PrimersAndMids.cpp:49-54).  Builds dense 4^kLen count profiles on the device (kLen <= 8). */
+int sdgpu_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen);
+/* Replaces: a.compareKmers(b) -> std::pair<uint32_t,double> (extractorPairedEnd.cpp:820-824)
+ * for nPairs (a[i], b[i]) index pairs into the store. */
+int sdgpu_kmer_compare(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs,
+                       uint32_t* sharedOut, double* fracOut);
+/* All-pairs form used by the qluster prefilter: every read in reads[] against every cluster
+ * in clusters[]; outputs are row-major [nReads][nClusters]. */
+int sdgpu_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nReads,
+                           const uint32_t* clusters, uint32_t nClusters, uint32_t* sharedOut,
+                           double* fracOut);
+
+/* Replaces, per pair i: alignerObj.alignCacheGlobal(seq[refIdx[i]], seq[readIdx[i]]) followed
+ * by alignerObj.profileAlignment(ref, read, checkKmer, usingQuality, doingMatchQuality)
+ * (clusterDown.cpp:739-741), returning aligner::comp_ in out[i].  If gapsOut != NULL the gap
+ * runs of pair i (alnInfoGlobal::gapInfos_, traceback order) are written to
+ * gapsOut[i*gapCap .. i*gapCap + min(nGapRuns, gapCap)); a longer list sets
+ * SDGPU_ST_GAPLIST_TRUNCATED in out[i].status. */
+int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx,
+                        uint32_t nPairs, uint32_t flags, sdgpu_comparison* out,
+                        sdgpu_gap* gapsOut, uint32_t gapCap);
+
+/* Device-resident variant for benchmarking the kernels alone: pair lists and outputs are
+ * device pointers (from sdgpu_dev_alloc); nothing crosses PCIe.  Asynchronous on the ctx stream. */
+int sdgpu_align_profile_dev(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx,
+                            uint32_t nPairs, uint32_t flags, sdgpu_comparison* dOut);
+int sdgpu_dev_alloc(sdgpu_ctx* ctx, uint64_t bytes, void** dptr);
+int sdgpu_dev_free(sdgpu_ctx* ctx, void* dptr);
+int sdgpu_memcpy_h2d(sdgpu_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int sdgpu_memcpy_d2h(sdgpu_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+
+/* Stream-ordered timing on the ctx's own stream (torch.cuda.Event only sees torch's stream). */
+int sdgpu_sync(sdgpu_ctx* ctx);
+int sdgpu_timer_start(sdgpu_ctx* ctx);
+int sdgpu_timer_stop(sdgpu_ctx* ctx, float* msOut); /* records, synchronizes, returns elapsed ms */
+/* Counters: kernels launched by this ctx and DP cells computed since creation. */
+int sdgpu_counters(sdgpu_ctx* ctx, uint64_t* kernelLaunches, uint64_t* cellUpdates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDGPU_H_ */

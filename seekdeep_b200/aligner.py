@@ -1,0 +1,188 @@
+"""GpuAligner — Python mirror of the reference-side `aligner` usage over the C ABI.
+
+The reference drives one pair at a time through stateful members
+(`alignerObj.alignCacheGlobal(ref, read); alignerObj.profileAlignment(ref, read, ...)` then
+reads `alignerObj.comp_`, clusterDown.cpp:739-753).  The GPU path takes pair *batches* and
+returns one `comparison` record per pair; names and argument meaning follow the reference.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+
+
+class SdgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sdgpu error {code}: {msg}")
+        self.code = code
+
+
+def pack_seqs(seqs, quals=None):
+    """list of str/bytes (+ list of uint8 arrays) -> (bases u8, quals u8|None, offsets u64)."""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    offsets = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offsets[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, np.uint8)
+    q = None
+    if quals is not None:
+        q = np.concatenate([np.asarray(x, dtype=np.uint8) for x in quals]) if len(quals) else np.zeros(0, np.uint8)
+        if q.size != bases.size:
+            raise ValueError("quals and bases differ in total length")
+    return bases, q, offsets
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GpuAligner:
+    """One context per host thread / GPU, like one njhseq aligner per thread (AlignerPool)."""
+
+    def __init__(self, params, device=0):
+        self._lib = _abi.load()
+        self._ctx = C.c_void_p()
+        self.params = params
+        rc = self._lib.sdgpu_create(device, C.byref(params), C.byref(self._ctx))
+        if rc != _abi.OK:
+            msg = self._lib.sdgpu_last_error(None)
+            self._ctx = None
+            raise SdgpuError(rc, msg.decode() if msg else "")
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != _abi.OK:
+            raise SdgpuError(rc, self._lib.sdgpu_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.sdgpu_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- sequence store
+    def upload_seqs(self, bases, quals, offsets, cnts=None):
+        bases = np.ascontiguousarray(bases, np.uint8)
+        quals = None if quals is None else np.ascontiguousarray(quals, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        cnts = None if cnts is None else np.ascontiguousarray(cnts, np.float64)
+        self._check(self._lib.sdgpu_upload_seqs(self._ctx, _ptr(bases), _ptr(quals), _ptr(offsets), _ptr(cnts),
+                                                len(offsets) - 1))
+
+    def append_seqs(self, bases, quals, offsets, cnts=None):
+        bases = np.ascontiguousarray(bases, np.uint8)
+        quals = None if quals is None else np.ascontiguousarray(quals, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        cnts = None if cnts is None else np.ascontiguousarray(cnts, np.float64)
+        first = C.c_uint32()
+        self._check(self._lib.sdgpu_append_seqs(self._ctx, _ptr(bases), _ptr(quals), _ptr(offsets), _ptr(cnts),
+                                                len(offsets) - 1, C.byref(first)))
+        return first.value
+
+    def num_seqs(self):
+        n = C.c_uint32()
+        self._check(self._lib.sdgpu_num_seqs(self._ctx, C.byref(n)))
+        return n.value
+
+    def set_params(self, params):
+        self.params = params
+        self._check(self._lib.sdgpu_set_params(self._ctx, C.byref(params)))
+
+    # -- k-mers
+    def index_kmers(self, kLength, runCutOff, kmersByPosition=True, expandKmerPos=False, expandKmerSize=0, seqIdx=None):
+        """≙ alignerObj.kMaps_ = indexKmers(clusters, kLength, runCutOff, kmersByPosition, expandKmerPos, expandKmerSize)."""
+        idx = None if seqIdx is None else np.ascontiguousarray(seqIdx, np.uint32)
+        self._check(self._lib.sdgpu_build_kmer_index(self._ctx, _ptr(idx), 0 if idx is None else len(idx), kLength,
+                                                     runCutOff, int(kmersByPosition), int(expandKmerPos), expandKmerSize))
+
+    def kmer_index_lookup(self, kmers, positions):
+        k = np.frombuffer(b"".join(x.encode() if isinstance(x, str) else x for x in kmers), np.uint8).copy()
+        pos = np.ascontiguousarray(positions, np.uint32)
+        out = np.zeros(len(pos), np.uint32)
+        self._check(self._lib.sdgpu_kmer_index_lookup(self._ctx, _ptr(k), _ptr(pos), len(pos), _ptr(out)))
+        return out
+
+    def build_kmer_profiles(self, kLen):
+        """≙ kmerInfo(seq, kLen, false) for every stored sequence."""
+        self._check(self._lib.sdgpu_build_kmer_profiles(self._ctx, kLen))
+
+    def compare_kmers(self, a, b):
+        """≙ [seq[a[i]].compareKmers(seq[b[i]]) for i] -> (shared u32[n], frac f64[n])."""
+        a = np.ascontiguousarray(a, np.uint32)
+        b = np.ascontiguousarray(b, np.uint32)
+        shared = np.zeros(len(a), np.uint32)
+        frac = np.zeros(len(a), np.float64)
+        self._check(self._lib.sdgpu_kmer_compare(self._ctx, _ptr(a), _ptr(b), len(a), _ptr(shared), _ptr(frac)))
+        return shared, frac
+
+    def compare_kmers_all(self, reads, clusters):
+        reads = np.ascontiguousarray(reads, np.uint32)
+        clusters = np.ascontiguousarray(clusters, np.uint32)
+        shared = np.zeros((len(reads), len(clusters)), np.uint32)
+        frac = np.zeros((len(reads), len(clusters)), np.float64)
+        self._check(self._lib.sdgpu_kmer_compare_all(self._ctx, _ptr(reads), len(reads), _ptr(clusters), len(clusters),
+                                                     _ptr(shared), _ptr(frac)))
+        return shared, frac
+
+    # -- alignment + errorProfile
+    def align_profile(self, refIdx, readIdx, checkKmer=False, usingQuality=True, doingMatchQuality=False, gapCap=0):
+        """≙ for each pair: alignCacheGlobal(ref, read); profileAlignment(ref, read, checkKmer,
+        usingQuality, doingMatchQuality) -> comp_.  Returns a structured array (COMPARISON_DTYPE)
+        and, if gapCap > 0, the gap runs (GAP_DTYPE[nPairs, gapCap])."""
+        refIdx = np.ascontiguousarray(refIdx, np.uint32)
+        readIdx = np.ascontiguousarray(readIdx, np.uint32)
+        n = len(refIdx)
+        flags = (_abi.CHECK_KMER if checkKmer else 0) | (_abi.USING_QUALITY if usingQuality else 0) | \
+                (_abi.MATCH_QUALITY if doingMatchQuality else 0)
+        out = np.zeros(n, _abi.COMPARISON_DTYPE)
+        gaps = np.zeros((n, gapCap), _abi.GAP_DTYPE) if gapCap else None
+        self._check(self._lib.sdgpu_align_profile(self._ctx, _ptr(refIdx), _ptr(readIdx), n, flags, _ptr(out),
+                                                  _ptr(gaps), gapCap))
+        return (out, gaps) if gapCap else out
+
+    # -- device-resident benchmarking helpers
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._lib.sdgpu_dev_alloc(self._ctx, nbytes, C.byref(p)))
+        return p
+
+    def dev_free(self, p):
+        self._check(self._lib.sdgpu_dev_free(self._ctx, p))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self._lib.sdgpu_memcpy_h2d(self._ctx, dptr, _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr, dptr):
+        self._check(self._lib.sdgpu_memcpy_d2h(self._ctx, _ptr(arr), dptr, arr.nbytes))
+
+    def align_profile_dev(self, dRef, dRead, nPairs, dOut, flags=_abi.USING_QUALITY):
+        self._check(self._lib.sdgpu_align_profile_dev(self._ctx, dRef, dRead, nPairs, flags, dOut))
+
+    def sync(self):
+        self._check(self._lib.sdgpu_sync(self._ctx))
+
+    def timer_start(self):
+        self._check(self._lib.sdgpu_timer_start(self._ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self._lib.sdgpu_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def counters(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.sdgpu_counters(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value

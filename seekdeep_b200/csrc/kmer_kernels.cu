@@ -1,0 +1,353 @@
+// kmer_kernels.cu — kernel 1 of the qluster hot path.
+//   (1a) KmerMaps: positional k-mer frequency table over the current clusters.  Replaces
+//        indexKmers(clusters, kLen, runCutOff, kmersByPosition, expandKmerPos, expandKmerSize)
+//        (reference call sites clusterDown.cpp:412-417, 505-510).  The reference hashes
+//        std::string k-mers per position; here every (position, k-mer) occurrence becomes a
+//        64-bit key (pos << 48 | 4-bit-coded k-mer), keys are radix-sorted and run-length
+//        reduced, and lookups (from the errorProfile kernel) are binary searches.
+//   (1b) kmerInfo profiles + compareKmers.  Replaces kmerInfo(seq, k, false) and
+//        a.compareKmers(b) (extractorPairedEnd.cpp:819-824; PrimersAndMids.cpp:49-54).
+//        Dense sigma^k uint16 count vectors, streamed 128 bits at a time; shared k-mers are
+//        SIMD min + add over packed 16-bit lanes.  HBM-bound by construction.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include "sdgpu_internal.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// keys a k-mer at `cursor` emits before it when positions are expanded by +-e
+__host__ __device__ inline uint64_t expandedBefore(uint64_t cursor, uint64_t e) {
+  if (cursor <= e) return cursor * (e + 1) + cursor * (cursor - 1) / 2;
+  return e * (e + 1) + e * (e - 1) / 2 + (cursor - e) * (2 * e + 1);
+}
+
+__global__ void kmerKeysKernel(DevSeqs seqs, const uint32_t* seqIdx, const uint64_t* keyStart, uint32_t nIdx,
+                               uint32_t kLen, uint32_t byPos, uint32_t expand, uint64_t* keys, uint32_t* weights) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= nIdx) return;
+  const uint32_t s = seqIdx ? seqIdx[warp] : warp;
+  const uint64_t off = seqs.offsets[s];
+  const uint32_t len = uint32_t(seqs.offsets[s + 1] - off);
+  if (len < kLen) return;
+  const uint8_t* c = seqs.codes + off;
+  const uint32_t w = uint32_t(llrint(seqs.cnts[s]));
+  const uint64_t base = keyStart[warp];
+  const uint32_t nk = len - kLen + 1;
+  for (uint32_t cursor = lane; cursor < nk; cursor += 32) {
+    uint64_t kmer = 0;
+    for (uint32_t x = 0; x < kLen; ++x) kmer = (kmer << 4) | c[cursor + x];
+    if (!byPos) {
+      keys[base + cursor] = kmer;
+      weights[base + cursor] = w;
+    } else {
+      const uint32_t lo = cursor > expand ? cursor - expand : 0, hi = cursor + expand;
+      uint64_t o = base + expandedBefore(cursor, expand);
+      for (uint32_t p = lo; p <= hi; ++p, ++o) {
+        keys[o] = (uint64_t(p) << 48) | kmer;
+        weights[o] = w;
+      }
+    }
+  }
+}
+
+__global__ void kmerLookupKernel(DevKmerIndex idx, const uint64_t* keys, uint32_t n, uint32_t* out) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  const uint64_t key = keys[x];
+  uint32_t lo = 0, hi = idx.n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (idx.keys[mid] < key) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  out[x] = (lo < idx.n && idx.keys[lo] == key) ? idx.counts[lo] : 0u;
+}
+
+// ---------------------------------------------------------------- dense profiles
+// One warp per sequence; the profile is accumulated in shared memory with 32-bit atomics on
+// packed uint16 pairs, then written out as full 128-bit lines.
+__global__ void kmerProfileKernel(DevSeqs seqs, uint32_t kLen, uint32_t sigma, uint32_t profSize, uint16_t* profiles) {
+  extern __shared__ uint32_t sProf[];  // warpsPerCta * profSize/2 words
+  const uint32_t warpInCta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warpsPerCta = blockDim.x >> 5;
+  const uint32_t words = profSize / 2;
+  uint32_t* mine = sProf + warpInCta * words;
+  for (uint32_t s = blockIdx.x * warpsPerCta + warpInCta; s < seqs.n; s += gridDim.x * warpsPerCta) {
+    for (uint32_t x = lane; x < words; x += 32) mine[x] = 0;
+    __syncwarp();
+    const uint64_t off = seqs.offsets[s];
+    const uint32_t len = uint32_t(seqs.offsets[s + 1] - off);
+    const uint8_t* c = seqs.codes + off;
+    if (len >= kLen) {
+      for (uint32_t cursor = lane; cursor + kLen <= len; cursor += 32) {
+        uint32_t id = 0;
+        for (uint32_t x = 0; x < kLen; ++x) id = id * sigma + c[cursor + x];
+        atomicAdd(&mine[id >> 1], 1u << (16 * (id & 1)));
+      }
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(profiles + size_t(s) * profSize);
+    const uint4* src = reinterpret_cast<const uint4*>(mine);
+    for (uint32_t x = lane; x < words / 4; x += 32) dst[x] = src[x];
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ uint32_t minSum8(const uint4& p, const uint4& q, uint32_t acc) {
+  acc = __vadd2(acc, __vminu2(p.x, q.x));
+  acc = __vadd2(acc, __vminu2(p.y, q.y));
+  acc = __vadd2(acc, __vminu2(p.z, q.z));
+  acc = __vadd2(acc, __vminu2(p.w, q.w));
+  return acc;
+}
+
+// One warp per pair.  pairs given explicitly (a[], b[]) or as a dense reads x clusters grid.
+__global__ void kmerCompareKernel(DevSeqs seqs, const uint16_t* profiles, uint32_t profSize, uint32_t kLen,
+                                  const uint32_t* a, const uint32_t* b, uint64_t nPairs, uint32_t nCols,
+                                  uint32_t* sharedOut, double* fracOut) {
+  const uint64_t warp0 = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nWarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t vecs = profSize / 8;
+  for (uint64_t p = warp0; p < nPairs; p += nWarps) {
+    uint32_t ia, ib;
+    if (nCols) {  // dense grid: row = read, col = cluster
+      ia = a[p / nCols];
+      ib = b[p % nCols];
+    } else {
+      ia = a[p];
+      ib = b[p];
+    }
+    const uint4* pa = reinterpret_cast<const uint4*>(profiles + size_t(ia) * profSize);
+    const uint4* pb = reinterpret_cast<const uint4*>(profiles + size_t(ib) * profSize);
+    uint32_t acc = 0;
+    for (uint32_t x = lane; x < vecs; x += 32) acc = minSum8(__ldg(pa + x), __ldg(pb + x), acc);
+    uint32_t sum = (acc & 0xffffu) + (acc >> 16);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    if (lane == 0) {
+      const uint32_t la = uint32_t(seqs.offsets[ia + 1] - seqs.offsets[ia]);
+      const uint32_t lb = uint32_t(seqs.offsets[ib + 1] - seqs.offsets[ib]);
+      const uint32_t minLen = la < lb ? la : lb;
+      sharedOut[p] = sum;
+      fracOut[p] = (minLen >= kLen) ? double(sum) / double(minLen - kLen + 1) : 0.0;
+    }
+  }
+}
+
+}  // namespace
+
+int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, uint32_t kLen, uint32_t runCutOff,
+                        int byPos, int expandPos, uint32_t expandSize) {
+  if (kLen == 0 || kLen > 12) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "k-mer index supports 1 <= kLen <= 12");
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  if (!hSeqIdx) nIdx = nSeqs;
+  const uint32_t e = (byPos && expandPos) ? expandSize : 0;
+  std::vector<uint64_t> start(size_t(nIdx) + 1, 0);
+  for (uint32_t n = 0; n < nIdx; ++n) {
+    const uint32_t s = hSeqIdx ? hSeqIdx[n] : n;
+    if (s >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "sequence index out of range");
+    const uint64_t len = ctx->hOffsets[s + 1] - ctx->hOffsets[s];
+    if (len >= 65536) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "k-mer index supports sequences < 65536 bases");
+    const uint64_t nk = len >= kLen ? len - kLen + 1 : 0;
+    start[n + 1] = start[n] + (byPos ? expandedBefore(nk, e) : nk);
+  }
+  const uint64_t total = start[nIdx];
+  if (total >= (1ull << 32)) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "k-mer index too large (>= 2^32 occurrences)");
+  if (ctx->dIdxKeys) cudaFree(ctx->dIdxKeys);
+  if (ctx->dIdxCnts) cudaFree(ctx->dIdxCnts);
+  ctx->dIdxKeys = nullptr;
+  ctx->dIdxCnts = nullptr;
+  ctx->nIdx = 0;
+  ctx->idxK = kLen;
+  ctx->idxRunCutOff = runCutOff;
+  ctx->idxByPos = byPos ? 1 : 0;
+  ctx->haveIndex = true;
+  if (total == 0) return SDGPU_OK;
+
+  uint64_t *dKeysIn = nullptr, *dKeysOut = nullptr, *dStart = nullptr;
+  uint32_t *dWIn = nullptr, *dWOut = nullptr, *dSeqIdx = nullptr, *dNumRuns = nullptr;
+  void* dTemp = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(dKeysIn); cudaFree(dKeysOut); cudaFree(dStart); cudaFree(dWIn); cudaFree(dWOut);
+    cudaFree(dSeqIdx); cudaFree(dNumRuns); cudaFree(dTemp);
+  };
+#define SD_CUDA_C(call)                                                              \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      cleanup();                                                                     \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                \
+      return SDGPU_E_CUDA;                                                           \
+    }                                                                                \
+  } while (0)
+  SD_CUDA_C(cudaMalloc(&dKeysIn, total * 8));
+  SD_CUDA_C(cudaMalloc(&dKeysOut, total * 8));
+  SD_CUDA_C(cudaMalloc(&dWIn, total * 4));
+  SD_CUDA_C(cudaMalloc(&dWOut, total * 4));
+  SD_CUDA_C(cudaMalloc(&dStart, (size_t(nIdx) + 1) * 8));
+  SD_CUDA_C(cudaMalloc(&dNumRuns, 4));
+  SD_CUDA_C(cudaMemcpyAsync(dStart, start.data(), (size_t(nIdx) + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (hSeqIdx) {
+    SD_CUDA_C(cudaMalloc(&dSeqIdx, size_t(nIdx) * 4));
+    SD_CUDA_C(cudaMemcpyAsync(dSeqIdx, hSeqIdx, size_t(nIdx) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  {
+    const uint32_t threads = 128, warpsPerCta = threads / 32;
+    const uint32_t grid = (nIdx + warpsPerCta - 1) / warpsPerCta;
+    kmerKeysKernel<<<grid, threads, 0, ctx->stream>>>(sd_dev_seqs(ctx), dSeqIdx, dStart, nIdx, kLen, byPos ? 1 : 0, e,
+                                                      dKeysIn, dWIn);
+    SD_CUDA_C(cudaGetLastError());
+    ++ctx->launches;
+  }
+  size_t tempSort = 0, tempReduce = 0;
+  const int endBit = byPos ? 64 : int(4 * kLen);
+  SD_CUDA_C(cub::DeviceRadixSort::SortPairs(nullptr, tempSort, dKeysIn, dKeysOut, dWIn, dWOut, int(total), 0, endBit,
+                                            ctx->stream));
+  SD_CUDA_C(cub::DeviceReduce::ReduceByKey(nullptr, tempReduce, dKeysOut, dKeysIn, dWOut, dWIn, dNumRuns, cub::Sum(),
+                                           int(total), ctx->stream));
+  SD_CUDA_C(cudaMalloc(&dTemp, std::max(tempSort, tempReduce)));
+  SD_CUDA_C(cub::DeviceRadixSort::SortPairs(dTemp, tempSort, dKeysIn, dKeysOut, dWIn, dWOut, int(total), 0, endBit,
+                                            ctx->stream));
+  SD_CUDA_C(cub::DeviceReduce::ReduceByKey(dTemp, tempReduce, dKeysOut, dKeysIn, dWOut, dWIn, dNumRuns, cub::Sum(),
+                                           int(total), ctx->stream));
+  ctx->launches += 2;
+  uint32_t numRuns = 0;
+  SD_CUDA_C(cudaMemcpyAsync(&numRuns, dNumRuns, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA_C(cudaStreamSynchronize(ctx->stream));
+  SD_CUDA_C(cudaMalloc(&ctx->dIdxKeys, size_t(numRuns) * 8));
+  SD_CUDA_C(cudaMalloc(&ctx->dIdxCnts, size_t(numRuns) * 4));
+  SD_CUDA_C(cudaMemcpyAsync(ctx->dIdxKeys, dKeysIn, size_t(numRuns) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  SD_CUDA_C(cudaMemcpyAsync(ctx->dIdxCnts, dWIn, size_t(numRuns) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  SD_CUDA_C(cudaStreamSynchronize(ctx->stream));
+  ctx->nIdx = numRuns;
+  cleanup();
+#undef SD_CUDA_C
+  return SDGPU_OK;
+}
+
+int sd_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers, const uint32_t* positions, uint32_t n,
+                         uint32_t* countsOut) {
+  if (!ctx->haveIndex) return sd_fail(ctx, SDGPU_E_STATE, "no k-mer index built");
+  if (n == 0) return SDGPU_OK;
+  std::vector<uint64_t> keys(n);
+  for (uint32_t x = 0; x < n; ++x) {
+    uint64_t kmer = 0;
+    bool known = true;
+    for (uint32_t y = 0; y < ctx->idxK; ++y) {
+      const int code = ctx->codeOf[kmers[size_t(x) * ctx->idxK + y]];
+      if (code < 0) known = false;
+      kmer = (kmer << 4) | uint64_t(code & 15);
+    }
+    keys[x] = known ? ((ctx->idxByPos ? (uint64_t(positions ? positions[x] : 0) << 48) : 0ull) | kmer) : ~0ull;
+  }
+  int rc = sd_ensure_stage(ctx, size_t(n) * 12);
+  if (rc) return rc;
+  uint64_t* dKeys = reinterpret_cast<uint64_t*>(ctx->dStage);
+  uint32_t* dOut = reinterpret_cast<uint32_t*>(dKeys + n);
+  SD_CUDA(ctx, cudaMemcpyAsync(dKeys, keys.data(), size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  kmerLookupKernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(sd_dev_index(ctx), dKeys, n, dOut);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  SD_CUDA(ctx, cudaMemcpyAsync(countsOut, dOut, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}
+
+int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
+  const uint32_t sigma = uint32_t(ctx->nSym < 4 ? 4 : ctx->nSym);
+  uint64_t size = 1;
+  for (uint32_t x = 0; x < kLen; ++x) {
+    size *= sigma;
+    if (size > 16384) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "dense k-mer profile larger than 16384 bins (kLen too large for this alphabet)");
+  }
+  if (kLen == 0) return sd_fail(ctx, SDGPU_E_ARG, "kLen must be >= 1");
+  const uint32_t profSize = uint32_t((size + 7) & ~7ull);  // multiple of 8 uint16 = 16 bytes
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  if (ctx->maxLen >= 65536) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "profiles need sequences < 65536 bases");
+  if (ctx->dProfiles) cudaFree(ctx->dProfiles);
+  ctx->dProfiles = nullptr;
+  ctx->profK = kLen;
+  ctx->profSize = profSize;
+  ctx->profSeqs = nSeqs;
+  if (nSeqs == 0) return SDGPU_OK;
+  SD_CUDA(ctx, cudaMalloc(&ctx->dProfiles, size_t(nSeqs) * profSize * 2));
+  const uint32_t warpsPerCta = 4;
+  const size_t smem = size_t(warpsPerCta) * profSize * 2;
+  SD_CUDA(ctx, cudaFuncSetAttribute(kmerProfileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  uint32_t grid = (nSeqs + warpsPerCta - 1) / warpsPerCta;
+  const uint32_t maxGrid = uint32_t(ctx->numSMs) * 8;
+  if (grid > maxGrid) grid = maxGrid;
+  kmerProfileKernel<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, profSize, ctx->dProfiles);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  return SDGPU_OK;
+}
+
+static int compareLaunch(sdgpu_ctx* ctx, const uint32_t* dA, const uint32_t* dB, uint64_t nPairs, uint32_t nCols,
+                         uint32_t* dShared, double* dFrac) {
+  uint64_t ctas = (nPairs + 3) / 4;
+  const uint64_t maxGrid = uint64_t(ctx->numSMs) * 16;
+  if (ctas > maxGrid) ctas = maxGrid;
+  kmerCompareKernel<<<uint32_t(ctas), 128, 0, ctx->stream>>>(sd_dev_seqs(ctx), ctx->dProfiles, ctx->profSize, ctx->profK, dA,
+                                                            dB, nPairs, nCols, dShared, dFrac);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  return SDGPU_OK;
+}
+
+int sd_kmer_compare_pairs(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, uint32_t* sharedOut,
+                          double* fracOut) {
+  if (!ctx->dProfiles) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_build_kmer_profiles has not been called");
+  if (nPairs == 0) return SDGPU_OK;
+  for (uint32_t x = 0; x < nPairs; ++x)
+    if (a[x] >= ctx->profSeqs || b[x] >= ctx->profSeqs) return sd_fail(ctx, SDGPU_E_ARG, "pair index outside the profiled store");
+  const size_t bytes = size_t(nPairs) * (4 + 4 + 4 + 8) + 64;
+  int rc = sd_ensure_stage(ctx, bytes);
+  if (rc) return rc;
+  double* dFrac = reinterpret_cast<double*>(ctx->dStage);
+  uint32_t* dA = reinterpret_cast<uint32_t*>(dFrac + nPairs);
+  uint32_t* dB = dA + nPairs;
+  uint32_t* dShared = dB + nPairs;
+  SD_CUDA(ctx, cudaMemcpyAsync(dA, a, size_t(nPairs) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(dB, b, size_t(nPairs) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = compareLaunch(ctx, dA, dB, nPairs, 0, dShared, dFrac);
+  if (rc) return rc;
+  SD_CUDA(ctx, cudaMemcpyAsync(sharedOut, dShared, size_t(nPairs) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(fracOut, dFrac, size_t(nPairs) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}
+
+int sd_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nReads, const uint32_t* clusters,
+                        uint32_t nClusters, uint32_t* sharedOut, double* fracOut) {
+  if (!ctx->dProfiles) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_build_kmer_profiles has not been called");
+  const uint64_t nPairs = uint64_t(nReads) * nClusters;
+  if (nPairs == 0) return SDGPU_OK;
+  for (uint32_t x = 0; x < nReads; ++x)
+    if (reads[x] >= ctx->profSeqs) return sd_fail(ctx, SDGPU_E_ARG, "read index outside the profiled store");
+  for (uint32_t x = 0; x < nClusters; ++x)
+    if (clusters[x] >= ctx->profSeqs) return sd_fail(ctx, SDGPU_E_ARG, "cluster index outside the profiled store");
+  const size_t bytes = nPairs * 12 + (size_t(nReads) + nClusters) * 4 + 64;
+  int rc = sd_ensure_stage(ctx, bytes);
+  if (rc) return rc;
+  double* dFrac = reinterpret_cast<double*>(ctx->dStage);
+  uint32_t* dShared = reinterpret_cast<uint32_t*>(dFrac + nPairs);
+  uint32_t* dA = dShared + nPairs;
+  uint32_t* dB = dA + nReads;
+  SD_CUDA(ctx, cudaMemcpyAsync(dA, reads, size_t(nReads) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(dB, clusters, size_t(nClusters) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  rc = compareLaunch(ctx, dA, dB, nPairs, nClusters, dShared, dFrac);
+  if (rc) return rc;
+  SD_CUDA(ctx, cudaMemcpyAsync(sharedOut, dShared, nPairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(fracOut, dFrac, nPairs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}

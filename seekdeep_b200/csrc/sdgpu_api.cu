@@ -1,0 +1,428 @@
+// sdgpu_api.cu — the C ABI declared in include/sdgpu.h: context, sequence store, dispatch.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "sdgpu_internal.cuh"
+
+static thread_local std::string g_createErr;
+
+int sd_fail(sdgpu_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+static int growDevice(sdgpu_ctx* ctx, void** p, uint64_t* cap, uint64_t need, uint64_t keepBytes) {
+  if (need <= *cap) return SDGPU_OK;
+  uint64_t n = std::max<uint64_t>(need, *cap * 2);
+  n = (n + 255) & ~255ull;
+  void* q = nullptr;
+  SD_CUDA(ctx, cudaMalloc(&q, n));
+  if (*p && keepBytes) SD_CUDA(ctx, cudaMemcpyAsync(q, *p, keepBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (*p) {
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(*p);
+  }
+  *p = q;
+  *cap = n;
+  return SDGPU_OK;
+}
+
+int sd_ensure_scratch(sdgpu_ctx* ctx, uint64_t bytes) {
+  return growDevice(ctx, reinterpret_cast<void**>(&ctx->dScratch), &ctx->scratchBytes, bytes, 0);
+}
+int sd_ensure_stage(sdgpu_ctx* ctx, uint64_t bytes) {
+  return growDevice(ctx, &ctx->dStage, &ctx->stageBytes, bytes, 0);
+}
+int sd_ensure_pinned(sdgpu_ctx* ctx, uint64_t bytes) {
+  if (bytes <= ctx->pinnedBytes) return SDGPU_OK;
+  if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  ctx->hPinned = nullptr;
+  ctx->pinnedBytes = 0;
+  const uint64_t n = std::max<uint64_t>(bytes, 1u << 20);
+  SD_CUDA(ctx, cudaMallocHost(&ctx->hPinned, n));
+  ctx->pinnedBytes = n;
+  return SDGPU_OK;
+}
+
+DevSeqs sd_dev_seqs(const sdgpu_ctx* ctx) {
+  DevSeqs s;
+  s.codes = ctx->dCodes;
+  s.quals = ctx->dQuals;
+  s.offsets = ctx->dOffsets;
+  s.cnts = ctx->dCnts;
+  s.n = uint32_t(ctx->hOffsets.size() - 1);
+  return s;
+}
+
+DevKmerIndex sd_dev_index(const sdgpu_ctx* ctx) {
+  DevKmerIndex k;
+  k.keys = ctx->dIdxKeys;
+  k.counts = ctx->dIdxCnts;
+  k.n = ctx->nIdx;
+  k.kLen = ctx->idxK;
+  k.runCutOff = ctx->idxRunCutOff;
+  k.byPos = ctx->idxByPos;
+  return k;
+}
+
+// (Re)derive the device scoring block from params + the current alphabet.
+static int refreshScoring(sdgpu_ctx* ctx) {
+  const sdgpu_params& p = ctx->params;
+  DevScoring& s = ctx->scoring;
+  s.go = p.gaps.gapOpen;
+  s.ge = p.gaps.gapExtend;
+  s.goLQ = p.gaps.gapLeftQueryOpen;
+  s.geLQ = p.gaps.gapLeftQueryExtend;
+  s.goRQ = p.gaps.gapRightQueryOpen;
+  s.geRQ = p.gaps.gapRightQueryExtend;
+  s.goLR = p.gaps.gapLeftRefOpen;
+  s.geLR = p.gaps.gapLeftRefExtend;
+  s.goRR = p.gaps.gapRightRefOpen;
+  s.geRR = p.gaps.gapRightRefExtend;
+  s.primaryQual = int(p.primaryQual);
+  s.secondaryQual = int(p.secondaryQual);
+  s.window = int(p.qualThresWindow);
+  s.countEndGaps = p.countEndGaps ? 1 : 0;
+  s.weighHomopolymers = p.weighHomopolymers ? 1 : 0;
+  for (int a = 0; a < SDGPU_MAX_SYMBOLS; ++a)
+    for (int b = 0; b < SDGPU_MAX_SYMBOLS; ++b) {
+      int v = 0;
+      if (a < ctx->nSym && b < ctx->nSym) v = p.scoreMat[size_t(ctx->charOf[a]) * SDGPU_MAT_DIM + ctx->charOf[b]];
+      if (v < -32768 || v > 32767) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "score matrix entry outside int16");
+      s.score[a * SDGPU_MAX_SYMBOLS + b] = int16_t(v);
+    }
+  return SDGPU_OK;
+}
+
+static int validateParams(sdgpu_ctx* ctx, const sdgpu_params* p) {
+  const int32_t* g = reinterpret_cast<const int32_t*>(&p->gaps);
+  for (int x = 0; x < 10; ++x)
+    if (g[x] < 0 || g[x] > 1000000) return sd_fail(ctx, SDGPU_E_ARG, "gap penalties must be in [0, 1e6]");
+  if (p->qualThresWindow > 64) return sd_fail(ctx, SDGPU_E_ARG, "qualThresWindow > 64");
+  return SDGPU_OK;
+}
+
+extern "C" {
+
+int sdgpu_abi_version(void) { return SDGPU_ABI_VERSION; }
+
+int sdgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int sdgpu_create(int device, const sdgpu_params* params, sdgpu_ctx** out) {
+  if (!params || !out) {
+    g_createErr = "sdgpu_create: null argument";
+    return SDGPU_E_ARG;
+  }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n) {
+    g_createErr = std::string("sdgpu_create: no usable CUDA device (") +
+                  (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range") + "); there is no CPU fallback";
+    cudaGetLastError();
+    return SDGPU_E_CUDA;
+  }
+  sdgpu_ctx* ctx = new (std::nothrow) sdgpu_ctx();
+  if (!ctx) return SDGPU_E_ARG;
+  ctx->device = device;
+  auto bail = [&](int rc) {
+    g_createErr = ctx->err;
+    sdgpu_destroy(ctx);
+    return rc;
+  };
+  if (validateParams(ctx, params)) return bail(SDGPU_E_ARG);
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+      (e = cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->dWork, 64)) != cudaSuccess || (e = cudaMemset(ctx->dWork, 0, 64)) != cudaSuccess) {
+    ctx->err = std::string("sdgpu_create: ") + cudaGetErrorString(e);
+    return bail(SDGPU_E_CUDA);
+  }
+  ctx->params = *params;
+  for (int x = 0; x < 256; ++x) ctx->codeOf[x] = -1;
+  // fixed head of the alphabet so that codes are stable across runs
+  const char* head = "ACGTN";
+  for (int x = 0; head[x]; ++x) {
+    ctx->codeOf[uint8_t(head[x])] = int16_t(ctx->nSym);
+    ctx->charOf[ctx->nSym++] = uint8_t(head[x]);
+  }
+  int rc = refreshScoring(ctx);
+  if (rc) return bail(rc);
+  *out = ctx;
+  return SDGPU_OK;
+}
+
+void sdgpu_destroy(sdgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->dCodes);
+  cudaFree(ctx->dQuals);
+  cudaFree(ctx->dOffsets);
+  cudaFree(ctx->dCnts);
+  cudaFree(ctx->dIdxKeys);
+  cudaFree(ctx->dIdxCnts);
+  cudaFree(ctx->dProfiles);
+  cudaFree(ctx->dScratch);
+  cudaFree(ctx->dWork);
+  cudaFree(ctx->dStage);
+  if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
+  delete ctx;
+}
+
+const char* sdgpu_last_error(sdgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createErr.c_str(); }
+
+int sdgpu_set_params(sdgpu_ctx* ctx, const sdgpu_params* params) {
+  if (!ctx || !params) return SDGPU_E_ARG;
+  int rc = validateParams(ctx, params);
+  if (rc) return rc;
+  ctx->params = *params;
+  return refreshScoring(ctx);
+}
+
+static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                      const double* cnts, uint32_t n, uint32_t* firstIndex) {
+  if (!ctx || (n && (!bases || !offsets))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t oldN = uint32_t(ctx->hOffsets.size() - 1);
+  if (firstIndex) *firstIndex = oldN;
+  if (n == 0) return SDGPU_OK;
+  if (offsets[0] != 0) return sd_fail(ctx, SDGPU_E_ARG, "offsets[0] must be 0");
+  const uint64_t oldBases = ctx->hOffsets.back();
+  const uint64_t addBases = offsets[n];
+  // alphabet + code translation on the host (one pass; the store is write-once, read-many)
+  int rc = sd_ensure_pinned(ctx, addBases * 2 + 64);
+  if (rc) return rc;
+  uint8_t* hCodes = reinterpret_cast<uint8_t*>(ctx->hPinned);
+  uint8_t* hQuals = hCodes + addBases;
+  bool newSym = false;
+  uint32_t maxLen = ctx->maxLen;
+  for (uint32_t s = 0; s < n; ++s) {
+    if (offsets[s + 1] < offsets[s]) return sd_fail(ctx, SDGPU_E_ARG, "offsets must be non-decreasing");
+    const uint64_t len = offsets[s + 1] - offsets[s];
+    if (len == 0) return sd_fail(ctx, SDGPU_E_ARG, "empty sequence");
+    if (len > 0x7fffffffu) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "sequence too long");
+    maxLen = std::max<uint32_t>(maxLen, uint32_t(len));
+  }
+  for (uint64_t x = 0; x < addBases; ++x) {
+    const uint8_t ch = bases[x];
+    int code = ctx->codeOf[ch];
+    if (code < 0) {
+      if (ch >= 128) return sd_fail(ctx, SDGPU_E_ALPHABET, "base outside 7-bit ASCII");
+      if (ctx->nSym >= SDGPU_MAX_SYMBOLS) return sd_fail(ctx, SDGPU_E_ALPHABET, "more than 16 distinct base characters");
+      code = ctx->nSym;
+      ctx->codeOf[ch] = int16_t(code);
+      ctx->charOf[ctx->nSym++] = ch;
+      newSym = true;
+    }
+    hCodes[x] = uint8_t(code);
+  }
+  if (quals) {
+    std::memcpy(hQuals, quals, addBases);
+  } else {
+    std::memset(hQuals, 0, addBases);
+  }
+  if (newSym && (rc = refreshScoring(ctx))) return rc;
+  // grow device arrays
+  uint64_t capB = ctx->capBases, capB2 = ctx->capBases;
+  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dCodes), &capB, oldBases + addBases, oldBases))) return rc;
+  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dQuals), &capB2, oldBases + addBases, oldBases))) return rc;
+  ctx->capBases = std::min(capB, capB2);
+  const uint64_t needSeqs = uint64_t(oldN) + n + 1;
+  uint64_t capO = uint64_t(ctx->capSeqs) * 8, capC = uint64_t(ctx->capSeqs) * 8;
+  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dOffsets), &capO, needSeqs * 8, (uint64_t(oldN) + 1) * 8))) return rc;
+  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dCnts), &capC, needSeqs * 8, uint64_t(oldN) * 8))) return rc;
+  ctx->capSeqs = uint32_t(std::min(capO, capC) / 8);
+  SD_CUDA(ctx, cudaMemcpyAsync(ctx->dCodes + oldBases, hCodes, addBases, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(ctx->dQuals + oldBases, hQuals, addBases, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging is reused below
+  ctx->hOffsets.reserve(needSeqs);
+  for (uint32_t s = 1; s <= n; ++s) ctx->hOffsets.push_back(oldBases + offsets[s]);
+  SD_CUDA(ctx, cudaMemcpyAsync(ctx->dOffsets + oldN, ctx->hOffsets.data() + oldN, (uint64_t(n) + 1) * 8,
+                               cudaMemcpyHostToDevice, ctx->stream));
+  double* hC = reinterpret_cast<double*>(ctx->hPinned);
+  if ((rc = sd_ensure_pinned(ctx, uint64_t(n) * 8))) return rc;
+  hC = reinterpret_cast<double*>(ctx->hPinned);
+  for (uint32_t s = 0; s < n; ++s) hC[s] = cnts ? cnts[s] : 1.0;
+  SD_CUDA(ctx, cudaMemcpyAsync(ctx->dCnts + oldN, hC, uint64_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->maxLen = maxLen;
+  return SDGPU_OK;
+}
+
+int sdgpu_upload_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                      const double* cnts, uint32_t n) {
+  if (!ctx) return SDGPU_E_ARG;
+  ctx->hOffsets.assign(1, 0);
+  ctx->maxLen = 0;
+  ctx->haveIndex = false;
+  ctx->profSeqs = 0;
+  return appendImpl(ctx, bases, quals, offsets, cnts, n, nullptr);
+}
+
+int sdgpu_append_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
+                      const double* cnts, uint32_t n, uint32_t* firstIndex) {
+  return appendImpl(ctx, bases, quals, offsets, cnts, n, firstIndex);
+}
+
+int sdgpu_num_seqs(sdgpu_ctx* ctx, uint32_t* n) {
+  if (!ctx || !n) return SDGPU_E_ARG;
+  *n = uint32_t(ctx->hOffsets.size() - 1);
+  return SDGPU_OK;
+}
+
+int sdgpu_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* seqIdx, uint32_t nIdx, uint32_t kLen, uint32_t runCutOff,
+                           int kmersByPosition, int expandKmerPos, uint32_t expandKmerSize) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_build_kmer_index(ctx, seqIdx, nIdx, kLen, runCutOff, kmersByPosition, expandKmerPos, expandKmerSize);
+}
+
+int sdgpu_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers, const uint32_t* positions, uint32_t n,
+                            uint32_t* countsOut) {
+  if (!ctx || (n && (!kmers || !countsOut))) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_kmer_index_lookup(ctx, kmers, positions, n, countsOut);
+}
+
+int sdgpu_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_build_kmer_profiles(ctx, kLen);
+}
+
+int sdgpu_kmer_compare(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, uint32_t* sharedOut,
+                       double* fracOut) {
+  if (!ctx || (nPairs && (!a || !b || !sharedOut || !fracOut))) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_kmer_compare_pairs(ctx, a, b, nPairs, sharedOut, fracOut);
+}
+
+int sdgpu_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nReads, const uint32_t* clusters,
+                           uint32_t nClusters, uint32_t* sharedOut, double* fracOut) {
+  if (!ctx || !reads || !clusters || !sharedOut || !fracOut) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_kmer_compare_all(ctx, reads, nReads, clusters, nClusters, sharedOut, fracOut);
+}
+
+int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,
+                        uint32_t flags, sdgpu_comparison* out, sdgpu_gap* gapsOut, uint32_t gapCap) {
+  if (!ctx || (nPairs && (!refIdx || !readIdx || !out))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  if (nPairs == 0) return SDGPU_OK;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  uint32_t maxA = 0, maxB = 0;
+  for (uint32_t x = 0; x < nPairs; ++x) {
+    if (refIdx[x] >= nSeqs || readIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "pair index out of range");
+    maxA = std::max<uint32_t>(maxA, uint32_t(ctx->hOffsets[refIdx[x] + 1] - ctx->hOffsets[refIdx[x]]));
+    maxB = std::max<uint32_t>(maxB, uint32_t(ctx->hOffsets[readIdx[x] + 1] - ctx->hOffsets[readIdx[x]]));
+  }
+  const bool wantGaps = gapsOut != nullptr && gapCap > 0;
+  const uint64_t bytesIdx = uint64_t(nPairs) * 4;
+  const uint64_t bytesOut = uint64_t(nPairs) * sizeof(sdgpu_comparison);
+  const uint64_t bytesGaps = wantGaps ? uint64_t(nPairs) * gapCap * sizeof(sdgpu_gap) : 0;
+  int rc = sd_ensure_stage(ctx, bytesOut + bytesGaps + 2 * bytesIdx + 256);
+  if (rc) return rc;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->dStage);
+  sdgpu_comparison* dOut = reinterpret_cast<sdgpu_comparison*>(base);
+  sdgpu_gap* dGaps = wantGaps ? reinterpret_cast<sdgpu_gap*>(base + bytesOut) : nullptr;
+  uint32_t* dRef = reinterpret_cast<uint32_t*>(base + bytesOut + ((bytesGaps + 15) & ~15ull));
+  uint32_t* dRead = dRef + nPairs;
+  SD_CUDA(ctx, cudaMemcpyAsync(dRef, refIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(dRead, readIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  if (wantGaps) SD_CUDA(ctx, cudaMemsetAsync(dGaps, 0, bytesGaps, ctx->stream));
+  rc = sd_launch_align(ctx, dRef, dRead, nPairs, flags, dOut, dGaps, wantGaps ? gapCap : 0, maxA, maxB);
+  if (rc) return rc;
+  SD_CUDA(ctx, cudaMemcpyAsync(out, dOut, bytesOut, cudaMemcpyDeviceToHost, ctx->stream));
+  if (wantGaps) SD_CUDA(ctx, cudaMemcpyAsync(gapsOut, dGaps, bytesGaps, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}
+
+int sdgpu_align_profile_dev(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx, uint32_t nPairs,
+                            uint32_t flags, sdgpu_comparison* dOut) {
+  if (!ctx || (nPairs && (!dRefIdx || !dReadIdx || !dOut))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_launch_align(ctx, dRefIdx, dReadIdx, nPairs, flags, dOut, nullptr, 0, ctx->maxLen, ctx->maxLen);
+}
+
+int sdgpu_dev_alloc(sdgpu_ctx* ctx, uint64_t bytes, void** dptr) {
+  if (!ctx || !dptr) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaMalloc(dptr, bytes));
+  return SDGPU_OK;
+}
+
+int sdgpu_dev_free(sdgpu_ctx* ctx, void* dptr) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  SD_CUDA(ctx, cudaFree(dptr));
+  return SDGPU_OK;
+}
+
+int sdgpu_memcpy_h2d(sdgpu_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}
+
+int sdgpu_memcpy_d2h(sdgpu_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}
+
+int sdgpu_sync(sdgpu_ctx* ctx) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}
+
+int sdgpu_timer_start(sdgpu_ctx* ctx) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return SDGPU_OK;
+}
+
+int sdgpu_timer_stop(sdgpu_ctx* ctx, float* msOut) {
+  if (!ctx || !msOut) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  SD_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  SD_CUDA(ctx, cudaEventElapsedTime(msOut, ctx->ev0, ctx->ev1));
+  return SDGPU_OK;
+}
+
+int sdgpu_counters(sdgpu_ctx* ctx, uint64_t* kernelLaunches, uint64_t* cellUpdates) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  uint64_t cells = 0;
+  SD_CUDA(ctx, cudaMemcpy(&cells, ctx->dWork + 2, 8, cudaMemcpyDeviceToHost));
+  if (kernelLaunches) *kernelLaunches = ctx->launches;
+  if (cellUpdates) *cellUpdates = cells;
+  return SDGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/sdgpu.h declares, POD layouts match, and compute entry points fail loudly (no CPU
+fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from seekdeep_b200 import _abi
+from seekdeep_b200.aligner import GpuAligner, SdgpuError
+from seekdeep_b200.scoring import make_params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for hdr in ("sdgpu.h", "sdgpu_qluster.h"):
+        path = os.path.join(ROOT, "include", hdr)
+        if not os.path.exists(path):
+            continue
+        txt = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+        names |= set(re.findall(r"\b(sdgpu_[a-z0-9_]+|sdq_[a-z0-9_]+)\s*\(", txt))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(_abi.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 24
+    for name in sorted(syms):
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported by libsdgpu.so"
+
+
+def test_python_signatures_cover_header():
+    hdr = {s for s in declared_symbols() if s.startswith("sdgpu_")}
+    assert hdr == set(_abi.SIGNATURES), hdr ^ set(_abi.SIGNATURES)
+
+
+def test_pod_layouts():
+    assert C.sizeof(_abi.GapPars) == 40
+    assert C.sizeof(_abi.Params) == 40 + 4 * 128 * 128 + 24
+    assert C.sizeof(_abi.Comparison) == 104 and C.sizeof(_abi.Gap) == 12
+    assert _abi.load().sdgpu_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    lib = _abi.load()
+    if lib.sdgpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(SdgpuError) as ei:
+        GpuAligner(make_params())
+    assert ei.value.code == _abi.E_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_does_not_reference_oracle():
+    """The shipped path must not include, link or import anything under oracle/."""
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "seekdeep_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"oracle|sdo_|libsdoracle", txt):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -1,0 +1,182 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+Integer / index fields bit-exact; float fields within 1e-6 relative (north_star tolerance)."""
+import numpy as np
+import pytest
+
+from seekdeep_b200 import _abi
+from seekdeep_b200.aligner import GpuAligner, SdgpuError, pack_seqs
+from seekdeep_b200.scoring import GapScoringParameters, make_params
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(oracle, params, bases, quals, offsets, cnts, refIdx, readIdx, flags, gapCap=0, kmer=None):
+    km = None
+    with GpuAligner(params) as al:
+        al.upload_seqs(bases, quals, offsets, cnts)
+        if kmer:
+            al.index_kmers(**kmer)
+            km = oracle.index_kmers(bases, offsets, cnts, kmer["kLength"], kmer["runCutOff"], kmer.get("kmersByPosition", True),
+                                    kmer.get("expandKmerPos", False), kmer.get("expandKmerSize", 0))
+        try:
+            got = al.align_profile(refIdx, readIdx, checkKmer=bool(flags & 1), usingQuality=bool(flags & 2),
+                                   doingMatchQuality=bool(flags & 4), gapCap=gapCap)
+            want = oracle.align_profile_batch(params, bases, quals, offsets, refIdx, readIdx, flags, kmaps=km, gapCap=gapCap)
+        finally:
+            if km:
+                oracle.free_kmaps(km)
+    return got, want
+
+
+@pytest.mark.parametrize("pname", sorted(H.PARAM_SETS))
+@pytest.mark.parametrize("length", [37, 150, 250, 301])
+def test_align_profile_matches_oracle(oracle, pname, length):
+    rng = np.random.default_rng(length * 131 + len(pname))
+    bases, quals, offsets, cnts, _, _ = H.make_store(rng, 48, length)
+    n = 400
+    refIdx = rng.integers(0, 48, n).astype(np.uint32)
+    readIdx = rng.integers(0, 48, n).astype(np.uint32)
+    (got, gg), (want, wg) = run_both(oracle, H.params_for(pname), bases, quals, offsets, cnts, refIdx, readIdx,
+                                     _abi.USING_QUALITY, gapCap=24)
+    H.assert_comparisons_equal(got, want)
+    assert np.array_equal(gg, wg)
+    for name in _abi.FLOAT_FIELDS:  # expected stronger than the 1e-6 bar: identical bits
+        assert np.array_equal(got[name], want[name]), name
+
+
+def test_unrelated_sequences_and_ragged_lengths(oracle):
+    rng = np.random.default_rng(11)
+    seqs = [H.rand_seq(rng, int(n)) for n in rng.integers(1, 330, 64)]
+    seqs[0] = H.rand_seq(rng, 1)
+    seqs[1] = H.rand_seq(rng, 2)
+    quals = [H.rand_quals(rng, len(s)) for s in seqs]
+    bases, q, offsets = H.np.concatenate(seqs), np.concatenate(quals), np.zeros(65, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    refIdx, readIdx = np.meshgrid(np.arange(64, dtype=np.uint32), np.arange(64, dtype=np.uint32))
+    refIdx, readIdx = refIdx.ravel(), readIdx.ravel()
+    for pname in ("qluster", "asym", "countEnds"):
+        (got, gg), (want, wg) = run_both(oracle, H.params_for(pname), bases, q, offsets, None, refIdx, readIdx,
+                                         _abi.USING_QUALITY | _abi.MATCH_QUALITY, gapCap=8)
+        H.assert_comparisons_equal(got, want)
+        assert np.array_equal(gg, wg)
+        assert (got["status"] & _abi.ST_GAPLIST_TRUNCATED).any()  # unrelated pairs overflow 8 runs
+
+
+def test_check_kmer_matches_oracle(oracle):
+    rng = np.random.default_rng(21)
+    bases, quals, offsets, cnts, _, _ = H.make_store(rng, 64, 250, lowFrac=0.05)
+    n = 600
+    refIdx = rng.integers(0, 8, n).astype(np.uint32)
+    readIdx = rng.integers(0, 64, n).astype(np.uint32)
+    for kw in (dict(kLength=9, runCutOff=1), dict(kLength=9, runCutOff=12, expandKmerPos=True, expandKmerSize=2),
+               dict(kLength=5, runCutOff=30, kmersByPosition=False)):
+        got, want = run_both(oracle, H.params_for("qluster"), bases, quals, offsets, cnts, refIdx, readIdx,
+                             _abi.USING_QUALITY | _abi.CHECK_KMER, kmer=kw)
+        H.assert_comparisons_equal(got, want)
+        assert got["lowKmerMismatches"].sum() > 0
+
+
+def test_degenerate_bases_and_n(oracle):
+    rng = np.random.default_rng(31)
+    alpha = np.frombuffer(b"ACGTNRYacgt", dtype=np.uint8)
+    bases, quals, offsets, cnts, _, _ = H.make_store(rng, 32, 120, alphabet=alpha)
+    refIdx = rng.integers(0, 32, 300).astype(np.uint32)
+    readIdx = rng.integers(0, 32, 300).astype(np.uint32)
+    for pname in ("qluster", "degenHomopolymer"):
+        got, want = run_both(oracle, H.params_for(pname), bases, quals, offsets, cnts, refIdx, readIdx, _abi.USING_QUALITY,
+                             kmer=None)
+        H.assert_comparisons_equal(got, want)
+
+
+def test_kmer_index_lookup(oracle):
+    rng = np.random.default_rng(41)
+    bases, quals, offsets, cnts, seqs, _ = H.make_store(rng, 40, 90)
+    for kw in (dict(k=9, cut=1, byPos=True, ex=False, es=0), dict(k=7, cut=1, byPos=True, ex=True, es=3),
+               dict(k=6, cut=1, byPos=False, ex=False, es=0)):
+        km = oracle.index_kmers(bases, offsets, cnts, kw["k"], kw["cut"], kw["byPos"], kw["ex"], kw["es"])
+        with GpuAligner(make_params()) as al:
+            al.upload_seqs(bases, quals, offsets, cnts)
+            al.index_kmers(kw["k"], kw["cut"], kw["byPos"], kw["ex"], kw["es"])
+            kmers, pos = [], []
+            for _ in range(500):
+                s = seqs[int(rng.integers(40))]
+                p = int(rng.integers(0, len(s) - kw["k"] + 1))
+                kmers.append(s[p:p + kw["k"]].tobytes())
+                pos.append(max(0, p + int(rng.integers(-4, 5))))
+            got = al.kmer_index_lookup(kmers, pos)
+        want = np.array([oracle.kmaps_count(km, k, p) for k, p in zip(kmers, pos)], np.uint32)
+        oracle.free_kmaps(km)
+        assert np.array_equal(got, want)
+
+
+def test_kmer_compare_matches_oracle(oracle):
+    rng = np.random.default_rng(51)
+    bases, quals, offsets, cnts, seqs, _ = H.make_store(rng, 50, 200, jitter=40, family=False)
+    fam = H.make_store(rng, 30, 200)
+    seqs = seqs + fam[4]
+    b2, q2, off2 = pack_seqs([s.tobytes() for s in seqs], [np.zeros(len(s), np.uint8) for s in seqs])
+    with GpuAligner(make_params()) as al:
+        al.upload_seqs(b2, q2, off2)
+        for k in (3, 5, 7):
+            al.build_kmer_profiles(k)
+            a = rng.integers(0, len(seqs), 400).astype(np.uint32)
+            b = rng.integers(0, len(seqs), 400).astype(np.uint32)
+            shared, frac = al.compare_kmers(a, b)
+            for i in range(400):
+                ws, wf = oracle.kmer_compare(seqs[a[i]].tobytes(), seqs[b[i]].tobytes(), k)
+                assert shared[i] == ws and abs(frac[i] - wf) <= 1e-6 * max(abs(wf), 1e-300) and frac[i] == wf
+            reads = np.arange(50, 80, dtype=np.uint32)
+            clus = np.arange(0, 12, dtype=np.uint32)
+            sh, fr = al.compare_kmers_all(reads, clus)
+            for i, r in enumerate(reads):
+                for j, c in enumerate(clus):
+                    ws, wf = oracle.kmer_compare(seqs[r].tobytes(), seqs[c].tobytes(), k)
+                    assert sh[i, j] == ws and fr[i, j] == wf
+
+
+def test_append_and_errors():
+    p = make_params()
+    with GpuAligner(p) as al:
+        b, q, off = pack_seqs(["ACGTACGT", "ACGAACGT"], [np.full(8, 30, np.uint8)] * 2)
+        al.upload_seqs(b, q, off)
+        first = al.append_seqs(*pack_seqs(["ACGTTACGT"], [np.full(9, 30, np.uint8)]))
+        assert first == 2 and al.num_seqs() == 3
+        out = al.align_profile([0, 0], [1, 2])
+        assert out["alnScore"][0] == 2 * 7 - 2 and out["oneBaseIndel"][1] == 1
+        with pytest.raises(SdgpuError) as ei:
+            al.align_profile([0], [7])
+        assert ei.value.code == _abi.E_ARG
+        with pytest.raises(SdgpuError) as ei:
+            al.align_profile([0], [1], checkKmer=True)
+        assert ei.value.code == _abi.E_STATE
+        long = "ACGT" * 200  # 800 columns: beyond the current strip limit -> loud, not silent
+        al.append_seqs(*pack_seqs([long], [np.full(800, 30, np.uint8)]))
+        with pytest.raises(SdgpuError) as ei:
+            al.align_profile([0], [3])
+        assert ei.value.code == _abi.E_UNSUPPORTED
+        out = al.align_profile([3], [0])  # long ref (rows) is fine
+        assert out["alnLen"][0] == 800
+
+
+def test_full_size_properties():
+    """BASELINE config-2 shaped batch (300 bp) without the oracle: size-independent properties."""
+    rng = np.random.default_rng(61)
+    bases, quals, offsets, cnts, seqs, _ = H.make_store(rng, 2000, 300)
+    n = 40000
+    a = rng.integers(0, 2000, n).astype(np.uint32)
+    b = rng.integers(0, 2000, n).astype(np.uint32)
+    b[:200] = a[:200]
+    with GpuAligner(make_params()) as al:
+        al.upload_seqs(bases, quals, offsets, cnts)
+        out = al.align_profile(a, b)
+        again = al.align_profile(a, b)
+    assert out.tobytes() == again.tobytes()  # deterministic / idempotent
+    lens = np.diff(offsets).astype(np.int64)
+    assert np.array_equal(out["alnScore"][:200], 2 * lens[a[:200]])  # self-alignment
+    assert (out["hqMismatches"][:200] + out["lqMismatches"][:200] + out["numGaps"][:200] == 0).all()
+    assert (out["alnLen"] >= np.maximum(lens[a], lens[b])).all() and (out["alnLen"] <= lens[a] + lens[b]).all()
+    cols = out["highQualityMatches"] + out["lowQualityMatches"] + out["hqMismatches"] + out["lqMismatches"] + out["lowKmerMismatches"]
+    assert (cols <= np.minimum(lens[a], lens[b])).all()
+    assert (out["alnScore"] <= 2 * np.minimum(lens[a], lens[b])).all()
+    assert ((out["eventBasedIdentity"] >= 0) & (out["eventBasedIdentity"] <= 1)).all()

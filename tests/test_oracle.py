@@ -1,0 +1,186 @@
+"""CPU tests of the oracle itself: hand-derived micro-cases for every tie / boundary rule,
+optimality against an independent textbook DP, and traceback self-consistency.
+(Parity to upstream njhseq is unpinned: the reference ships no golden vectors — DESIGN.md.)"""
+import numpy as np
+import pytest
+
+from seekdeep_b200 import _abi
+from seekdeep_b200.scoring import GapScoringParameters, SubstituteMatrix, make_params
+from tests import helpers as H
+
+
+def test_identical(oracle):
+    p = make_params()
+    s = "ACGTTGCAAGGCTTAACCGG"
+    q = np.full(len(s), 38, np.uint8)
+    comp, gaps, a, b = oracle.align_profile(p, s, q, s, q)
+    assert comp.alnScore == 2 * len(s) and len(gaps) == 0 and a == s and b == s
+    assert comp.highQualityMatches == len(s) and comp.hqMismatches == 0 and comp.numGaps == 0
+    assert comp.eventBasedIdentity == 1.0 and comp.refCoverage == 1.0 and comp.queryCoverage == 1.0
+
+
+def test_tie_prefers_gap_over_diagonal_all_costly(oracle):
+    # A="AA", B="A", every gap 5/1: both placements score -3; needleMaximum picks 'U' at the
+    # corner (u == d > l), so the read's base pairs with A[0] and the gap trails.
+    p = make_params(gaps=GapScoringParameters.from_strings("5,1", "5,1", "5,1"))
+    score, gaps = oracle.align_global(p, "AA", "A")
+    assert score == -3
+    assert [(g["pos"], g["size"], g["gapInA"]) for g in gaps] == [(1, 1, 0)]
+
+
+def test_free_right_gap(oracle):
+    p = make_params()  # qluster: right gaps free
+    comp, gaps, a, b = oracle.align_profile(p, "AA", None, "A", None, flags=0)
+    assert comp.alnScore == 2 and a == "AA" and b == "A-"
+    assert comp.numGaps == 0 and comp.oneBaseIndel == 0  # end gap not counted
+    assert comp.queryCoverage == 1.0 and comp.refCoverage == 0.5
+
+
+def test_internal_one_base_deletion(oracle):
+    p = make_params()
+    ref = "ACGTTGCAAGGCTTAACCGGATCG"
+    read = ref[:10] + ref[11:]
+    comp, gaps, a, b = oracle.align_profile(p, ref, None, read, None, flags=0)
+    assert comp.alnScore == 2 * len(read) - 5
+    assert comp.oneBaseIndel == 1 and comp.twoBaseIndel == 0 and comp.largeBaseIndel == 0 and comp.numGaps == 1
+    assert a == ref and b.replace("-", "") == read and b.count("-") == 1
+    assert len(gaps) == 1 and gaps[0]["gapInA"] == 0 and gaps[0]["size"] == 1
+
+
+def test_indel_size_classes(oracle):
+    p = make_params()
+    rng = np.random.default_rng(5)
+    ref = H.rand_seq(rng, 60).tobytes().decode()
+    for size, field in ((1, "oneBaseIndel"), (2, "twoBaseIndel"), (3, "largeBaseIndel"), (5, "largeBaseIndel")):
+        read = ref[:30] + ref[30 + size:]
+        comp, gaps, a, b = oracle.align_profile(p, ref, None, read, None, flags=0)
+        assert getattr(comp, field) == 1, (size, a, b)
+        assert comp.oneBaseIndel + comp.twoBaseIndel + comp.largeBaseIndel == 1
+
+
+def test_quality_classes(oracle):
+    p = make_params(primaryQual=25, secondaryQual=20, qualThresWindow=2)
+    ref = "ACGTTGCAAGGCTTAACCGGATCG"
+    read = ref[:12] + "A" + ref[13:]  # T->A mismatch at 12
+    assert read != ref
+    hi = np.full(len(ref), 38, np.uint8)
+    comp, *_ = oracle.align_profile(p, ref, hi, read, hi)
+    assert (comp.hqMismatches, comp.lqMismatches) == (1, 0)
+    q = hi.copy(); q[12] = 25  # not strictly above primary
+    comp, *_ = oracle.align_profile(p, ref, hi, read, q)
+    assert (comp.hqMismatches, comp.lqMismatches) == (0, 1)
+    q = hi.copy(); q[12] = 26
+    comp, *_ = oracle.align_profile(p, ref, hi, read, q)
+    assert (comp.hqMismatches, comp.lqMismatches) == (1, 0)
+    q = hi.copy(); q[10] = 20  # neighbour inside the window, not strictly above secondary
+    comp, *_ = oracle.align_profile(p, ref, hi, read, q)
+    assert (comp.hqMismatches, comp.lqMismatches) == (0, 1)
+    q = hi.copy(); q[9] = 2  # outside the window
+    comp, *_ = oracle.align_profile(p, ref, hi, read, q)
+    assert (comp.hqMismatches, comp.lqMismatches) == (1, 0)
+    q = hi.copy(); q[14] = 20  # trailing neighbour
+    comp, *_ = oracle.align_profile(p, ref, q, read, hi)
+    assert (comp.hqMismatches, comp.lqMismatches) == (0, 1)
+    comp, *_ = oracle.align_profile(p, ref, q, read, hi, flags=0)  # not using quality: all HQ
+    assert (comp.hqMismatches, comp.lqMismatches) == (1, 0)
+
+
+def test_homopolymer_weighting(oracle):
+    ref = "ACGTCAAAAAGTCCGTAGGCT"
+    read = "ACGTCAAAAGTCCGTAGGCT"  # one A fewer in a 5-run
+    hi = np.full(30, 38, np.uint8)
+    p = make_params(weighHomopolymers=False)
+    comp, *_ = oracle.align_profile(p, ref, hi[:len(ref)], read, hi[:len(read)])
+    assert comp.oneBaseIndel == 1.0
+    p = make_params(weighHomopolymers=True)
+    comp, gaps, a, b = oracle.align_profile(p, ref, hi[:len(ref)], read, hi[:len(read)])
+    # run of 5 vs run of 4: |5-4| / (5+4)
+    assert comp.oneBaseIndel == pytest.approx(1.0 / 9.0, abs=0)
+    assert comp.numGaps == 1
+
+
+def test_low_kmer_mismatch(oracle):
+    rng = np.random.default_rng(9)
+    ref = H.rand_seq(rng, 80)
+    read = ref.copy()
+    read[40] = H.BASES[(np.nonzero(H.BASES == ref[40])[0][0] + 1) % 4]
+    bases = np.concatenate([ref, read])
+    offsets = np.array([0, 80, 160], np.uint64)
+    cnts = np.array([10.0, 1.0])
+    km = oracle.index_kmers(bases, offsets, cnts, 9, 1, byPos=True)
+    try:
+        hi = np.full(80, 38, np.uint8)
+        p = make_params()
+        comp, *_ = oracle.align_profile(p, ref.tobytes(), hi, read.tobytes(), hi,
+                                        flags=_abi.USING_QUALITY | _abi.CHECK_KMER, kmaps=km)
+        # the read's k-mer around the mismatch occurs once (count 1 <= runCutOff 1)
+        assert (comp.hqMismatches, comp.lowKmerMismatches) == (0, 1)
+        comp, *_ = oracle.align_profile(p, ref.tobytes(), hi, read.tobytes(), hi, flags=_abi.USING_QUALITY, kmaps=km)
+        assert (comp.hqMismatches, comp.lowKmerMismatches) == (1, 0)
+        assert oracle.kmaps_count(km, ref[:9].tobytes(), 0) == 11
+        assert oracle.kmaps_count(km, read[36:45].tobytes(), 36) == 1
+    finally:
+        oracle.free_kmaps(km)
+
+
+def test_kmer_compare(oracle):
+    shared, frac = oracle.kmer_compare("AAAAAAA", "AAAAA", 3)
+    assert shared == 3 and frac == 1.0  # min(5,3) shared 3-mers / (5-3+1)
+    shared, frac = oracle.kmer_compare("ACGTACGT", "TTTTTTTT", 3)
+    assert shared == 0 and frac == 0.0
+    shared, frac = oracle.kmer_compare("ACGTACGTAA", "ACGTACGTCC", 5)
+    assert shared == 4 and frac == pytest.approx(4 / 6)
+
+
+@pytest.mark.parametrize("pname", sorted(H.PARAM_SETS))
+def test_score_optimal_and_traceback_consistent(oracle, pname):
+    """Oracle score == independent textbook DP; the gapped strings it reports score the same."""
+    p = H.params_for(pname)
+    gp = H.PARAM_SETS[pname]["gaps"]
+    mat = np.ctypeslib.as_array(p.scoreMat).reshape(128, 128)
+    rng = np.random.default_rng(hash(pname) % 2**32)
+    for trial in range(40):
+        la = int(rng.integers(1, 40))
+        a = H.rand_seq(rng, la)
+        if trial % 2:
+            b = H.mutate(rng, a, int(rng.integers(0, 4)), int(rng.integers(0, 3)), int(rng.integers(0, 3)))
+        else:
+            b = H.rand_seq(rng, int(rng.integers(1, 40)))
+        if len(b) == 0:
+            continue
+        comp, gaps, alnA, alnB = oracle.align_profile(p, a.tobytes(), None, b.tobytes(), None, flags=0)
+        want = H.gotoh_score(list(a), list(b), gp, mat)
+        assert comp.alnScore == want, (pname, trial, a.tobytes(), b.tobytes())
+        assert alnA.replace("-", "").encode() == a.tobytes() and alnB.replace("-", "").encode() == b.tobytes()
+        assert len(alnA) == len(alnB) == comp.alnLen
+        assert all(not (x == "-" and y == "-") for x, y in zip(alnA, alnB))
+        assert H.score_of_alignment(alnA, alnB, gp, mat) == comp.alnScore, (alnA, alnB)
+
+
+def test_gap_list_matches_gapped_strings(oracle):
+    p = make_params()
+    rng = np.random.default_rng(77)
+    for _ in range(50):
+        a = H.rand_seq(rng, int(rng.integers(20, 60)))
+        b = H.mutate(rng, a, 2, 1, 1)
+        comp, gaps, alnA, alnB = oracle.align_profile(p, a.tobytes(), None, b.tobytes(), None, flags=0)
+        sa, sb = a.tobytes().decode(), b.tobytes().decode()
+        for g in gaps:  # descending positions: inserting in list order never shifts later ones
+            if g["gapInA"]:
+                sa = sa[:g["pos"]] + "-" * int(g["size"]) + sa[g["pos"]:]
+            else:
+                sb = sb[:g["pos"]] + "-" * int(g["size"]) + sb[g["pos"]:]
+        assert (sa, sb) == (alnA, alnB)
+        assert comp.nGapRuns == len(gaps)
+
+
+def test_identity_fields(oracle):
+    p = make_params()
+    ref = "ACGTTGCAAGGCTTAACCGGATCGTTAGC"
+    read = ref[:8] + "T" + ref[9:20] + ref[21:]
+    hi = np.full(len(ref), 38, np.uint8)
+    comp, *_ = oracle.align_profile(p, ref, hi, read, hi[:len(read)])
+    ev = comp.highQualityMatches + comp.hqMismatches + comp.lqMismatches + comp.lowKmerMismatches + comp.numGaps
+    assert comp.overLappingEvents == ev
+    assert comp.eventBasedIdentity == comp.highQualityMatches / ev
+    assert comp.basesInAln == len(read)
