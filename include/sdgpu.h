@@ -189,6 +189,9 @@ int sdgpu_timer_start(sdgpu_ctx* ctx);
 int sdgpu_timer_stop(sdgpu_ctx* ctx, float* msOut); /* records, synchronizes, returns elapsed ms */
 /* Counters: kernels launched by this ctx and DP cells computed since creation. */
 int sdgpu_counters(sdgpu_ctx* ctx, uint64_t* kernelLaunches, uint64_t* cellUpdates);
+/* Roofline denominator for the alignment kernel: measured thread-level INT32 instructions per
+ * second of one kind (0 add, 1 max(+sub), 2 fused add-max VIADDMNMX, 3 max3(+sub)) on this GPU. */
+int sdgpu_measure_int32_peak(sdgpu_ctx* ctx, int which, double* instrPerSec);
 
 #ifdef __cplusplus
 }

@@ -182,6 +182,11 @@ class GpuAligner:
         self._check(self._lib.sdgpu_timer_stop(self._ctx, C.byref(ms)))
         return ms.value
 
+    def measure_int32_peak(self, which=0):
+        v = C.c_double()
+        self._check(self._lib.sdgpu_measure_int32_peak(self._ctx, which, C.byref(v)))
+        return v.value
+
     def counters(self):
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._lib.sdgpu_counters(self._ctx, C.byref(a), C.byref(b)))

@@ -262,7 +262,7 @@ int sd_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers, const uint32_t* p
 }
 
 int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
-  const uint32_t sigma = uint32_t(ctx->nSym < 4 ? 4 : ctx->nSym);
+  const uint32_t sigma = uint32_t(ctx->usedSym < 4 ? 4 : ctx->usedSym);
   uint64_t size = 1;
   for (uint32_t x = 0; x < kLen; ++x) {
     size *= sigma;

@@ -230,6 +230,7 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
       newSym = true;
     }
     hCodes[x] = uint8_t(code);
+    if (code + 1 > ctx->usedSym) ctx->usedSym = code + 1;
   }
   if (quals) {
     std::memcpy(hQuals, quals, addBases);
@@ -269,6 +270,7 @@ int sdgpu_upload_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
   if (!ctx) return SDGPU_E_ARG;
   ctx->hOffsets.assign(1, 0);
   ctx->maxLen = 0;
+  ctx->usedSym = 0;
   ctx->haveIndex = false;
   ctx->profSeqs = 0;
   return appendImpl(ctx, bases, quals, offsets, cnts, n, nullptr);

@@ -50,6 +50,7 @@ struct sdgpu_ctx {
   int16_t codeOf[256];
   uint8_t charOf[SDGPU_MAX_SYMBOLS];
   int nSym = 0;
+  int usedSym = 0;  // highest code present in the store + 1 (A,C,G,T,N are pre-assigned 0..4)
   // sequence store
   uint8_t* dCodes = nullptr;
   uint8_t* dQuals = nullptr;

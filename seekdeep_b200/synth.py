@@ -112,3 +112,61 @@ def config3(seed=3, n=20_000, length=400, nRoots=50):
             out.append(s)
     quals = [np.full(len(s), 35, np.uint8) for s in out]
     return out, quals
+
+
+def fast_reads(rng, haps, nReads, subRate, zipf=1.2, hpIndelRate=0.0, qMean=36.0, qSd=3.0, errQMean=12.0, errQSd=6.0):
+    """Vectorised sample_reads (same error model) for the 200k-read configs."""
+    w = 1.0 / np.arange(1, len(haps) + 1) ** zipf
+    w /= w.sum()
+    which = rng.choice(len(haps), size=nReads, p=w)
+    seqs = [None] * nReads
+    quals = [None] * nReads
+    for h, hap in enumerate(haps):
+        idx = np.nonzero(which == h)[0]
+        if idx.size == 0:
+            continue
+        L = len(hap)
+        S = np.tile(hap, (idx.size, 1))
+        Q = np.clip(np.rint(rng.normal(qMean, qSd, S.shape)), 2, 40).astype(np.uint8)
+        err = rng.random(S.shape) < subRate
+        ne = int(err.sum())
+        if ne:
+            shift = rng.integers(1, 4, ne)
+            code = np.searchsorted(BASES, S[err])  # BASES is sorted: A C G T
+            S[err] = BASES[(code + shift) % 4]
+            Q[err] = np.clip(np.rint(rng.normal(errQMean, errQSd, ne)), 2, 40).astype(np.uint8)
+        runs = []
+        if hpIndelRate > 0:
+            i = 0
+            while i < L:
+                j = i
+                while j < L and hap[j] == hap[i]:
+                    j += 1
+                if j - i >= 3:
+                    runs.append((i, j - i))
+                i = j
+        ev = None
+        if runs:
+            p = np.array([hpIndelRate * ln for _, ln in runs])
+            ev = rng.random((idx.size, len(runs))) < p
+        for k, r in enumerate(idx):
+            s, q = S[k], Q[k]
+            if ev is not None and ev[k].any():
+                for ri in np.nonzero(ev[k])[0][::-1]:  # right to left keeps earlier offsets valid
+                    st, ln = runs[ri]
+                    if rng.random() < 0.5:
+                        s = np.delete(s, st + ln - 1)
+                        q = np.delete(q, st + ln - 1)
+                    else:
+                        s = np.insert(s, st + ln, hap[st])
+                        q = np.insert(q, st + ln, np.uint8(max(2, min(40, int(rng.normal(errQMean, errQSd))))))
+            seqs[r] = s
+            quals[r] = q
+    return seqs, quals, which
+
+
+def config2_fast(seed=2, nReads=200_000, length=300, nHaps=200):
+    rng = np.random.default_rng(seed)
+    haps = make_haplotypes(rng, nHaps, length, 1, 8)
+    seqs, quals, which = fast_reads(rng, haps, nReads, 0.01, hpIndelRate=0.002)
+    return haps, seqs, quals, which
