@@ -51,17 +51,24 @@ struct AlignArgs {
 
 enum { ST_D = 0, ST_U = 1, ST_L = 2 };
 
-// bits: 0 L>=D | 1 U>=max(L,D) | 2 U-ge>=max(L,D)-go | 3 L-ge>=D-go | 4 U-go>=max(L-ge,D-go)
-__device__ __forceinline__ int nextFromDiag(unsigned b) { return (b & 2u) ? ST_U : ((b & 1u) ? ST_L : ST_D); }
-__device__ __forceinline__ int nextFromUp(unsigned b) { return (b & 4u) ? ST_U : ((b & 1u) ? ST_L : ST_D); }
-__device__ __forceinline__ int nextFromLeft(unsigned b) { return (b & 16u) ? ST_U : ((b & 8u) ? ST_L : ST_D); }
+// Traceback bits.  Each cell contributes the SIGN BITS of five differences, pushed into a
+// 32-bit accumulator with one funnel shift each (6 cells = 30 bits per word):
+//   g4 = L < D | g3 = U < max(L,D) | g2 = U-ge < max(L,D)-go | g1 = L-ge < D-go | g0 = U-go < max(L-ge,D-go)
+// cellBits() returns the complemented group, so bit set == ">=" (njhseq's tie order U, L, D).
+constexpr int CELLS_PER_WORD = 6;
+__device__ __forceinline__ int nextFromDiag(unsigned b) { return (b & 8u) ? ST_U : ((b & 16u) ? ST_L : ST_D); }
+__device__ __forceinline__ int nextFromUp(unsigned b) { return (b & 4u) ? ST_U : ((b & 16u) ? ST_L : ST_D); }
+__device__ __forceinline__ int nextFromLeft(unsigned b) { return (b & 1u) ? ST_U : ((b & 2u) ? ST_L : ST_D); }
 
 template <int C>
 __device__ __forceinline__ unsigned cellBits(const uint8_t* ptr, int i, int j) {
-  constexpr int CW = (C + 3) / 4;
+  constexpr int CW = (C + CELLS_PER_WORD - 1) / CELLS_PER_WORD;
   const int lj = (j - 1) / C, c = (j - 1) - lj * C;
   const int t = i + lj;
-  return __ldcg(ptr + (size_t(t - 1) * CW + (c >> 2)) * 128 + lj * 4 + (c & 3));
+  const int wi = c / CELLS_PER_WORD, k = c - wi * CELLS_PER_WORD;
+  const int inWord = (C - wi * CELLS_PER_WORD) < CELLS_PER_WORD ? (C - wi * CELLS_PER_WORD) : CELLS_PER_WORD;
+  const unsigned w = __ldcg(reinterpret_cast<const unsigned*>(ptr) + (size_t(t - 1) * CW + wi) * 32 + lj);
+  return ~(w >> (5 * (inWord - 1 - k))) & 31u;
 }
 
 // njhseq seqInfo::checkQual (strictly-greater thresholds, trailing window stops before the last base)
@@ -107,7 +114,7 @@ __device__ __forceinline__ unsigned warpSum(unsigned v) {
 
 template <int C>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const AlignArgs a) {
-  constexpr int CW = (C + 3) / 4;
+  constexpr int CW = (C + CELLS_PER_WORD - 1) / CELLS_PER_WORD;
   __shared__ int sTab[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];
   for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS; x += blockDim.x) sTab[x] = a.sc.score[x];
   __syncthreads();
@@ -151,6 +158,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
       const bool lastCol = (j == lb);
       gocol[c] = lastCol ? sc.goRQ : sc.go;
       dcol[c] = lastCol ? (sc.goRQ - sc.geRQ) : dInt;
+      // keep the per-column penalties in registers (ptxas otherwise rematerialises the
+      // j == lb select in every cell: three extra ALU instructions per cell update)
+      asm volatile("" : "+r"(gocol[c]), "+r"(dcol[c]));
       U[c] = L0 - gocol[c];  // upInherit of row 1 (njhseq's i == 1 case)
       T[c] = L0;             // feeds diagInherit of row 1, column j+1
     }
@@ -189,20 +199,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
           const int D = Tin + s;
           Tin = T[c];
           const int Uc = U[c];
-          const bool pLD = Lin >= D;
-          const int W = pLD ? Lin : D;
-          const bool pU = Uc >= W;
-          T[c] = pU ? Uc : W;
+          uint32_t acc = w[c / CELLS_PER_WORD];
+          const int W = max(Lin, D);
+          acc = __funnelshift_l(uint32_t(Lin - D), acc, 1);
+          T[c] = max(Uc, W);
+          acc = __funnelshift_l(uint32_t(Uc - W), acc, 1);
           const int Ud = Uc + dcol[c];
-          const bool pDn = Ud >= W;
-          U[c] = (pDn ? Ud : W) - gocol[c];
+          U[c] = max(Ud, W) - gocol[c];
+          acc = __funnelshift_l(uint32_t(Ud - W), acc, 1);
           const int Ld = Lin + drow;
-          const bool pL2 = Ld >= D;
-          const int tt = pL2 ? Ld : D;
-          const bool pU2 = Uc >= tt;
-          Lin = (pU2 ? Uc : tt) - gorow;
-          const uint32_t bits = (pLD ? 1u : 0u) | (pU ? 2u : 0u) | (pDn ? 4u : 0u) | (pL2 ? 8u : 0u) | (pU2 ? 16u : 0u);
-          w[c >> 2] |= bits << (8 * (c & 3));
+          const int tt = max(Ld, D);
+          acc = __funnelshift_l(uint32_t(Ld - D), acc, 1);
+          Lin = max(Uc, tt) - gorow;
+          acc = __funnelshift_l(uint32_t(Uc - tt), acc, 1);
+          w[c / CELLS_PER_WORD] = acc;
         }
         outR = Lin;
         outT = T[C - 1];
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
 
 template <int C>
 int launchC(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
-  constexpr int CW = (C + 3) / 4;
+  constexpr int CW = (C + CELLS_PER_WORD - 1) / CELLS_PER_WORD;
   int ctasPerSM = 0;
   SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, alignProfileKernel<C>, WARPS_PER_CTA * 32, 0));
   if (ctasPerSM < 1) ctasPerSM = 1;
