@@ -129,8 +129,10 @@ const char* sdgpu_last_error(sdgpu_ctx* ctx); /* ctx may be NULL: last create() 
 int sdgpu_set_params(sdgpu_ctx* ctx, const sdgpu_params* params); /* e.g. `alignerObj.weighHomopolymers_ = x` */
 
 /* Sequence store.  Replaces the caller-owned std::vector<cluster>/seqInfo the aligner reads
- * (seqBase_.seq_, seqBase_.qual_, seqBase_.cnt_; clusterDown.cpp:274-285).  `bases` is ASCII
- * (case-insensitive IUPAC), `quals` phred values (may be NULL: all 0), `offsets` has n+1
+ * (seqBase_.seq_, seqBase_.qual_, seqBase_.cnt_; clusterDown.cpp:274-285).  `bases` is 7-bit
+ * ASCII, compared character by character through scoreMat exactly like mat_[a][b] (so case
+ * matters unless the matrix says otherwise); at most 16 distinct characters per ctx.
+ * `quals` are phred values (may be NULL: all 0), `offsets` has n+1
  * entries, `cnts` may be NULL (all 1).  upload replaces the store; append adds to it and
  * returns the index of the first appended sequence in *firstIndex. */
 int sdgpu_upload_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals,
@@ -139,6 +141,9 @@ int sdgpu_append_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
                       const uint64_t* offsets, const double* cnts, uint32_t n,
                       uint32_t* firstIndex);
 int sdgpu_num_seqs(sdgpu_ctx* ctx, uint32_t* n);
+/* Overwrites seqBase_.cnt_ of stored sequences (clusters grow as they absorb reads; the k-mer
+ * index weights every k-mer by the current count, clusterDown.cpp:505-510). */
+int sdgpu_update_cnts(sdgpu_ctx* ctx, const uint32_t* seqIdx, const double* cnts, uint32_t n);
 
 /* Replaces: indexKmers(clusters, kLength_, runCutOff_, kmersByPosition_, expandKmerPos_,
  * expandKmerSize_) -> KmerMaps, clusterDown.cpp:412-417 and 505-510, followed by

@@ -1,0 +1,86 @@
+/*
+ * sdgpu_qluster.h — C ABI of the host-side collapse loop that drives the sdgpu kernels.
+ *
+ * Replaces, for one sample, the part of SeekDeep's qluster body that sits on the hot path:
+ * src/SeekDeepPrograms/SeekDeepProgram/clusterDown/clusterDown.cpp:230-563 —
+ *   exact-sequence dedupe (:272-288), per-base median quality (:293-359), std::sort (:389),
+ *   indexKmers (:412-417), singlet split (:467-484), collapser::runFullClustering x3
+ *   (:488-490, :492-499, :502-519) and the final sortReadVector "totalCount" (:560).
+ * The loop keeps njhseq's sequential, size-ordered greedy semantics (first passing cluster wins,
+ * consensus rebuilt at the end of each par-file iteration); the GPU is fed speculative batches of
+ * the candidate (cluster, read) pairs each iteration can ask for, and the results are served to
+ * the unchanged sequential logic from a pair cache — the same "lookup-or-compute" contract
+ * aligner::alignCacheGlobal already has (clusterDown.cpp:694, 739).
+ *
+ * Out of scope here (left to the caller, as in the reference): FASTQ parsing, Illumina sample
+ * filtering / down-sampling (:83-181), chimera marking (:566-598), output files.
+ */
+#ifndef SDGPU_QLUSTER_H_
+#define SDGPU_QLUSTER_H_
+
+#include "sdgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One par-file line (etc/SeekDeepParameterFiles/illumina_lkmer1:2-23; column meaning documented in
+ * clusterDownSetUp.cpp:63-84) or one OTU line (etc/SeekDeepParameterFiles/otu_99:2-5). */
+typedef struct sdq_iter_par {
+  uint32_t stopCheck;
+  uint32_t smallCutoff;
+  double oneBaseIndel, twoBaseIndel, largeBaseIndel;
+  double hqMismatches, lqMismatches, lowKmerMismatches;
+  uint32_t onPerId;   /* --onPerId / --otu: compare identity against perId instead */
+  uint32_t onHqPerId; /* !--regOtu (clusterDownSetUp.cpp:295) */
+  double perId;
+} sdq_iter_par;
+
+/* The qluster options that shape the hot path (setUpPars.hpp:112-187 + seqSetUp kmerOpts_). */
+typedef struct sdq_opts {
+  uint32_t kLen;             /* kmerOpts_.kLength_ */
+  uint32_t runCutOff;        /* kmerOpts_.runCutOff_ (after processRunCutoff, clusterDown.cpp:397) */
+  uint32_t kmersByPosition;  /* kmerOpts_.kmersByPosition_ */
+  uint32_t expandKmerPos;    /* pars_.expandKmerPos_ */
+  uint32_t expandKmerSize;   /* pars_.expandKmerSize_ */
+  uint32_t checkKmers;       /* kmerOpts_.checkKmers_ */
+  uint32_t startWithSingles; /* --startWithSingles */
+  uint32_t leaveOutSinglets; /* --leaveOutSinglets */
+  uint32_t dontRecalLowFreq; /* --dontRecalLowFreqMismatchAndReRun */
+  uint32_t smallReadSize;    /* reads with len <= this are dropped (clusterDown.cpp:269) */
+} sdq_opts;
+
+typedef struct sdq_result sdq_result;
+
+/* Statistics of one run (the reference logs only the alignment count, clusterDown.cpp:1008). */
+typedef struct sdq_stats {
+  uint64_t inputReads, uniqueSeqs, finalClusters;
+  uint64_t pairsComputed;   /* (cluster, read) comparisons computed on the GPU */
+  uint64_t pairsConsumed;   /* comparisons the sequential loop actually looked at */
+  uint64_t consensusAligns; /* member-vs-consensus alignments */
+  uint64_t cellUpdates;     /* DP cells of all of the above */
+  uint64_t gpuBatches;      /* alignment kernel launches */
+  uint64_t onDemandPairs;   /* pairs computed outside the speculative batches */
+  double secondsGpu;        /* wall time inside sdgpu_align_profile calls */
+  double secondsTotal;
+} sdq_stats;
+
+/* Runs the collapse for one sample on ctx's GPU.  Reads are packed like sdgpu_upload_seqs
+ * (quals required).  The ctx's sequence store and k-mer index are replaced. */
+int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, uint32_t nInit,
+            const sdq_iter_par* pars, uint32_t nPars, const uint8_t* bases, const uint8_t* quals,
+            const uint64_t* offsets, uint32_t n, sdq_result** out);
+void sdq_free(sdq_result* r);
+const char* sdq_last_error(void);
+int sdq_get_stats(const sdq_result* r, sdq_stats* out);
+uint32_t sdq_num_clusters(const sdq_result* r);
+uint32_t sdq_cluster_len(const sdq_result* r, uint32_t c);
+double sdq_cluster_cnt(const sdq_result* r, uint32_t c);
+int sdq_cluster_seq(const sdq_result* r, uint32_t c, uint8_t* seq, uint8_t* qual);
+/* final cluster index of every input read (UINT32_MAX: dropped as a small read) */
+int sdq_membership(const sdq_result* r, uint32_t* clusterOfRead);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDGPU_QLUSTER_H_ */

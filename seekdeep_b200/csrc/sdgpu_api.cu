@@ -287,6 +287,22 @@ int sdgpu_num_seqs(sdgpu_ctx* ctx, uint32_t* n) {
   return SDGPU_OK;
 }
 
+int sdgpu_update_cnts(sdgpu_ctx* ctx, const uint32_t* seqIdx, const double* cnts, uint32_t n) {
+  if (!ctx || (n && (!seqIdx || !cnts))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  // contiguous runs become one copy each; cluster lists are short, so this stays cheap
+  for (uint32_t x = 0; x < n;) {
+    if (seqIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "sequence index out of range");
+    uint32_t y = x + 1;
+    while (y < n && seqIdx[y] == seqIdx[y - 1] + 1 && seqIdx[y] < nSeqs) ++y;
+    SD_CUDA(ctx, cudaMemcpyAsync(ctx->dCnts + seqIdx[x], cnts + x, size_t(y - x) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    x = y;
+  }
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}
+
 int sdgpu_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* seqIdx, uint32_t nIdx, uint32_t kLen, uint32_t runCutOff,
                            int kmersByPosition, int expandKmerPos, uint32_t expandKmerSize) {
   if (!ctx) return SDGPU_E_ARG;

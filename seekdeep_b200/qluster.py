@@ -1,0 +1,133 @@
+"""Host-side mirror of `SeekDeep qluster` for one sample over the C ABI (include/sdgpu_qluster.h).
+
+Reference: src/SeekDeepPrograms/SeekDeepProgram/clusterDown/clusterDown.cpp:230-563 (call
+sequence) and clusterDownSetUp.cpp:254-312 (technology defaults).  Sharding of many samples over
+GPUs follows the reference's own model: one independent qluster per sample
+(SeekDeepUtilsRunner_setUpTarAmpAnalysis.cpp:998-1001, runMultipleCommands)."""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi
+from .aligner import GpuAligner, SdgpuError, _ptr
+from .iterpars import CollapseIterations
+
+
+class IterParC(C.Structure):
+    _fields_ = [("stopCheck", C.c_uint32), ("smallCutoff", C.c_uint32), ("oneBaseIndel", C.c_double),
+                ("twoBaseIndel", C.c_double), ("largeBaseIndel", C.c_double), ("hqMismatches", C.c_double),
+                ("lqMismatches", C.c_double), ("lowKmerMismatches", C.c_double), ("onPerId", C.c_uint32),
+                ("onHqPerId", C.c_uint32), ("perId", C.c_double)]
+
+
+class QlusterOptsC(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("kLen", "runCutOff", "kmersByPosition", "expandKmerPos", "expandKmerSize",
+                                          "checkKmers", "startWithSingles", "leaveOutSinglets", "dontRecalLowFreq",
+                                          "smallReadSize")]
+
+
+class StatsC(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("inputReads", "uniqueSeqs", "finalClusters", "pairsComputed", "pairsConsumed",
+                                          "consensusAligns", "cellUpdates", "gpuBatches", "onDemandPairs")] + \
+               [("secondsGpu", C.c_double), ("secondsTotal", C.c_double)]
+
+
+@dataclass
+class QlusterPars:
+    """The subset of clusterDownPars / seqSetUp options that shapes the hot path; defaults are
+    `SeekDeep qluster --illumina` (kLength 9, runCutOff 1, k-mers by position, check k-mers)."""
+    kLength: int = 9
+    runCutOff: int = 1
+    kmersByPosition: bool = True
+    expandKmerPos: bool = False
+    expandKmerSize: int = 5
+    checkKmers: bool = True
+    startWithSingles: bool = False
+    leaveOutSinglets: bool = False
+    dontRecalLowFreqMismatchAndReRun: bool = False
+    smallReadSize: int = 18  # 2 * kLength (clusterDownSetUp.cpp:406)
+
+    def to_c(self):
+        return QlusterOptsC(self.kLength, self.runCutOff, int(self.kmersByPosition), int(self.expandKmerPos),
+                            self.expandKmerSize, int(self.checkKmers), int(self.startWithSingles),
+                            int(self.leaveOutSinglets), int(self.dontRecalLowFreqMismatchAndReRun), self.smallReadSize)
+
+
+def iter_pars_to_c(iters):
+    iters = list(iters)
+    arr = (IterParC * max(1, len(iters)))()
+    for i, it in enumerate(iters):
+        arr[i] = IterParC(it.stopCheck, it.smallCutoff, it.oneBaseIndel, it.twoBaseIndel, it.largeBaseIndel,
+                          it.hqMismatches, it.lqMismatches, it.lowKmerMismatches, int(it.onPerId), int(it.onHqPerId),
+                          it.perId)
+    return arr, len(iters)
+
+
+_bound = False
+
+
+def _bind(lib):
+    global _bound
+    if _bound:
+        return
+    v = C.c_void_p
+    lib.sdq_run.restype = C.c_int
+    lib.sdq_run.argtypes = [v, C.POINTER(QlusterOptsC), v, C.c_uint32, v, C.c_uint32, v, v, v, C.c_uint32, C.POINTER(v)]
+    lib.sdq_free.argtypes = [v]
+    lib.sdq_last_error.restype = C.c_char_p
+    lib.sdq_get_stats.argtypes = [v, C.POINTER(StatsC)]
+    lib.sdq_num_clusters.restype = C.c_uint32
+    lib.sdq_num_clusters.argtypes = [v]
+    lib.sdq_cluster_len.restype = C.c_uint32
+    lib.sdq_cluster_len.argtypes = [v, C.c_uint32]
+    lib.sdq_cluster_cnt.restype = C.c_double
+    lib.sdq_cluster_cnt.argtypes = [v, C.c_uint32]
+    lib.sdq_cluster_seq.argtypes = [v, C.c_uint32, v, v]
+    lib.sdq_membership.argtypes = [v, v]
+    _bound = True
+
+
+def qluster(aligner: GpuAligner, bases, quals, offsets, pars: QlusterPars = None, iteratorMap: CollapseIterations = None,
+            intialParameters: CollapseIterations = None, want_clusters=True):
+    """Run the collapse of one sample on `aligner`'s GPU.  `iteratorMap` / `intialParameters` are
+    the reference's names (clusterDownPars, setUpPars.hpp:126-127); both default to
+    genIlluminaDefaultPars(100) like `--illumina`."""
+    lib = aligner._lib
+    _bind(lib)
+    pars = pars or QlusterPars()
+    iteratorMap = iteratorMap or CollapseIterations.gen_illumina_default_pars(100)
+    intialParameters = intialParameters or iteratorMap
+    bases = np.ascontiguousarray(bases, np.uint8)
+    quals = np.ascontiguousarray(quals, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    n = len(offsets) - 1
+    opts = pars.to_c()
+    ip, nip = iter_pars_to_c(intialParameters)
+    pp, npp = iter_pars_to_c(iteratorMap)
+    h = C.c_void_p()
+    rc = lib.sdq_run(aligner._ctx, C.byref(opts), ip, nip, pp, npp, _ptr(bases), _ptr(quals), _ptr(offsets), n, C.byref(h))
+    if rc != _abi.OK:
+        raise SdgpuError(rc, (lib.sdq_last_error() or b"").decode())
+    try:
+        st = StatsC()
+        lib.sdq_get_stats(h, C.byref(st))
+        res = {"stats": {k: getattr(st, k) for k, _ in StatsC._fields_}, "clusters": []}
+        if want_clusters:
+            for c in range(lib.sdq_num_clusters(h)):
+                ln = lib.sdq_cluster_len(h, c)
+                s = np.zeros(ln, np.uint8)
+                q = np.zeros(ln, np.uint8)
+                lib.sdq_cluster_seq(h, c, _ptr(s), _ptr(q))
+                res["clusters"].append((s.tobytes().decode(), q, lib.sdq_cluster_cnt(h, c)))
+        mem = np.zeros(n, np.uint32)
+        lib.sdq_membership(h, _ptr(mem))
+        res["membership"] = mem
+        return res
+    finally:
+        lib.sdq_free(h)
+
+
+def shard_samples(nSamples, rank, world):
+    """Static round-robin of independent samples over ranks (no data-path collective)."""
+    return list(range(rank, nSamples, world))

@@ -1,0 +1,84 @@
+"""End-to-end parity of the collapse loop: GPU-driven sdq_run vs the oracle's sequential
+qluster on the same seeded reads — cluster count, membership, consensus sequences, consensus
+qualities and counts must be identical (north_star: bit-identical clusters and haplotypes)."""
+import numpy as np
+import pytest
+
+import seekdeep_b200 as sd
+from seekdeep_b200 import synth
+from seekdeep_b200.iterpars import CollapseIterations
+from tests import oracle_binding
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_opts(p: sd.QlusterPars):
+    return oracle_binding.QlusterOptsC(p.kLength, p.runCutOff, int(p.kmersByPosition), int(p.expandKmerPos),
+                                       p.expandKmerSize, int(p.checkKmers), int(p.startWithSingles),
+                                       int(p.leaveOutSinglets), int(p.dontRecalLowFreqMismatchAndReRun), p.smallReadSize)
+
+
+def assert_same(got, want):
+    assert len(got["clusters"]) == len(want["clusters"])
+    assert np.array_equal(got["membership"], want["membership"])
+    for (gs, gq, gc), (ws, wq, wc) in zip(got["clusters"], want["clusters"]):
+        assert gs == ws and gc == wc and np.array_equal(gq, wq)
+
+
+def run_pair(oracle, params, pars, iters, bases, quals, offsets, init=None):
+    with sd.GpuAligner(params) as al:
+        got = sd.qluster(al, bases, quals, offsets, pars, iters, init)
+    want = oracle.qluster(params, oracle_opts(pars), (init or iters).iters, iters.iters, bases, quals, offsets)
+    return got, want
+
+
+@pytest.mark.parametrize("seed,nReads,length,nHaps,weigh", [(1, 1500, 120, 6, False), (2, 2500, 250, 12, False),
+                                                             (3, 1200, 150, 8, True)])
+def test_qluster_matches_oracle(oracle, seed, nReads, length, nHaps, weigh):
+    rng = np.random.default_rng(seed)
+    haps = synth.make_haplotypes(rng, nHaps, length, 1, 5)
+    seqs, quals, _ = synth.fast_reads(rng, haps, nReads, 0.004, hpIndelRate=0.002 if weigh else 0.0)
+    bases, q, offsets = synth.pack(seqs, quals)
+    params = sd.make_params(weighHomopolymers=weigh)
+    iters = CollapseIterations.gen_illumina_default_pars(100)
+    got, want = run_pair(oracle, params, sd.QlusterPars(), iters, bases, q, offsets)
+    assert_same(got, want)
+    st = got["stats"]
+    assert st["uniqueSeqs"] == want["nUnique"] and st["finalClusters"] == len(want["clusters"])
+    assert st["pairsComputed"] > 0 and st["gpuBatches"] > 0 and st["cellUpdates"] > 0
+    # sanity of the result itself: the abundant haplotypes are recovered exactly
+    top = {s for s, _, c in got["clusters"] if c >= 0.02 * nReads}
+    assert top <= {h.tobytes().decode() for h in haps}
+
+
+def test_qluster_options(oracle):
+    rng = np.random.default_rng(9)
+    haps = synth.make_haplotypes(rng, 5, 100, 2, 6)
+    seqs, quals, _ = synth.fast_reads(rng, haps, 800, 0.006)
+    seqs.append(np.frombuffer(b"ACGTACGTAC", np.uint8))  # dropped: len <= smallReadSize
+    quals.append(np.full(10, 30, np.uint8))
+    bases, q, offsets = synth.pack(seqs, quals)
+    params = sd.make_params()
+    for pars, iters in (
+            (sd.QlusterPars(startWithSingles=True), CollapseIterations.gen_illumina_default_pars(20)),
+            (sd.QlusterPars(leaveOutSinglets=True, dontRecalLowFreqMismatchAndReRun=True), CollapseIterations.gen_illumina_default_pars(100)),
+            (sd.QlusterPars(checkKmers=False, kmersByPosition=False, runCutOff=3), CollapseIterations.gen_illumina_default_pars(3)),
+            (sd.QlusterPars(runCutOff=1), CollapseIterations.gen_otu_pars(100, 0.97, True)),
+            (sd.QlusterPars(expandKmerPos=True, expandKmerSize=2), CollapseIterations.gen_otu_pars(100, 0.98, False))):
+        got, want = run_pair(oracle, params, pars, iters, bases, q, offsets)
+        assert_same(got, want)
+        assert got["membership"][-1] == np.uint32(0xFFFFFFFF)
+
+
+def test_qluster_tiny_and_empty(oracle):
+    params = sd.make_params()
+    iters = CollapseIterations.gen_illumina_default_pars(100)
+    s = np.frombuffer(b"ACGTTGCAAGGCTTAACCGGATCGTTAGCAAT", np.uint8)
+    for seqs in ([s], [s, s, s], [s, s, s[:-1].copy(), s[:-1].copy()]):
+        quals = [np.full(len(x), 35, np.uint8) for x in seqs]
+        bases, q, offsets = synth.pack(seqs, quals)
+        got, want = run_pair(oracle, params, sd.QlusterPars(), iters, bases, q, offsets)
+        assert_same(got, want)
+    with sd.GpuAligner(params) as al:
+        got = sd.qluster(al, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert got["clusters"] == [] and got["stats"]["uniqueSeqs"] == 0
