@@ -115,6 +115,20 @@ typedef struct sdgpu_comparison {
 #define SDGPU_USING_QUALITY 2u
 #define SDGPU_MATCH_QUALITY 4u
 
+/* One par-file line (etc/SeekDeepParameterFiles/illumina_lkmer1:2-23; columns documented in
+ * clusterDownSetUp.cpp:63-84) or one OTU line (etc/SeekDeepParameterFiles/otu_99:2-5): njhseq's
+ * IterPar, i.e. the thresholds comparison::passErrorProfile tests an errorProfile against. */
+typedef struct sdgpu_iter_par {
+  uint32_t stopCheck;
+  uint32_t smallCutoff;
+  double oneBaseIndel, twoBaseIndel, largeBaseIndel;
+  double hqMismatches, lqMismatches, lowKmerMismatches;
+  uint32_t onPerId;   /* --onPerId / --otu: compare identity against perId instead */
+  uint32_t onHqPerId; /* !--regOtu (clusterDownSetUp.cpp:295) */
+  double perId;
+} sdgpu_iter_par;
+#define SDGPU_MAX_PASS_LINES 64
+
 typedef struct sdgpu_ctx sdgpu_ctx; /* opaque; one per host thread; owns one device + one stream */
 
 /* Library / device probing (no reference counterpart). */
@@ -178,6 +192,16 @@ int sdgpu_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nRead
 int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx,
                         uint32_t nPairs, uint32_t flags, sdgpu_comparison* out,
                         sdgpu_gap* gapsOut, uint32_t gapCap);
+
+/* Replaces: iteration.errors_.passErrorProfile(alignerObj.comp_) / the OTU identity test
+ * (ControlBencher.hpp:120; clusterDownSetUp.cpp:289-312) for up to 64 par-file lines at once.
+ * sdgpu_set_pass_table uploads the lines; sdgpu_align_pass runs alignCacheGlobal +
+ * profileAlignment per pair like sdgpu_align_profile but returns only a verdict mask per pair
+ * (bit l set <=> the pair's errorProfile passes line l): 8 bytes per pair cross PCIe instead of
+ * a whole comparison struct.  The collapse loop (sdgpu_qluster.h) runs on this. */
+int sdgpu_set_pass_table(sdgpu_ctx* ctx, const sdgpu_iter_par* lines, uint32_t nLines);
+int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,
+                     uint32_t flags, uint64_t* passMaskOut);
 
 /* Device-resident variant for benchmarking the kernels alone: pair lists and outputs are
  * device pointers (from sdgpu_dev_alloc); nothing crosses PCIe.  Asynchronous on the ctx stream. */

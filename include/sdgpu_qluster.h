@@ -26,15 +26,7 @@ extern "C" {
 
 /* One par-file line (etc/SeekDeepParameterFiles/illumina_lkmer1:2-23; column meaning documented in
  * clusterDownSetUp.cpp:63-84) or one OTU line (etc/SeekDeepParameterFiles/otu_99:2-5). */
-typedef struct sdq_iter_par {
-  uint32_t stopCheck;
-  uint32_t smallCutoff;
-  double oneBaseIndel, twoBaseIndel, largeBaseIndel;
-  double hqMismatches, lqMismatches, lowKmerMismatches;
-  uint32_t onPerId;   /* --onPerId / --otu: compare identity against perId instead */
-  uint32_t onHqPerId; /* !--regOtu (clusterDownSetUp.cpp:295) */
-  double perId;
-} sdq_iter_par;
+typedef sdgpu_iter_par sdq_iter_par;
 
 /* The qluster options that shape the hot path (setUpPars.hpp:112-187 + seqSetUp kmerOpts_). */
 typedef struct sdq_opts {

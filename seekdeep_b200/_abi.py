@@ -76,6 +76,8 @@ SIGNATURES = {
     "sdgpu_kmer_compare": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "sdgpu_kmer_compare_all": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "sdgpu_align_profile": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sdgpu_set_pass_table": (C.c_int, [_ctx, C.c_void_p, C.c_uint32]),
+    "sdgpu_align_pass": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sdgpu_align_profile_dev": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sdgpu_dev_alloc": (C.c_int, [_ctx, C.c_uint64, C.POINTER(C.c_void_p)]),
     "sdgpu_dev_free": (C.c_int, [_ctx, C.c_void_p]),

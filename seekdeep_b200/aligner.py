@@ -182,6 +182,22 @@ class GpuAligner:
         self._check(self._lib.sdgpu_timer_stop(self._ctx, C.byref(ms)))
         return ms.value
 
+    def set_pass_table(self, iters):
+        """Upload par-file lines (IterPar list) for on-device comparison::passErrorProfile."""
+        from .qluster import iter_pars_to_c
+        arr, n = iter_pars_to_c(iters)
+        self._check(self._lib.sdgpu_set_pass_table(self._ctx, C.cast(arr, C.c_void_p), n))
+
+    def align_pass(self, refIdx, readIdx, checkKmer=False, usingQuality=True, doingMatchQuality=False):
+        """Like align_profile, but returns uint64 masks: bit l <=> errorProfile passes table line l."""
+        refIdx = np.ascontiguousarray(refIdx, np.uint32)
+        readIdx = np.ascontiguousarray(readIdx, np.uint32)
+        flags = (_abi.CHECK_KMER if checkKmer else 0) | (_abi.USING_QUALITY if usingQuality else 0) | \
+                (_abi.MATCH_QUALITY if doingMatchQuality else 0)
+        out = np.zeros(len(refIdx), np.uint64)
+        self._check(self._lib.sdgpu_align_pass(self._ctx, _ptr(refIdx), _ptr(readIdx), len(refIdx), flags, _ptr(out)))
+        return out
+
     def measure_int32_peak(self, which=0):
         v = C.c_double()
         self._check(self._lib.sdgpu_measure_int32_peak(self._ctx, which, C.byref(v)))

@@ -47,6 +47,9 @@ struct AlignArgs {
   uint32_t ptrBytes;   // bytes of the pointer region in a slab
   uint32_t maxAln;     // capacity of each gapped string
   uint32_t* work;      // [0] = next pair, [2..3] = cell counter (uint64)
+  const sdgpu_iter_par* lines;  // par-file lines for the verdict mask (device)
+  uint32_t nLines;
+  uint64_t* passOut;   // per pair: bit l = passes line l (or NULL)
 };
 
 enum { ST_D = 0, ST_U = 1, ST_L = 2 };
@@ -394,7 +397,34 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
       }
     }
 
-    if (lane == 0) {
+    // comparison::passErrorProfile against every par-file line at once: lane l judges lines l and
+    // l + 32, two ballots give the 64-bit verdict mask the host collapse loop consumes
+    if (a.passOut) {
+      const unsigned events = hqM + lqM + hq + lq + lk + numGaps;
+      const double id = events ? double(hqM + lqM) / double(events) : 0.0;
+      const double idHq = events ? double(hqM + lqM + lq + lk) / double(events) : 0.0;
+      unsigned halves[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const unsigned li = unsigned(lane) + 32u * h;
+        bool pass = false;
+        if (li < a.nLines) {
+          const sdgpu_iter_par it = a.lines[li];
+          if (it.onPerId) {
+            pass = (it.onHqPerId ? idHq : id) >= it.perId;
+          } else {
+            pass = it.oneBaseIndel >= one && it.twoBaseIndel >= two && it.largeBaseIndel >= large &&
+                   it.hqMismatches >= double(hq) && it.lqMismatches >= double(lq) && it.lowKmerMismatches >= double(lk);
+          }
+        }
+        halves[h] = __ballot_sync(FULL, pass);
+      }
+      if (lane == 0) {
+        a.passOut[pair] = (uint64_t(halves[1]) << 32) | halves[0];
+        if (!a.out) atomicAdd(reinterpret_cast<unsigned long long*>(a.work + 2), (unsigned long long)la * (unsigned long long)lb);
+      }
+    }
+    if (lane == 0 && a.out) {
       sdgpu_comparison c;
       c.alnScore = score;
       c.hqMismatches = hq;
@@ -457,7 +487,7 @@ int launchC(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB)
 
 int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx, uint32_t nPairs,
                     uint32_t flags, sdgpu_comparison* dOut, sdgpu_gap* dGaps, uint32_t gapCap, uint32_t maxLenA,
-                    uint32_t maxLenB) {
+                    uint32_t maxLenB, uint64_t* dPassOut) {
   if (nPairs == 0) return SDGPU_OK;
   if ((flags & SDGPU_CHECK_KMER) && !ctx->haveIndex)
     return sd_fail(ctx, SDGPU_E_STATE, "SDGPU_CHECK_KMER requires sdgpu_build_kmer_index first");
@@ -473,6 +503,10 @@ int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dRe
   args.gapsOut = dGaps;
   args.gapCap = gapCap;
   args.work = ctx->dWork;
+  args.lines = ctx->dLines;
+  args.nLines = ctx->nLines;
+  args.passOut = dPassOut;
+  if (dPassOut && ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
   const uint32_t needC = (maxLenB + 31) / 32;
   if (needC <= 4) return launchC<4>(ctx, args, maxLenA, maxLenB);
   if (needC <= 6) return launchC<6>(ctx, args, maxLenA, maxLenB);

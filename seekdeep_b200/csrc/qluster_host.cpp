@@ -4,19 +4,25 @@
 // collapser::runFullClustering / collapseWithParameters / findMatch / cluster::compare /
 // baseCluster::calculateConsensus as the reference drives them (clusterDown.cpp:488-518).
 // The sequential greedy logic is unchanged; what differs is where comparisons come from:
-//   * before an iteration's sequential pass, every (cluster, read) pair the pass can ask for
-//     (each live read against the first `stopCheck` eligible clusters) that is not cached yet
-//     goes to the GPU in large batches (sdgpu_align_profile: DP + traceback + errorProfile);
-//   * the pass then reads comparisons from a pair cache keyed by the two sequence-store
-//     indices.  A store index names one immutable (sequence, quality) version, so a cached
-//     comparison is a pure function of its key (+ the k-mer index, on whose rebuild the cache is
-//     dropped) — the same transparency njhseq's previousErrorChecks_ / alnHolder_ caches have;
+//   * all par-file lines of the run are uploaded once (sdgpu_set_pass_table); for every pair the
+//     GPU returns a 64-bit verdict mask (bit l: errorProfile passes line l), so one alignment
+//     answers the same pair for every later iteration;
+//   * before an iteration's sequential pass, every (cluster, read) pair the pass can ask for —
+//     each live read against the first stopCheck(+1) eligible clusters, the "window" — that the
+//     read's row does not hold yet goes to the GPU in large batches.  A read whose row was
+//     complete for the previous window only needs the window's new entries;
+//   * verdicts live in per-read rows keyed by the cluster's sequence-store index.  A store index
+//     names one immutable (sequence, quality) version, so a cached verdict is a pure function of
+//     its key (+ the k-mer index, on whose rebuild all rows are dropped) — the same transparency
+//     njhseq's previousErrorChecks_ / alnHolder_ caches have;
 //   * consensus rebuilding aligns all members of all changed clusters in one batch with gap
 //     lists returned, builds the column counters on the host, and appends changed consensus
 //     versions to the device sequence store.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -33,86 +39,67 @@ double nowSec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// What the sequential pass needs from a comparison (passErrorProfile / identity thresholds).
-struct Verdict {
-  double one, two, large, id, idHq;
-  uint32_t hq, lq, lk;
-  uint32_t valid;
-};
-
-// Open-addressing map (storeIdxA << 32 | storeIdxB) -> Verdict.
-class PairCache {
+// Per-read verdict row: cluster store index -> pass mask (tiny open-addressing table).
+class Row {
  public:
-  PairCache() { rehash(1u << 16); }
-  const Verdict* find(uint64_t key) const {
-    size_t h = hash(key) & mask_;
+  static constexpr uint32_t EMPTY = 0xffffffffu;
+  const uint64_t* find(uint32_t k) const {
+    if (keys_.empty()) return nullptr;
+    uint32_t h = (k * 2654435761u) & mask_;
     while (keys_[h] != EMPTY) {
-      if (keys_[h] == key) return &vals_[h];
+      if (keys_[h] == k) return &vals_[h];
       h = (h + 1) & mask_;
     }
     return nullptr;
   }
-  void insert(uint64_t key, const Verdict& v) {
-    if ((size_ + 1) * 10 > (mask_ + 1) * 6) rehash((mask_ + 1) * 2);
-    size_t h = hash(key) & mask_;
+  void insert(uint32_t k, uint64_t v) {
+    if (keys_.empty() || (n_ + 1) * 3 > (mask_ + 1) * 2) grow();
+    uint32_t h = (k * 2654435761u) & mask_;
     while (keys_[h] != EMPTY) {
-      if (keys_[h] == key) {
+      if (keys_[h] == k) {
         vals_[h] = v;
         return;
       }
       h = (h + 1) & mask_;
     }
-    keys_[h] = key;
+    keys_[h] = k;
     vals_[h] = v;
-    ++size_;
+    ++n_;
   }
   void clear() {
-    std::fill(keys_.begin(), keys_.end(), EMPTY);
-    size_ = 0;
+    std::vector<uint32_t>().swap(keys_);
+    std::vector<uint64_t>().swap(vals_);
+    n_ = 0;
+    mask_ = 0;
   }
-  // keep only entries whose two store indices are still alive
+  uint32_t size() const { return n_; }
+  // drop verdicts against cluster versions that no longer exist
   void prune(const std::vector<uint8_t>& live) {
-    std::vector<uint64_t> k;
-    std::vector<Verdict> v;
+    std::vector<uint32_t> k;
+    std::vector<uint64_t> v;
     k.swap(keys_);
     v.swap(vals_);
-    size_t cap = 1u << 16;
-    size_t keep = 0;
+    n_ = 0;
+    mask_ = 0;
     for (size_t i = 0; i < k.size(); ++i)
-      if (k[i] != EMPTY && live[k[i] >> 32] && live[k[i] & 0xffffffffu]) ++keep;
-    while (cap * 6 < (keep + 1) * 10 * 2) cap *= 2;
-    keys_.assign(cap, EMPTY);
-    vals_.resize(cap);
-    mask_ = cap - 1;
-    size_ = 0;
-    for (size_t i = 0; i < k.size(); ++i)
-      if (k[i] != EMPTY && live[k[i] >> 32] && live[k[i] & 0xffffffffu]) insert(k[i], v[i]);
+      if (k[i] != EMPTY && live[k[i]]) insert(k[i], v[i]);
   }
-  size_t size() const { return size_; }
 
  private:
-  static constexpr uint64_t EMPTY = ~0ull;
-  static uint64_t hash(uint64_t x) {
-    x ^= x >> 33;
-    x *= 0xff51afd7ed558ccdULL;
-    x ^= x >> 33;
-    x *= 0xc4ceb9fe1a85ec53ULL;
-    x ^= x >> 33;
-    return x;
-  }
-  void rehash(size_t cap) {
-    std::vector<uint64_t> k(cap, EMPTY);
-    std::vector<Verdict> v(cap);
+  void grow() {
+    const uint32_t cap = keys_.empty() ? 64u : uint32_t(keys_.size()) * 2u;
+    std::vector<uint32_t> k(cap, EMPTY);
+    std::vector<uint64_t> v(cap);
     k.swap(keys_);
     v.swap(vals_);
     mask_ = cap - 1;
-    size_ = 0;
+    n_ = 0;
     for (size_t i = 0; i < k.size(); ++i)
       if (k[i] != EMPTY) insert(k[i], v[i]);
   }
-  std::vector<uint64_t> keys_;
-  std::vector<Verdict> vals_;
-  size_t mask_ = 0, size_ = 0;
+  std::vector<uint32_t> keys_;
+  std::vector<uint64_t> vals_;
+  uint32_t n_ = 0, mask_ = 0;
 };
 
 struct Uniq {  // one exact-unique input sequence; its store index is its position in `uniq`
@@ -126,17 +113,27 @@ struct Clus {
   std::string seq;
   std::vector<uint8_t> qual;
   double cnt = 0;
-  uint32_t firstId = 0;  // cluster::firstReadName_ stand-in (tie-break of the sort)
-  uint32_t storeIdx = 0; // device sequence-store entry holding (seq, qual)
+  uint32_t firstId = 0;   // cluster::firstReadName_ stand-in (tie-break of the sort)
+  uint32_t storeIdx = 0;  // device sequence-store entry holding (seq, qual)
   std::vector<uint32_t> members;
   bool remove = false, needCons = false;
   double avgErr = 0;
+  Row row;                 // verdicts of this cluster *as the read* against larger clusters
+  uint64_t rowSerial = 0;  // iteration serial at which `row` was complete for that window
+};
+
+struct ErrLut {
+  double v[256];
+  ErrLut() {
+    for (int q = 0; q < 256; ++q) v[q] = std::pow(10.0, -(double(q) / 10.0));
+  }
 };
 
 double averageErrorRate(const std::vector<uint8_t>& q) {
+  static const ErrLut lut;  // same pow() values, evaluated once
   if (q.empty()) return 0;
   double s = 0;
-  for (uint8_t v : q) s += std::pow(10.0, -(double(v) / 10.0));
+  for (uint8_t x : q) s += lut.v[x];
   return s / double(q.size());
 }
 
@@ -145,12 +142,6 @@ bool clusLess(const Clus& a, const Clus& b) {  // readVecSorter "totalCount"
   if (a.avgErr != b.avgErr) return a.avgErr < b.avgErr;
   if (a.seq != b.seq) return a.seq < b.seq;
   return a.firstId < b.firstId;
-}
-
-bool passErrorCheck(const sdq_iter_par& it, const Verdict& g) {  // comparison::passErrorProfile
-  if (it.onPerId) return (it.onHqPerId ? g.idHq : g.id) >= it.perId;
-  return it.oneBaseIndel >= g.one && it.twoBaseIndel >= g.two && it.largeBaseIndel >= g.large &&
-         it.hqMismatches >= double(g.hq) && it.lqMismatches >= double(g.lq) && it.lowKmerMismatches >= double(g.lk);
 }
 
 struct CharCounter {
@@ -182,19 +173,29 @@ struct CharCounter {
   }
 };
 
+bool sameLine(const sdq_iter_par& a, const sdq_iter_par& b) {  // thresholds only: stopCheck/smallCutoff do not affect verdicts
+  return a.oneBaseIndel == b.oneBaseIndel && a.twoBaseIndel == b.twoBaseIndel && a.largeBaseIndel == b.largeBaseIndel &&
+         a.hqMismatches == b.hqMismatches && a.lqMismatches == b.lqMismatches && a.lowKmerMismatches == b.lowKmerMismatches &&
+         a.onPerId == b.onPerId && a.onHqPerId == b.onHqPerId && a.perId == b.perId;
+}
+
 class Runner {
  public:
   Runner(sdgpu_ctx* ctx, const sdq_opts& o) : ctx_(ctx), O(o) {}
   sdgpu_ctx* ctx_;
   const sdq_opts& O;
   std::vector<Uniq> uniq;
-  PairCache cache;
+  std::vector<sdq_iter_par> lines;  // distinct par-file lines == bits of a verdict mask
   sdq_stats st{};
-  // host mirror of the store contents appended after the unique reads (consensus versions)
   uint32_t storeSize = 0;
+  uint64_t serial = 0;                // iteration counter across the three clustering runs
+  std::vector<uint32_t> prevWindow;   // store indices of the previous iteration's window
+  std::vector<uint8_t> inPrevWindow;  // by store index
   static constexpr uint32_t BATCH = 1u << 21;
+  std::vector<uint64_t> maskBuf;
   std::vector<sdgpu_comparison> cmpBuf;
   std::vector<sdgpu_gap> gapBuf;
+  double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0;
 
   int fail(int rc) {
     g_err = sdgpu_last_error(ctx_);
@@ -203,61 +204,88 @@ class Runner {
 
   uint32_t flags() const { return (O.checkKmers ? SDGPU_CHECK_KMER : 0u) | SDGPU_USING_QUALITY; }
 
-  // comparisons for (a[i], b[i]) store-index pairs -> cache
-  int computeToCache(const std::vector<uint32_t>& a, const std::vector<uint32_t>& b) {
+  int lineOf(const sdq_iter_par& it) {
+    for (size_t i = 0; i < lines.size(); ++i)
+      if (sameLine(lines[i], it)) return int(i);
+    lines.push_back(it);
+    return int(lines.size()) - 1;
+  }
+
+  // verdict masks for (a[i], b[i]) store-index pairs -> row of the read at cs[owner[i]]
+  int computeToRows(std::vector<Clus>& cs, const std::vector<uint32_t>& a, const std::vector<uint32_t>& b,
+                    const std::vector<uint32_t>& owner) {
     const size_t n = a.size();
     for (size_t off = 0; off < n; off += BATCH) {
       const uint32_t m = uint32_t(std::min<size_t>(BATCH, n - off));
-      if (cmpBuf.size() < m) cmpBuf.resize(m);
+      if (maskBuf.size() < m) maskBuf.resize(m);
       const double t0 = nowSec();
-      int rc = sdgpu_align_profile(ctx_, a.data() + off, b.data() + off, m, flags(), cmpBuf.data(), nullptr, 0);
+      int rc = sdgpu_align_pass(ctx_, a.data() + off, b.data() + off, m, flags(), maskBuf.data());
       st.secondsGpu += nowSec() - t0;
       if (rc) return fail(rc);
       ++st.gpuBatches;
       st.pairsComputed += m;
-      for (uint32_t i = 0; i < m; ++i) {
-        const sdgpu_comparison& c = cmpBuf[i];
-        Verdict v{c.oneBaseIndel, c.twoBaseIndel, c.largeBaseIndel, c.eventBasedIdentity, c.eventBasedIdentityHq,
-                  c.hqMismatches, c.lqMismatches, c.lowKmerMismatches, 1u};
-        cache.insert((uint64_t(a[off + i]) << 32) | b[off + i], v);
-      }
+      const double ti0 = nowSec();
+      for (uint32_t i = 0; i < m; ++i) cs[owner[off + i]].row.insert(a[off + i], maskBuf[i]);
+      tInsert += nowSec() - ti0;
     }
     return 0;
   }
 
-  static uint64_t key(const Clus& clus, const Clus& read) { return (uint64_t(clus.storeIdx) << 32) | read.storeIdx; }
-
-  // candidate scan shared by speculation and the sequential pass: eligible clusters in sorted
-  // order, skipping `rp` itself (njhseq findMatch: remove / smallCutoff / same-name skips)
-  int collapseWithParameters(std::vector<Clus>& cs, const sdq_iter_par& it) {
+  // njhseq collapser::collapseWithParameters + findMatch for one par-file line
+  int collapseWithParameters(std::vector<Clus>& cs, const sdq_iter_par& it, int line) {
+    ++serial;
     size_t alive = 0;
     for (const Clus& c : cs) alive += !c.remove;
     if (alive < 2) return 0;
-    std::vector<uint32_t> elig;
+    const uint64_t bit = 1ull << line;
+    std::vector<uint32_t> elig;  // candidate clusters in sorted order (smallCutoff rule)
     for (uint32_t cp = 0; cp < cs.size(); ++cp)
       if (!cs[cp].remove && cs[cp].cnt > double(it.smallCutoff)) elig.push_back(cp);
-    // ---- speculative batch: everything the pass below can ask for and the cache lacks
+    // ---- speculative batch: the window = first stopCheck(+1: a read skips itself) candidates
+    double tt0 = nowSec();
     {
-      std::vector<uint32_t> a, b;
+      const uint32_t wn = uint32_t(std::min<uint64_t>(elig.size(), uint64_t(it.stopCheck) + 1));
+      std::vector<uint32_t> window(wn), fresh;
+      if (inPrevWindow.size() < storeSize) inPrevWindow.resize(storeSize, 0);
+      for (uint32_t w = 0; w < wn; ++w) {
+        window[w] = elig[w];
+        if (!inPrevWindow[cs[elig[w]].storeIdx]) fresh.push_back(elig[w]);
+      }
+      std::vector<uint32_t> a, b, owner;
       for (uint32_t rp = 0; rp < cs.size(); ++rp) {
-        if (cs[rp].remove) continue;
-        uint32_t count = 0;
-        for (uint32_t e = 0; e < elig.size() && count < it.stopCheck; ++e) {
-          const uint32_t cp = elig[e];
-          if (cp == rp) continue;
-          ++count;
-          if (!cache.find(key(cs[cp], cs[rp]))) {
+        Clus& read = cs[rp];
+        if (read.remove) continue;
+        if (read.rowSerial + 1 == serial) {  // row complete for the previous window: only new entries
+          for (uint32_t cp : fresh) {
+            if (cp == rp) continue;
             a.push_back(cs[cp].storeIdx);
-            b.push_back(cs[rp].storeIdx);
+            b.push_back(read.storeIdx);
+            owner.push_back(rp);
+          }
+        } else {
+          for (uint32_t cp : window) {
+            if (cp == rp || read.row.find(cs[cp].storeIdx)) continue;
+            a.push_back(cs[cp].storeIdx);
+            b.push_back(read.storeIdx);
+            owner.push_back(rp);
           }
         }
+        read.rowSerial = serial;
       }
-      int rc = computeToCache(a, b);
+      for (uint32_t s : prevWindow) inPrevWindow[s] = 0;
+      prevWindow.clear();
+      for (uint32_t cp : window) {
+        prevWindow.push_back(cs[cp].storeIdx);
+        inPrevWindow[cs[cp].storeIdx] = 1;
+      }
+      tSpec += nowSec() - tt0;
+      int rc = computeToRows(cs, a, b, owner);
       if (rc) return rc;
     }
+    tt0 = nowSec();
     // ---- the sequential pass (smallest cluster first; first passing candidate absorbs it)
     size_t amountAdded = 0;
-    std::vector<uint32_t> da, db;
+    std::vector<uint32_t> da(1), db(1), downer(1);
     for (size_t rp = cs.size(); rp-- > 0;) {
       Clus& read = cs[rp];
       if (read.remove) continue;
@@ -269,27 +297,35 @@ class Runner {
         if (cp == rp) continue;
         ++count;
         if (count > it.stopCheck) break;
-        const Verdict* v = cache.find(key(clus, read));
+        const uint64_t* v = read.row.find(clus.storeIdx);
         if (!v) {  // a candidate that slid into the window because earlier ones were absorbed
-          da.assign(1, clus.storeIdx);
-          db.assign(1, read.storeIdx);
-          int rc = computeToCache(da, db);
+          da[0] = clus.storeIdx;
+          db[0] = read.storeIdx;
+          downer[0] = uint32_t(rp);
+          int rc = computeToRows(cs, da, db, downer);
           if (rc) return rc;
           ++st.onDemandPairs;
-          v = cache.find(key(clus, read));
+          v = read.row.find(clus.storeIdx);
         }
         ++st.pairsConsumed;
-        if (passErrorCheck(it, *v)) {
+        if (*v & bit) {
           clus.cnt += read.cnt;
           clus.members.insert(clus.members.end(), read.members.begin(), read.members.end());
           clus.needCons = true;
           read.remove = true;
+          read.row.clear();
           ++amountAdded;
           break;
         }
       }
     }
-    if (amountAdded > 0) return calculateConsensusBatch(cs);
+    tPass += nowSec() - tt0;
+    if (amountAdded > 0) {
+      tt0 = nowSec();
+      int rc = calculateConsensusBatch(cs);
+      tCons += nowSec() - tt0;
+      return rc;
+    }
     return 0;
   }
 
@@ -299,7 +335,6 @@ class Runner {
       uint32_t clus;
       uint32_t baseStore;  // store index of the sequence members are aligned to
       const std::string* baseSeq;
-      const std::vector<uint8_t>* baseQual;
       size_t firstPair;
     };
     std::vector<Job> jobs;
@@ -315,7 +350,7 @@ class Runner {
         totalCnt += uniq[u].cnt;
       }
       const double avgLen = totalLen / totalCnt;
-      Job j{ci, cl.storeIdx, &cl.seq, &cl.qual, a.size()};
+      Job j{ci, cl.storeIdx, &cl.seq, a.size()};
       if (std::fabs(double(cl.seq.size()) - avgLen) > 0.1 * avgLen) {  // restart from the longest member
         size_t biggest = 0;
         for (uint32_t u : cl.members)
@@ -323,7 +358,6 @@ class Runner {
             biggest = uniq[u].seq.size();
             j.baseStore = u;
             j.baseSeq = &uniq[u].seq;
-            j.baseQual = &uniq[u].qual;
           }
       }
       for (uint32_t u : cl.members) {
@@ -341,8 +375,9 @@ class Runner {
     for (size_t i = 0; i < n; ++i) todo[i] = uint32_t(i);
     while (!todo.empty()) {
       std::vector<uint32_t> next;
-      for (size_t off = 0; off < todo.size(); off += BATCH / 4) {
-        const uint32_t m = uint32_t(std::min<size_t>(BATCH / 4, todo.size() - off));
+      const size_t chunk = std::max<size_t>(1024, (BATCH / 4) / (gapCap / 8));
+      for (size_t off = 0; off < todo.size(); off += chunk) {
+        const uint32_t m = uint32_t(std::min<size_t>(chunk, todo.size() - off));
         std::vector<uint32_t> pa(m), pb(m);
         for (uint32_t i = 0; i < m; ++i) {
           pa[i] = a[todo[off + i]];
@@ -374,17 +409,22 @@ class Runner {
     std::vector<uint8_t> gq;
     for (const Job& j : jobs) {
       Clus& cl = cs[j.clus];
-      const std::string base = *j.baseSeq;  // copies: cl.seq may be replaced below
+      const std::string base = *j.baseSeq;  // copy: cl.seq may be replaced below
       std::vector<CharCounter> counters(base.size());
       std::map<uint32_t, std::map<uint32_t, CharCounter>> insertions;
       std::map<uint32_t, CharCounter> beginningGap;
       for (size_t m = 0; m < cl.members.size(); ++m) {
         const Uniq& r = uniq[cl.members[m]];
         const uint32_t w = uint32_t(std::llround(r.cnt));
+        const std::vector<sdgpu_gap>& gl = gaps[j.firstPair + m];
+        if (gl.empty() && r.seq.size() == base.size()) {  // ungapped: column i is base position i
+          for (uint32_t i = 0; i < base.size(); ++i) counters[i].add(r.seq[i], r.qual[i], w);
+          continue;
+        }
         ga = base;
         gb = r.seq;
         gq = r.qual;
-        for (const sdgpu_gap& g : gaps[j.firstPair + m]) {  // descending positions
+        for (const sdgpu_gap& g : gl) {  // descending positions
           if (g.gapInA) {
             ga.insert(g.pos, g.size, '-');
           } else {
@@ -472,7 +512,12 @@ class Runner {
       uint32_t first = 0;
       int rc = sdgpu_append_seqs(ctx_, bases.data(), quals.data(), offs.data(), cnts.data(), uint32_t(changed.size()), &first);
       if (rc) return fail(rc);
-      for (size_t i = 0; i < changed.size(); ++i) cs[changed[i]].storeIdx = first + uint32_t(i);
+      for (size_t i = 0; i < changed.size(); ++i) {
+        Clus& cl = cs[changed[i]];
+        cl.storeIdx = first + uint32_t(i);
+        cl.row.clear();  // its verdicts as a read were for the old version
+        cl.rowSerial = 0;
+      }
       storeSize = first + uint32_t(changed.size());
     }
     return 0;
@@ -487,19 +532,20 @@ class Runner {
     for (uint32_t i = 0; i < nIts; ++i) {
       dropRemovedAndSort(cs);
       if (cs.size() < 2) break;
-      if (cache.size() > (1u << 22)) {  // forget pairs that can never be asked for again
+      if ((serial & 7) == 7) {  // forget verdicts against cluster versions that are gone
         std::vector<uint8_t> live(storeSize, 0);
         for (const Clus& c : cs) live[c.storeIdx] = 1;
-        cache.prune(live);
+        for (Clus& c : cs)
+          if (c.row.size() > 256) c.row.prune(live);
       }
-      int rc = collapseWithParameters(cs, its[i]);
+      int rc = collapseWithParameters(cs, its[i], lineOf(its[i]));
       if (rc) return rc;
     }
     dropRemovedAndSort(cs);
     return 0;
   }
 
-  int buildIndex(const std::vector<Clus>& cs) {  // indexKmers over the current clusters
+  int buildIndex(std::vector<Clus>& cs) {  // indexKmers over the current clusters
     std::vector<uint32_t> idx(cs.size());
     std::vector<double> cnts(cs.size());
     std::vector<uint32_t> order(cs.size());
@@ -514,7 +560,10 @@ class Runner {
     rc = sdgpu_build_kmer_index(ctx_, idx.data(), uint32_t(idx.size()), O.kLen, O.runCutOff, int(O.kmersByPosition),
                                 int(O.expandKmerPos), O.expandKmerSize);
     if (rc) return fail(rc);
-    cache.clear();  // comparisons depend on the index through lowKmerMismatches
+    for (Clus& c : cs) {  // verdicts depend on the index through lowKmerMismatches
+      c.row.clear();
+      c.rowSerial = 0;
+    }
     return 0;
   }
 };
@@ -549,6 +598,14 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   res->membership.assign(n, UINT32_MAX);
   uint64_t launches0 = 0, cells0 = 0;
   if (sdgpu_counters(ctx, &launches0, &cells0)) return bail(R.fail(SDGPU_E_CUDA));
+  // every distinct par-file line becomes one bit of the verdict mask
+  for (uint32_t i = 0; i < nInit; ++i) R.lineOf(initPars[i]);
+  for (uint32_t i = 0; i < nPars; ++i) R.lineOf(pars[i]);
+  if (R.lines.size() > SDGPU_MAX_PASS_LINES) {
+    g_err = "more than 64 distinct par-file lines";
+    return bail(SDGPU_E_UNSUPPORTED);
+  }
+  if (sdgpu_set_pass_table(ctx, R.lines.data(), uint32_t(R.lines.size()))) return bail(R.fail(SDGPU_E_CUDA));
   // exact-sequence dedupe in first-seen order (clusterDown.cpp:272-288; hashing instead of the
   // reference's O(N*U) scan, same result)
   {
@@ -620,6 +677,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     c.members = {u};
     c.avgErr = averageErrorRate(c.qual);
   }
+  const double tPrep = nowSec() - tStart;
   std::sort(clusters.begin(), clusters.end(), clusLess);  // clusterDown.cpp:389
   int rc = R.buildIndex(clusters);                         // clusterDown.cpp:412-417
   if (rc) return bail(rc);
@@ -639,9 +697,11 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     if ((rc = R.runFullClustering(clusters, pars, nPars))) return bail(rc);
   }
   std::sort(clusters.begin(), clusters.end(), clusLess);  // :560
-  for (uint32_t c = 0; c < clusters.size(); ++c)
+  for (uint32_t c = 0; c < clusters.size(); ++c) {
+    clusters[c].row.clear();
     for (uint32_t u : clusters[c].members)
       for (uint32_t r : R.uniq[u].inputIdx) res->membership[r] = c;
+  }
   uint64_t launches1 = 0, cells1 = 0;
   if (sdgpu_counters(ctx, &launches1, &cells1)) return bail(R.fail(SDGPU_E_CUDA));
   res->clusters = std::move(clusters);
@@ -651,6 +711,9 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   res->stats.finalClusters = res->clusters.size();
   res->stats.cellUpdates = cells1 - cells0;
   res->stats.secondsTotal = nowSec() - tStart;
+  if (getenv("SDQ_TIMING"))
+    fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f lines %zu\n",
+            res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSpec, R.tInsert, R.tPass, R.tCons, R.lines.size());
   *out = res;
   return SDGPU_OK;
 }

@@ -176,6 +176,7 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   cudaFree(ctx->dScratch);
   cudaFree(ctx->dWork);
   cudaFree(ctx->dStage);
+  cudaFree(ctx->dLines);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -367,6 +368,45 @@ int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* 
   if (rc) return rc;
   SD_CUDA(ctx, cudaMemcpyAsync(out, dOut, bytesOut, cudaMemcpyDeviceToHost, ctx->stream));
   if (wantGaps) SD_CUDA(ctx, cudaMemcpyAsync(gapsOut, dGaps, bytesGaps, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
+}
+
+int sdgpu_set_pass_table(sdgpu_ctx* ctx, const sdgpu_iter_par* lines, uint32_t nLines) {
+  if (!ctx || (nLines && !lines)) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  if (nLines > SDGPU_MAX_PASS_LINES) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "more than 64 par-file lines in one pass table");
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->dLines) SD_CUDA(ctx, cudaMalloc(&ctx->dLines, SDGPU_MAX_PASS_LINES * sizeof(sdgpu_iter_par)));
+  if (nLines) SD_CUDA(ctx, cudaMemcpyAsync(ctx->dLines, lines, size_t(nLines) * sizeof(sdgpu_iter_par), cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nLines = nLines;
+  return SDGPU_OK;
+}
+
+int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs, uint32_t flags,
+                     uint64_t* passMaskOut) {
+  if (!ctx || (nPairs && (!refIdx || !readIdx || !passMaskOut))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  if (nPairs == 0) return SDGPU_OK;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  uint32_t maxA = 0, maxB = 0;
+  for (uint32_t x = 0; x < nPairs; ++x) {
+    if (refIdx[x] >= nSeqs || readIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "pair index out of range");
+    maxA = std::max<uint32_t>(maxA, uint32_t(ctx->hOffsets[refIdx[x] + 1] - ctx->hOffsets[refIdx[x]]));
+    maxB = std::max<uint32_t>(maxB, uint32_t(ctx->hOffsets[readIdx[x] + 1] - ctx->hOffsets[readIdx[x]]));
+  }
+  const uint64_t bytesIdx = uint64_t(nPairs) * 4, bytesOut = uint64_t(nPairs) * 8;
+  int rc = sd_ensure_stage(ctx, bytesOut + 2 * bytesIdx + 256);
+  if (rc) return rc;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->dStage);
+  uint64_t* dPass = reinterpret_cast<uint64_t*>(base);
+  uint32_t* dRef = reinterpret_cast<uint32_t*>(base + bytesOut);
+  uint32_t* dRead = dRef + nPairs;
+  SD_CUDA(ctx, cudaMemcpyAsync(dRef, refIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(dRead, readIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  rc = sd_launch_align(ctx, dRef, dRead, nPairs, flags, nullptr, nullptr, 0, maxA, maxB, dPass);
+  if (rc) return rc;
+  SD_CUDA(ctx, cudaMemcpyAsync(passMaskOut, dPass, bytesOut, cudaMemcpyDeviceToHost, ctx->stream));
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SDGPU_OK;
 }

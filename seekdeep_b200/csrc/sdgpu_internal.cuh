@@ -76,6 +76,9 @@ struct sdgpu_ctx {
   uint64_t stageBytes = 0;
   void* hPinned = nullptr;
   uint64_t pinnedBytes = 0;
+  // par-file lines for on-device passErrorProfile
+  sdgpu_iter_par* dLines = nullptr;
+  uint32_t nLines = 0;
   // bookkeeping
   uint64_t launches = 0, cells = 0;
   std::string err;
@@ -100,7 +103,7 @@ DevKmerIndex sd_dev_index(const sdgpu_ctx* ctx);
 // align_kernel.cu
 int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx, uint32_t nPairs,
                     uint32_t flags, sdgpu_comparison* dOut, sdgpu_gap* dGaps, uint32_t gapCap,
-                    uint32_t maxLenA, uint32_t maxLenB);
+                    uint32_t maxLenA, uint32_t maxLenB, uint64_t* dPassOut = nullptr);
 // kmer_kernels.cu
 int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, uint32_t kLen, uint32_t runCutOff,
                         int byPos, int expandPos, uint32_t expandSize);

@@ -180,3 +180,34 @@ def test_full_size_properties():
     assert (cols <= np.minimum(lens[a], lens[b])).all()
     assert (out["alnScore"] <= 2 * np.minimum(lens[a], lens[b])).all()
     assert ((out["eventBasedIdentity"] >= 0) & (out["eventBasedIdentity"] <= 1)).all()
+
+
+def test_align_pass_matches_pass_error_profile(oracle):
+    """On-device comparison::passErrorProfile over a par table == thresholds applied on the host
+    to the oracle's errorProfiles (rows a5/a6)."""
+    from seekdeep_b200.iterpars import CollapseIterations, IterPar
+    rng = np.random.default_rng(71)
+    bases, quals, offsets, cnts, _, _ = H.make_store(rng, 64, 200)
+    n = 800
+    refIdx = rng.integers(0, 64, n).astype(np.uint32)
+    readIdx = rng.integers(0, 64, n).astype(np.uint32)
+    iters = CollapseIterations.gen_illumina_default_pars(100).iters[:11]
+    iters += [IterPar(100, 3, 0.99, 0.5, 0.25, 1, 2, 0), IterPar(100, 0, onPerId=True, onHqPerId=True, perId=0.985),
+              IterPar(100, 0, onPerId=True, onHqPerId=False, perId=0.97)]
+    params = H.params_for("countEnds")  # weighHomopolymers: fractional indel tallies
+    with GpuAligner(params) as al:
+        al.upload_seqs(bases, quals, offsets, cnts)
+        al.set_pass_table(iters)
+        masks = al.align_pass(refIdx, readIdx)
+    want = oracle.align_profile_batch(params, bases, quals, offsets, refIdx, readIdx, _abi.USING_QUALITY)
+    for l, it in enumerate(iters):
+        if it.onPerId:
+            ok = (want["eventBasedIdentityHq"] if it.onHqPerId else want["eventBasedIdentity"]) >= it.perId
+        else:
+            ok = ((it.oneBaseIndel >= want["oneBaseIndel"]) & (it.twoBaseIndel >= want["twoBaseIndel"]) &
+                  (it.largeBaseIndel >= want["largeBaseIndel"]) & (it.hqMismatches >= want["hqMismatches"]) &
+                  (it.lqMismatches >= want["lqMismatches"]) & (it.lowKmerMismatches >= want["lowKmerMismatches"]))
+        got = ((masks >> np.uint64(l)) & np.uint64(1)).astype(bool)
+        assert np.array_equal(got, ok), l
+    assert (masks >> np.uint64(len(iters)) == 0).all()
+    assert 0 < int(((masks & np.uint64(1)) != 0).sum()) < n
