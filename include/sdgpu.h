@@ -218,6 +218,18 @@ int sdgpu_timer_start(sdgpu_ctx* ctx);
 int sdgpu_timer_stop(sdgpu_ctx* ctx, float* msOut); /* records, synchronizes, returns elapsed ms */
 /* Counters: kernels launched by this ctx and DP cells computed since creation. */
 int sdgpu_counters(sdgpu_ctx* ctx, uint64_t* kernelLaunches, uint64_t* cellUpdates);
+/* Measurement bookkeeping for bench.py: with profiling enabled every alignment-kernel launch is
+ * bracketed by CUDA events on the ctx stream; sdgpu_profile_read sums them (optionally resets). */
+typedef struct sdgpu_profile {
+  double alignKernelMs;        /* sum of per-launch device time of the alignment kernel */
+  uint64_t alignKernelLaunches;
+  uint64_t kernelLaunches;     /* all kernels this library launched on the ctx */
+  uint64_t cellUpdates;        /* DP cells computed by those launches */
+  uint64_t h2dBytes, d2hBytes; /* bytes the library copied across PCIe */
+} sdgpu_profile;
+int sdgpu_profile_enable(sdgpu_ctx* ctx, int on);
+int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset);
+
 /* Roofline denominator for the alignment kernel: measured thread-level INT32 instructions per
  * second of one kind (0 add, 1 max(+sub), 2 fused add-max VIADDMNMX, 3 max3(+sub)) on this GPU. */
 int sdgpu_measure_int32_peak(sdgpu_ctx* ctx, int which, double* instrPerSec);

@@ -55,6 +55,7 @@ typedef struct sdq_stats {
   uint64_t onDemandPairs;   /* pairs computed outside the speculative batches */
   double secondsGpu;        /* wall time inside sdgpu_align_profile calls */
   double secondsTotal;
+  double msResident;        /* CUDA-event time on the ctx stream from "unique reads resident in HBM" to the end */
 } sdq_stats;
 
 /* Runs the collapse for one sample on ctx's GPU.  Reads are packed like sdgpu_upload_seqs

@@ -198,6 +198,17 @@ class GpuAligner:
         self._check(self._lib.sdgpu_align_pass(self._ctx, _ptr(refIdx), _ptr(readIdx), len(refIdx), flags, _ptr(out)))
         return out
 
+    def profile_enable(self, on=True):
+        self._check(self._lib.sdgpu_profile_enable(self._ctx, int(on)))
+
+    def profile_read(self, reset=True):
+        class Prof(C.Structure):
+            _fields_ = [("alignKernelMs", C.c_double), ("alignKernelLaunches", C.c_uint64), ("kernelLaunches", C.c_uint64),
+                        ("cellUpdates", C.c_uint64), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64)]
+        p = Prof()
+        self._check(self._lib.sdgpu_profile_read(self._ctx, C.byref(p), int(reset)))
+        return {k: getattr(p, k) for k, _ in Prof._fields_}
+
     def measure_int32_peak(self, which=0):
         v = C.c_double()
         self._check(self._lib.sdgpu_measure_int32_peak(self._ctx, which, C.byref(v)))

@@ -477,9 +477,23 @@ int launchC(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB)
   if (rc) return rc;
   args.scratch = ctx->dScratch;
   SD_CUDA(ctx, cudaMemsetAsync(ctx->dWork, 0, sizeof(uint32_t), ctx->stream));
+  // per-launch device time (CUDA events on the launching stream) for the roofline bookkeeping
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timeKernels) {
+    if (ctx->evUsed + 2 > ctx->evPool.size()) {
+      const size_t old = ctx->evPool.size();
+      ctx->evPool.resize(old + 256, nullptr);
+      for (size_t x = old; x < ctx->evPool.size(); ++x) SD_CUDA(ctx, cudaEventCreate(&ctx->evPool[x]));
+    }
+    e0 = ctx->evPool[ctx->evUsed++];
+    e1 = ctx->evPool[ctx->evUsed++];
+    SD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  }
   alignProfileKernel<C><<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(args);
   SD_CUDA(ctx, cudaGetLastError());
+  if (e1) SD_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
   ++ctx->launches;
+  ++ctx->alignLaunches;
   return SDGPU_OK;
 }
 

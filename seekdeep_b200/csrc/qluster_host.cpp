@@ -665,6 +665,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     }
     if (sdgpu_upload_seqs(ctx, b.data(), q.data(), off.data(), cn.data(), nU)) return bail(R.fail(SDGPU_E_CUDA));
     R.storeSize = nU;
+    if (sdgpu_timer_start(ctx)) return bail(R.fail(SDGPU_E_CUDA));  // inputs are resident from here on
   }
   std::vector<Clus> clusters(nU);
   for (uint32_t u = 0; u < nU; ++u) {
@@ -703,8 +704,11 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
       for (uint32_t r : R.uniq[u].inputIdx) res->membership[r] = c;
   }
   uint64_t launches1 = 0, cells1 = 0;
+  float msResident = 0;
+  if (sdgpu_timer_stop(ctx, &msResident)) return bail(R.fail(SDGPU_E_CUDA));
   if (sdgpu_counters(ctx, &launches1, &cells1)) return bail(R.fail(SDGPU_E_CUDA));
   res->clusters = std::move(clusters);
+  R.st.msResident = msResident;
   res->stats = R.st;
   res->stats.inputReads = n;
   res->stats.uniqueSeqs = nU;

@@ -249,6 +249,7 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
   if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dOffsets), &capO, needSeqs * 8, (uint64_t(oldN) + 1) * 8))) return rc;
   if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dCnts), &capC, needSeqs * 8, uint64_t(oldN) * 8))) return rc;
   ctx->capSeqs = uint32_t(std::min(capO, capC) / 8);
+  ctx->h2dBytes += 2 * addBases + (uint64_t(n) + 1) * 8 + uint64_t(n) * 8;
   SD_CUDA(ctx, cudaMemcpyAsync(ctx->dCodes + oldBases, hCodes, addBases, cudaMemcpyHostToDevice, ctx->stream));
   SD_CUDA(ctx, cudaMemcpyAsync(ctx->dQuals + oldBases, hQuals, addBases, cudaMemcpyHostToDevice, ctx->stream));
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging is reused below
@@ -369,6 +370,8 @@ int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* 
   SD_CUDA(ctx, cudaMemcpyAsync(out, dOut, bytesOut, cudaMemcpyDeviceToHost, ctx->stream));
   if (wantGaps) SD_CUDA(ctx, cudaMemcpyAsync(gapsOut, dGaps, bytesGaps, cudaMemcpyDeviceToHost, ctx->stream));
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->h2dBytes += 2 * bytesIdx;
+  ctx->d2hBytes += bytesOut + bytesGaps;
   return SDGPU_OK;
 }
 
@@ -408,6 +411,42 @@ int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* rea
   if (rc) return rc;
   SD_CUDA(ctx, cudaMemcpyAsync(passMaskOut, dPass, bytesOut, cudaMemcpyDeviceToHost, ctx->stream));
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->h2dBytes += 2 * bytesIdx;
+  ctx->d2hBytes += bytesOut;
+  return SDGPU_OK;
+}
+
+int sdgpu_profile_enable(sdgpu_ctx* ctx, int on) {
+  if (!ctx) return SDGPU_E_ARG;
+  ctx->timeKernels = on != 0;
+  return SDGPU_OK;
+}
+
+int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset) {
+  if (!ctx || !out) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t x = 0; x + 1 < ctx->evUsed; x += 2) {
+    float ms = 0;
+    SD_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evPool[x], ctx->evPool[x + 1]));
+    ctx->alignMs += ms;
+  }
+  ctx->evUsed = 0;
+  uint64_t cells = 0;
+  SD_CUDA(ctx, cudaMemcpy(&cells, ctx->dWork + 2, 8, cudaMemcpyDeviceToHost));
+  out->alignKernelMs = ctx->alignMs;
+  out->alignKernelLaunches = ctx->alignLaunches;
+  out->kernelLaunches = ctx->launches;
+  out->cellUpdates = cells - ctx->cells;
+  out->h2dBytes = ctx->h2dBytes;
+  out->d2hBytes = ctx->d2hBytes;
+  if (reset) {
+    ctx->alignMs = 0;
+    ctx->alignLaunches = 0;
+    ctx->launches = 0;
+    ctx->cells = cells;
+    ctx->h2dBytes = ctx->d2hBytes = 0;
+  }
   return SDGPU_OK;
 }
 

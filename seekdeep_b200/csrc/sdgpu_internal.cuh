@@ -79,6 +79,13 @@ struct sdgpu_ctx {
   // par-file lines for on-device passErrorProfile
   sdgpu_iter_par* dLines = nullptr;
   uint32_t nLines = 0;
+  // profiling bookkeeping (sdgpu_profile_*): per-launch events of the alignment kernel, PCIe bytes
+  bool timeKernels = false;
+  std::vector<cudaEvent_t> evPool;
+  size_t evUsed = 0;
+  double alignMs = 0;
+  uint64_t alignLaunches = 0;
+  uint64_t h2dBytes = 0, d2hBytes = 0;
   // bookkeeping
   uint64_t launches = 0, cells = 0;
   std::string err;

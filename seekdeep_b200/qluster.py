@@ -30,7 +30,7 @@ class QlusterOptsC(C.Structure):
 class StatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("inputReads", "uniqueSeqs", "finalClusters", "pairsComputed", "pairsConsumed",
                                           "consensusAligns", "cellUpdates", "gpuBatches", "onDemandPairs")] + \
-               [("secondsGpu", C.c_double), ("secondsTotal", C.c_double)]
+               [("secondsGpu", C.c_double), ("secondsTotal", C.c_double), ("msResident", C.c_double)]
 
 
 @dataclass
