@@ -141,6 +141,7 @@ int sdgpu_create(int device, const sdgpu_params* params, sdgpu_ctx** out);
 void sdgpu_destroy(sdgpu_ctx* ctx);
 const char* sdgpu_last_error(sdgpu_ctx* ctx); /* ctx may be NULL: last create() error of this thread */
 int sdgpu_set_params(sdgpu_ctx* ctx, const sdgpu_params* params); /* e.g. `alignerObj.weighHomopolymers_ = x` */
+int sdgpu_get_params(sdgpu_ctx* ctx, sdgpu_params* out);          /* e.g. reading `alignerObj.qScorePars_` (clusterDown.cpp:429) */
 
 /* Sequence store.  Replaces the caller-owned std::vector<cluster>/seqInfo the aligner reads
  * (seqBase_.seq_, seqBase_.qual_, seqBase_.cnt_; clusterDown.cpp:274-285).  `bases` is 7-bit

@@ -66,6 +66,7 @@ SIGNATURES = {
     "sdgpu_destroy": (None, [_ctx]),
     "sdgpu_last_error": (C.c_char_p, [_ctx]),
     "sdgpu_set_params": (C.c_int, [_ctx, C.POINTER(Params)]),
+    "sdgpu_get_params": (C.c_int, [_ctx, C.POINTER(Params)]),
     "sdgpu_upload_seqs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_append_seqs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, _u32p]),
     "sdgpu_num_seqs": (C.c_int, [_ctx, _u32p]),

@@ -14,10 +14,12 @@
 //   * verdicts live in per-read rows keyed by the cluster's sequence-store index.  A store index
 //     names one immutable (sequence, quality) version, so a cached verdict is a pure function of
 //     its key (+ the k-mer index, on whose rebuild all rows are dropped) — the same transparency
-//     njhseq's previousErrorChecks_ / alnHolder_ caches have;
-//   * consensus rebuilding aligns all members of all changed clusters in one batch with gap
-//     lists returned, builds the column counters on the host, and appends changed consensus
-//     versions to the device sequence store.
+//     njhseq's previousErrorChecks_ / alnHolder_ caches have.  A cluster whose consensus moved
+//     only in quality values keeps its device version as long as seqInfo::checkQual gives the
+//     same answer at every base: qualities enter an errorProfile only through checkQual;
+//   * consensus rebuilding keeps the per-column counters of a cluster while its base sequence
+//     stays the same, aligns only the newly absorbed members (one GPU batch per iteration, gap
+//     lists returned) and re-reads the consensus off the counters (integer sums: exact).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -25,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -54,6 +57,7 @@ class Row {
   }
   void insert(uint32_t k, uint64_t v) {
     if (keys_.empty() || (n_ + 1) * 3 > (mask_ + 1) * 2) grow();
+    or_ |= v;
     uint32_t h = (k * 2654435761u) & mask_;
     while (keys_[h] != EMPTY) {
       if (keys_[h] == k) {
@@ -71,8 +75,10 @@ class Row {
     std::vector<uint64_t>().swap(vals_);
     n_ = 0;
     mask_ = 0;
+    or_ = 0;
   }
   uint32_t size() const { return n_; }
+  uint64_t orMask() const { return or_; }  // superset of every verdict bit held in the row
   // drop verdicts against cluster versions that no longer exist
   void prune(const std::vector<uint8_t>& live) {
     std::vector<uint32_t> k;
@@ -81,6 +87,7 @@ class Row {
     v.swap(vals_);
     n_ = 0;
     mask_ = 0;
+    or_ = 0;
     for (size_t i = 0; i < k.size(); ++i)
       if (k[i] != EMPTY && live[k[i]]) insert(k[i], v[i]);
   }
@@ -100,6 +107,7 @@ class Row {
   std::vector<uint32_t> keys_;
   std::vector<uint64_t> vals_;
   uint32_t n_ = 0, mask_ = 0;
+  uint64_t or_ = 0;
 };
 
 struct Uniq {  // one exact-unique input sequence; its store index is its position in `uniq`
@@ -109,18 +117,61 @@ struct Uniq {  // one exact-unique input sequence; its store index is its positi
   std::vector<uint32_t> inputIdx;
 };
 
+// njhseq charCounter restricted to what consensus building uses, over the few symbols that occur
+constexpr int NSYM = 18;
+struct Col {
+  uint32_t cnt[NSYM];
+  uint32_t qual[NSYM];
+  Col() {
+    std::memset(cnt, 0, sizeof(cnt));
+    std::memset(qual, 0, sizeof(qual));
+  }
+  uint32_t total() const {
+    uint32_t t = 0;
+    for (uint32_t v : cnt) t += v;
+    return t;
+  }
+};
+
+struct ConsState {  // column counters of one cluster against one base sequence
+  std::string baseSeq;
+  uint32_t baseStore = 0;
+  size_t nDone = 0;  // members already counted
+  std::vector<Col> counters;
+  std::map<uint32_t, std::map<uint32_t, Col>> insertions;
+  std::map<uint32_t, Col> beginningGap;
+};
+
 struct Clus {
   std::string seq;
   std::vector<uint8_t> qual;
   double cnt = 0;
   uint32_t firstId = 0;   // cluster::firstReadName_ stand-in (tie-break of the sort)
-  uint32_t storeIdx = 0;  // device sequence-store entry holding (seq, qual)
+  uint32_t storeIdx = 0;  // device sequence-store entry (verdict-equivalent to (seq, qual))
   std::vector<uint32_t> members;
   bool remove = false, needCons = false;
   double avgErr = 0;
   Row row;                 // verdicts of this cluster *as the read* against larger clusters
   uint64_t rowSerial = 0;  // iteration serial at which `row` was complete for that window
+  std::vector<uint8_t> devSig;  // checkQual outcome per base of the device version (empty: exact copy)
+  std::unique_ptr<ConsState> cons;
 };
+
+// seqInfo::checkQual for every base (strictly-greater thresholds, trailing window stops before
+// the last base) — the only way qualities enter profileAlignment.
+void qualSignature(const std::vector<uint8_t>& q, const sdgpu_params& P, std::vector<uint8_t>& sig) {
+  const int len = int(q.size()), out = int(P.qualThresWindow);
+  sig.assign(q.size(), 0);
+  for (int pos = 0; pos < len; ++pos) {
+    bool ok = q[pos] > P.primaryQual;
+    const int lower = pos > out ? pos - out : 0;
+    for (int i = lower; ok && i < pos; ++i) ok = q[i] > P.secondaryQual;
+    int higher = len - 1;
+    if (pos + out + 1 < len) higher = pos + out + 1;
+    for (int i = pos + 1; ok && i < higher; ++i) ok = q[i] > P.secondaryQual;
+    sig[pos] = ok ? 1 : 0;
+  }
+}
 
 struct ErrLut {
   double v[256];
@@ -144,35 +195,6 @@ bool clusLess(const Clus& a, const Clus& b) {  // readVecSorter "totalCount"
   return a.firstId < b.firstId;
 }
 
-struct CharCounter {
-  uint32_t cnt[128];
-  uint32_t qual[128];
-  CharCounter() {
-    std::memset(cnt, 0, sizeof(cnt));
-    std::memset(qual, 0, sizeof(qual));
-  }
-  void add(char b, uint32_t q, uint32_t w) {
-    cnt[uint8_t(b) & 127] += w;
-    qual[uint8_t(b) & 127] += q * w;
-  }
-  uint32_t total() const {
-    uint32_t t = 0;
-    for (uint32_t v : cnt) t += v;
-    return t;
-  }
-  void best(char& b, uint32_t& q) const {
-    uint32_t bc = 0;
-    b = ' ';
-    q = 0;
-    for (int ch = 0; ch < 128; ++ch)
-      if (cnt[ch] > bc) {
-        bc = cnt[ch];
-        b = char(ch);
-        q = qual[ch];
-      }
-  }
-};
-
 bool sameLine(const sdq_iter_par& a, const sdq_iter_par& b) {  // thresholds only: stopCheck/smallCutoff do not affect verdicts
   return a.oneBaseIndel == b.oneBaseIndel && a.twoBaseIndel == b.twoBaseIndel && a.largeBaseIndel == b.largeBaseIndel &&
          a.hqMismatches == b.hqMismatches && a.lqMismatches == b.lqMismatches && a.lowKmerMismatches == b.lowKmerMismatches &&
@@ -181,9 +203,12 @@ bool sameLine(const sdq_iter_par& a, const sdq_iter_par& b) {  // thresholds onl
 
 class Runner {
  public:
-  Runner(sdgpu_ctx* ctx, const sdq_opts& o) : ctx_(ctx), O(o) {}
+  Runner(sdgpu_ctx* ctx, const sdq_opts& o) : ctx_(ctx), O(o) {
+    std::memset(slotOf, -1, sizeof(slotOf));
+  }
   sdgpu_ctx* ctx_;
   const sdq_opts& O;
+  sdgpu_params P;  // the ctx's scoring / quality parameters (for qualSignature)
   std::vector<Uniq> uniq;
   std::vector<sdq_iter_par> lines;  // distinct par-file lines == bits of a verdict mask
   sdq_stats st{};
@@ -195,7 +220,12 @@ class Runner {
   std::vector<uint64_t> maskBuf;
   std::vector<sdgpu_comparison> cmpBuf;
   std::vector<sdgpu_gap> gapBuf;
-  double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0;
+  double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0;
+  uint64_t keptVersions = 0, skippedScans = 0;
+  // symbols of the consensus counters (bases + '-'), ASCII order kept for njhseq's tie rule
+  int8_t slotOf[128];
+  int nSlots = 0;
+  std::vector<std::pair<char, int>> slotOrder;
 
   int fail(int rc) {
     g_err = sdgpu_last_error(ctx_);
@@ -209,6 +239,35 @@ class Runner {
       if (sameLine(lines[i], it)) return int(i);
     lines.push_back(it);
     return int(lines.size()) - 1;
+  }
+
+  int slot(char ch) {
+    const int c = uint8_t(ch) & 127;
+    if (slotOf[c] < 0) {
+      if (nSlots >= NSYM) return -1;
+      slotOf[c] = int8_t(nSlots++);
+      slotOrder.emplace_back(char(c), int(slotOf[c]));
+      std::sort(slotOrder.begin(), slotOrder.end());
+    }
+    return slotOf[c];
+  }
+  bool add(Col& col, char b, uint32_t q, uint32_t w) {
+    const int s = slot(b);
+    if (s < 0) return false;
+    col.cnt[s] += w;
+    col.qual[s] += q * w;
+    return true;
+  }
+  void best(const Col& col, char& b, uint32_t& q, uint32_t& bc) const {  // first strictly-greatest in ASCII order
+    bc = 0;
+    b = ' ';
+    q = 0;
+    for (const auto& so : slotOrder)
+      if (col.cnt[so.second] > bc) {
+        bc = col.cnt[so.second];
+        b = so.first;
+        q = col.qual[so.second];
+      }
   }
 
   // verdict masks for (a[i], b[i]) store-index pairs -> row of the read at cs[owner[i]]
@@ -243,16 +302,17 @@ class Runner {
       if (!cs[cp].remove && cs[cp].cnt > double(it.smallCutoff)) elig.push_back(cp);
     // ---- speculative batch: the window = first stopCheck(+1: a read skips itself) candidates
     double tt0 = nowSec();
+    const uint32_t wn = uint32_t(std::min<uint64_t>(elig.size(), uint64_t(it.stopCheck) + 1));
+    std::vector<uint8_t> inWindow(cs.size(), 0);
     {
-      const uint32_t wn = uint32_t(std::min<uint64_t>(elig.size(), uint64_t(it.stopCheck) + 1));
-      std::vector<uint32_t> window(wn), fresh;
+      std::vector<uint32_t> fresh;
       if (inPrevWindow.size() < storeSize) inPrevWindow.resize(storeSize, 0);
       for (uint32_t w = 0; w < wn; ++w) {
-        window[w] = elig[w];
+        inWindow[elig[w]] = 1;
         if (!inPrevWindow[cs[elig[w]].storeIdx]) fresh.push_back(elig[w]);
       }
       std::vector<uint32_t> a, b, owner;
-      for (uint32_t rp = 0; rp < cs.size(); ++rp) {
+      for (uint32_t rp = uint32_t(cs.size()); rp-- > 0;) {  // same order as the pass below
         Clus& read = cs[rp];
         if (read.remove) continue;
         if (read.rowSerial + 1 == serial) {  // row complete for the previous window: only new entries
@@ -263,7 +323,8 @@ class Runner {
             owner.push_back(rp);
           }
         } else {
-          for (uint32_t cp : window) {
+          for (uint32_t w = 0; w < wn; ++w) {
+            const uint32_t cp = elig[w];
             if (cp == rp || read.row.find(cs[cp].storeIdx)) continue;
             a.push_back(cs[cp].storeIdx);
             b.push_back(read.storeIdx);
@@ -274,9 +335,9 @@ class Runner {
       }
       for (uint32_t s : prevWindow) inPrevWindow[s] = 0;
       prevWindow.clear();
-      for (uint32_t cp : window) {
-        prevWindow.push_back(cs[cp].storeIdx);
-        inPrevWindow[cs[cp].storeIdx] = 1;
+      for (uint32_t w = 0; w < wn; ++w) {
+        prevWindow.push_back(cs[elig[w]].storeIdx);
+        inPrevWindow[cs[elig[w]].storeIdx] = 1;
       }
       tSpec += nowSec() - tt0;
       int rc = computeToRows(cs, a, b, owner);
@@ -285,10 +346,16 @@ class Runner {
     tt0 = nowSec();
     // ---- the sequential pass (smallest cluster first; first passing candidate absorbs it)
     size_t amountAdded = 0;
-    std::vector<uint32_t> da(1), db(1), downer(1);
+    bool windowIntact = true;  // no window cluster absorbed yet: every read sees the static window
+    std::vector<uint32_t> da, db, downer;
     for (size_t rp = cs.size(); rp-- > 0;) {
       Clus& read = cs[rp];
       if (read.remove) continue;
+      // its row holds every window verdict; if none has this line's bit there is nothing to find
+      if (windowIntact && read.rowSerial == serial && !(read.row.orMask() & bit)) {
+        ++skippedScans;
+        continue;
+      }
       uint32_t count = 0;
       for (uint32_t e = 0; e < elig.size(); ++e) {
         const uint32_t cp = elig[e];
@@ -298,13 +365,21 @@ class Runner {
         ++count;
         if (count > it.stopCheck) break;
         const uint64_t* v = read.row.find(clus.storeIdx);
-        if (!v) {  // a candidate that slid into the window because earlier ones were absorbed
-          da[0] = clus.storeIdx;
-          db[0] = read.storeIdx;
-          downer[0] = uint32_t(rp);
+        if (!v) {
+          // a candidate that slid into the window because earlier ones were absorbed: the reads
+          // still to come will meet it too, so judge it against all of them in one batch
+          da.clear();
+          db.clear();
+          downer.clear();
+          for (size_t r2 = rp + 1; r2-- > 0;) {
+            if (cs[r2].remove || r2 == cp || cs[r2].row.find(clus.storeIdx)) continue;
+            da.push_back(clus.storeIdx);
+            db.push_back(cs[r2].storeIdx);
+            downer.push_back(uint32_t(r2));
+          }
           int rc = computeToRows(cs, da, db, downer);
           if (rc) return rc;
-          ++st.onDemandPairs;
+          st.onDemandPairs += da.size();
           v = read.row.find(clus.storeIdx);
         }
         ++st.pairsConsumed;
@@ -314,6 +389,8 @@ class Runner {
           clus.needCons = true;
           read.remove = true;
           read.row.clear();
+          read.cons.reset();
+          if (inWindow[rp]) windowIntact = false;
           ++amountAdded;
           break;
         }
@@ -333,9 +410,7 @@ class Runner {
   int calculateConsensusBatch(std::vector<Clus>& cs) {
     struct Job {
       uint32_t clus;
-      uint32_t baseStore;  // store index of the sequence members are aligned to
-      const std::string* baseSeq;
-      size_t firstPair;
+      size_t firstPair, firstMember;
     };
     std::vector<Job> jobs;
     std::vector<uint32_t> a, b;
@@ -350,19 +425,27 @@ class Runner {
         totalCnt += uniq[u].cnt;
       }
       const double avgLen = totalLen / totalCnt;
-      Job j{ci, cl.storeIdx, &cl.seq, a.size()};
+      uint32_t baseStore = cl.storeIdx;
+      const std::string* baseSeq = &cl.seq;
       if (std::fabs(double(cl.seq.size()) - avgLen) > 0.1 * avgLen) {  // restart from the longest member
         size_t biggest = 0;
         for (uint32_t u : cl.members)
           if (uniq[u].seq.size() > biggest) {
             biggest = uniq[u].seq.size();
-            j.baseStore = u;
-            j.baseSeq = &uniq[u].seq;
+            baseStore = u;
+            baseSeq = &uniq[u].seq;
           }
       }
-      for (uint32_t u : cl.members) {
-        a.push_back(j.baseStore);
-        b.push_back(u);
+      if (!cl.cons || cl.cons->baseSeq != *baseSeq) {  // new base: counters start over
+        cl.cons.reset(new ConsState());
+        cl.cons->baseSeq = *baseSeq;
+        cl.cons->counters.assign(baseSeq->size(), Col());
+      }
+      cl.cons->baseStore = baseStore;
+      Job j{ci, a.size(), cl.cons->nDone};
+      for (size_t m = cl.cons->nDone; m < cl.members.size(); ++m) {
+        a.push_back(baseStore);
+        b.push_back(cl.members[m]);
       }
       jobs.push_back(j);
     }
@@ -407,18 +490,17 @@ class Runner {
     std::vector<uint32_t> changed;
     std::string ga, gb;
     std::vector<uint8_t> gq;
+    bool symOk = true;
     for (const Job& j : jobs) {
       Clus& cl = cs[j.clus];
-      const std::string base = *j.baseSeq;  // copy: cl.seq may be replaced below
-      std::vector<CharCounter> counters(base.size());
-      std::map<uint32_t, std::map<uint32_t, CharCounter>> insertions;
-      std::map<uint32_t, CharCounter> beginningGap;
-      for (size_t m = 0; m < cl.members.size(); ++m) {
+      ConsState& S = *cl.cons;
+      const std::string& base = S.baseSeq;
+      for (size_t m = j.firstMember; m < cl.members.size(); ++m) {
         const Uniq& r = uniq[cl.members[m]];
         const uint32_t w = uint32_t(std::llround(r.cnt));
-        const std::vector<sdgpu_gap>& gl = gaps[j.firstPair + m];
+        const std::vector<sdgpu_gap>& gl = gaps[j.firstPair + (m - j.firstMember)];
         if (gl.empty() && r.seq.size() == base.size()) {  // ungapped: column i is base position i
-          for (uint32_t i = 0; i < base.size(); ++i) counters[i].add(r.seq[i], r.qual[i], w);
+          for (uint32_t i = 0; i < base.size(); ++i) symOk &= add(S.counters[i], r.seq[i], r.qual[i], w);
           continue;
         }
         ga = base;
@@ -436,60 +518,75 @@ class Runner {
         const uint32_t len = uint32_t(ga.size());
         if (len && ga[0] == '-') {
           while (start < len && ga[start] == '-') ++start;
-          for (uint32_t i = 0; i < start; ++i) beginningGap[i].add(gb[i], gq[i], w);
+          for (uint32_t i = 0; i < start; ++i) symOk &= add(S.beginningGap[i], gb[i], gq[i], w);
           offSet = start;
         }
         for (uint32_t i = start; i < len; ++i) {
           if (ga[i] == '-') {
-            insertions[i - offSet][currentOffset].add(gb[i], gq[i], w);
+            symOk &= add(S.insertions[i - offSet][currentOffset], gb[i], gq[i], w);
             ++currentOffset;
             ++offSet;
             continue;
           }
           currentOffset = 1;
-          counters[i - offSet].add(gb[i], gq[i], w);
+          symOk &= add(S.counters[i - offSet], gb[i], gq[i], w);
         }
+      }
+      S.nDone = cl.members.size();
+      if (!symOk) {
+        g_err = "more than 18 distinct symbols in consensus columns";
+        return SDGPU_E_ALPHABET;
       }
       std::string ns;
       std::vector<uint8_t> nq;
       const double fortyPercent = 0.40 * cl.cnt;
       const uint32_t size = uint32_t(std::llround(cl.cnt));
-      for (const auto& bg : beginningGap) {
-        char bch;
-        uint32_t q;
-        bg.second.best(bch, q);
+      char bch;
+      uint32_t q, bc;
+      for (const auto& bg : S.beginningGap) {
+        best(bg.second, bch, q, bc);
         const uint32_t tot = bg.second.total();
         if (bch == '-' || tot < fortyPercent) continue;
         ns.push_back(bch);
         nq.push_back(uint8_t(q / tot));
       }
-      for (uint32_t pos = 0; pos < counters.size(); ++pos) {
-        auto ins = insertions.find(pos);
-        if (ins != insertions.end()) {
-          for (const auto& ci : ins->second) {
-            char bch;
-            uint32_t q;
-            ci.second.best(bch, q);
-            const uint32_t tot = ci.second.total();
-            const uint32_t bc = ci.second.cnt[uint8_t(bch) & 127];
-            const uint32_t nonInserting = size > tot ? size - tot : 0;
-            if (bch == ' ' || bc <= nonInserting) continue;
-            ns.push_back(bch);
-            nq.push_back(uint8_t(q / bc));
+      for (uint32_t pos = 0; pos < S.counters.size(); ++pos) {
+        if (!S.insertions.empty()) {
+          auto ins = S.insertions.find(pos);
+          if (ins != S.insertions.end()) {
+            for (const auto& ci : ins->second) {
+              best(ci.second, bch, q, bc);
+              const uint32_t tot = ci.second.total();
+              const uint32_t nonInserting = size > tot ? size - tot : 0;
+              if (bch == ' ' || bc <= nonInserting) continue;
+              ns.push_back(bch);
+              nq.push_back(uint8_t(q / bc));
+            }
           }
         }
-        char bch;
-        uint32_t q;
-        counters[pos].best(bch, q);
-        const uint32_t tot = counters[pos].total();
+        best(S.counters[pos], bch, q, bc);
+        const uint32_t tot = S.counters[pos].total();
         if (bch == '-' || bch == ' ' || tot < fortyPercent) continue;
         ns.push_back(bch);
         nq.push_back(uint8_t(q / tot));
       }
-      if (ns != cl.seq || nq != cl.qual) {
+      const bool seqChanged = ns != cl.seq;
+      if (seqChanged || nq != cl.qual) {
+        std::vector<uint8_t> newSig;
+        qualSignature(nq, P, newSig);
+        bool needUpload = seqChanged;
+        if (!seqChanged) {  // same sequence: a new device version is needed only if checkQual flips somewhere
+          if (cl.devSig.empty()) qualSignature(cl.qual, P, cl.devSig);
+          needUpload = newSig != cl.devSig;
+        }
         cl.seq.swap(ns);
         cl.qual.swap(nq);
-        changed.push_back(j.clus);
+        if (needUpload) {
+          changed.push_back(j.clus);
+          cl.devSig.swap(newSig);
+        } else {
+          ++keptVersions;
+        }
       }
       cl.avgErr = averageErrorRate(cl.qual);
     }
@@ -523,9 +620,22 @@ class Runner {
     return 0;
   }
 
+  // drop absorbed clusters, then readVecSorter "totalCount" (index sort: a Clus is heavy to move)
   void dropRemovedAndSort(std::vector<Clus>& cs) {
+    const double t0 = nowSec();
     cs.erase(std::remove_if(cs.begin(), cs.end(), [](const Clus& c) { return c.remove; }), cs.end());
-    std::sort(cs.begin(), cs.end(), clusLess);
+    std::vector<uint32_t> idx(cs.size());
+    for (uint32_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return clusLess(cs[x], cs[y]); });
+    bool sorted = true;
+    for (uint32_t i = 0; i < idx.size() && sorted; ++i) sorted = idx[i] == i;
+    if (!sorted) {
+      std::vector<Clus> tmp;
+      tmp.reserve(cs.size());
+      for (uint32_t i : idx) tmp.push_back(std::move(cs[i]));
+      cs.swap(tmp);
+    }
+    tSort += nowSec() - t0;
   }
 
   int runFullClustering(std::vector<Clus>& cs, const sdq_iter_par* its, uint32_t nIts) {
@@ -598,6 +708,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   res->membership.assign(n, UINT32_MAX);
   uint64_t launches0 = 0, cells0 = 0;
   if (sdgpu_counters(ctx, &launches0, &cells0)) return bail(R.fail(SDGPU_E_CUDA));
+  if (sdgpu_get_params(ctx, &R.P)) return bail(R.fail(SDGPU_E_CUDA));
   // every distinct par-file line becomes one bit of the verdict mask
   for (uint32_t i = 0; i < nInit; ++i) R.lineOf(initPars[i]);
   for (uint32_t i = 0; i < nPars; ++i) R.lineOf(pars[i]);
@@ -679,8 +790,8 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     c.avgErr = averageErrorRate(c.qual);
   }
   const double tPrep = nowSec() - tStart;
-  std::sort(clusters.begin(), clusters.end(), clusLess);  // clusterDown.cpp:389
-  int rc = R.buildIndex(clusters);                         // clusterDown.cpp:412-417
+  R.dropRemovedAndSort(clusters);     // clusterDown.cpp:389
+  int rc = R.buildIndex(clusters);    // clusterDown.cpp:412-417
   if (rc) return bail(rc);
   std::vector<Clus> singletons;
   if (!opts->startWithSingles) {  // clusterDown.cpp:467-484
@@ -697,9 +808,10 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     if ((rc = R.buildIndex(clusters))) return bail(rc);
     if ((rc = R.runFullClustering(clusters, pars, nPars))) return bail(rc);
   }
-  std::sort(clusters.begin(), clusters.end(), clusLess);  // :560
+  R.dropRemovedAndSort(clusters);  // :560
   for (uint32_t c = 0; c < clusters.size(); ++c) {
     clusters[c].row.clear();
+    clusters[c].cons.reset();
     for (uint32_t u : clusters[c].members)
       for (uint32_t r : R.uniq[u].inputIdx) res->membership[r] = c;
   }
@@ -715,9 +827,12 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   res->stats.finalClusters = res->clusters.size();
   res->stats.cellUpdates = cells1 - cells0;
   res->stats.secondsTotal = nowSec() - tStart;
-  if (getenv("SDQ_TIMING"))
-    fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f lines %zu\n",
-            res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSpec, R.tInsert, R.tPass, R.tCons, R.lines.size());
+  if (getenv("SDQ_TIMING")) {
+    fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f sort %.3f lines %zu\n",
+            res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSpec, R.tInsert, R.tPass, R.tCons, R.tSort, R.lines.size());
+    fprintf(stderr, "[sdq] consensus updates kept on the device version: %llu, store entries: %u (unique reads %u), scans skipped %llu\n",
+            (unsigned long long)R.keptVersions, R.storeSize, nU, (unsigned long long)R.skippedScans);
+  }
   *out = res;
   return SDGPU_OK;
 }

@@ -195,6 +195,12 @@ int sdgpu_set_params(sdgpu_ctx* ctx, const sdgpu_params* params) {
   return refreshScoring(ctx);
 }
 
+int sdgpu_get_params(sdgpu_ctx* ctx, sdgpu_params* out) {
+  if (!ctx || !out) return SDGPU_E_ARG;
+  *out = ctx->params;
+  return SDGPU_OK;
+}
+
 static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
                       const double* cnts, uint32_t n, uint32_t* firstIndex) {
   if (!ctx || (n && (!bases || !offsets))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
