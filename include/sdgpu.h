@@ -204,6 +204,15 @@ int sdgpu_set_pass_table(sdgpu_ctx* ctx, const sdgpu_iter_par* lines, uint32_t n
 int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,
                      uint32_t flags, uint64_t* passMaskOut);
 
+/* Asynchronous, double-buffered form of sdgpu_align_pass: two slots (0, 1) per ctx.  submit copies
+ * the pair lists into pinned staging and enqueues H2D + kernel + D2H on the ctx stream, then
+ * returns; wait blocks until that slot's masks are on the host and hands back a pointer to them
+ * (valid until the slot is submitted again).  Lets the caller prepare / consume one batch while
+ * the GPU works on the other. */
+int sdgpu_align_pass_submit(sdgpu_ctx* ctx, int slot, const uint32_t* refIdx, const uint32_t* readIdx,
+                            uint32_t nPairs, uint32_t flags);
+int sdgpu_align_pass_wait(sdgpu_ctx* ctx, int slot, const uint64_t** masks, uint32_t* nPairs);
+
 /* Device-resident variant for benchmarking the kernels alone: pair lists and outputs are
  * device pointers (from sdgpu_dev_alloc); nothing crosses PCIe.  Asynchronous on the ctx stream. */
 int sdgpu_align_profile_dev(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx,

@@ -79,6 +79,8 @@ SIGNATURES = {
     "sdgpu_align_profile": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_set_pass_table": (C.c_int, [_ctx, C.c_void_p, C.c_uint32]),
     "sdgpu_align_pass": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "sdgpu_align_pass_submit": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "sdgpu_align_pass_wait": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_void_p), _u32p]),
     "sdgpu_align_profile_dev": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sdgpu_dev_alloc": (C.c_int, [_ctx, C.c_uint64, C.POINTER(C.c_void_p)]),
     "sdgpu_dev_free": (C.c_int, [_ctx, C.c_void_p]),

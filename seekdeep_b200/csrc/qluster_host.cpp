@@ -222,6 +222,7 @@ class Runner {
   std::vector<sdgpu_gap> gapBuf;
   double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0;
   uint64_t keptVersions = 0, skippedScans = 0;
+  bool orderDirty = true;
   // symbols of the consensus counters (bases + '-'), ASCII order kept for njhseq's tie rule
   int8_t slotOf[128];
   int nSlots = 0;
@@ -270,25 +271,65 @@ class Runner {
       }
   }
 
-  // verdict masks for (a[i], b[i]) store-index pairs -> row of the read at cs[owner[i]]
-  int computeToRows(std::vector<Clus>& cs, const std::vector<uint32_t>& a, const std::vector<uint32_t>& b,
-                    const std::vector<uint32_t>& owner) {
-    const size_t n = a.size();
-    for (size_t off = 0; off < n; off += BATCH) {
-      const uint32_t m = uint32_t(std::min<size_t>(BATCH, n - off));
-      if (maskBuf.size() < m) maskBuf.resize(m);
-      const double t0 = nowSec();
-      int rc = sdgpu_align_pass(ctx_, a.data() + off, b.data() + off, m, flags(), maskBuf.data());
-      st.secondsGpu += nowSec() - t0;
-      if (rc) return fail(rc);
-      ++st.gpuBatches;
-      st.pairsComputed += m;
-      const double ti0 = nowSec();
-      for (uint32_t i = 0; i < m; ++i) cs[owner[off + i]].row.insert(a[off + i], maskBuf[i]);
-      tInsert += nowSec() - ti0;
+  // Streams (cluster, read) pairs to the GPU in chunks through the two asynchronous slots of
+  // sdgpu_align_pass_submit/_wait: while the GPU aligns chunk k the host files chunk k-1's
+  // verdict masks into the reads' rows and lists chunk k+1.
+  struct PassPipe {
+    Runner& R;
+    std::vector<Clus>& cs;
+    std::vector<uint32_t> a[2], b[2], owner[2];
+    bool inflight[2] = {false, false};
+    int cur = 0;
+    int rc = 0;
+    uint32_t chunk;
+    PassPipe(Runner& r, std::vector<Clus>& c, uint32_t chunkPairs = BATCH / 2) : R(r), cs(c), chunk(chunkPairs) {}
+    void push(uint32_t clusStore, uint32_t readStore, uint32_t ownerPos) {
+      a[cur].push_back(clusStore);
+      b[cur].push_back(readStore);
+      owner[cur].push_back(ownerPos);
+      if (a[cur].size() >= chunk) flush();
     }
-    return 0;
-  }
+    void drain(int s) {
+      const uint64_t* masks = nullptr;
+      uint32_t n = 0;
+      double t0 = nowSec();
+      int r = sdgpu_align_pass_wait(R.ctx_, s, &masks, &n);
+      R.st.secondsGpu += nowSec() - t0;
+      inflight[s] = false;
+      if (r) {
+        rc = R.fail(r);
+        return;
+      }
+      t0 = nowSec();
+      for (uint32_t i = 0; i < n; ++i) cs[owner[s][i]].row.insert(a[s][i], masks[i]);
+      R.tInsert += nowSec() - t0;
+      a[s].clear();
+      b[s].clear();
+      owner[s].clear();
+    }
+    void flush() {
+      if (rc || a[cur].empty()) return;
+      const double t0 = nowSec();
+      int r = sdgpu_align_pass_submit(R.ctx_, cur, a[cur].data(), b[cur].data(), uint32_t(a[cur].size()), R.flags());
+      R.st.secondsGpu += nowSec() - t0;
+      if (r) {
+        rc = R.fail(r);
+        return;
+      }
+      inflight[cur] = true;
+      ++R.st.gpuBatches;
+      R.st.pairsComputed += a[cur].size();
+      const int other = cur ^ 1;
+      if (inflight[other]) drain(other);
+      cur = other;
+    }
+    int finish() {
+      flush();
+      for (int s = 0; s < 2; ++s)
+        if (inflight[s]) drain(s);
+      return rc;
+    }
+  };
 
   // njhseq collapser::collapseWithParameters + findMatch for one par-file line
   int collapseWithParameters(std::vector<Clus>& cs, const sdq_iter_par& it, int line) {
@@ -311,24 +352,20 @@ class Runner {
         inWindow[elig[w]] = 1;
         if (!inPrevWindow[cs[elig[w]].storeIdx]) fresh.push_back(elig[w]);
       }
-      std::vector<uint32_t> a, b, owner;
+      PassPipe pipe(*this, cs);
       for (uint32_t rp = uint32_t(cs.size()); rp-- > 0;) {  // same order as the pass below
         Clus& read = cs[rp];
         if (read.remove) continue;
         if (read.rowSerial + 1 == serial) {  // row complete for the previous window: only new entries
           for (uint32_t cp : fresh) {
             if (cp == rp) continue;
-            a.push_back(cs[cp].storeIdx);
-            b.push_back(read.storeIdx);
-            owner.push_back(rp);
+            pipe.push(cs[cp].storeIdx, read.storeIdx, rp);
           }
         } else {
           for (uint32_t w = 0; w < wn; ++w) {
             const uint32_t cp = elig[w];
             if (cp == rp || read.row.find(cs[cp].storeIdx)) continue;
-            a.push_back(cs[cp].storeIdx);
-            b.push_back(read.storeIdx);
-            owner.push_back(rp);
+            pipe.push(cs[cp].storeIdx, read.storeIdx, rp);
           }
         }
         read.rowSerial = serial;
@@ -339,15 +376,14 @@ class Runner {
         prevWindow.push_back(cs[elig[w]].storeIdx);
         inPrevWindow[cs[elig[w]].storeIdx] = 1;
       }
-      tSpec += nowSec() - tt0;
-      int rc = computeToRows(cs, a, b, owner);
+      int rc = pipe.finish();
+      tSpec += nowSec() - tt0;  // listing + GPU + filing, overlapped
       if (rc) return rc;
     }
     tt0 = nowSec();
     // ---- the sequential pass (smallest cluster first; first passing candidate absorbs it)
     size_t amountAdded = 0;
     bool windowIntact = true;  // no window cluster absorbed yet: every read sees the static window
-    std::vector<uint32_t> da, db, downer;
     for (size_t rp = cs.size(); rp-- > 0;) {
       Clus& read = cs[rp];
       if (read.remove) continue;
@@ -368,18 +404,14 @@ class Runner {
         if (!v) {
           // a candidate that slid into the window because earlier ones were absorbed: the reads
           // still to come will meet it too, so judge it against all of them in one batch
-          da.clear();
-          db.clear();
-          downer.clear();
+          PassPipe pipe(*this, cs);
           for (size_t r2 = rp + 1; r2-- > 0;) {
             if (cs[r2].remove || r2 == cp || cs[r2].row.find(clus.storeIdx)) continue;
-            da.push_back(clus.storeIdx);
-            db.push_back(cs[r2].storeIdx);
-            downer.push_back(uint32_t(r2));
+            pipe.push(clus.storeIdx, cs[r2].storeIdx, uint32_t(r2));
+            ++st.onDemandPairs;
           }
-          int rc = computeToRows(cs, da, db, downer);
+          int rc = pipe.finish();
           if (rc) return rc;
-          st.onDemandPairs += da.size();
           v = read.row.find(clus.storeIdx);
         }
         ++st.pairsConsumed;
@@ -398,6 +430,7 @@ class Runner {
     }
     tPass += nowSec() - tt0;
     if (amountAdded > 0) {
+      orderDirty = true;
       tt0 = nowSec();
       int rc = calculateConsensusBatch(cs);
       tCons += nowSec() - tt0;
@@ -639,8 +672,10 @@ class Runner {
   }
 
   int runFullClustering(std::vector<Clus>& cs, const sdq_iter_par* its, uint32_t nIts) {
+    orderDirty = true;
     for (uint32_t i = 0; i < nIts; ++i) {
-      dropRemovedAndSort(cs);
+      if (orderDirty) dropRemovedAndSort(cs);  // counts / members only change when something merged
+      orderDirty = false;
       if (cs.size() < 2) break;
       if ((serial & 7) == 7) {  // forget verdicts against cluster versions that are gone
         std::vector<uint8_t> live(storeSize, 0);
@@ -720,19 +755,44 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   // exact-sequence dedupe in first-seen order (clusterDown.cpp:272-288; hashing instead of the
   // reference's O(N*U) scan, same result)
   {
-    std::unordered_map<std::string, uint32_t> seen;
-    seen.reserve(n);
+    // open addressing on a 64-bit hash of the bases; equal hashes are confirmed byte for byte
+    size_t cap = 1024;
+    while (cap < size_t(n) * 2 + 16) cap <<= 1;
+    std::vector<uint32_t> table(cap, UINT32_MAX);
+    std::vector<uint64_t> hashes;
+    hashes.reserve(n);
     for (uint32_t r = 0; r < n; ++r) {
       const uint32_t len = uint32_t(offsets[r + 1] - offsets[r]);
       if (len <= opts->smallReadSize) continue;
-      std::string s(reinterpret_cast<const char*>(bases + offsets[r]), len);
-      auto it = seen.find(s);
-      if (it == seen.end()) {
-        it = seen.emplace(s, uint32_t(R.uniq.size())).first;
-        R.uniq.emplace_back();
-        R.uniq.back().seq = std::move(s);
+      const uint8_t* p = bases + offsets[r];
+      uint64_t h = 0x9e3779b97f4a7c15ull ^ len;
+      uint32_t i = 0;
+      for (; i + 8 <= len; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0xff51afd7ed558ccdull;
+        h ^= h >> 32;
       }
-      Uniq& u = R.uniq[it->second];
+      for (; i < len; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+      h ^= h >> 29;
+      size_t slot = size_t(h) & (cap - 1);
+      uint32_t found = UINT32_MAX;
+      while (table[slot] != UINT32_MAX) {
+        const uint32_t u = table[slot];
+        if (hashes[u] == h && R.uniq[u].seq.size() == len && std::memcmp(R.uniq[u].seq.data(), p, len) == 0) {
+          found = u;
+          break;
+        }
+        slot = (slot + 1) & (cap - 1);
+      }
+      if (found == UINT32_MAX) {
+        found = uint32_t(R.uniq.size());
+        table[slot] = found;
+        hashes.push_back(h);
+        R.uniq.emplace_back();
+        R.uniq.back().seq.assign(reinterpret_cast<const char*>(p), len);
+      }
+      Uniq& u = R.uniq[found];
       u.cnt += 1.0;
       u.inputIdx.push_back(r);
     }

@@ -177,6 +177,13 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   cudaFree(ctx->dWork);
   cudaFree(ctx->dStage);
   cudaFree(ctx->dLines);
+  for (auto& S : ctx->passSlots) {
+    if (S.hPinned) cudaFreeHost(S.hPinned);
+    cudaFree(S.dBuf);
+    if (S.done) cudaEventDestroy(S.done);
+  }
+  for (cudaEvent_t e : ctx->evPool)
+    if (e) cudaEventDestroy(e);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -419,6 +426,61 @@ int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* rea
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->h2dBytes += 2 * bytesIdx;
   ctx->d2hBytes += bytesOut;
+  return SDGPU_OK;
+}
+
+int sdgpu_align_pass_submit(sdgpu_ctx* ctx, int slot, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,
+                            uint32_t flags) {
+  if (!ctx || slot < 0 || slot > 1 || !nPairs || !refIdx || !readIdx) return sd_fail(ctx, SDGPU_E_ARG, "bad argument");
+  sdgpu_ctx::PassSlot& S = ctx->passSlots[slot];
+  if (S.busy) return sd_fail(ctx, SDGPU_E_STATE, "slot still in flight: call sdgpu_align_pass_wait first");
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  uint32_t maxA = 0, maxB = 0;
+  for (uint32_t x = 0; x < nPairs; ++x) {
+    if (refIdx[x] >= nSeqs || readIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "pair index out of range");
+    maxA = std::max<uint32_t>(maxA, uint32_t(ctx->hOffsets[refIdx[x] + 1] - ctx->hOffsets[refIdx[x]]));
+    maxB = std::max<uint32_t>(maxB, uint32_t(ctx->hOffsets[readIdx[x] + 1] - ctx->hOffsets[readIdx[x]]));
+  }
+  if (nPairs > S.capPairs) {
+    if (S.hPinned) cudaFreeHost(S.hPinned);
+    if (S.dBuf) cudaFree(S.dBuf);
+    S.hPinned = nullptr;
+    S.dBuf = nullptr;
+    S.capPairs = 0;
+    const uint64_t cap = std::max<uint64_t>(nPairs, 1u << 16);
+    SD_CUDA(ctx, cudaMallocHost(&S.hPinned, cap * 16));
+    SD_CUDA(ctx, cudaMalloc(&S.dBuf, cap * 16));
+    S.capPairs = cap;
+  }
+  if (!S.done) SD_CUDA(ctx, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+  const uint64_t bytesIdx = uint64_t(nPairs) * 4;
+  std::memcpy(S.hPinned, refIdx, bytesIdx);
+  std::memcpy(S.hPinned + bytesIdx, readIdx, bytesIdx);
+  uint32_t* dRef = reinterpret_cast<uint32_t*>(S.dBuf);
+  uint32_t* dRead = dRef + nPairs;
+  uint64_t* dPass = reinterpret_cast<uint64_t*>(S.dBuf + S.capPairs * 8);
+  SD_CUDA(ctx, cudaMemcpyAsync(dRef, S.hPinned, 2 * bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = sd_launch_align(ctx, dRef, dRead, nPairs, flags, nullptr, nullptr, 0, maxA, maxB, dPass);
+  if (rc) return rc;
+  SD_CUDA(ctx, cudaMemcpyAsync(S.hPinned + S.capPairs * 8, dPass, uint64_t(nPairs) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaEventRecord(S.done, ctx->stream));
+  S.n = nPairs;
+  S.busy = true;
+  ctx->h2dBytes += 2 * bytesIdx;
+  ctx->d2hBytes += uint64_t(nPairs) * 8;
+  return SDGPU_OK;
+}
+
+int sdgpu_align_pass_wait(sdgpu_ctx* ctx, int slot, const uint64_t** masks, uint32_t* nPairs) {
+  if (!ctx || slot < 0 || slot > 1 || !masks) return sd_fail(ctx, SDGPU_E_ARG, "bad argument");
+  sdgpu_ctx::PassSlot& S = ctx->passSlots[slot];
+  if (!S.busy) return sd_fail(ctx, SDGPU_E_STATE, "nothing submitted on this slot");
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  SD_CUDA(ctx, cudaEventSynchronize(S.done));
+  S.busy = false;
+  *masks = reinterpret_cast<const uint64_t*>(S.hPinned + S.capPairs * 8);
+  if (nPairs) *nPairs = S.n;
   return SDGPU_OK;
 }
 

@@ -76,6 +76,15 @@ struct sdgpu_ctx {
   uint64_t stageBytes = 0;
   void* hPinned = nullptr;
   uint64_t pinnedBytes = 0;
+  // double-buffered asynchronous sdgpu_align_pass_submit / _wait
+  struct PassSlot {
+    uint8_t* hPinned = nullptr;  // [refIdx | readIdx | masks]
+    uint8_t* dBuf = nullptr;
+    uint64_t capPairs = 0;
+    cudaEvent_t done = nullptr;
+    uint32_t n = 0;
+    bool busy = false;
+  } passSlots[2];
   // par-file lines for on-device passErrorProfile
   sdgpu_iter_par* dLines = nullptr;
   uint32_t nLines = 0;
