@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 
 OPS_PER_CELL = 13  # algorithmic INT32 ops of one 3-state affine cell update
 CPU_SAMPLE_READS = 600
+TRAFFIC_BYTES_PER_CELL = 1.40  # measured: (dram__bytes_read.sum + dram__bytes_write.sum) / cells, profiles/r1b_*
 
 
 def make_sample(seed, nReads):
@@ -138,9 +139,29 @@ def kmer_roofline(al, bases, quals, offsets, peaks):
     algo = float(lens.sum() + len(lens) * (16 + 1024 * 2))  # codes + offsets in, uint16[4^5] profile out, per read
     gbs = algo / (best * 1e-3) / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
-    return {"bound": "hbm", "kernel": "kmerProfileKernel(k=5)", "achieved": gbs, "peak": peak, "unit": "GB/s",
-            "frac": gbs / peak, "traffic": None, "ms": best,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+    out = {"bound": "hbm", "kernel": "kmerProfileKernel(k=5)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+           "frac": gbs / peak, "traffic": None, "ms": best, "algorithmic_bytes": algo,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+    # reads x clusters compareKmers grid (every read vs the 100 first sequences), device-resident
+    import ctypes as C
+    nR, nC = len(lens), min(100, len(lens))
+    dR, dC = al.dev_alloc(nR * 4), al.dev_alloc(nC * 4)
+    dS, dF = al.dev_alloc(nR * nC * 4), al.dev_alloc(nR * nC * 8)
+    al.h2d(dR, np.arange(nR, dtype=np.uint32))
+    al.h2d(dC, np.arange(nC, dtype=np.uint32))
+    bestc = 1e9
+    for _ in range(4):
+        al.timer_start()
+        al._check(al._lib.sdgpu_kmer_compare_all_dev(al._ctx, dR, nR, dC, nC, dS, dF))
+        bestc = min(bestc, al.timer_stop())
+    for p in (dR, dC, dS, dF):
+        al.dev_free(p)
+    algoc = float((nR + nC) * 1024 * 2 + nR * nC * 12)  # (R + C) * P + R * C * 12 B
+    out["compare"] = {"kernel": "kmerCompareKernel(reads x 100 clusters)", "ms": bestc, "pairs_per_s": nR * nC / (bestc * 1e-3),
+                      "achieved": algoc / (bestc * 1e-3) / 1e9, "unit": "GB/s", "frac": algoc / (bestc * 1e-3) / 1e9 / peak,
+                      "algorithmic_bytes": algoc,
+                      "note": "cluster-side reuse makes this form L1/L2- and ALU-bound (4 KB of profile reads per pair from cache), not HBM-bound"}
+    return out
 
 
 def main():
@@ -229,7 +250,11 @@ def main():
             "gpu_launches": int(prof["kernelLaunches"]),
             "clocks": sampler.summary(),
             "roofline": {"bound": "int32", "kernel": "alignProfileKernel", "achieved": kernel_gcups, "peak": peak_gcups,
-                         "unit": "GCUPS", "frac": kernel_gcups / peak_gcups, "traffic": None,
+                         "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
+                         # dram read+write bytes per launch: bytes/cell from the ncu --set full capture in
+                         # profiles/r1b_align_kernel_ncu_full.csv (35.36 GB for a 2.52e10-cell launch) x cells per launch
+                         "traffic": TRAFFIC_BYTES_PER_CELL * prof["cellUpdates"] / max(1, prof["alignKernelLaunches"]),
+                         "algorithmic_hbm_bytes_per_cell": 0.94,
                          "launches": int(prof["alignKernelLaunches"]), "avg_launch_ms": prof["alignKernelMs"] / max(1, prof["alignKernelLaunches"]),
                          "kernel_share_of_step": prof["alignKernelMs"] / resident_ms,
                          "peak_source": f"measured on this GPU in this run: {int32_peak / 1e12:.2f} T INT32 thread-instr/s "

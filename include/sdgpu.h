@@ -204,6 +204,21 @@ int sdgpu_set_pass_table(sdgpu_ctx* ctx, const sdgpu_iter_par* lines, uint32_t n
 int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,
                      uint32_t flags, uint64_t* passMaskOut);
 
+/* All-vs-all alignment of the sequences listed in seqIdx (NULL: the whole store): the pair list
+ * is the upper triangle (i < j) in row-major order, ref = seqIdx[i], read = seqIdx[j]; the call
+ * computes pairs [firstPair, firstPair + nPairs) of it, so disjoint blocks can run on different
+ * GPUs with no exchange (BASELINE config 3).  Replaces the all-by-all loop of
+ * clusterDown.cpp:727-805 (alignCacheGlobal + profileAlignment per pair, the same columns) and is
+ * the kernel of processClusters' population comparisons (processClusters.cpp:226).  Pair lists are
+ * generated on the device; 28 bytes per pair come back. */
+typedef struct sdgpu_pair_summary {
+  int32_t alnScore;
+  uint16_t hqMismatches, lqMismatches, lowKmerMismatches, numGaps;
+  float oneBaseIndel, twoBaseIndel, largeBaseIndel, eventBasedIdentity;
+} sdgpu_pair_summary;
+int sdgpu_all_vs_all(sdgpu_ctx* ctx, const uint32_t* seqIdx, uint32_t n, uint32_t flags, uint64_t firstPair,
+                     uint64_t nPairs, sdgpu_pair_summary* out);
+
 /* Asynchronous, double-buffered form of sdgpu_align_pass: two slots (0, 1) per ctx.  submit copies
  * the pair lists into pinned staging and enqueues H2D + kernel + D2H on the ctx stream, then
  * returns; wait blocks until that slot's masks are on the host and hands back a pointer to them
@@ -217,6 +232,9 @@ int sdgpu_align_pass_wait(sdgpu_ctx* ctx, int slot, const uint64_t** masks, uint
  * device pointers (from sdgpu_dev_alloc); nothing crosses PCIe.  Asynchronous on the ctx stream. */
 int sdgpu_align_profile_dev(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx,
                             uint32_t nPairs, uint32_t flags, sdgpu_comparison* dOut);
+int sdgpu_kmer_compare_all_dev(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nReads,
+                               const uint32_t* dClusters, uint32_t nClusters, uint32_t* dSharedOut,
+                               double* dFracOut); /* device pointers; indices are not range-checked */
 int sdgpu_dev_alloc(sdgpu_ctx* ctx, uint64_t bytes, void** dptr);
 int sdgpu_dev_free(sdgpu_ctx* ctx, void* dptr);
 int sdgpu_memcpy_h2d(sdgpu_ctx* ctx, void* dst, const void* src, uint64_t bytes);

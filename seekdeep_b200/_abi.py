@@ -52,6 +52,10 @@ import numpy as _np  # noqa: E402
 COMPARISON_DTYPE = _np.dtype([("alnScore", "<i4")] + [(n, "<u4") for n in INT_FIELDS[1:]] +
                              [(n, "<f8") for n in FLOAT_FIELDS])
 GAP_DTYPE = _np.dtype([("pos", "<u4"), ("size", "<u4"), ("gapInA", "<u4")])
+PAIR_SUMMARY_DTYPE = _np.dtype([("alnScore", "<i4"), ("hqMismatches", "<u2"), ("lqMismatches", "<u2"),
+                                ("lowKmerMismatches", "<u2"), ("numGaps", "<u2"), ("oneBaseIndel", "<f4"),
+                                ("twoBaseIndel", "<f4"), ("largeBaseIndel", "<f4"), ("eventBasedIdentity", "<f4")])
+assert PAIR_SUMMARY_DTYPE.itemsize == 28
 assert COMPARISON_DTYPE.itemsize == C.sizeof(Comparison) == 104
 assert GAP_DTYPE.itemsize == C.sizeof(Gap) == 12
 
@@ -79,6 +83,8 @@ SIGNATURES = {
     "sdgpu_align_profile": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_set_pass_table": (C.c_int, [_ctx, C.c_void_p, C.c_uint32]),
     "sdgpu_align_pass": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "sdgpu_kmer_compare_all_dev": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sdgpu_all_vs_all": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
     "sdgpu_align_pass_submit": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
     "sdgpu_align_pass_wait": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_void_p), _u32p]),
     "sdgpu_align_profile_dev": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),

@@ -198,6 +198,18 @@ class GpuAligner:
         self._check(self._lib.sdgpu_align_pass(self._ctx, _ptr(refIdx), _ptr(readIdx), len(refIdx), flags, _ptr(out)))
         return out
 
+    def all_vs_all(self, seqIdx=None, n=None, firstPair=0, nPairs=None, checkKmer=False, usingQuality=True):
+        """Upper-triangle all-vs-all alignment (config 3).  Returns PAIR_SUMMARY_DTYPE[nPairs] for the pair
+        block [firstPair, firstPair + nPairs) in row-major (i < j) order."""
+        idx = None if seqIdx is None else np.ascontiguousarray(seqIdx, np.uint32)
+        n = (self.num_seqs() if idx is None else len(idx)) if n is None else n
+        total = n * (n - 1) // 2
+        nPairs = total - firstPair if nPairs is None else nPairs
+        flags = (_abi.CHECK_KMER if checkKmer else 0) | (_abi.USING_QUALITY if usingQuality else 0)
+        out = np.zeros(nPairs, _abi.PAIR_SUMMARY_DTYPE)
+        self._check(self._lib.sdgpu_all_vs_all(self._ctx, _ptr(idx), n, flags, firstPair, nPairs, _ptr(out)))
+        return out
+
     def profile_enable(self, on=True):
         self._check(self._lib.sdgpu_profile_enable(self._ctx, int(on)))
 

@@ -71,31 +71,43 @@ __global__ void kmerLookupKernel(DevKmerIndex idx, const uint64_t* keys, uint32_
 }
 
 // ---------------------------------------------------------------- dense profiles
-// One warp per sequence; the profile is accumulated in shared memory with 32-bit atomics on
-// packed uint16 pairs, then written out as full 128-bit lines.
-__global__ void kmerProfileKernel(DevSeqs seqs, uint32_t kLen, uint32_t sigma, uint32_t profSize, uint16_t* profiles) {
-  extern __shared__ uint32_t sProf[];  // warpsPerCta * profSize/2 words
+// One warp per sequence.  Each lane owns a contiguous run of k-mer start positions and rolls the
+// k-mer id (one new base per position); counts accumulate in shared memory with 32-bit atomics
+// on packed uint16 pairs; the finished profile leaves as full 128-bit lines.  HBM-bound:
+// L code bytes in, 2 * sigma^k profile bytes out per sequence.
+__global__ void __launch_bounds__(256) kmerProfileKernel(DevSeqs seqs, uint32_t kLen, uint32_t sigma, uint32_t top,
+                                                         uint32_t profSize, uint16_t* profiles) {
+  extern __shared__ uint4 sProfVec[];  // warpsPerCta * profSize/8 vectors
   const uint32_t warpInCta = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t warpsPerCta = blockDim.x >> 5;
-  const uint32_t words = profSize / 2;
-  uint32_t* mine = sProf + warpInCta * words;
+  const uint32_t vecs = profSize / 8;
+  uint4* mineVec = sProfVec + warpInCta * vecs;
+  uint32_t* mine = reinterpret_cast<uint32_t*>(mineVec);
   for (uint32_t s = blockIdx.x * warpsPerCta + warpInCta; s < seqs.n; s += gridDim.x * warpsPerCta) {
-    for (uint32_t x = lane; x < words; x += 32) mine[x] = 0;
-    __syncwarp();
+    for (uint32_t x = lane; x < vecs; x += 32) mineVec[x] = make_uint4(0, 0, 0, 0);
     const uint64_t off = seqs.offsets[s];
     const uint32_t len = uint32_t(seqs.offsets[s + 1] - off);
     const uint8_t* c = seqs.codes + off;
+    __syncwarp();
     if (len >= kLen) {
-      for (uint32_t cursor = lane; cursor + kLen <= len; cursor += 32) {
+      const uint32_t nk = len - kLen + 1;
+      const uint32_t chunk = (nk + 31) / 32;
+      const uint32_t p0 = lane * chunk;
+      const uint32_t p1 = min(nk, p0 + chunk);
+      if (p0 < p1) {
         uint32_t id = 0;
-        for (uint32_t x = 0; x < kLen; ++x) id = id * sigma + c[cursor + x];
-        atomicAdd(&mine[id >> 1], 1u << (16 * (id & 1)));
+        for (uint32_t x = 0; x + 1 < kLen; ++x) id = id * sigma + c[p0 + x];
+        uint32_t lead = 0;  // base leaving the window, times sigma^(k-1)
+        for (uint32_t p = p0; p < p1; ++p) {
+          id = (id - lead) * sigma + c[p + kLen - 1];
+          lead = uint32_t(c[p]) * top;
+          atomicAdd(&mine[id >> 1], 1u << (16 * (id & 1)));
+        }
       }
     }
     __syncwarp();
     uint4* dst = reinterpret_cast<uint4*>(profiles + size_t(s) * profSize);
-    const uint4* src = reinterpret_cast<const uint4*>(mine);
-    for (uint32_t x = lane; x < words / 4; x += 32) dst[x] = src[x];
+    for (uint32_t x = lane; x < vecs; x += 32) dst[x] = mineVec[x];
     __syncwarp();
   }
 }
@@ -272,20 +284,28 @@ int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   const uint32_t profSize = uint32_t((size + 7) & ~7ull);  // multiple of 8 uint16 = 16 bytes
   const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
   if (ctx->maxLen >= 65536) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "profiles need sequences < 65536 bases");
-  if (ctx->dProfiles) cudaFree(ctx->dProfiles);
-  ctx->dProfiles = nullptr;
   ctx->profK = kLen;
   ctx->profSize = profSize;
   ctx->profSeqs = nSeqs;
   if (nSeqs == 0) return SDGPU_OK;
-  SD_CUDA(ctx, cudaMalloc(&ctx->dProfiles, size_t(nSeqs) * profSize * 2));
-  const uint32_t warpsPerCta = 4;
+  const uint64_t need = uint64_t(nSeqs) * profSize * 2;
+  if (need > ctx->profCapBytes) {  // keep the buffer across rebuilds: cudaMalloc/cudaFree stall the stream
+    if (ctx->dProfiles) cudaFree(ctx->dProfiles);
+    ctx->dProfiles = nullptr;
+    ctx->profCapBytes = 0;
+    SD_CUDA(ctx, cudaMalloc(&ctx->dProfiles, need));
+    ctx->profCapBytes = need;
+  }
+  uint32_t top = 1;
+  for (uint32_t x = 0; x + 1 < kLen; ++x) top *= sigma;
+  uint32_t warpsPerCta = uint32_t((200u << 10) / (size_t(profSize) * 2));  // stay under the 227 KB shared-memory limit
+  warpsPerCta = warpsPerCta < 1 ? 1 : (warpsPerCta > 8 ? 8 : warpsPerCta);
   const size_t smem = size_t(warpsPerCta) * profSize * 2;
   SD_CUDA(ctx, cudaFuncSetAttribute(kmerProfileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   uint32_t grid = (nSeqs + warpsPerCta - 1) / warpsPerCta;
-  const uint32_t maxGrid = uint32_t(ctx->numSMs) * 8;
+  const uint32_t maxGrid = uint32_t(ctx->numSMs) * 32;
   if (grid > maxGrid) grid = maxGrid;
-  kmerProfileKernel<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, profSize, ctx->dProfiles);
+  kmerProfileKernel<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, top, profSize, ctx->dProfiles);
   SD_CUDA(ctx, cudaGetLastError());
   ++ctx->launches;
   return SDGPU_OK;
@@ -301,6 +321,14 @@ static int compareLaunch(sdgpu_ctx* ctx, const uint32_t* dA, const uint32_t* dB,
   SD_CUDA(ctx, cudaGetLastError());
   ++ctx->launches;
   return SDGPU_OK;
+}
+
+int sd_kmer_compare_all_dev(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nReads, const uint32_t* dClusters,
+                            uint32_t nClusters, uint32_t* dShared, double* dFrac) {
+  if (!ctx->dProfiles) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_build_kmer_profiles has not been called");
+  const uint64_t nPairs = uint64_t(nReads) * nClusters;
+  if (nPairs == 0) return SDGPU_OK;
+  return compareLaunch(ctx, dReads, dClusters, nPairs, nClusters, dShared, dFrac);
 }
 
 int sd_kmer_compare_pairs(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, uint32_t* sharedOut,

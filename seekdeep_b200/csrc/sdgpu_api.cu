@@ -345,6 +345,13 @@ int sdgpu_kmer_compare(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uin
   return sd_kmer_compare_pairs(ctx, a, b, nPairs, sharedOut, fracOut);
 }
 
+int sdgpu_kmer_compare_all_dev(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nReads, const uint32_t* dClusters,
+                               uint32_t nClusters, uint32_t* dShared, double* dFrac) {
+  if (!ctx || !dReads || !dClusters || !dShared || !dFrac) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_kmer_compare_all_dev(ctx, dReads, nReads, dClusters, nClusters, dShared, dFrac);
+}
+
 int sdgpu_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nReads, const uint32_t* clusters,
                            uint32_t nClusters, uint32_t* sharedOut, double* fracOut) {
   if (!ctx || !reads || !clusters || !sharedOut || !fracOut) return SDGPU_E_ARG;

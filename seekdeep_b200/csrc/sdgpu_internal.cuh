@@ -68,6 +68,7 @@ struct sdgpu_ctx {
   // dense k-mer profiles
   uint16_t* dProfiles = nullptr;
   uint32_t profK = 0, profSize = 0, profSeqs = 0;
+  uint64_t profCapBytes = 0;
   // scratch for the alignment kernel (pointer slabs), pair staging, work counter
   uint8_t* dScratch = nullptr;
   uint64_t scratchBytes = 0;
@@ -128,5 +129,7 @@ int sd_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers, const uint32_t* p
 int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen);
 int sd_kmer_compare_pairs(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs,
                           uint32_t* sharedOut, double* fracOut);
+int sd_kmer_compare_all_dev(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nReads, const uint32_t* dClusters,
+                            uint32_t nClusters, uint32_t* dShared, double* dFrac);
 int sd_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nReads, const uint32_t* clusters,
                         uint32_t nClusters, uint32_t* sharedOut, double* fracOut);

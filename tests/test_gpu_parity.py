@@ -211,3 +211,32 @@ def test_align_pass_matches_pass_error_profile(oracle):
         assert np.array_equal(got, ok), l
     assert (masks >> np.uint64(len(iters)) == 0).all()
     assert 0 < int(((masks & np.uint64(1)) != 0).sum()) < n
+
+
+def test_all_vs_all_matches_oracle(oracle):
+    """Config-3 shaped case at oracle-checkable size: every unordered pair of 70 related 400-mers,
+    computed as two disjoint pair blocks (the multi-GPU pair-block sharding) + a seqIdx subset."""
+    from seekdeep_b200 import synth
+    seqs, quals = synth.config3(seed=3, n=70, length=400, nRoots=4)
+    bases, q, offsets = synth.pack(seqs, quals)
+    n = len(seqs)
+    ii, jj = np.triu_indices(n, 1)
+    params = make_params()
+    want = oracle.align_profile_batch(params, bases, q, offsets, ii.astype(np.uint32), jj.astype(np.uint32), _abi.USING_QUALITY)
+    with GpuAligner(params) as al:
+        al.upload_seqs(bases, q, offsets)
+        total = n * (n - 1) // 2
+        cut = total // 3
+        got = np.concatenate([al.all_vs_all(firstPair=0, nPairs=cut), al.all_vs_all(firstPair=cut, nPairs=total - cut)])
+        sub = np.array([5, 9, 2, 40, 33], np.uint32)
+        gsub = al.all_vs_all(seqIdx=sub)
+        with pytest.raises(SdgpuError):
+            al.all_vs_all(firstPair=total, nPairs=1)
+    assert len(got) == total
+    for f in ("alnScore", "hqMismatches", "lqMismatches", "lowKmerMismatches", "numGaps"):
+        assert np.array_equal(got[f].astype(np.int64), want[f].astype(np.int64)), f
+    for f in ("oneBaseIndel", "twoBaseIndel", "largeBaseIndel", "eventBasedIdentity"):
+        assert np.array_equal(got[f], want[f].astype(np.float32)), f
+    si, sj = np.triu_indices(len(sub), 1)
+    wsub = oracle.align_profile_batch(params, bases, q, offsets, sub[si], sub[sj], _abi.USING_QUALITY)
+    assert np.array_equal(gsub["alnScore"], wsub["alnScore"]) and np.array_equal(gsub["hqMismatches"], wsub["hqMismatches"])
