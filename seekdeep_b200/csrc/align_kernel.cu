@@ -203,16 +203,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
           Tin = T[c];
           const int Uc = U[c];
           uint32_t acc = w[c / CELLS_PER_WORD];
+          // maxima on the ALU pipe (two of them fused add+max, VIADDMNMX), differences on the
+          // FMA pipe (IMAD.IADD); the shifted differences reuse d1/d2 instead of the sums
           const int W = max(Lin, D);
-          acc = __funnelshift_l(uint32_t(Lin - D), acc, 1);
+          const int d1 = Lin - D;
+          acc = __funnelshift_l(uint32_t(d1), acc, 1);
           T[c] = max(Uc, W);
-          acc = __funnelshift_l(uint32_t(Uc - W), acc, 1);
-          const int Ud = Uc + dcol[c];
-          U[c] = max(Ud, W) - gocol[c];
-          acc = __funnelshift_l(uint32_t(Ud - W), acc, 1);
-          const int Ld = Lin + drow;
-          const int tt = max(Ld, D);
-          acc = __funnelshift_l(uint32_t(Ld - D), acc, 1);
+          const int d2 = Uc - W;
+          acc = __funnelshift_l(uint32_t(d2), acc, 1);
+          U[c] = __viaddmax_s32(Uc, dcol[c], W) - gocol[c];
+          acc = __funnelshift_l(uint32_t(d2 + dcol[c]), acc, 1);
+          const int tt = __viaddmax_s32(Lin, drow, D);
+          acc = __funnelshift_l(uint32_t(d1 + drow), acc, 1);
           Lin = max(Uc, tt) - gorow;
           acc = __funnelshift_l(uint32_t(Uc - tt), acc, 1);
           w[c / CELLS_PER_WORD] = acc;

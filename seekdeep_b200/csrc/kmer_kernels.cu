@@ -173,10 +173,6 @@ int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, 
   }
   const uint64_t total = start[nIdx];
   if (total >= (1ull << 32)) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "k-mer index too large (>= 2^32 occurrences)");
-  if (ctx->dIdxKeys) cudaFree(ctx->dIdxKeys);
-  if (ctx->dIdxCnts) cudaFree(ctx->dIdxCnts);
-  ctx->dIdxKeys = nullptr;
-  ctx->dIdxCnts = nullptr;
   ctx->nIdx = 0;
   ctx->idxK = kLen;
   ctx->idxRunCutOff = runCutOff;
@@ -184,33 +180,42 @@ int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, 
   ctx->haveIndex = true;
   if (total == 0) return SDGPU_OK;
 
+  // one grow-only work arena per ctx: cudaMalloc/cudaFree of GB-sized buffers cost (variable)
+  // hundreds of milliseconds and the index is rebuilt in every qluster run
   uint64_t *dKeysIn = nullptr, *dKeysOut = nullptr, *dStart = nullptr;
   uint32_t *dWIn = nullptr, *dWOut = nullptr, *dSeqIdx = nullptr, *dNumRuns = nullptr;
   void* dTemp = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(dKeysIn); cudaFree(dKeysOut); cudaFree(dStart); cudaFree(dWIn); cudaFree(dWOut);
-    cudaFree(dSeqIdx); cudaFree(dNumRuns); cudaFree(dTemp);
-  };
-#define SD_CUDA_C(call)                                                              \
-  do {                                                                               \
-    cudaError_t e__ = (call);                                                        \
-    if (e__ != cudaSuccess) {                                                        \
-      cleanup();                                                                     \
-      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                \
-      return SDGPU_E_CUDA;                                                           \
-    }                                                                                \
-  } while (0)
-  SD_CUDA_C(cudaMalloc(&dKeysIn, total * 8));
-  SD_CUDA_C(cudaMalloc(&dKeysOut, total * 8));
-  SD_CUDA_C(cudaMalloc(&dWIn, total * 4));
-  SD_CUDA_C(cudaMalloc(&dWOut, total * 4));
-  SD_CUDA_C(cudaMalloc(&dStart, (size_t(nIdx) + 1) * 8));
-  SD_CUDA_C(cudaMalloc(&dNumRuns, 4));
-  SD_CUDA_C(cudaMemcpyAsync(dStart, start.data(), (size_t(nIdx) + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  if (hSeqIdx) {
-    SD_CUDA_C(cudaMalloc(&dSeqIdx, size_t(nIdx) * 4));
-    SD_CUDA_C(cudaMemcpyAsync(dSeqIdx, hSeqIdx, size_t(nIdx) * 4, cudaMemcpyHostToDevice, ctx->stream));
+#define SD_CUDA_C(call) SD_CUDA(ctx, call)
+  size_t tempSort = 0, tempReduce = 0;
+  const int endBit = byPos ? 64 : int(4 * kLen);
+  SD_CUDA_C(cub::DeviceRadixSort::SortPairs(nullptr, tempSort, dKeysIn, dKeysOut, dWIn, dWOut, int(total), 0, endBit,
+                                            ctx->stream));
+  SD_CUDA_C(cub::DeviceReduce::ReduceByKey(nullptr, tempReduce, dKeysOut, dKeysIn, dWOut, dWIn, dNumRuns, cub::Sum(),
+                                           int(total), ctx->stream));
+  auto up = [](uint64_t v) { return (v + 255) & ~255ull; };
+  const uint64_t bKeys = up(total * 8), bW = up(total * 4), bStart = up((uint64_t(nIdx) + 1) * 8), bIdx = up(uint64_t(nIdx) * 4);
+  const uint64_t bTemp = up(std::max(tempSort, tempReduce));
+  const uint64_t need = 2 * bKeys + 2 * bW + bStart + bIdx + 256 + bTemp;
+  if (need > ctx->idxWorkBytes) {
+    if (ctx->dIdxWork) cudaFree(ctx->dIdxWork);
+    ctx->dIdxWork = nullptr;
+    ctx->idxWorkBytes = 0;
+    SD_CUDA_C(cudaMalloc(&ctx->dIdxWork, need));
+    ctx->idxWorkBytes = need;
   }
+  {
+    uint8_t* p = reinterpret_cast<uint8_t*>(ctx->dIdxWork);
+    dKeysIn = reinterpret_cast<uint64_t*>(p); p += bKeys;
+    dKeysOut = reinterpret_cast<uint64_t*>(p); p += bKeys;
+    dWIn = reinterpret_cast<uint32_t*>(p); p += bW;
+    dWOut = reinterpret_cast<uint32_t*>(p); p += bW;
+    dStart = reinterpret_cast<uint64_t*>(p); p += bStart;
+    dSeqIdx = hSeqIdx ? reinterpret_cast<uint32_t*>(p) : nullptr; p += bIdx;
+    dNumRuns = reinterpret_cast<uint32_t*>(p); p += 256;
+    dTemp = p;
+  }
+  SD_CUDA_C(cudaMemcpyAsync(dStart, start.data(), (size_t(nIdx) + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (hSeqIdx) SD_CUDA_C(cudaMemcpyAsync(dSeqIdx, hSeqIdx, size_t(nIdx) * 4, cudaMemcpyHostToDevice, ctx->stream));
   {
     const uint32_t threads = 128, warpsPerCta = threads / 32;
     const uint32_t grid = (nIdx + warpsPerCta - 1) / warpsPerCta;
@@ -219,13 +224,6 @@ int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, 
     SD_CUDA_C(cudaGetLastError());
     ++ctx->launches;
   }
-  size_t tempSort = 0, tempReduce = 0;
-  const int endBit = byPos ? 64 : int(4 * kLen);
-  SD_CUDA_C(cub::DeviceRadixSort::SortPairs(nullptr, tempSort, dKeysIn, dKeysOut, dWIn, dWOut, int(total), 0, endBit,
-                                            ctx->stream));
-  SD_CUDA_C(cub::DeviceReduce::ReduceByKey(nullptr, tempReduce, dKeysOut, dKeysIn, dWOut, dWIn, dNumRuns, cub::Sum(),
-                                           int(total), ctx->stream));
-  SD_CUDA_C(cudaMalloc(&dTemp, std::max(tempSort, tempReduce)));
   SD_CUDA_C(cub::DeviceRadixSort::SortPairs(dTemp, tempSort, dKeysIn, dKeysOut, dWIn, dWOut, int(total), 0, endBit,
                                             ctx->stream));
   SD_CUDA_C(cub::DeviceReduce::ReduceByKey(dTemp, tempReduce, dKeysOut, dKeysIn, dWOut, dWIn, dNumRuns, cub::Sum(),
@@ -234,13 +232,20 @@ int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, 
   uint32_t numRuns = 0;
   SD_CUDA_C(cudaMemcpyAsync(&numRuns, dNumRuns, 4, cudaMemcpyDeviceToHost, ctx->stream));
   SD_CUDA_C(cudaStreamSynchronize(ctx->stream));
-  SD_CUDA_C(cudaMalloc(&ctx->dIdxKeys, size_t(numRuns) * 8));
-  SD_CUDA_C(cudaMalloc(&ctx->dIdxCnts, size_t(numRuns) * 4));
+  if (numRuns > ctx->idxCapRuns) {
+    if (ctx->dIdxKeys) cudaFree(ctx->dIdxKeys);
+    if (ctx->dIdxCnts) cudaFree(ctx->dIdxCnts);
+    ctx->dIdxKeys = nullptr;
+    ctx->dIdxCnts = nullptr;
+    ctx->idxCapRuns = 0;
+    SD_CUDA_C(cudaMalloc(&ctx->dIdxKeys, size_t(numRuns) * 8));
+    SD_CUDA_C(cudaMalloc(&ctx->dIdxCnts, size_t(numRuns) * 4));
+    ctx->idxCapRuns = numRuns;
+  }
   SD_CUDA_C(cudaMemcpyAsync(ctx->dIdxKeys, dKeysIn, size_t(numRuns) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   SD_CUDA_C(cudaMemcpyAsync(ctx->dIdxCnts, dWIn, size_t(numRuns) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   SD_CUDA_C(cudaStreamSynchronize(ctx->stream));
   ctx->nIdx = numRuns;
-  cleanup();
 #undef SD_CUDA_C
   return SDGPU_OK;
 }

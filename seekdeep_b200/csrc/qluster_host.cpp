@@ -220,7 +220,7 @@ class Runner {
   std::vector<uint64_t> maskBuf;
   std::vector<sdgpu_comparison> cmpBuf;
   std::vector<sdgpu_gap> gapBuf;
-  double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0;
+  double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0, tIndex = 0;
   uint64_t keptVersions = 0, skippedScans = 0;
   bool orderDirty = true;
   // symbols of the consensus counters (bases + '-'), ASCII order kept for njhseq's tie rule
@@ -657,15 +657,22 @@ class Runner {
   void dropRemovedAndSort(std::vector<Clus>& cs) {
     const double t0 = nowSec();
     cs.erase(std::remove_if(cs.begin(), cs.end(), [](const Clus& c) { return c.remove; }), cs.end());
-    std::vector<uint32_t> idx(cs.size());
-    for (uint32_t i = 0; i < idx.size(); ++i) idx[i] = i;
-    std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return clusLess(cs[x], cs[y]); });
-    bool sorted = true;
-    for (uint32_t i = 0; i < idx.size() && sorted; ++i) sorted = idx[i] == i;
-    if (!sorted) {
+    struct Key {  // the two leading sort keys packed contiguously; sequence / first id only on ties
+      double cnt, avgErr;
+      uint32_t idx;
+    };
+    std::vector<Key> keys(cs.size());
+    for (uint32_t i = 0; i < keys.size(); ++i) keys[i] = Key{cs[i].cnt, cs[i].avgErr, i};
+    auto less = [&](const Key& a, const Key& b) {
+      if (a.cnt != b.cnt) return a.cnt > b.cnt;
+      if (a.avgErr != b.avgErr) return a.avgErr < b.avgErr;
+      return clusLess(cs[a.idx], cs[b.idx]);
+    };
+    if (!std::is_sorted(keys.begin(), keys.end(), less)) {
+      std::sort(keys.begin(), keys.end(), less);
       std::vector<Clus> tmp;
       tmp.reserve(cs.size());
-      for (uint32_t i : idx) tmp.push_back(std::move(cs[i]));
+      for (const Key& k : keys) tmp.push_back(std::move(cs[k.idx]));
       cs.swap(tmp);
     }
     tSort += nowSec() - t0;
@@ -691,6 +698,12 @@ class Runner {
   }
 
   int buildIndex(std::vector<Clus>& cs) {  // indexKmers over the current clusters
+    const double t0 = nowSec();
+    struct Tick {
+      double& acc;
+      double t0;
+      ~Tick() { acc += nowSec() - t0; }
+    } tick{tIndex, t0};
     std::vector<uint32_t> idx(cs.size());
     std::vector<double> cnts(cs.size());
     std::vector<uint32_t> order(cs.size());
@@ -888,8 +901,8 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   res->stats.cellUpdates = cells1 - cells0;
   res->stats.secondsTotal = nowSec() - tStart;
   if (getenv("SDQ_TIMING")) {
-    fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f sort %.3f lines %zu\n",
-            res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSpec, R.tInsert, R.tPass, R.tCons, R.tSort, R.lines.size());
+    fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f sort %.3f index %.3f lines %zu\n",
+            res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSpec, R.tInsert, R.tPass, R.tCons, R.tSort, R.tIndex, R.lines.size());
     fprintf(stderr, "[sdq] consensus updates kept on the device version: %llu, store entries: %u (unique reads %u), scans skipped %llu\n",
             (unsigned long long)R.keptVersions, R.storeSize, nU, (unsigned long long)R.skippedScans);
   }

@@ -177,6 +177,7 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   cudaFree(ctx->dWork);
   cudaFree(ctx->dStage);
   cudaFree(ctx->dLines);
+  cudaFree(ctx->dIdxWork);
   for (auto& S : ctx->passSlots) {
     if (S.hPinned) cudaFreeHost(S.hPinned);
     cudaFree(S.dBuf);

@@ -65,6 +65,9 @@ struct sdgpu_ctx {
   uint32_t* dIdxCnts = nullptr;
   uint32_t nIdx = 0, idxK = 0, idxRunCutOff = 0, idxByPos = 0;
   bool haveIndex = false;
+  uint32_t idxCapRuns = 0;
+  void* dIdxWork = nullptr;  // grow-only arena for the index build (keys, weights, CUB temp)
+  uint64_t idxWorkBytes = 0;
   // dense k-mer profiles
   uint16_t* dProfiles = nullptr;
   uint32_t profK = 0, profSize = 0, profSeqs = 0;
