@@ -246,6 +246,14 @@ int sdgpu_timer_start(sdgpu_ctx* ctx);
 int sdgpu_timer_stop(sdgpu_ctx* ctx, float* msOut); /* records, synchronizes, returns elapsed ms */
 /* Counters: kernels launched by this ctx and DP cells computed since creation. */
 int sdgpu_counters(sdgpu_ctx* ctx, uint64_t* kernelLaunches, uint64_t* cellUpdates);
+/* The alignment kernel has two exact forward passes: int32 (one pair per warp) and packed fp16
+ * (two pairs per warp; used when the launch's bases are within A,C,G,T,N and every DP value is an
+ * integer of magnitude <= 2047, which fp16 represents exactly).  mode 0 = choose automatically,
+ * 1 = int32 only, 2 = packed only (fails with SDGPU_E_UNSUPPORTED when not applicable).
+ * sdgpu_last_kernel reports which one the last launch used (1 or 2).  For tests / profiling. */
+int sdgpu_set_kernel(sdgpu_ctx* ctx, int mode);
+int sdgpu_last_kernel(sdgpu_ctx* ctx);
+
 /* Measurement bookkeeping for bench.py: with profiling enabled every alignment-kernel launch is
  * bracketed by CUDA events on the ctx stream; sdgpu_profile_read sums them (optionally resets). */
 typedef struct sdgpu_profile {

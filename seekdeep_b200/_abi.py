@@ -96,6 +96,8 @@ SIGNATURES = {
     "sdgpu_timer_start": (C.c_int, [_ctx]),
     "sdgpu_timer_stop": (C.c_int, [_ctx, C.POINTER(C.c_float)]),
     "sdgpu_counters": (C.c_int, [_ctx, _u64p, _u64p]),
+    "sdgpu_set_kernel": (C.c_int, [_ctx, C.c_int]),
+    "sdgpu_last_kernel": (C.c_int, [_ctx]),
     "sdgpu_profile_enable": (C.c_int, [_ctx, C.c_int]),
     "sdgpu_profile_read": (C.c_int, [_ctx, C.c_void_p, C.c_int]),
     "sdgpu_measure_int32_peak": (C.c_int, [_ctx, C.c_int, _f64p]),

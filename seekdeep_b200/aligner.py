@@ -210,6 +210,13 @@ class GpuAligner:
         self._check(self._lib.sdgpu_all_vs_all(self._ctx, _ptr(idx), n, flags, firstPair, nPairs, _ptr(out)))
         return out
 
+    def set_kernel(self, mode):
+        """0 = automatic, 1 = int32 forward pass only, 2 = packed fp16 forward pass only."""
+        self._check(self._lib.sdgpu_set_kernel(self._ctx, mode))
+
+    def last_kernel(self):
+        return self._lib.sdgpu_last_kernel(self._ctx)
+
     def profile_enable(self, on=True):
         self._check(self._lib.sdgpu_profile_enable(self._ctx, int(on)))
 

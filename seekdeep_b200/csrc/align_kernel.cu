@@ -1,25 +1,36 @@
 // align_kernel.cu — kernels 2+3 of the qluster hot path, fused:
 //   forward affine-gap global DP (njhseq alignCalc::runNeedleSave semantics) with packed
 //   traceback bits -> warp-cooperative traceback -> gapped strings -> errorProfile
-//   (aligner::profileAlignment semantics) -> one sdgpu_comparison per pair.
+//   (aligner::profileAlignment semantics) -> one sdgpu_comparison and/or par-line verdict mask.
 //
-// Replaces, per (ref, read) pair: aligner::alignCacheGlobal + aligner::profileAlignment
-// (reference call sites clusterDown.cpp:694-696, 739-741; ControlBencher.hpp:117-118).
+// Replaces, per (ref, read) pair: aligner::alignCacheGlobal + aligner::profileAlignment (+
+// comparison::passErrorProfile) — reference call sites clusterDown.cpp:694-696, 739-741;
+// ControlBencher.hpp:117-120.
 //
 // Formulation (deliberately different from the reference's cell-of-three-scores matrix):
-//   one alignment per warp; the read (B, DP columns) is cut into 32 strips of C columns, each
-//   lane keeps its strip's state in registers; the ref (A, DP rows) streams through the lanes
-//   as a skewed wavefront (lane l works on row t-l at step t).  Each cell produces its three
-//   OUTGOING maxima
+//   the read (B, DP columns) is cut into 32 strips of C columns, each lane keeps its strip's
+//   state in registers; the ref (A, DP rows) streams through the lanes as a skewed wavefront
+//   (lane l works on row t-l at step t).  Each cell produces its three OUTGOING maxima
 //       toDiag  = max(U, L, D)                -> D of the cell down-right  (+ score)
 //       toDown  = max(U-ge, L-go, D-go)       -> U of the cell below
 //       toRight = max(U-go, L-ge, D-go)       -> L of the cell to the right
 //   with njhseq's needleMaximum tie order (U, then L, then D; its 'B' pointer behaves as 'U'
-//   everywhere in the traceback), recorded as 5 comparison bits per cell.  Neighbouring lanes
-//   exchange toRight/toDiag of their last column with two shuffles per row.  Bits go to a
-//   per-warp slab in HBM/L2 in (step, word, lane) order so every store is a full 128-byte line.
-//   End-gap penalties: last row via per-row registers, last column via per-column registers,
-//   first row/column through the initial register state and lane 0's boundary feed.
+//   everywhere in the traceback), recorded as the sign bits of five differences per cell.
+//   Neighbouring lanes exchange toRight/toDiag of their last column with two shuffles per row.
+//   Bits go to a per-warp slab in HBM/L2 in (step, word, lane) order so every store is a full
+//   128-byte line.  End-gap penalties: last row via per-row registers, last column via
+//   per-column registers, first row/column through the initial register state and lane 0's
+//   boundary feed.
+//
+// Two forward passes share the traceback / errorProfile code:
+//   alignProfileKernel<C>    one pair per warp, int32 lanes: maxima (two of them fused add+max)
+//                            and funnel shifts on the ALU pipe, differences on the FMA pipe.
+//   alignProfileKernelH2<C>  TWO pairs per warp in the halves of __half2 registers.  Every DP
+//                            value of a launch is an integer of magnitude <= 2047 (checked on
+//                            the host), which fp16 represents exactly, so HADD2/HMNMX2 compute
+//                            the same numbers as the int32 path with half the instructions per
+//                            cell; the sign bits of both halves are collected with one LOP3.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -30,6 +41,7 @@ namespace {
 
 constexpr int WARPS_PER_CTA = 4;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int H2_SYMS = 5;  // the packed kernel scores through a joint (A,C,G,T,N)^2 x (A,C,G,T,N)^2 table
 
 struct AlignArgs {
   DevScoring sc;
@@ -46,7 +58,7 @@ struct AlignArgs {
   uint64_t slabBytes;  // per warp
   uint32_t ptrBytes;   // bytes of the pointer region in a slab
   uint32_t maxAln;     // capacity of each gapped string
-  uint32_t* work;      // [0] = next pair, [2..3] = cell counter (uint64)
+  uint32_t* work;      // [0] = next work item, [2..3] = cell counter (uint64)
   const sdgpu_iter_par* lines;  // par-file lines for the verdict mask (device)
   uint32_t nLines;
   uint64_t* passOut;   // per pair: bit l = passes line l (or NULL)
@@ -54,25 +66,46 @@ struct AlignArgs {
 
 enum { ST_D = 0, ST_U = 1, ST_L = 2 };
 
-// Traceback bits.  Each cell contributes the SIGN BITS of five differences, pushed into a
-// 32-bit accumulator with one funnel shift each (6 cells = 30 bits per word):
-//   g4 = L < D | g3 = U < max(L,D) | g2 = U-ge < max(L,D)-go | g1 = L-ge < D-go | g0 = U-go < max(L-ge,D-go)
-// cellBits() returns the complemented group, so bit set == ">=" (njhseq's tie order U, L, D).
-constexpr int CELLS_PER_WORD = 6;
-__device__ __forceinline__ int nextFromDiag(unsigned b) { return (b & 8u) ? ST_U : ((b & 16u) ? ST_L : ST_D); }
-__device__ __forceinline__ int nextFromUp(unsigned b) { return (b & 4u) ? ST_U : ((b & 16u) ? ST_L : ST_D); }
-__device__ __forceinline__ int nextFromLeft(unsigned b) { return (b & 1u) ? ST_U : ((b & 2u) ? ST_L : ST_D); }
+// Canonical decision bits of a cell (set == ">=", njhseq's tie order U, L, D):
+//   b0: L >= D | b1: U >= max(L,D) | b2: U-ge >= max(L,D)-go | b3: L-ge >= D-go | b4: U-go >= max(L-ge,D-go)
+__device__ __forceinline__ int nextFromDiag(unsigned b) { return (b & 2u) ? ST_U : ((b & 1u) ? ST_L : ST_D); }
+__device__ __forceinline__ int nextFromUp(unsigned b) { return (b & 4u) ? ST_U : ((b & 1u) ? ST_L : ST_D); }
+__device__ __forceinline__ int nextFromLeft(unsigned b) { return (b & 16u) ? ST_U : ((b & 8u) ? ST_L : ST_D); }
 
+// int32 forward pass: five sign bits per cell pushed MSB-first with funnel shifts, 6 cells per word
 template <int C>
-__device__ __forceinline__ unsigned cellBits(const uint8_t* ptr, int i, int j) {
-  constexpr int CW = (C + CELLS_PER_WORD - 1) / CELLS_PER_WORD;
-  const int lj = (j - 1) / C, c = (j - 1) - lj * C;
-  const int t = i + lj;
-  const int wi = c / CELLS_PER_WORD, k = c - wi * CELLS_PER_WORD;
-  const int inWord = (C - wi * CELLS_PER_WORD) < CELLS_PER_WORD ? (C - wi * CELLS_PER_WORD) : CELLS_PER_WORD;
-  const unsigned w = __ldcg(reinterpret_cast<const unsigned*>(ptr) + (size_t(t - 1) * CW + wi) * 32 + lj);
-  return ~(w >> (5 * (inWord - 1 - k))) & 31u;
-}
+struct BitsI32 {
+  static constexpr int CPW = 6;
+  static constexpr int CW = (C + CPW - 1) / CPW;
+  const unsigned* words;
+  __device__ __forceinline__ unsigned operator()(int i, int j) const {
+    const int lj = (j - 1) / C, c = (j - 1) - lj * C;
+    const int t = i + lj;
+    const int wi = c / CPW, k = c - wi * CPW;
+    const int inWord = (C - wi * CPW) < CPW ? (C - wi * CPW) : CPW;
+    const unsigned w = __ldcg(words + (size_t(t - 1) * CW + wi) * 32 + lj);
+    const unsigned g = ~(w >> (5 * (inWord - 1 - k))) & 31u;  // g4 = first pushed
+    return __brev(g) >> 27;
+  }
+};
+
+// half2 forward pass: sign bits of both halves inserted at bits 15 / 31 and shifted right,
+// 3 cells (15 bits) per 16-bit half; `half` selects the pair
+template <int C>
+struct BitsH2 {
+  static constexpr int CPW = 3;
+  static constexpr int CW = (C + CPW - 1) / CPW;
+  const unsigned* words;
+  int half;
+  __device__ __forceinline__ unsigned operator()(int i, int j) const {
+    const int lj = (j - 1) / C, c = (j - 1) - lj * C;
+    const int t = i + lj;
+    const int wi = c / CPW, k = c - wi * CPW;
+    const int inWord = (C - wi * CPW) < CPW ? (C - wi * CPW) : CPW;
+    const unsigned w = __ldcg(words + (size_t(t - 1) * CW + wi) * 32 + lj);
+    return ~(w >> (16 * half + 16 - 5 * inWord + 5 * k)) & 31u;  // bit 0 = first inserted
+  }
+};
 
 // njhseq seqInfo::checkQual (strictly-greater thresholds, trailing window stops before the last base)
 __device__ bool checkQualDev(const uint8_t* q, int len, int pos, const DevScoring& sc) {
@@ -115,318 +148,233 @@ __device__ __forceinline__ unsigned warpSum(unsigned v) {
   return v;
 }
 
-template <int C>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const AlignArgs a) {
-  constexpr int CW = (C + CELLS_PER_WORD - 1) / CELLS_PER_WORD;
-  __shared__ int sTab[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];
-  for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS; x += blockDim.x) sTab[x] = a.sc.score[x];
-  __syncthreads();
-  const char* sTabBytes = reinterpret_cast<const char*>(sTab);
+struct PairView {
+  uint32_t pair;
+  int la, lb;
+  const uint8_t *cA, *cB, *qA, *qB;
+};
 
-  const int lane = threadIdx.x & 31;
-  const int warpInCta = threadIdx.x >> 5;
-  const size_t warpGlobal = size_t(blockIdx.x) * WARPS_PER_CTA + warpInCta;
-  uint8_t* slab = a.scratch + warpGlobal * a.slabBytes;
-  uint32_t* ptrWords = reinterpret_cast<uint32_t*>(slab);
-  const uint8_t* ptrBytes = slab;
-  uint8_t* alnA = slab + a.ptrBytes;
-  uint8_t* alnB = alnA + a.maxAln;
-  uint32_t* gapRecs = reinterpret_cast<uint32_t*>(alnB + a.maxAln);  // (colAbs, size, inA) triples
-
+// Traceback (njhseq runNeedleSave's pointer walk + gapInfo records), gapped strings
+// (rearrangeGlobal), errorProfile (profileAlignment + setEventBaseIdentity), verdict mask
+// (passErrorProfile) and outputs for one pair; warp-cooperative, `bits` reads the forward
+// pass's decision bits.
+// SCORE_FROM_PATH: the caller did not keep the DP's corner value; the score is re-derived as the
+// score of the traced alignment (substitution scores of the aligned columns minus each gap run's
+// open + extends under the ten position-dependent penalties), which equals it by construction.
+template <bool SCORE_FROM_PATH, class Bits>
+__device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView& pv, int score, uint8_t* alnA,
+                           uint8_t* alnB, uint32_t* gapRecs, const int* sTab, int lane) {
   const DevScoring& sc = a.sc;
-  const int dInt = sc.go - sc.ge;
-
-  for (;;) {
-    uint32_t pair = 0;
-    if (lane == 0) pair = atomicAdd(&a.work[0], 1u);
-    pair = __shfl_sync(FULL, pair, 0);
-    if (pair >= a.nPairs) break;
-
-    const uint32_t ia = a.refIdx[pair], ib = a.readIdx[pair];
-    const uint64_t offA = a.seqs.offsets[ia], offB = a.seqs.offsets[ib];
-    const int la = int(a.seqs.offsets[ia + 1] - offA), lb = int(a.seqs.offsets[ib + 1] - offB);
-    const uint8_t* cA = a.seqs.codes + offA;
-    const uint8_t* cB = a.seqs.codes + offB;
-    const uint8_t* qA = a.seqs.quals + offA;
-    const uint8_t* qB = a.seqs.quals + offB;
-
-    // ------------------------------------------------------------------ forward DP
-    int U[C], T[C], dcol[C], gocol[C], colofs[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int j = lane * C + c + 1;
-      const int code = (j <= lb) ? int(cB[j - 1]) : 0;
-      colofs[c] = code * 4;
-      const int L0 = -sc.goLR - (j - 1) * sc.geLR;  // leftInherit of row 0
-      const bool lastCol = (j == lb);
-      gocol[c] = lastCol ? sc.goRQ : sc.go;
-      dcol[c] = lastCol ? (sc.goRQ - sc.geRQ) : dInt;
-      // keep the per-column penalties in registers (ptxas otherwise rematerialises the
-      // j == lb select in every cell: three extra ALU instructions per cell update)
-      asm volatile("" : "+r"(gocol[c]), "+r"(dcol[c]));
-      U[c] = L0 - gocol[c];  // upInherit of row 1 (njhseq's i == 1 case)
-      T[c] = L0;             // feeds diagInherit of row 1, column j+1
+  const int la = pv.la, lb = pv.lb;
+  const uint8_t *cA = pv.cA, *cB = pv.cB, *qA = pv.qA, *qB = pv.qB;
+  const uint32_t pair = pv.pair;
+  // ------------------------------------------------------------------ traceback
+  int i = la, j = lb;
+  int state = nextFromDiag(bits(la, lb));  // arg-max of the bottom-right cell = first state
+  int wp = la + lb - 1;                    // next free column (filled backwards)
+  uint32_t gapA = 0, gapB = 0, nRecs = 0;
+  while (i > 0 || j > 0) {
+    const int di = (state != ST_L), dj = (state != ST_U);
+    const int ik = i - lane * di, jk = j - lane * dj;
+    bool valid;
+    int ns = ST_D;
+    if (state == ST_U) {
+      valid = ik >= 1;
+      if (valid) ns = (jk == 0) ? ST_U : (ik == 1 ? ST_L : nextFromUp(bits(ik - 1, jk)));
+    } else if (state == ST_L) {
+      valid = jk >= 1;
+      if (valid) ns = (ik == 0) ? ST_L : (jk == 1 ? ST_U : nextFromLeft(bits(ik, jk - 1)));
+    } else {
+      valid = ik >= 1 && jk >= 1;
+      if (valid) ns = (ik == 1) ? ST_L : (jk == 1 ? ST_U : nextFromDiag(bits(ik - 1, jk - 1)));
     }
-    int outT = T[C - 1], outR = 0;
-    int prevRecvT = __shfl_up_sync(FULL, outT, 1);
-    const int nLanes = (lb + C - 1) / C;
-    const int steps = la + nLanes - 1;
-    int aCode = (lane == 0) ? int(cA[0]) : 0;  // base of the row this lane works on at t = 1
-    for (int t = 1; t <= steps; ++t) {
-      const int recvR = __shfl_up_sync(FULL, outR, 1);
-      const int recvT = __shfl_up_sync(FULL, outT, 1);
-      const int i = t - lane;
-      // prefetch next row's base
-      const int iNext = i + 1;
-      const int aNext = (iNext >= 1 && iNext <= la) ? int(cA[iNext - 1]) : 0;
-      if (lane < nLanes && i >= 1 && i <= la) {
-        const bool lastRow = (i == la);
-        const int gorow = lastRow ? sc.goRR : sc.go;
-        const int drow = lastRow ? (sc.goRR - sc.geRR) : dInt;
-        int Lin, Tin;
+    const unsigned cont = __ballot_sync(FULL, valid && ns == state);
+    // lanes 0..n-1 continue in this state; lane n either takes the run's last step (and its
+    // arg-max names the next state) or lies beyond (0,0)
+    const int n = (cont == FULL) ? 32 : (__ffs(~cont) - 1);
+    const unsigned validMask = __ballot_sync(FULL, valid);
+    const bool lastTaken = (n < 32) && ((validMask >> n) & 1u);
+    const int nsteps = n + (lastTaken ? 1 : 0);
+    const int newState = lastTaken ? __shfl_sync(FULL, ns, n & 31) : state;
+    if (lane < nsteps) {
+      alnA[wp - lane] = (state == ST_L) ? uint8_t(SDGPU_GAP_CODE) : cA[ik - 1];
+      alnB[wp - lane] = (state == ST_U) ? uint8_t(SDGPU_GAP_CODE) : cB[jk - 1];
+    }
+    i -= nsteps * di;
+    j -= nsteps * dj;
+    wp -= nsteps;
+    if (state == ST_U) {
+      gapB += nsteps;
+      if (newState != ST_U) {  // gapInfo(jcursor, gapBSize, false)
         if (lane == 0) {
-          const int bnd = -sc.goLQ - (i - 1) * sc.geLQ;  // upInherit of column 0
-          Lin = bnd - gorow;                             // njhseq's j == 1 case
-          Tin = (i == 1) ? 0 : bnd + sc.geLQ;
+          gapRecs[3 * nRecs + 0] = uint32_t(wp + 1);
+          gapRecs[3 * nRecs + 1] = gapB;
+          gapRecs[3 * nRecs + 2] = uint32_t(j) << 1;
+          if (a.gapsOut && nRecs < a.gapCap) a.gapsOut[size_t(pair) * a.gapCap + nRecs] = sdgpu_gap{uint32_t(j), gapB, 0u};
+        }
+        ++nRecs;
+        gapB = 0;
+      }
+    } else if (state == ST_L) {
+      gapA += nsteps;
+      if (newState != ST_L) {  // gapInfo(icursor, gapASize, true)
+        if (lane == 0) {
+          gapRecs[3 * nRecs + 0] = uint32_t(wp + 1);
+          gapRecs[3 * nRecs + 1] = gapA;
+          gapRecs[3 * nRecs + 2] = (uint32_t(i) << 1) | 1u;
+          if (a.gapsOut && nRecs < a.gapCap) a.gapsOut[size_t(pair) * a.gapCap + nRecs] = sdgpu_gap{uint32_t(i), gapA, 1u};
+        }
+        ++nRecs;
+        gapA = 0;
+      }
+    }
+    state = newState;
+  }
+  if (gapB != 0 || gapA != 0) {  // run still open when (0,0) is reached
+    const bool inA = gapA != 0;
+    if (lane == 0) {
+      gapRecs[3 * nRecs + 0] = uint32_t(wp + 1);
+      gapRecs[3 * nRecs + 1] = inA ? gapA : gapB;
+      gapRecs[3 * nRecs + 2] = inA ? 1u : 0u;  // position 0
+      if (a.gapsOut && nRecs < a.gapCap)
+        a.gapsOut[size_t(pair) * a.gapCap + nRecs] = sdgpu_gap{0u, inA ? gapA : gapB, inA ? 1u : 0u};
+    }
+    ++nRecs;
+  }
+  __syncwarp();
+  const int alnStart = wp + 1;
+  const int alnLen = la + lb - alnStart;
+  const uint8_t* gA = alnA + alnStart;
+  const uint8_t* gB = alnB + alnStart;
+
+  // ------------------------------------------------------------------ errorProfile
+  const bool checkKmer = (a.flags & SDGPU_CHECK_KMER) != 0;
+  const bool usingQuality = (a.flags & SDGPU_USING_QUALITY) != 0;
+  const bool matchQuality = (a.flags & SDGPU_MATCH_QUALITY) != 0;
+  unsigned hq = 0, lq = 0, lk = 0, hqM = 0, lqM = 0;
+  int matchSum = 0;
+  int baseA = 0, baseB = 0;
+  const unsigned ltMask = (1u << lane) - 1u;
+  for (int cs = 0; cs < alnLen; cs += 32) {
+    const int k = cs + lane;
+    const bool inb = k < alnLen;
+    const int ca = inb ? int(gA[k]) : SDGPU_GAP_CODE;
+    const int cb = inb ? int(gB[k]) : SDGPU_GAP_CODE;
+    const unsigned hasA = __ballot_sync(FULL, inb && ca != SDGPU_GAP_CODE);
+    const unsigned hasB = __ballot_sync(FULL, inb && cb != SDGPU_GAP_CODE);
+    if (inb && ca != SDGPU_GAP_CODE && cb != SDGPU_GAP_CODE) {
+      const int pa = baseA + __popc(hasA & ltMask), pb = baseB + __popc(hasB & ltMask);
+      const int sub = sTab[ca * SDGPU_MAX_SYMBOLS + cb];
+      if (SCORE_FROM_PATH) matchSum += sub;
+      if (sub < 0) {
+        bool good = true;
+        if (usingQuality) good = checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc);
+        if (!good) {
+          ++lq;
+        } else if (checkKmer && (lowFreqDev(a.idx, cA, la, pa) || lowFreqDev(a.idx, cB, lb, pb))) {
+          ++lk;
         } else {
-          Lin = recvR;
-          Tin = prevRecvT;
+          ++hq;
         }
-        const char* rowTab = sTabBytes + aCode * (SDGPU_MAX_SYMBOLS * 4);
-        uint32_t w[CW];
-#pragma unroll
-        for (int x = 0; x < CW; ++x) w[x] = 0;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int s = *reinterpret_cast<const int*>(rowTab + colofs[c]);
-          const int D = Tin + s;
-          Tin = T[c];
-          const int Uc = U[c];
-          uint32_t acc = w[c / CELLS_PER_WORD];
-          // maxima on the ALU pipe (two of them fused add+max, VIADDMNMX), differences on the
-          // FMA pipe (IMAD.IADD); the shifted differences reuse d1/d2 instead of the sums
-          const int W = max(Lin, D);
-          const int d1 = Lin - D;
-          acc = __funnelshift_l(uint32_t(d1), acc, 1);
-          T[c] = max(Uc, W);
-          const int d2 = Uc - W;
-          acc = __funnelshift_l(uint32_t(d2), acc, 1);
-          U[c] = __viaddmax_s32(Uc, dcol[c], W) - gocol[c];
-          acc = __funnelshift_l(uint32_t(d2 + dcol[c]), acc, 1);
-          const int tt = __viaddmax_s32(Lin, drow, D);
-          acc = __funnelshift_l(uint32_t(d1 + drow), acc, 1);
-          Lin = max(Uc, tt) - gorow;
-          acc = __funnelshift_l(uint32_t(Uc - tt), acc, 1);
-          w[c / CELLS_PER_WORD] = acc;
-        }
-        outR = Lin;
-        outT = T[C - 1];
-        uint32_t* dst = ptrWords + size_t(t - 1) * (CW * 32) + lane;
-#pragma unroll
-        for (int x = 0; x < CW; ++x) dst[x * 32] = w[x];
-      }
-      prevRecvT = recvT;
-      aCode = aNext;
-    }
-    // score = toDiag of the bottom-right cell; its arg-max is the traceback's first state
-    const int lastLane = (lb - 1) / C, lastC = (lb - 1) - lastLane * C;
-    int score = 0;
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-      if (c == lastC) score = T[c];
-    score = __shfl_sync(FULL, score, lastLane);
-    __syncwarp();
-
-    // ------------------------------------------------------------------ traceback
-    int i = la, j = lb;
-    int state = nextFromDiag(cellBits<C>(ptrBytes, la, lb));
-    int wp = la + lb - 1;  // next free column (filled backwards)
-    uint32_t gapA = 0, gapB = 0, nRecs = 0;
-    while (i > 0 || j > 0) {
-      const int di = (state != ST_L), dj = (state != ST_U);
-      const int ik = i - lane * di, jk = j - lane * dj;
-      bool valid;
-      int ns = ST_D;
-      if (state == ST_U) {
-        valid = ik >= 1;
-        if (valid) ns = (jk == 0) ? ST_U : (ik == 1 ? ST_L : nextFromUp(cellBits<C>(ptrBytes, ik - 1, jk)));
-      } else if (state == ST_L) {
-        valid = jk >= 1;
-        if (valid) ns = (ik == 0) ? ST_L : (jk == 1 ? ST_U : nextFromLeft(cellBits<C>(ptrBytes, ik, jk - 1)));
       } else {
-        valid = ik >= 1 && jk >= 1;
-        if (valid) ns = (ik == 1) ? ST_L : (jk == 1 ? ST_U : nextFromDiag(cellBits<C>(ptrBytes, ik - 1, jk - 1)));
-      }
-      const unsigned cont = __ballot_sync(FULL, valid && ns == state);
-      // lanes 0..n-1 continue in this state; lane n either takes the run's last step (and its
-      // arg-max names the next state) or lies beyond (0,0)
-      const int n = (cont == FULL) ? 32 : (__ffs(~cont) - 1);
-      const unsigned validMask = __ballot_sync(FULL, valid);
-      const bool lastTaken = (n < 32) && ((validMask >> n) & 1u);
-      const int nsteps = n + (lastTaken ? 1 : 0);
-      const int newState = lastTaken ? __shfl_sync(FULL, ns, n & 31) : state;
-      if (lane < nsteps) {
-        alnA[wp - lane] = (state == ST_L) ? uint8_t(SDGPU_GAP_CODE) : cA[ik - 1];
-        alnB[wp - lane] = (state == ST_U) ? uint8_t(SDGPU_GAP_CODE) : cB[jk - 1];
-      }
-      i -= nsteps * di;
-      j -= nsteps * dj;
-      wp -= nsteps;
-      if (state == ST_U) {
-        gapB += nsteps;
-        if (newState != ST_U) {  // gapInfo(jcursor, gapBSize, false)
-          if (lane == 0) {
-            gapRecs[3 * nRecs + 0] = uint32_t(wp + 1);
-            gapRecs[3 * nRecs + 1] = gapB;
-            gapRecs[3 * nRecs + 2] = 0u;
-            if (a.gapsOut && nRecs < a.gapCap) a.gapsOut[size_t(pair) * a.gapCap + nRecs] = sdgpu_gap{uint32_t(j), gapB, 0u};
-          }
-          ++nRecs;
-          gapB = 0;
-        }
-      } else if (state == ST_L) {
-        gapA += nsteps;
-        if (newState != ST_L) {  // gapInfo(icursor, gapASize, true)
-          if (lane == 0) {
-            gapRecs[3 * nRecs + 0] = uint32_t(wp + 1);
-            gapRecs[3 * nRecs + 1] = gapA;
-            gapRecs[3 * nRecs + 2] = 1u;
-            if (a.gapsOut && nRecs < a.gapCap) a.gapsOut[size_t(pair) * a.gapCap + nRecs] = sdgpu_gap{uint32_t(i), gapA, 1u};
-          }
-          ++nRecs;
-          gapA = 0;
-        }
-      }
-      state = newState;
-    }
-    if (gapB != 0 || gapA != 0) {  // run still open when (0,0) is reached
-      const bool inA = gapA != 0;
-      if (lane == 0) {
-        gapRecs[3 * nRecs + 0] = uint32_t(wp + 1);
-        gapRecs[3 * nRecs + 1] = inA ? gapA : gapB;
-        gapRecs[3 * nRecs + 2] = inA ? 1u : 0u;
-        if (a.gapsOut && nRecs < a.gapCap)
-          a.gapsOut[size_t(pair) * a.gapCap + nRecs] = sdgpu_gap{0u, inA ? gapA : gapB, inA ? 1u : 0u};
-      }
-      ++nRecs;
-    }
-    __syncwarp();
-    const int alnStart = wp + 1;
-    const int alnLen = la + lb - alnStart;
-    const uint8_t* gA = alnA + alnStart;
-    const uint8_t* gB = alnB + alnStart;
-
-    // ------------------------------------------------------------------ errorProfile
-    const bool checkKmer = (a.flags & SDGPU_CHECK_KMER) != 0;
-    const bool usingQuality = (a.flags & SDGPU_USING_QUALITY) != 0;
-    const bool matchQuality = (a.flags & SDGPU_MATCH_QUALITY) != 0;
-    unsigned hq = 0, lq = 0, lk = 0, hqM = 0, lqM = 0;
-    int baseA = 0, baseB = 0;
-    const unsigned ltMask = (1u << lane) - 1u;
-    for (int cs = 0; cs < alnLen; cs += 32) {
-      const int k = cs + lane;
-      const bool inb = k < alnLen;
-      const int ca = inb ? int(gA[k]) : SDGPU_GAP_CODE;
-      const int cb = inb ? int(gB[k]) : SDGPU_GAP_CODE;
-      const unsigned hasA = __ballot_sync(FULL, inb && ca != SDGPU_GAP_CODE);
-      const unsigned hasB = __ballot_sync(FULL, inb && cb != SDGPU_GAP_CODE);
-      if (inb && ca != SDGPU_GAP_CODE && cb != SDGPU_GAP_CODE) {
-        const int pa = baseA + __popc(hasA & ltMask), pb = baseB + __popc(hasB & ltMask);
-        if (sTab[ca * SDGPU_MAX_SYMBOLS + cb] < 0) {
-          bool good = true;
-          if (usingQuality) good = checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc);
-          if (!good) {
-            ++lq;
-          } else if (checkKmer && (lowFreqDev(a.idx, cA, la, pa) || lowFreqDev(a.idx, cB, lb, pb))) {
-            ++lk;
-          } else {
-            ++hq;
-          }
+        if (matchQuality && !(checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc))) {
+          ++lqM;
         } else {
-          if (matchQuality && !(checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc))) {
-            ++lqM;
-          } else {
-            ++hqM;
-          }
+          ++hqM;
         }
       }
-      baseA += __popc(hasA);
-      baseB += __popc(hasB);
     }
-    hq = warpSum(hq);
-    lq = warpSum(lq);
-    lk = warpSum(lk);
-    hqM = warpSum(hqM);
-    lqM = warpSum(lqM);
+    baseA += __popc(hasA);
+    baseB += __popc(hasB);
+  }
+  hq = warpSum(hq);
+  lq = warpSum(lq);
+  lk = warpSum(lk);
+  hqM = warpSum(hqM);
+  lqM = warpSum(lqM);
 
-    // gap runs in forward order (the records are in traceback order); uniform across the warp
-    double one = 0, two = 0, large = 0;
-    unsigned numGaps = 0, endA = 0, endB = 0, regA = 0, regB = 0;
-    for (int r = int(nRecs) - 1; r >= 0; --r) {
-      const int startPos = int(gapRecs[3 * r + 0]) - alnStart;
-      const int size = int(gapRecs[3 * r + 1]);
-      const bool inA = gapRecs[3 * r + 2] != 0;
-      const bool endGap = (startPos + size >= alnLen) || startPos == 0;
-      if (endGap) {
-        (inA ? endA : endB) += size;
-        if (!sc.countEndGaps) continue;
-      } else {
-        (inA ? regA : regB) += size;
+  // gap runs in forward order (the records are in traceback order); uniform across the warp
+  double one = 0, two = 0, large = 0;
+  int gapCost = 0;
+  unsigned numGaps = 0, endA = 0, endB = 0, regA = 0, regB = 0;
+  for (int r = int(nRecs) - 1; r >= 0; --r) {
+    const int startPos = int(gapRecs[3 * r + 0]) - alnStart;
+    const int size = int(gapRecs[3 * r + 1]);
+    const bool inA = (gapRecs[3 * r + 2] & 1u) != 0;
+    if (SCORE_FROM_PATH) {
+      const int pos = int(gapRecs[3 * r + 2] >> 1);
+      int open, ext;
+      if (inA) {  // '-' in the ref: moves along row `pos`
+        open = pos == 0 ? sc.goLR : (pos == la ? sc.goRR : sc.go);
+        ext = pos == 0 ? sc.geLR : (pos == la ? sc.geRR : sc.ge);
+      } else {    // '-' in the read: moves along column `pos`
+        open = pos == 0 ? sc.goLQ : (pos == lb ? sc.goRQ : sc.go);
+        ext = pos == 0 ? sc.geLQ : (pos == lb ? sc.geRQ : sc.ge);
       }
-      ++numGaps;
-      double wgt = 1.0;
-      if (sc.weighHomopolymers) {
-        const uint8_t* gs = inA ? gA : gB;  // string holding the '-' run
-        const uint8_t* os = inA ? gB : gA;  // string holding the gapped bases
-        const int base = os[startPos];
-        bool homo = true;
-        for (int x = 1; x < size; ++x) homo = homo && (os[startPos + x] == base);
-        if (homo) {
-          double gapSide = 0, baseSide = size;
-          for (int cur = startPos + size; cur < alnLen && gs[cur] == base; ++cur) gapSide += 1;
-          for (int cur = 1; cur <= startPos && gs[startPos - cur] == base; ++cur) gapSide += 1;
-          for (int cur = startPos + size; cur < alnLen && os[cur] == base; ++cur) baseSide += 1;
-          for (int cur = 1; cur <= startPos && os[startPos - cur] == base; ++cur) baseSide += 1;
-          wgt = fabs(gapSide - baseSide) / (gapSide + baseSide);
-        }
-      }
-      if (size >= 3) {
-        large += wgt;
-      } else if (size == 2) {
-        two += wgt;
-      } else {
-        one += wgt;
+      gapCost += open + (size - 1) * ext;
+    }
+    const bool endGap = (startPos + size >= alnLen) || startPos == 0;
+    if (endGap) {
+      (inA ? endA : endB) += size;
+      if (!sc.countEndGaps) continue;
+    } else {
+      (inA ? regA : regB) += size;
+    }
+    ++numGaps;
+    double wgt = 1.0;
+    if (sc.weighHomopolymers) {
+      const uint8_t* gs = inA ? gA : gB;  // string holding the '-' run
+      const uint8_t* os = inA ? gB : gA;  // string holding the gapped bases
+      const int base = os[startPos];
+      bool homo = true;
+      for (int x = 1; x < size; ++x) homo = homo && (os[startPos + x] == base);
+      if (homo) {
+        double gapSide = 0, baseSide = size;
+        for (int cur = startPos + size; cur < alnLen && gs[cur] == base; ++cur) gapSide += 1;
+        for (int cur = 1; cur <= startPos && gs[startPos - cur] == base; ++cur) gapSide += 1;
+        for (int cur = startPos + size; cur < alnLen && os[cur] == base; ++cur) baseSide += 1;
+        for (int cur = 1; cur <= startPos && os[startPos - cur] == base; ++cur) baseSide += 1;
+        wgt = fabs(gapSide - baseSide) / (gapSide + baseSide);
       }
     }
+    if (size >= 3) {
+      large += wgt;
+    } else if (size == 2) {
+      two += wgt;
+    } else {
+      one += wgt;
+    }
+  }
 
-    // comparison::passErrorProfile against every par-file line at once: lane l judges lines l and
-    // l + 32, two ballots give the 64-bit verdict mask the host collapse loop consumes
-    if (a.passOut) {
-      const unsigned events = hqM + lqM + hq + lq + lk + numGaps;
-      const double id = events ? double(hqM + lqM) / double(events) : 0.0;
-      const double idHq = events ? double(hqM + lqM + lq + lk) / double(events) : 0.0;
-      unsigned halves[2];
+  if (SCORE_FROM_PATH) score = int(warpSum(unsigned(matchSum))) - gapCost;
+
+  // comparison::passErrorProfile against every par-file line at once: lane l judges lines l and
+  // l + 32, two ballots give the 64-bit verdict mask the host collapse loop consumes
+  if (a.passOut) {
+    const unsigned events = hqM + lqM + hq + lq + lk + numGaps;
+    const double id = events ? double(hqM + lqM) / double(events) : 0.0;
+    const double idHq = events ? double(hqM + lqM + lq + lk) / double(events) : 0.0;
+    unsigned halves[2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const unsigned li = unsigned(lane) + 32u * h;
-        bool pass = false;
-        if (li < a.nLines) {
-          const sdgpu_iter_par it = a.lines[li];
-          if (it.onPerId) {
-            pass = (it.onHqPerId ? idHq : id) >= it.perId;
-          } else {
-            pass = it.oneBaseIndel >= one && it.twoBaseIndel >= two && it.largeBaseIndel >= large &&
-                   it.hqMismatches >= double(hq) && it.lqMismatches >= double(lq) && it.lowKmerMismatches >= double(lk);
-          }
+    for (int h = 0; h < 2; ++h) {
+      const unsigned li = unsigned(lane) + 32u * h;
+      bool pass = false;
+      if (li < a.nLines) {
+        const sdgpu_iter_par it = a.lines[li];
+        if (it.onPerId) {
+          pass = (it.onHqPerId ? idHq : id) >= it.perId;
+        } else {
+          pass = it.oneBaseIndel >= one && it.twoBaseIndel >= two && it.largeBaseIndel >= large &&
+                 it.hqMismatches >= double(hq) && it.lqMismatches >= double(lq) && it.lowKmerMismatches >= double(lk);
         }
-        halves[h] = __ballot_sync(FULL, pass);
       }
-      if (lane == 0) {
-        a.passOut[pair] = (uint64_t(halves[1]) << 32) | halves[0];
-        if (!a.out) atomicAdd(reinterpret_cast<unsigned long long*>(a.work + 2), (unsigned long long)la * (unsigned long long)lb);
-      }
+      halves[h] = __ballot_sync(FULL, pass);
     }
-    if (lane == 0 && a.out) {
+    if (lane == 0) a.passOut[pair] = (uint64_t(halves[1]) << 32) | halves[0];
+  }
+  if (lane == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.work + 2), (unsigned long long)la * (unsigned long long)lb);
+    if (a.out) {
       sdgpu_comparison c;
       c.alnScore = score;
       c.hqMismatches = hq;
@@ -454,20 +402,301 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
         c.eventBasedIdentityHq = double(hqM + lqM + lq + lk) / double(c.overLappingEvents);
       }
       a.out[pair] = c;
-      atomicAdd(reinterpret_cast<unsigned long long*>(a.work + 2), (unsigned long long)la * (unsigned long long)lb);
     }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ PairView viewOf(const AlignArgs& a, uint32_t pair) {
+  PairView pv;
+  pv.pair = pair;
+  const uint32_t ia = a.refIdx[pair], ib = a.readIdx[pair];
+  const uint64_t offA = a.seqs.offsets[ia], offB = a.seqs.offsets[ib];
+  pv.la = int(a.seqs.offsets[ia + 1] - offA);
+  pv.lb = int(a.seqs.offsets[ib + 1] - offB);
+  pv.cA = a.seqs.codes + offA;
+  pv.cB = a.seqs.codes + offB;
+  pv.qA = a.seqs.quals + offA;
+  pv.qB = a.seqs.quals + offB;
+  return pv;
+}
+
+// =====================================================================================
+// int32 forward pass, one pair per warp
+// =====================================================================================
+template <int C>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const AlignArgs a) {
+  using Bits = BitsI32<C>;
+  constexpr int CW = Bits::CW;
+  __shared__ int sTab[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];
+  for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS; x += blockDim.x) sTab[x] = a.sc.score[x];
+  __syncthreads();
+  const char* sTabBytes = reinterpret_cast<const char*>(sTab);
+
+  const int lane = threadIdx.x & 31;
+  const int warpInCta = threadIdx.x >> 5;
+  const size_t warpGlobal = size_t(blockIdx.x) * WARPS_PER_CTA + warpInCta;
+  uint8_t* slab = a.scratch + warpGlobal * a.slabBytes;
+  uint32_t* ptrWords = reinterpret_cast<uint32_t*>(slab);
+  uint8_t* alnA = slab + a.ptrBytes;
+  uint8_t* alnB = alnA + a.maxAln;
+  uint32_t* gapRecs = reinterpret_cast<uint32_t*>(alnB + a.maxAln);  // (colAbs, size, inA) triples
+
+  const DevScoring& sc = a.sc;
+  const int dInt = sc.go - sc.ge;
+
+  for (;;) {
+    uint32_t pair = 0;
+    if (lane == 0) pair = atomicAdd(&a.work[0], 1u);
+    pair = __shfl_sync(FULL, pair, 0);
+    if (pair >= a.nPairs) break;
+    const PairView pv = viewOf(a, pair);
+    const int la = pv.la, lb = pv.lb;
+    const uint8_t *cA = pv.cA, *cB = pv.cB;
+
+    int U[C], T[C], dcol[C], gocol[C], colofs[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = lane * C + c + 1;
+      const int code = (j <= lb) ? int(cB[j - 1]) : 0;
+      colofs[c] = code * 4;
+      const int L0 = -sc.goLR - (j - 1) * sc.geLR;  // leftInherit of row 0
+      const bool lastCol = (j == lb);
+      gocol[c] = lastCol ? sc.goRQ : sc.go;
+      dcol[c] = lastCol ? (sc.goRQ - sc.geRQ) : dInt;
+      // keep the per-column penalties in registers (ptxas otherwise rematerialises the
+      // j == lb select in every cell: three extra ALU instructions per cell update)
+      asm volatile("" : "+r"(gocol[c]), "+r"(dcol[c]));
+      U[c] = L0 - gocol[c];  // upInherit of row 1 (njhseq's i == 1 case)
+      T[c] = L0;             // feeds diagInherit of row 1, column j+1
+    }
+    int outT = T[C - 1], outR = 0;
+    int prevRecvT = __shfl_up_sync(FULL, outT, 1);
+    const int nLanes = (lb + C - 1) / C;
+    const int steps = la + nLanes - 1;
+    int aCode = (lane == 0) ? int(cA[0]) : 0;  // base of the row this lane works on at t = 1
+    for (int t = 1; t <= steps; ++t) {
+      const int recvR = __shfl_up_sync(FULL, outR, 1);
+      const int recvT = __shfl_up_sync(FULL, outT, 1);
+      const int i = t - lane;
+      const int iNext = i + 1;  // prefetch next row's base
+      const int aNext = (iNext >= 1 && iNext <= la) ? int(cA[iNext - 1]) : 0;
+      if (lane < nLanes && i >= 1 && i <= la) {
+        const bool lastRow = (i == la);
+        const int gorow = lastRow ? sc.goRR : sc.go;
+        const int drow = lastRow ? (sc.goRR - sc.geRR) : dInt;
+        int Lin, Tin;
+        if (lane == 0) {
+          const int bnd = -sc.goLQ - (i - 1) * sc.geLQ;  // upInherit of column 0
+          Lin = bnd - gorow;                             // njhseq's j == 1 case
+          Tin = (i == 1) ? 0 : bnd + sc.geLQ;
+        } else {
+          Lin = recvR;
+          Tin = prevRecvT;
+        }
+        const char* rowTab = sTabBytes + aCode * (SDGPU_MAX_SYMBOLS * 4);
+        uint32_t w[CW];
+#pragma unroll
+        for (int x = 0; x < CW; ++x) w[x] = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int s = *reinterpret_cast<const int*>(rowTab + colofs[c]);
+          const int D = Tin + s;
+          Tin = T[c];
+          const int Uc = U[c];
+          uint32_t acc = w[c / Bits::CPW];
+          // maxima on the ALU pipe (two of them fused add+max, VIADDMNMX), differences on the
+          // FMA pipe (IMAD.IADD); the shifted differences reuse d1/d2 instead of the sums
+          const int W = max(Lin, D);
+          const int d1 = Lin - D;
+          acc = __funnelshift_l(uint32_t(d1), acc, 1);
+          T[c] = max(Uc, W);
+          const int d2 = Uc - W;
+          acc = __funnelshift_l(uint32_t(d2), acc, 1);
+          U[c] = __viaddmax_s32(Uc, dcol[c], W) - gocol[c];
+          acc = __funnelshift_l(uint32_t(d2 + dcol[c]), acc, 1);
+          const int tt = __viaddmax_s32(Lin, drow, D);
+          acc = __funnelshift_l(uint32_t(d1 + drow), acc, 1);
+          Lin = max(Uc, tt) - gorow;
+          acc = __funnelshift_l(uint32_t(Uc - tt), acc, 1);
+          w[c / Bits::CPW] = acc;
+        }
+        outR = Lin;
+        outT = T[C - 1];
+        uint32_t* dst = ptrWords + size_t(t - 1) * (CW * 32) + lane;
+#pragma unroll
+        for (int x = 0; x < CW; ++x) dst[x * 32] = w[x];
+      }
+      prevRecvT = recvT;
+      aCode = aNext;
+    }
+    // score = toDiag of the bottom-right cell
+    const int lastLane = (lb - 1) / C, lastC = (lb - 1) - lastLane * C;
+    int score = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (c == lastC) score = T[c];
+    score = __shfl_sync(FULL, score, lastLane);
     __syncwarp();
+    finishPair<false>(a, Bits{ptrWords}, viewOf(a, pair), score, alnA, alnB, gapRecs, sTab, lane);
   }
 }
 
+// =====================================================================================
+// half2 forward pass, two pairs per warp (pair X in the low halves, pair Y in the high halves)
+// =====================================================================================
+__device__ __forceinline__ uint32_t h2bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 h2from(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+// (x, y) as exact fp16 integers, packed with integer ops so the pair lives in ONE register
+__device__ __forceinline__ __half2 h2of(int x, int y) {
+  const uint32_t lo = __half_as_ushort(__int2half_rn(x)), hi = __half_as_ushort(__int2half_rn(y));
+  return h2from(lo | (hi << 16));
+}
+
 template <int C>
-int launchC(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
-  constexpr int CW = (C + CELLS_PER_WORD - 1) / CELLS_PER_WORD;
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernelH2(const AlignArgs a) {
+  using Bits = BitsH2<C>;
+  constexpr int CW = Bits::CW;
+  __shared__ int sTab[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];
+  __shared__ __half2 sTab2[H2_SYMS * H2_SYMS * H2_SYMS * H2_SYMS];  // [aX*5+aY][bX*5+bY] = (s(aX,bX), s(aY,bY))
+  for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS; x += blockDim.x) sTab[x] = a.sc.score[x];
+  for (int x = threadIdx.x; x < H2_SYMS * H2_SYMS * H2_SYMS * H2_SYMS; x += blockDim.x) {
+    const int r = x / (H2_SYMS * H2_SYMS), q = x - r * (H2_SYMS * H2_SYMS);
+    const int aX = r / H2_SYMS, aY = r - aX * H2_SYMS, bX = q / H2_SYMS, bY = q - bX * H2_SYMS;
+    sTab2[x] = h2of(a.sc.score[aX * SDGPU_MAX_SYMBOLS + bX], a.sc.score[aY * SDGPU_MAX_SYMBOLS + bY]);
+  }
+  __syncthreads();
+  const char* sTab2Bytes = reinterpret_cast<const char*>(sTab2);
+
+  const int lane = threadIdx.x & 31;
+  const int warpInCta = threadIdx.x >> 5;
+  const size_t warpGlobal = size_t(blockIdx.x) * WARPS_PER_CTA + warpInCta;
+  uint8_t* slab = a.scratch + warpGlobal * a.slabBytes;
+  uint32_t* ptrWords = reinterpret_cast<uint32_t*>(slab);
+  uint8_t* alnA = slab + a.ptrBytes;
+  uint8_t* alnB = alnA + a.maxAln;
+  uint32_t* gapRecs = reinterpret_cast<uint32_t*>(alnB + a.maxAln);
+
+  const DevScoring& sc = a.sc;
+  const int dInt = sc.go - sc.ge;
+  const uint32_t nItems = (a.nPairs + 1) / 2;
+
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(&a.work[0], 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= nItems) break;
+    const bool haveY = 2 * item + 1 < a.nPairs;
+    const PairView px = viewOf(a, 2 * item);
+    const PairView py = viewOf(a, haveY ? 2 * item + 1 : 2 * item);
+    const int laM = max(px.la, py.la), lbM = max(px.lb, py.lb);
+
+    __half2 U[C], T[C];
+    uint32_t dcolU[C], gocolU[C];  // packed fp16 pairs, held as raw registers
+    int colofs[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = lane * C + c + 1;
+      const int codeX = (j <= px.lb) ? int(px.cB[j - 1]) : 0;
+      const int codeY = (j <= py.lb) ? int(py.cB[j - 1]) : 0;
+      colofs[c] = (codeX * H2_SYMS + codeY) * 4;
+      const int L0 = -sc.goLR - (j - 1) * sc.geLR;
+      const bool lastX = (j == px.lb), lastY = (j == py.lb);
+      gocolU[c] = h2bits(h2of(lastX ? sc.goRQ : sc.go, lastY ? sc.goRQ : sc.go));
+      dcolU[c] = h2bits(h2of(lastX ? (sc.goRQ - sc.geRQ) : dInt, lastY ? (sc.goRQ - sc.geRQ) : dInt));
+      asm volatile("" : "+r"(gocolU[c]), "+r"(dcolU[c]));  // keep the per-column penalties in registers
+      const __half2 L0h = h2of(L0, L0);
+      U[c] = __hsub2(L0h, h2from(gocolU[c]));
+      T[c] = L0h;
+    }
+    __half2 outT = T[C - 1], outR = h2of(0, 0);
+    __half2 prevRecvT = __shfl_up_sync(FULL, outT, 1);
+    const int nLanes = (lbM + C - 1) / C;
+    const int steps = laM + nLanes - 1;
+    int rowCode = (lane == 0) ? (int(px.cA[0]) * H2_SYMS + int(py.cA[0])) : 0;
+    // per-row penalties for the four (last row of X?, last row of Y?) cases, converted once
+    const int dRR = sc.goRR - sc.geRR;
+    const __half2 hGo = h2of(sc.go, sc.go), hD = h2of(dInt, dInt);
+    const __half2 hGoX = h2of(sc.goRR, sc.go), hDX = h2of(dRR, dInt);
+    const __half2 hGoY = h2of(sc.go, sc.goRR), hDY = h2of(dInt, dRR);
+    const __half2 hGoXY = h2of(sc.goRR, sc.goRR), hDXY = h2of(dRR, dRR);
+    // lane 0's boundary feed (upInherit of column 0), kept as a running fp16 pair
+    const __half2 hGeLQ = h2of(sc.geLQ, sc.geLQ);
+    __half2 bndH = h2of(-sc.goLQ, -sc.goLQ);  // value for row 1
+    const int laX = px.la, laY = py.la;
+    const uint8_t *cAx = px.cA, *cAy = py.cA;
+    for (int t = 1; t <= steps; ++t) {
+      const __half2 recvR = __shfl_up_sync(FULL, outR, 1);
+      const __half2 recvT = __shfl_up_sync(FULL, outT, 1);
+      const int i = t - lane;
+      const int iNext = i + 1;
+      const int aXn = (iNext >= 1 && iNext <= laX) ? int(cAx[iNext - 1]) : 0;
+      const int aYn = (iNext >= 1 && iNext <= laY) ? int(cAy[iNext - 1]) : 0;
+      if (lane < nLanes && i >= 1 && i <= laM) {
+        const bool lastRowX = (i == laX), lastRowY = (i == laY);
+        const __half2 gorow = lastRowX ? (lastRowY ? hGoXY : hGoX) : (lastRowY ? hGoY : hGo);
+        const __half2 drow = lastRowX ? (lastRowY ? hDXY : hDX) : (lastRowY ? hDY : hD);
+        __half2 Lin, Tin;
+        if (lane == 0) {
+          Lin = __hsub2(bndH, gorow);                                // njhseq's j == 1 case
+          Tin = (i == 1) ? h2of(0, 0) : __hadd2(bndH, hGeLQ);        // upInherit of (i-1, 0)
+          bndH = __hsub2(bndH, hGeLQ);
+        } else {
+          Lin = recvR;
+          Tin = prevRecvT;
+        }
+        const char* rowTab = sTab2Bytes + rowCode * (H2_SYMS * H2_SYMS * 4);
+        uint32_t w[CW];
+#pragma unroll
+        for (int x = 0; x < CW; ++x) w[x] = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const __half2 s = *reinterpret_cast<const __half2*>(rowTab + colofs[c]);
+          const __half2 D = __hadd2(Tin, s);
+          Tin = T[c];
+          const __half2 Uc = U[c];
+          uint32_t acc = w[c / Bits::CPW];
+          const __half2 W = __hmax2(Lin, D);
+          const __half2 d1 = __hsub2(Lin, D);
+          acc = (acc >> 1) | (h2bits(d1) & 0x80008000u);
+          T[c] = __hmax2(Uc, W);
+          const __half2 d2 = __hsub2(Uc, W);
+          acc = (acc >> 1) | (h2bits(d2) & 0x80008000u);
+          const __half2 dc = h2from(dcolU[c]);
+          U[c] = __hsub2(__hmax2(__hadd2(Uc, dc), W), h2from(gocolU[c]));
+          acc = (acc >> 1) | (h2bits(__hadd2(d2, dc)) & 0x80008000u);
+          const __half2 tt = __hmax2(__hadd2(Lin, drow), D);
+          acc = (acc >> 1) | (h2bits(__hadd2(d1, drow)) & 0x80008000u);
+          Lin = __hsub2(__hmax2(Uc, tt), gorow);
+          acc = (acc >> 1) | (h2bits(__hsub2(Uc, tt)) & 0x80008000u);
+          w[c / Bits::CPW] = acc;
+        }
+        outR = Lin;
+        outT = T[C - 1];
+        uint32_t* dst = ptrWords + size_t(t - 1) * (CW * 32) + lane;
+#pragma unroll
+        for (int x = 0; x < CW; ++x) dst[x * 32] = w[x];
+      }
+      prevRecvT = recvT;
+      rowCode = aXn * H2_SYMS + aYn;
+    }
+    __syncwarp();
+    // The shorter pair's registers keep running on padding rows, so the corner values are not kept:
+    // each pair's score is re-derived from its traced alignment (finishPair<true>).
+    // (views are re-read here so their eight pointers do not stay live across the DP loop)
+    finishPair<true>(a, Bits{ptrWords, 0}, viewOf(a, 2 * item), 0, alnA, alnB, gapRecs, sTab, lane);
+    if (haveY) finishPair<true>(a, Bits{ptrWords, 1}, viewOf(a, 2 * item + 1), 0, alnA, alnB, gapRecs, sTab, lane);
+  }
+}
+
+template <class Kernel>
+int launchKernel(sdgpu_ctx* ctx, Kernel kernel, AlignArgs& args, uint32_t workItems, int CW, uint32_t maxLenA,
+                 uint32_t maxLenB) {
   int ctasPerSM = 0;
-  SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, alignProfileKernel<C>, WARPS_PER_CTA * 32, 0));
+  SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kernel, WARPS_PER_CTA * 32, 0));
   if (ctasPerSM < 1) ctasPerSM = 1;
   uint32_t grid = uint32_t(ctx->numSMs) * uint32_t(ctasPerSM);
-  const uint32_t needCtas = (args.nPairs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const uint32_t needCtas = (workItems + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   if (grid > needCtas) grid = needCtas;
   const uint64_t maxSteps = uint64_t(maxLenA) + 31;
   args.ptrBytes = uint32_t(maxSteps * CW * 128);
@@ -491,12 +720,40 @@ int launchC(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB)
     e1 = ctx->evPool[ctx->evUsed++];
     SD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
   }
-  alignProfileKernel<C><<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(args);
+  kernel<<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(args);
   SD_CUDA(ctx, cudaGetLastError());
   if (e1) SD_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
   ++ctx->launches;
   ++ctx->alignLaunches;
   return SDGPU_OK;
+}
+
+template <int C>
+int launchI32(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
+  return launchKernel(ctx, alignProfileKernel<C>, args, args.nPairs, BitsI32<C>::CW, maxLenA, maxLenB);
+}
+template <int C>
+int launchH2(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
+  return launchKernel(ctx, alignProfileKernelH2<C>, args, (args.nPairs + 1) / 2, BitsH2<C>::CW, maxLenA, maxLenB);
+}
+
+// Every DP value of the launch (real and padding cells) must be an integer fp16 holds exactly and
+// every difference of two of them too: |v| <= 2047 with room for the subtraction.
+bool halfRangeOk(const sdgpu_ctx* ctx, uint32_t maxLenA, uint32_t cols) {
+  const DevScoring& s = ctx->scoring;
+  int maxPos = 0, maxNeg = 0;
+  for (int a = 0; a < H2_SYMS; ++a)
+    for (int b = 0; b < H2_SYMS; ++b) {
+      const int v = s.score[a * SDGPU_MAX_SYMBOLS + b];
+      maxPos = std::max(maxPos, v);
+      maxNeg = std::max(maxNeg, -v);
+    }
+  const int maxOpen = std::max({s.go, s.goLQ, s.goRQ, s.goLR, s.goRR});
+  const int maxExt = std::max({s.ge, s.geLQ, s.geRQ, s.geLR, s.geRR});
+  const int64_t len = int64_t(maxLenA) + cols;
+  const int64_t hi = int64_t(maxPos) * std::min<int64_t>(maxLenA, cols) + maxOpen;
+  const int64_t lo = 3ll * maxOpen + int64_t(maxExt) * len + maxNeg + maxPos;  // magnitude of the most negative value
+  return hi <= 1000 && lo <= 1040 && hi + lo <= 2040;
 }
 
 }  // namespace
@@ -524,11 +781,29 @@ int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dRe
   args.passOut = dPassOut;
   if (dPassOut && ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
   const uint32_t needC = (maxLenB + 31) / 32;
-  if (needC <= 4) return launchC<4>(ctx, args, maxLenA, maxLenB);
-  if (needC <= 6) return launchC<6>(ctx, args, maxLenA, maxLenB);
-  if (needC <= 8) return launchC<8>(ctx, args, maxLenA, maxLenB);
-  if (needC <= 10) return launchC<10>(ctx, args, maxLenA, maxLenB);
-  if (needC <= 13) return launchC<13>(ctx, args, maxLenA, maxLenB);
-  if (needC <= 16) return launchC<16>(ctx, args, maxLenA, maxLenB);
-  return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "read longer than 512 bases: column strip-mining not implemented yet");
+  if (needC > 16)
+    return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "read longer than 512 bases: column strip-mining not implemented yet");
+  const uint32_t C = needC <= 4 ? 4 : needC <= 6 ? 6 : needC <= 8 ? 8 : needC <= 10 ? 10 : needC <= 13 ? 13 : 16;
+  // packed fp16 path: bases within A,C,G,T,N (codes 0..4), exact-integer range, enough pairs to pair up
+  const bool useH2 = ctx->forceKernel != 1 && ctx->usedSym <= H2_SYMS && nPairs >= 2 && halfRangeOk(ctx, maxLenA + 1, 32 * C);
+  if (ctx->forceKernel == 2 && !useH2) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "packed fp16 alignment kernel not applicable to this launch");
+  ctx->lastKernelWasH2 = useH2;
+  if (useH2) {
+    switch (C) {
+      case 4: return launchH2<4>(ctx, args, maxLenA, maxLenB);
+      case 6: return launchH2<6>(ctx, args, maxLenA, maxLenB);
+      case 8: return launchH2<8>(ctx, args, maxLenA, maxLenB);
+      case 10: return launchH2<10>(ctx, args, maxLenA, maxLenB);
+      case 13: return launchH2<13>(ctx, args, maxLenA, maxLenB);
+      default: return launchH2<16>(ctx, args, maxLenA, maxLenB);
+    }
+  }
+  switch (C) {
+    case 4: return launchI32<4>(ctx, args, maxLenA, maxLenB);
+    case 6: return launchI32<6>(ctx, args, maxLenA, maxLenB);
+    case 8: return launchI32<8>(ctx, args, maxLenA, maxLenB);
+    case 10: return launchI32<10>(ctx, args, maxLenA, maxLenB);
+    case 13: return launchI32<13>(ctx, args, maxLenA, maxLenB);
+    default: return launchI32<16>(ctx, args, maxLenA, maxLenB);
+  }
 }

@@ -492,6 +492,14 @@ int sdgpu_align_pass_wait(sdgpu_ctx* ctx, int slot, const uint64_t** masks, uint
   return SDGPU_OK;
 }
 
+int sdgpu_set_kernel(sdgpu_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2) return sd_fail(ctx, SDGPU_E_ARG, "mode must be 0 (auto), 1 (int32) or 2 (packed fp16)");
+  ctx->forceKernel = mode;
+  return SDGPU_OK;
+}
+
+int sdgpu_last_kernel(sdgpu_ctx* ctx) { return ctx ? (ctx->lastKernelWasH2 ? 2 : 1) : 0; }
+
 int sdgpu_profile_enable(sdgpu_ctx* ctx, int on) {
   if (!ctx) return SDGPU_E_ARG;
   ctx->timeKernels = on != 0;

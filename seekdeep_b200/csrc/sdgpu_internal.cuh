@@ -99,6 +99,9 @@ struct sdgpu_ctx {
   double alignMs = 0;
   uint64_t alignLaunches = 0;
   uint64_t h2dBytes = 0, d2hBytes = 0;
+  // alignment kernel selection: 0 = automatic, 1 = int32 only, 2 = packed fp16 only (tests)
+  int forceKernel = 0;
+  bool lastKernelWasH2 = false;
   // bookkeeping
   uint64_t launches = 0, cells = 0;
   std::string err;

@@ -240,3 +240,63 @@ def test_all_vs_all_matches_oracle(oracle):
     si, sj = np.triu_indices(len(sub), 1)
     wsub = oracle.align_profile_batch(params, bases, q, offsets, sub[si], sub[sj], _abi.USING_QUALITY)
     assert np.array_equal(gsub["alnScore"], wsub["alnScore"]) and np.array_equal(gsub["hqMismatches"], wsub["hqMismatches"])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("pname", ["qluster", "asym", "countEnds", "stitch"])
+def test_both_forward_kernels_match_oracle(oracle, mode, pname):
+    """The int32 forward pass (mode 1) and the packed fp16 two-pairs-per-warp pass (mode 2) are both
+    exact: same scores, gap lists and errorProfiles as the oracle on ragged ACGT(N) inputs."""
+    rng = np.random.default_rng(1000 + mode)
+    alpha = np.frombuffer(b"ACGTACGTACGTACGTN", dtype=np.uint8)
+    seqs = []
+    for fam in range(4):
+        # 'asym' extends gaps at 2 per base: keep its fp16 value range exact by using shorter reads
+        root = H.rand_seq(rng, int(rng.integers(60, 150 if pname == "asym" else 330)), alpha)
+        seqs.append(root)
+        for _ in range(11):
+            seqs.append(H.mutate(rng, root, int(rng.integers(0, 6)), int(rng.integers(0, 2)), int(rng.integers(0, 2)), hp=True))
+    seqs += [H.rand_seq(rng, 1), H.rand_seq(rng, 2), H.rand_seq(rng, 3)]
+    quals = [H.rand_quals(rng, len(s)) for s in seqs]
+    bases, q, offsets = np.concatenate(seqs), np.concatenate(quals), np.zeros(len(seqs) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    n = 701  # odd: the packed kernel's last work item holds a single pair
+    refIdx = rng.integers(0, len(seqs), n).astype(np.uint32)
+    readIdx = rng.integers(0, len(seqs), n).astype(np.uint32)
+    params = H.params_for(pname)
+    with GpuAligner(params) as al:
+        al.set_kernel(mode)
+        al.upload_seqs(bases, q, offsets)
+        al.index_kmers(7, 2, True)
+        got, gg = al.align_profile(refIdx, readIdx, checkKmer=True, usingQuality=True, gapCap=40)
+        assert al.last_kernel() == mode
+    km = oracle.index_kmers(bases, offsets, None, 7, 2, True)
+    want, wg = oracle.align_profile_batch(params, bases, q, offsets, refIdx, readIdx, _abi.USING_QUALITY | _abi.CHECK_KMER,
+                                          kmaps=km, gapCap=40)
+    oracle.free_kmaps(km)
+    H.assert_comparisons_equal(got, want)
+    assert np.array_equal(gg, wg)
+
+
+def test_packed_kernel_refuses_out_of_range():
+    """fp16 exactness is a precondition, checked on the host: large scores / extra symbols fall back
+    to the int32 pass automatically and fail loudly when the packed pass is forced."""
+    from seekdeep_b200.scoring import SubstituteMatrix
+    rng = np.random.default_rng(5)
+    bases, quals, offsets, cnts, _, _ = H.make_store(rng, 8, 120)
+    idx = np.arange(8, dtype=np.uint32)
+    with GpuAligner(make_params(scoring=SubstituteMatrix.create_score_matrix(20, -20))) as al:
+        al.upload_seqs(bases, quals, offsets, cnts)
+        al.align_profile(idx, idx[::-1].copy())
+        assert al.last_kernel() == 1
+        al.set_kernel(2)
+        with pytest.raises(SdgpuError) as ei:
+            al.align_profile(idx, idx[::-1].copy())
+        assert ei.value.code == _abi.E_UNSUPPORTED
+    with GpuAligner(make_params()) as al:
+        al.upload_seqs(bases, quals, offsets, cnts)
+        al.align_profile(idx, idx[::-1].copy())
+        assert al.last_kernel() == 2
+        al.append_seqs(*pack_seqs(["ACGTRYACGT"], [np.full(10, 30, np.uint8)]))  # R, Y: beyond A,C,G,T,N
+        al.align_profile(idx, idx[::-1].copy())
+        assert al.last_kernel() == 1
