@@ -73,6 +73,15 @@ int sdq_cluster_seq(const sdq_result* r, uint32_t c, uint8_t* seq, uint8_t* qual
 /* final cluster index of every input read (UINT32_MAX: dropped as a small read) */
 int sdq_membership(const sdq_result* r, uint32_t* clusterOfRead);
 
+/* Many independent samples (one qluster each, like qlusterCmds.txt + runMultipleCommands,
+ * SeekDeepUtilsRunner.cpp:294-356) on ONE GPU: nWorkers host threads, each with its own ctx on
+ * `device`, pull samples from a shared queue, so one sample's host-only phases overlap another's
+ * alignment batches.  out[s] receives sample s's result (free each with sdq_free). */
+int sdq_run_many(int device, const sdgpu_params* params, const sdq_opts* opts, const sdq_iter_par* initPars,
+                 uint32_t nInit, const sdq_iter_par* pars, uint32_t nPars, uint32_t nSamples,
+                 const uint8_t* const* bases, const uint8_t* const* quals, const uint64_t* const* offsets,
+                 const uint32_t* nReads, uint32_t nWorkers, sdq_result** out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@
 //     stays the same, aligns only the newly absorbed members (one GPU batch per iteration, gap
 //     lists returned) and re-reads the consensus off the counters (integer sums: exact).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -28,6 +29,8 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -934,6 +937,59 @@ int sdq_membership(const sdq_result* r, uint32_t* clusterOfRead) {
   if (!r || !clusterOfRead) return SDGPU_E_ARG;
   std::memcpy(clusterOfRead, r->membership.data(), r->membership.size() * sizeof(uint32_t));
   return SDGPU_OK;
+}
+
+// Many independent samples on one GPU: `nWorkers` host threads, each with its own ctx (stream,
+// scratch, sequence store) on `device`, pull samples from a shared counter.  While one worker is
+// in a host-only phase (dedupe, the sequential pass, consensus, sorting) another one's alignment
+// batches keep the GPU busy.  Same model as the reference's runMultipleCommands over
+// qlusterCmds.txt (SeekDeepUtilsRunner.cpp:294-356): samples never interact.
+int sdq_run_many(int device, const sdgpu_params* params, const sdq_opts* opts, const sdq_iter_par* initPars, uint32_t nInit,
+                 const sdq_iter_par* pars, uint32_t nPars, uint32_t nSamples, const uint8_t* const* bases,
+                 const uint8_t* const* quals, const uint64_t* const* offsets, const uint32_t* nReads, uint32_t nWorkers,
+                 sdq_result** out) {
+  if (!params || !opts || !out || (nSamples && (!bases || !quals || !offsets || !nReads))) {
+    g_err = "sdq_run_many: null argument";
+    return SDGPU_E_ARG;
+  }
+  if (nWorkers == 0) nWorkers = 1;
+  if (nWorkers > nSamples) nWorkers = nSamples ? nSamples : 1;
+  for (uint32_t s = 0; s < nSamples; ++s) out[s] = nullptr;
+  std::atomic<uint32_t> next{0};
+  std::atomic<int> firstRc{0};
+  std::mutex errMutex;
+  std::string firstErr;
+  auto worker = [&]() {
+    sdgpu_ctx* ctx = nullptr;
+    int rc = sdgpu_create(device, params, &ctx);
+    if (rc) {
+      std::lock_guard<std::mutex> g(errMutex);
+      if (!firstRc.exchange(rc)) firstErr = sdgpu_last_error(nullptr);
+      return;
+    }
+    for (;;) {
+      const uint32_t s = next.fetch_add(1);
+      if (s >= nSamples || firstRc.load()) break;
+      rc = sdq_run(ctx, opts, initPars, nInit, pars, nPars, bases[s], quals[s], offsets[s], nReads[s], &out[s]);
+      if (rc) {
+        std::lock_guard<std::mutex> g(errMutex);
+        if (!firstRc.exchange(rc)) firstErr = g_err;  // g_err is thread-local: copy it out
+        break;
+      }
+    }
+    sdgpu_destroy(ctx);
+  };
+  std::vector<std::thread> threads;
+  for (uint32_t w = 0; w < nWorkers; ++w) threads.emplace_back(worker);
+  for (auto& t : threads) t.join();
+  if (firstRc.load()) {
+    for (uint32_t s = 0; s < nSamples; ++s) {
+      delete out[s];
+      out[s] = nullptr;
+    }
+    g_err = firstErr;
+  }
+  return firstRc.load();
 }
 
 }  // extern "C"

@@ -128,6 +128,59 @@ def qluster(aligner: GpuAligner, bases, quals, offsets, pars: QlusterPars = None
         lib.sdq_free(h)
 
 
+def _result_to_dict(lib, h, n, want_clusters):
+    st = StatsC()
+    lib.sdq_get_stats(h, C.byref(st))
+    res = {"stats": {k: getattr(st, k) for k, _ in StatsC._fields_}, "clusters": []}
+    if want_clusters:
+        for c in range(lib.sdq_num_clusters(h)):
+            ln = lib.sdq_cluster_len(h, c)
+            s = np.zeros(ln, np.uint8)
+            q = np.zeros(ln, np.uint8)
+            lib.sdq_cluster_seq(h, c, _ptr(s), _ptr(q))
+            res["clusters"].append((s.tobytes().decode(), q, lib.sdq_cluster_cnt(h, c)))
+    mem = np.zeros(n, np.uint32)
+    lib.sdq_membership(h, _ptr(mem))
+    res["membership"] = mem
+    return res
+
+
+def qluster_many(params, samples, device=0, nWorkers=2, pars: QlusterPars = None, iteratorMap: CollapseIterations = None,
+                 intialParameters: CollapseIterations = None, want_clusters=True):
+    """Many independent samples on one GPU (`sdq_run_many`): `samples` is a list of (bases, quals, offsets);
+    nWorkers host threads, each with its own ctx, overlap one sample's host phases with another's GPU batches."""
+    lib = _abi.load()
+    _bind(lib)
+    v = C.c_void_p
+    lib.sdq_run_many.restype = C.c_int
+    lib.sdq_run_many.argtypes = [C.c_int, C.POINTER(_abi.Params), C.POINTER(QlusterOptsC), v, C.c_uint32, v, C.c_uint32,
+                                 C.c_uint32, v, v, v, v, C.c_uint32, v]
+    pars = pars or QlusterPars()
+    iteratorMap = iteratorMap or CollapseIterations.gen_illumina_default_pars(100)
+    intialParameters = intialParameters or iteratorMap
+    opts = pars.to_c()
+    ip, nip = iter_pars_to_c(intialParameters)
+    pp, npp = iter_pars_to_c(iteratorMap)
+    keep = [(np.ascontiguousarray(b, np.uint8), np.ascontiguousarray(q, np.uint8), np.ascontiguousarray(o, np.uint64))
+            for b, q, o in samples]
+    n = len(keep)
+    bp = (C.c_void_p * n)(*[k[0].ctypes.data for k in keep])
+    qp = (C.c_void_p * n)(*[k[1].ctypes.data for k in keep])
+    op = (C.c_void_p * n)(*[k[2].ctypes.data for k in keep])
+    nr = (C.c_uint32 * n)(*[len(k[2]) - 1 for k in keep])
+    out = (C.c_void_p * n)()
+    rc = lib.sdq_run_many(device, C.byref(params), C.byref(opts), ip, nip, pp, npp, n, bp, qp, op, nr, nWorkers, out)
+    if rc != _abi.OK:
+        raise SdgpuError(rc, (lib.sdq_last_error() or b"").decode())
+    results = []
+    for s in range(n):
+        try:
+            results.append(_result_to_dict(lib, out[s], nr[s], want_clusters))
+        finally:
+            lib.sdq_free(out[s])
+    return results
+
+
 def shard_samples(nSamples, rank, world):
     """Static round-robin of independent samples over ranks (no data-path collective)."""
     return list(range(rank, nSamples, world))

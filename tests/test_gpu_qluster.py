@@ -82,3 +82,25 @@ def test_qluster_tiny_and_empty(oracle):
     with sd.GpuAligner(params) as al:
         got = sd.qluster(al, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint64))
     assert got["clusters"] == [] and got["stats"]["uniqueSeqs"] == 0
+
+
+def test_qluster_many_equals_single_runs(oracle):
+    """Several samples on one GPU through concurrent worker contexts give exactly the per-sample
+    results of separate runs (samples never interact, whatever the interleaving)."""
+    from seekdeep_b200.qluster import qluster_many
+    params = sd.make_params()
+    samples = []
+    for seed in (11, 12, 13, 14, 15):
+        rng = np.random.default_rng(seed)
+        haps = synth.make_haplotypes(rng, 5, 110 + seed, 1, 5)
+        seqs, quals, _ = synth.fast_reads(rng, haps, 600, 0.005)
+        samples.append(synth.pack(seqs, quals))
+    many = qluster_many(params, samples, nWorkers=3)
+    assert len(many) == len(samples)
+    with sd.GpuAligner(params) as al:
+        for got, (b, q, o) in zip(many, samples):
+            single = sd.qluster(al, b, q, o)
+            assert_same(got, single)
+    want = oracle.qluster(params, oracle_opts(sd.QlusterPars()), CollapseIterations.gen_illumina_default_pars(100).iters,
+                          CollapseIterations.gen_illumina_default_pars(100).iters, *samples[0])
+    assert_same(many[0], want)
