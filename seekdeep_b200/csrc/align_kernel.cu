@@ -58,6 +58,9 @@ struct AlignArgs {
   uint64_t slabBytes;  // per warp
   uint32_t ptrBytes;   // bytes of the pointer region in a slab
   uint32_t maxAln;     // capacity of each gapped string
+  uint32_t edgeOff;    // WIDE: byte offset of the block-edge buffers in a slab
+  uint32_t edgeLen;    // WIDE: entries per edge buffer
+  uint64_t blockWords; // WIDE: words of one column block's bit region
   uint32_t* work;      // [0] = next work item, [2..3] = cell counter (uint64)
   const sdgpu_iter_par* lines;  // par-file lines for the verdict mask (device)
   uint32_t nLines;
@@ -78,12 +81,14 @@ struct BitsI32 {
   static constexpr int CPW = 6;
   static constexpr int CW = (C + CPW - 1) / CPW;
   const unsigned* words;
+  size_t blockWords;  // words of one column block's bit region (reads wider than 32*C columns are strip-mined)
   __device__ __forceinline__ unsigned operator()(int i, int j) const {
-    const int lj = (j - 1) / C, c = (j - 1) - lj * C;
+    const int gj = (j - 1) / C, c = (j - 1) - gj * C;
+    const int blk = gj >> 5, lj = gj & 31;
     const int t = i + lj;
     const int wi = c / CPW, k = c - wi * CPW;
     const int inWord = (C - wi * CPW) < CPW ? (C - wi * CPW) : CPW;
-    const unsigned w = __ldcg(words + (size_t(t - 1) * CW + wi) * 32 + lj);
+    const unsigned w = __ldcg(words + size_t(blk) * blockWords + (size_t(t - 1) * CW + wi) * 32 + lj);
     const unsigned g = ~(w >> (5 * (inWord - 1 - k))) & 31u;  // g4 = first pushed
     return __brev(g) >> 27;
   }
@@ -422,9 +427,11 @@ __device__ __forceinline__ PairView viewOf(const AlignArgs& a, uint32_t pair) {
 }
 
 // =====================================================================================
-// int32 forward pass, one pair per warp
+// int32 forward pass, one pair per warp.  WIDE = reads wider than 32*C columns: the columns are
+// strip-mined in blocks of 32*C; lane 31 leaves its per-row toRight / toDiag in an edge buffer and
+// lane 0 of the next block picks them up instead of the closed-form column-0 boundary.
 // =====================================================================================
-template <int C>
+template <int C, bool WIDE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const AlignArgs a) {
   using Bits = BitsI32<C>;
   constexpr int CW = Bits::CW;
@@ -440,7 +447,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
   uint32_t* ptrWords = reinterpret_cast<uint32_t*>(slab);
   uint8_t* alnA = slab + a.ptrBytes;
   uint8_t* alnB = alnA + a.maxAln;
-  uint32_t* gapRecs = reinterpret_cast<uint32_t*>(alnB + a.maxAln);  // (colAbs, size, inA) triples
+  uint32_t* gapRecs = reinterpret_cast<uint32_t*>(alnB + a.maxAln);  // (colAbs, size, inA<<0 | pos<<1) triples
+  int2* edges = reinterpret_cast<int2*>(slab + a.edgeOff);           // WIDE: two ping-pong arrays of a.edgeLen entries
 
   const DevScoring& sc = a.sc;
   const int dInt = sc.go - sc.ge;
@@ -453,92 +461,108 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
     const PairView pv = viewOf(a, pair);
     const int la = pv.la, lb = pv.lb;
     const uint8_t *cA = pv.cA, *cB = pv.cB;
-
-    int U[C], T[C], dcol[C], gocol[C], colofs[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int j = lane * C + c + 1;
-      const int code = (j <= lb) ? int(cB[j - 1]) : 0;
-      colofs[c] = code * 4;
-      const int L0 = -sc.goLR - (j - 1) * sc.geLR;  // leftInherit of row 0
-      const bool lastCol = (j == lb);
-      gocol[c] = lastCol ? sc.goRQ : sc.go;
-      dcol[c] = lastCol ? (sc.goRQ - sc.geRQ) : dInt;
-      // keep the per-column penalties in registers (ptxas otherwise rematerialises the
-      // j == lb select in every cell: three extra ALU instructions per cell update)
-      asm volatile("" : "+r"(gocol[c]), "+r"(dcol[c]));
-      U[c] = L0 - gocol[c];  // upInherit of row 1 (njhseq's i == 1 case)
-      T[c] = L0;             // feeds diagInherit of row 1, column j+1
-    }
-    int outT = T[C - 1], outR = 0;
-    int prevRecvT = __shfl_up_sync(FULL, outT, 1);
-    const int nLanes = (lb + C - 1) / C;
-    const int steps = la + nLanes - 1;
-    int aCode = (lane == 0) ? int(cA[0]) : 0;  // base of the row this lane works on at t = 1
-    for (int t = 1; t <= steps; ++t) {
-      const int recvR = __shfl_up_sync(FULL, outR, 1);
-      const int recvT = __shfl_up_sync(FULL, outT, 1);
-      const int i = t - lane;
-      const int iNext = i + 1;  // prefetch next row's base
-      const int aNext = (iNext >= 1 && iNext <= la) ? int(cA[iNext - 1]) : 0;
-      if (lane < nLanes && i >= 1 && i <= la) {
-        const bool lastRow = (i == la);
-        const int gorow = lastRow ? sc.goRR : sc.go;
-        const int drow = lastRow ? (sc.goRR - sc.geRR) : dInt;
-        int Lin, Tin;
-        if (lane == 0) {
-          const int bnd = -sc.goLQ - (i - 1) * sc.geLQ;  // upInherit of column 0
-          Lin = bnd - gorow;                             // njhseq's j == 1 case
-          Tin = (i == 1) ? 0 : bnd + sc.geLQ;
-        } else {
-          Lin = recvR;
-          Tin = prevRecvT;
-        }
-        const char* rowTab = sTabBytes + aCode * (SDGPU_MAX_SYMBOLS * 4);
-        uint32_t w[CW];
-#pragma unroll
-        for (int x = 0; x < CW; ++x) w[x] = 0;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int s = *reinterpret_cast<const int*>(rowTab + colofs[c]);
-          const int D = Tin + s;
-          Tin = T[c];
-          const int Uc = U[c];
-          uint32_t acc = w[c / Bits::CPW];
-          // maxima on the ALU pipe (two of them fused add+max, VIADDMNMX), differences on the
-          // FMA pipe (IMAD.IADD); the shifted differences reuse d1/d2 instead of the sums
-          const int W = max(Lin, D);
-          const int d1 = Lin - D;
-          acc = __funnelshift_l(uint32_t(d1), acc, 1);
-          T[c] = max(Uc, W);
-          const int d2 = Uc - W;
-          acc = __funnelshift_l(uint32_t(d2), acc, 1);
-          U[c] = __viaddmax_s32(Uc, dcol[c], W) - gocol[c];
-          acc = __funnelshift_l(uint32_t(d2 + dcol[c]), acc, 1);
-          const int tt = __viaddmax_s32(Lin, drow, D);
-          acc = __funnelshift_l(uint32_t(d1 + drow), acc, 1);
-          Lin = max(Uc, tt) - gorow;
-          acc = __funnelshift_l(uint32_t(Uc - tt), acc, 1);
-          w[c / Bits::CPW] = acc;
-        }
-        outR = Lin;
-        outT = T[C - 1];
-        uint32_t* dst = ptrWords + size_t(t - 1) * (CW * 32) + lane;
-#pragma unroll
-        for (int x = 0; x < CW; ++x) dst[x * 32] = w[x];
-      }
-      prevRecvT = recvT;
-      aCode = aNext;
-    }
-    // score = toDiag of the bottom-right cell
-    const int lastLane = (lb - 1) / C, lastC = (lb - 1) - lastLane * C;
+    const int nBlocks = WIDE ? (lb + 32 * C - 1) / (32 * C) : 1;
     int score = 0;
+
+    for (int blk = 0; blk < nBlocks; ++blk) {
+      const int jBase = WIDE ? blk * 32 * C : 0;
+      int U[C], T[C], dcol[C], gocol[C], colofs[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-      if (c == lastC) score = T[c];
-    score = __shfl_sync(FULL, score, lastLane);
-    __syncwarp();
-    finishPair<false>(a, Bits{ptrWords}, viewOf(a, pair), score, alnA, alnB, gapRecs, sTab, lane);
+      for (int c = 0; c < C; ++c) {
+        const int j = jBase + lane * C + c + 1;
+        const int code = (j <= lb) ? int(cB[j - 1]) : 0;
+        colofs[c] = code * 4;
+        const int L0 = -sc.goLR - (j - 1) * sc.geLR;  // leftInherit of row 0
+        const bool lastCol = (j == lb);
+        gocol[c] = lastCol ? sc.goRQ : sc.go;
+        dcol[c] = lastCol ? (sc.goRQ - sc.geRQ) : dInt;
+        // keep the per-column penalties in registers (ptxas otherwise rematerialises the
+        // j == lb select in every cell: three extra ALU instructions per cell update)
+        asm volatile("" : "+r"(gocol[c]), "+r"(dcol[c]));
+        U[c] = L0 - gocol[c];  // upInherit of row 1 (njhseq's i == 1 case)
+        T[c] = L0;             // feeds diagInherit of row 1, column j+1
+      }
+      int outT = T[C - 1], outR = 0;
+      int prevRecvT = __shfl_up_sync(FULL, outT, 1);
+      const int colsHere = WIDE ? min(lb - jBase, 32 * C) : lb;
+      const int nLanes = (colsHere + C - 1) / C;
+      const int steps = la + nLanes - 1;
+      const int2* edgeIn = edges + size_t((blk + 1) & 1) * a.edgeLen;  // written by the previous block
+      int2* edgeOut = edges + size_t(blk & 1) * a.edgeLen;
+      const bool feedNext = WIDE && (blk + 1 < nBlocks);
+      uint32_t* blkWords = ptrWords + (WIDE ? size_t(blk) * a.blockWords : 0);
+      int aCode = (lane == 0) ? int(cA[0]) : 0;  // base of the row this lane works on at t = 1
+      for (int t = 1; t <= steps; ++t) {
+        const int recvR = __shfl_up_sync(FULL, outR, 1);
+        const int recvT = __shfl_up_sync(FULL, outT, 1);
+        const int i = t - lane;
+        const int iNext = i + 1;  // prefetch next row's base
+        const int aNext = (iNext >= 1 && iNext <= la) ? int(cA[iNext - 1]) : 0;
+        if (lane < nLanes && i >= 1 && i <= la) {
+          const bool lastRow = (i == la);
+          const int gorow = lastRow ? sc.goRR : sc.go;
+          const int drow = lastRow ? (sc.goRR - sc.geRR) : dInt;
+          int Lin, Tin;
+          if (lane == 0) {
+            if (WIDE && blk > 0) {
+              Lin = edgeIn[i].x;                                              // toRight(i, jBase)
+              Tin = (i == 1) ? (-sc.goLR - (jBase - 1) * sc.geLR) : edgeIn[i - 1].y;  // toDiag(i-1, jBase)
+            } else {
+              const int bnd = -sc.goLQ - (i - 1) * sc.geLQ;  // upInherit of column 0
+              Lin = bnd - gorow;                             // njhseq's j == 1 case
+              Tin = (i == 1) ? 0 : bnd + sc.geLQ;
+            }
+          } else {
+            Lin = recvR;
+            Tin = prevRecvT;
+          }
+          const char* rowTab = sTabBytes + aCode * (SDGPU_MAX_SYMBOLS * 4);
+          uint32_t w[CW];
+#pragma unroll
+          for (int x = 0; x < CW; ++x) w[x] = 0;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int s = *reinterpret_cast<const int*>(rowTab + colofs[c]);
+            const int D = Tin + s;
+            Tin = T[c];
+            const int Uc = U[c];
+            uint32_t acc = w[c / Bits::CPW];
+            // maxima on the ALU pipe (two of them fused add+max, VIADDMNMX), differences on the
+            // FMA pipe (IMAD.IADD); the shifted differences reuse d1/d2 instead of the sums
+            const int W = max(Lin, D);
+            const int d1 = Lin - D;
+            acc = __funnelshift_l(uint32_t(d1), acc, 1);
+            T[c] = max(Uc, W);
+            const int d2 = Uc - W;
+            acc = __funnelshift_l(uint32_t(d2), acc, 1);
+            U[c] = __viaddmax_s32(Uc, dcol[c], W) - gocol[c];
+            acc = __funnelshift_l(uint32_t(d2 + dcol[c]), acc, 1);
+            const int tt = __viaddmax_s32(Lin, drow, D);
+            acc = __funnelshift_l(uint32_t(d1 + drow), acc, 1);
+            Lin = max(Uc, tt) - gorow;
+            acc = __funnelshift_l(uint32_t(Uc - tt), acc, 1);
+            w[c / Bits::CPW] = acc;
+          }
+          outR = Lin;
+          outT = T[C - 1];
+          uint32_t* dst = blkWords + size_t(t - 1) * (CW * 32) + lane;
+#pragma unroll
+          for (int x = 0; x < CW; ++x) dst[x * 32] = w[x];
+          if (feedNext && lane == 31) edgeOut[i] = make_int2(outR, outT);
+        }
+        prevRecvT = recvT;
+        aCode = aNext;
+      }
+      if (blk + 1 == nBlocks) {  // score = toDiag of the bottom-right cell
+        const int lastLane = ((lb - 1) / C) & 31, lastC = (lb - 1) % C;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (c == lastC) score = T[c];
+        score = __shfl_sync(FULL, score, lastLane);
+      }
+      __syncwarp();
+    }
+    finishPair<false>(a, Bits{ptrWords, size_t(a.blockWords)}, viewOf(a, pair), score, alnA, alnB, gapRecs, sTab, lane);
   }
 }
 
@@ -691,7 +715,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernelH2(const
 
 template <class Kernel>
 int launchKernel(sdgpu_ctx* ctx, Kernel kernel, AlignArgs& args, uint32_t workItems, int CW, uint32_t maxLenA,
-                 uint32_t maxLenB) {
+                 uint32_t maxLenB, uint32_t nBlocks = 1) {
   int ctasPerSM = 0;
   SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kernel, WARPS_PER_CTA * 32, 0));
   if (ctasPerSM < 1) ctasPerSM = 1;
@@ -699,11 +723,21 @@ int launchKernel(sdgpu_ctx* ctx, Kernel kernel, AlignArgs& args, uint32_t workIt
   const uint32_t needCtas = (workItems + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   if (grid > needCtas) grid = needCtas;
   const uint64_t maxSteps = uint64_t(maxLenA) + 31;
-  args.ptrBytes = uint32_t(maxSteps * CW * 128);
+  const uint64_t blockBytes = maxSteps * CW * 128;
+  if (blockBytes * nBlocks >= (1ull << 32)) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "alignment too large (traceback bits >= 4 GiB per pair)");
+  args.blockWords = blockBytes / 4;
+  args.ptrBytes = uint32_t(blockBytes * nBlocks);
   args.maxAln = (maxLenA + maxLenB + 15) & ~15u;
   uint64_t slab = uint64_t(args.ptrBytes) + 2ull * args.maxAln + 12ull * (uint64_t(args.maxAln) + 2);
+  slab = (slab + 15) & ~15ull;
+  args.edgeOff = uint32_t(slab);
+  args.edgeLen = maxLenA + 2;
+  if (nBlocks > 1) slab += 2ull * args.edgeLen * sizeof(int2);
   slab = (slab + 255) & ~255ull;
   args.slabBytes = slab;
+  // wide alignments: keep the resident slabs within a fixed HBM budget by running fewer warps
+  const uint64_t budget = 48ull << 30;
+  if (slab * grid * WARPS_PER_CTA > budget) grid = uint32_t(std::max<uint64_t>(1, budget / (slab * WARPS_PER_CTA)));
   int rc = sd_ensure_scratch(ctx, slab * grid * WARPS_PER_CTA);
   if (rc) return rc;
   args.scratch = ctx->dScratch;
@@ -730,7 +764,12 @@ int launchKernel(sdgpu_ctx* ctx, Kernel kernel, AlignArgs& args, uint32_t workIt
 
 template <int C>
 int launchI32(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
-  return launchKernel(ctx, alignProfileKernel<C>, args, args.nPairs, BitsI32<C>::CW, maxLenA, maxLenB);
+  return launchKernel(ctx, alignProfileKernel<C, false>, args, args.nPairs, BitsI32<C>::CW, maxLenA, maxLenB);
+}
+int launchWide(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
+  constexpr int C = 16;
+  const uint32_t nBlocks = (maxLenB + 32 * C - 1) / (32 * C);
+  return launchKernel(ctx, alignProfileKernel<C, true>, args, args.nPairs, BitsI32<C>::CW, maxLenA, maxLenB, nBlocks);
 }
 template <int C>
 int launchH2(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
@@ -781,8 +820,11 @@ int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dRe
   args.passOut = dPassOut;
   if (dPassOut && ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
   const uint32_t needC = (maxLenB + 31) / 32;
-  if (needC > 16)
-    return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "read longer than 512 bases: column strip-mining not implemented yet");
+  if (needC > 16) {  // reads wider than 512 columns: strip-mined int32 pass
+    if (ctx->forceKernel == 2) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "packed fp16 alignment kernel not applicable to this launch");
+    ctx->lastKernelWasH2 = false;
+    return launchWide(ctx, args, maxLenA, maxLenB);
+  }
   const uint32_t C = needC <= 4 ? 4 : needC <= 6 ? 6 : needC <= 8 ? 8 : needC <= 10 ? 10 : needC <= 13 ? 13 : 16;
   // packed fp16 path: bases within A,C,G,T,N (codes 0..4), exact-integer range, enough pairs to pair up
   const bool useH2 = ctx->forceKernel != 1 && ctx->usedSym <= H2_SYMS && nPairs >= 2 && halfRangeOk(ctx, maxLenA + 1, 32 * C);

@@ -150,13 +150,10 @@ def test_append_and_errors():
         with pytest.raises(SdgpuError) as ei:
             al.align_profile([0], [1], checkKmer=True)
         assert ei.value.code == _abi.E_STATE
-        long = "ACGT" * 200  # 800 columns: beyond the current strip limit -> loud, not silent
+        long = "ACGT" * 200  # 800 columns: strip-mined in two column blocks
         al.append_seqs(*pack_seqs([long], [np.full(800, 30, np.uint8)]))
-        with pytest.raises(SdgpuError) as ei:
-            al.align_profile([0], [3])
-        assert ei.value.code == _abi.E_UNSUPPORTED
-        out = al.align_profile([3], [0])  # long ref (rows) is fine
-        assert out["alnLen"][0] == 800
+        out = al.align_profile([0, 3], [3, 0])
+        assert out["alnLen"][0] == 800 and out["alnLen"][1] == 800
 
 
 def test_full_size_properties():
@@ -300,3 +297,32 @@ def test_packed_kernel_refuses_out_of_range():
         al.append_seqs(*pack_seqs(["ACGTRYACGT"], [np.full(10, 30, np.uint8)]))  # R, Y: beyond A,C,G,T,N
         al.align_profile(idx, idx[::-1].copy())
         assert al.last_kernel() == 1
+
+
+def test_wide_reads_strip_mined(oracle):
+    """Reads wider than 512 columns run through the strip-mined int32 pass (column blocks of 512 with
+    edge buffers between them): same scores, gap lists and errorProfiles as the oracle."""
+    rng = np.random.default_rng(77)
+    seqs = []
+    for length in (530, 1024, 1025, 1500):
+        root = H.rand_seq(rng, length)
+        seqs.append(root)
+        for _ in range(3):
+            seqs.append(H.mutate(rng, root, int(rng.integers(0, 12)), int(rng.integers(0, 3)), int(rng.integers(0, 3)), hp=True))
+    seqs.append(H.rand_seq(rng, 40))
+    seqs.append(H.rand_seq(rng, 700))
+    quals = [H.rand_quals(rng, len(s)) for s in seqs]
+    bases, q, offsets = np.concatenate(seqs), np.concatenate(quals), np.zeros(len(seqs) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    n = len(seqs)
+    refIdx, readIdx = np.meshgrid(np.arange(n, dtype=np.uint32), np.arange(n, dtype=np.uint32))
+    refIdx, readIdx = refIdx.ravel(), readIdx.ravel()
+    for pname in ("qluster", "asym"):
+        params = H.params_for(pname)
+        with GpuAligner(params) as al:
+            al.upload_seqs(bases, q, offsets)
+            got, gg = al.align_profile(refIdx, readIdx, gapCap=64)
+            assert al.last_kernel() == 1
+        want, wg = oracle.align_profile_batch(params, bases, q, offsets, refIdx, readIdx, _abi.USING_QUALITY, gapCap=64)
+        H.assert_comparisons_equal(got, want)
+        assert np.array_equal(gg, wg)
