@@ -40,6 +40,10 @@
 namespace {
 
 thread_local std::string g_err;
+// Pairs per asynchronous alignment chunk (0 = default 1 M).  Workers that share a GPU use small
+// chunks: kernels are persistent (they hold every SM until their chunk is done), so another
+// worker's latency-sensitive small batches can only slip in at chunk boundaries.
+thread_local uint32_t g_chunkPairs = 0;
 
 double nowSec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -285,7 +289,7 @@ class Runner {
     int cur = 0;
     int rc = 0;
     uint32_t chunk;
-    PassPipe(Runner& r, std::vector<Clus>& c, uint32_t chunkPairs = BATCH / 2) : R(r), cs(c), chunk(chunkPairs) {}
+    PassPipe(Runner& r, std::vector<Clus>& c) : R(r), cs(c), chunk(g_chunkPairs ? g_chunkPairs : BATCH / 2) {}
     void push(uint32_t clusStore, uint32_t readStore, uint32_t ownerPos) {
       a[cur].push_back(clusStore);
       b[cur].push_back(readStore);
@@ -960,6 +964,7 @@ int sdq_run_many(int device, const sdgpu_params* params, const sdq_opts* opts, c
   std::mutex errMutex;
   std::string firstErr;
   auto worker = [&]() {
+    g_chunkPairs = nWorkers > 1 ? (1u << 16) : 0u;
     sdgpu_ctx* ctx = nullptr;
     int rc = sdgpu_create(device, params, &ctx);
     if (rc) {

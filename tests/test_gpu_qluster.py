@@ -104,3 +104,32 @@ def test_qluster_many_equals_single_runs(oracle):
     want = oracle.qluster(params, oracle_opts(sd.QlusterPars()), CollapseIterations.gen_illumina_default_pars(100).iters,
                           CollapseIterations.gen_illumina_default_pars(100).iters, *samples[0])
     assert_same(many[0], want)
+
+
+def test_config1_full_size_properties():
+    """BASELINE config 1 at full size (10k reads x 250 bp, 20 haplotypes), without the oracle:
+    size-independent properties of the collapse — conservation of reads, determinism, exact recovery
+    of the abundant haplotypes, consensus/membership consistency."""
+    haps, seqs, quals, which = synth.config1()
+    bases, q, offsets = synth.pack(seqs, quals)
+    with sd.GpuAligner(sd.make_params()) as al:
+        a = sd.qluster(al, bases, q, offsets)
+        b = sd.qluster(al, bases, q, offsets)
+    assert np.array_equal(a["membership"], b["membership"]) and len(a["clusters"]) == len(b["clusters"])
+    for (s1, q1, c1), (s2, q2, c2) in zip(a["clusters"], b["clusters"]):
+        assert s1 == s2 and c1 == c2 and np.array_equal(q1, q2)
+    n = len(seqs)
+    mem = a["membership"]
+    assert mem.max() < len(a["clusters"]) and (mem != np.uint32(0xFFFFFFFF)).all()
+    counts = np.bincount(mem, minlength=len(a["clusters"]))
+    assert counts.sum() == n
+    assert [int(c) for _, _, c in a["clusters"]] == counts.tolist()          # cnt == members
+    assert counts.tolist() == sorted(counts.tolist(), reverse=True)          # sorted by total count
+    hs = {h.tobytes().decode(): k for k, h in enumerate(haps)}
+    big = [(s, c) for s, _, c in a["clusters"] if c >= 0.01 * n]
+    assert len(big) >= 15 and all(s in hs for s, _ in big)                   # abundant clusters are true haplotypes
+    # reads assigned to an abundant cluster overwhelmingly come from that haplotype
+    for ci, (s, _) in enumerate(big):
+        src = which[mem == ci]
+        assert (src == hs[s]).mean() > 0.97
+    assert a["stats"]["uniqueSeqs"] == len({x.tobytes() for x in seqs})
