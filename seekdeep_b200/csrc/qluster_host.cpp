@@ -202,6 +202,31 @@ bool clusLess(const Clus& a, const Clus& b) {  // readVecSorter "totalCount"
   return a.firstId < b.firstId;
 }
 
+// The working set of clusters in sorted order.  A Clus is heavy (strings, vectors, a verdict row),
+// so the storage never moves (one pool per run) and sorting / dropping only shuffles pointers.
+class ClusVec {
+ public:
+  struct Iter {
+    Clus* const* p;
+    Clus& operator*() const { return **p; }
+    Iter& operator++() {
+      ++p;
+      return *this;
+    }
+    bool operator!=(const Iter& o) const { return p != o.p; }
+  };
+  Clus& operator[](size_t i) { return *v_[i]; }
+  const Clus& operator[](size_t i) const { return *v_[i]; }
+  size_t size() const { return v_.size(); }
+  void push_back(Clus* c) { v_.push_back(c); }
+  Iter begin() const { return Iter{v_.data()}; }
+  Iter end() const { return Iter{v_.data() + v_.size()}; }
+  std::vector<Clus*>& ptrs() { return v_; }
+
+ private:
+  std::vector<Clus*> v_;
+};
+
 bool sameLine(const sdq_iter_par& a, const sdq_iter_par& b) {  // thresholds only: stopCheck/smallCutoff do not affect verdicts
   return a.oneBaseIndel == b.oneBaseIndel && a.twoBaseIndel == b.twoBaseIndel && a.largeBaseIndel == b.largeBaseIndel &&
          a.hqMismatches == b.hqMismatches && a.lqMismatches == b.lqMismatches && a.lowKmerMismatches == b.lowKmerMismatches &&
@@ -283,13 +308,13 @@ class Runner {
   // verdict masks into the reads' rows and lists chunk k+1.
   struct PassPipe {
     Runner& R;
-    std::vector<Clus>& cs;
+    ClusVec& cs;
     std::vector<uint32_t> a[2], b[2], owner[2];
     bool inflight[2] = {false, false};
     int cur = 0;
     int rc = 0;
     uint32_t chunk;
-    PassPipe(Runner& r, std::vector<Clus>& c) : R(r), cs(c), chunk(g_chunkPairs ? g_chunkPairs : BATCH / 2) {}
+    PassPipe(Runner& r, ClusVec& c) : R(r), cs(c), chunk(g_chunkPairs ? g_chunkPairs : BATCH / 2) {}
     void push(uint32_t clusStore, uint32_t readStore, uint32_t ownerPos) {
       a[cur].push_back(clusStore);
       b[cur].push_back(readStore);
@@ -339,7 +364,7 @@ class Runner {
   };
 
   // njhseq collapser::collapseWithParameters + findMatch for one par-file line
-  int collapseWithParameters(std::vector<Clus>& cs, const sdq_iter_par& it, int line) {
+  int collapseWithParameters(ClusVec& cs, const sdq_iter_par& it, int line) {
     ++serial;
     size_t alive = 0;
     for (const Clus& c : cs) alive += !c.remove;
@@ -447,7 +472,7 @@ class Runner {
   }
 
   // baseCluster::calculateConsensus for every cluster that absorbed reads, one GPU batch.
-  int calculateConsensusBatch(std::vector<Clus>& cs) {
+  int calculateConsensusBatch(ClusVec& cs) {
     struct Job {
       uint32_t clus;
       size_t firstPair, firstMember;
@@ -661,31 +686,29 @@ class Runner {
   }
 
   // drop absorbed clusters, then readVecSorter "totalCount" (index sort: a Clus is heavy to move)
-  void dropRemovedAndSort(std::vector<Clus>& cs) {
+  void dropRemovedAndSort(ClusVec& cs) {
     const double t0 = nowSec();
-    cs.erase(std::remove_if(cs.begin(), cs.end(), [](const Clus& c) { return c.remove; }), cs.end());
+    std::vector<Clus*>& v = cs.ptrs();
+    v.erase(std::remove_if(v.begin(), v.end(), [](const Clus* c) { return c->remove; }), v.end());
     struct Key {  // the two leading sort keys packed contiguously; sequence / first id only on ties
       double cnt, avgErr;
-      uint32_t idx;
+      Clus* c;
     };
-    std::vector<Key> keys(cs.size());
-    for (uint32_t i = 0; i < keys.size(); ++i) keys[i] = Key{cs[i].cnt, cs[i].avgErr, i};
-    auto less = [&](const Key& a, const Key& b) {
+    std::vector<Key> keys(v.size());
+    for (size_t i = 0; i < v.size(); ++i) keys[i] = Key{v[i]->cnt, v[i]->avgErr, v[i]};
+    auto less = [](const Key& a, const Key& b) {
       if (a.cnt != b.cnt) return a.cnt > b.cnt;
       if (a.avgErr != b.avgErr) return a.avgErr < b.avgErr;
-      return clusLess(cs[a.idx], cs[b.idx]);
+      return clusLess(*a.c, *b.c);
     };
     if (!std::is_sorted(keys.begin(), keys.end(), less)) {
       std::sort(keys.begin(), keys.end(), less);
-      std::vector<Clus> tmp;
-      tmp.reserve(cs.size());
-      for (const Key& k : keys) tmp.push_back(std::move(cs[k.idx]));
-      cs.swap(tmp);
+      for (size_t i = 0; i < v.size(); ++i) v[i] = keys[i].c;
     }
     tSort += nowSec() - t0;
   }
 
-  int runFullClustering(std::vector<Clus>& cs, const sdq_iter_par* its, uint32_t nIts) {
+  int runFullClustering(ClusVec& cs, const sdq_iter_par* its, uint32_t nIts) {
     orderDirty = true;
     for (uint32_t i = 0; i < nIts; ++i) {
       if (orderDirty) dropRemovedAndSort(cs);  // counts / members only change when something merged
@@ -704,7 +727,7 @@ class Runner {
     return 0;
   }
 
-  int buildIndex(std::vector<Clus>& cs) {  // indexKmers over the current clusters
+  int buildIndex(ClusVec& cs) {  // indexKmers over the current clusters
     const double t0 = nowSec();
     struct Tick {
       double& acc;
@@ -736,7 +759,8 @@ class Runner {
 }  // namespace
 
 struct sdq_result {
-  std::vector<Clus> clusters;
+  std::vector<Clus> pool;  // storage of every cluster object of the run
+  ClusVec clusters;        // the final clusters, sorted
   std::vector<uint32_t> membership;
   sdq_stats stats;
 };
@@ -858,9 +882,11 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     R.storeSize = nU;
     if (sdgpu_timer_start(ctx)) return bail(R.fail(SDGPU_E_CUDA));  // inputs are resident from here on
   }
-  std::vector<Clus> clusters(nU);
+  res->pool.resize(nU);  // never resized again: ClusVec holds pointers into it
+  ClusVec clusters;
   for (uint32_t u = 0; u < nU; ++u) {
-    Clus& c = clusters[u];
+    Clus& c = res->pool[u];
+    clusters.push_back(&c);
     c.seq = R.uniq[u].seq;
     c.qual = R.uniq[u].qual;
     c.cnt = R.uniq[u].cnt;
@@ -873,15 +899,15 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   R.dropRemovedAndSort(clusters);     // clusterDown.cpp:389
   int rc = R.buildIndex(clusters);    // clusterDown.cpp:412-417
   if (rc) return bail(rc);
-  std::vector<Clus> singletons;
+  ClusVec singletons;
   if (!opts->startWithSingles) {  // clusterDown.cpp:467-484
-    std::vector<Clus> keep;
-    for (Clus& c : clusters) (c.cnt <= 1.01 ? singletons : keep).push_back(std::move(c));
-    clusters.swap(keep);
+    ClusVec keep;
+    for (Clus& c : clusters) (c.cnt <= 1.01 ? singletons : keep).push_back(&c);
+    clusters.ptrs().swap(keep.ptrs());
   }
   if ((rc = R.runFullClustering(clusters, initPars, nInit))) return bail(rc);  // :488-490
   if (!opts->startWithSingles && !opts->leaveOutSinglets) {                  // :492-499
-    for (Clus& c : singletons) clusters.push_back(std::move(c));
+    for (Clus& c : singletons) clusters.push_back(&c);
     if ((rc = R.runFullClustering(clusters, pars, nPars))) return bail(rc);
   }
   if (!opts->dontRecalLowFreq) {  // :502-519
@@ -899,7 +925,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   float msResident = 0;
   if (sdgpu_timer_stop(ctx, &msResident)) return bail(R.fail(SDGPU_E_CUDA));
   if (sdgpu_counters(ctx, &launches1, &cells1)) return bail(R.fail(SDGPU_E_CUDA));
-  res->clusters = std::move(clusters);
+  res->clusters = clusters;
   R.st.msResident = msResident;
   res->stats = R.st;
   res->stats.inputReads = n;
