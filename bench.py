@@ -160,7 +160,8 @@ def kmer_roofline(al, bases, quals, offsets, peaks):
     out["compare"] = {"kernel": "kmerCompareKernel(reads x 100 clusters)", "ms": bestc, "pairs_per_s": nR * nC / (bestc * 1e-3),
                       "achieved": algoc / (bestc * 1e-3) / 1e9, "unit": "GB/s", "frac": algoc / (bestc * 1e-3) / 1e9 / peak,
                       "algorithmic_bytes": algoc,
-                      "note": "cluster-side reuse makes this form L1/L2- and ALU-bound (4 KB of profile reads per pair from cache), not HBM-bound"}
+                      "note": "cluster tile in shared memory, each read profile fetched from HBM once: HBM traffic is the compulsory "
+                              "bytes, the kernel is bound by min/add SIMD on the ALU pipe + LDS, not by HBM"}
     return out
 
 

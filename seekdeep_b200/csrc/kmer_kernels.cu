@@ -316,8 +316,103 @@ int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   return SDGPU_OK;
 }
 
+// reads x clusters grid: a tile of cluster profiles sits in shared memory, every read profile is
+// fetched from HBM once per tile into registers (VPL uint4 per lane) and compared against the whole
+// tile; results for 32 clusters leave as one coalesced line.  HBM traffic is the compulsory
+// (R + C) * P + R * C * 12 bytes; the work is min/add SIMD on the ALU pipe + LDS.
+template <int VPL>
+__global__ void __launch_bounds__(512) kmerCompareGridKernel(DevSeqs seqs, const uint16_t* profiles, uint32_t profSize,
+                                                             uint32_t kLen, const uint32_t* reads, uint32_t nReads,
+                                                             const uint32_t* clusters, uint32_t nClusters, uint32_t tileC,
+                                                             uint32_t* sharedOut, double* fracOut) {
+  extern __shared__ uint4 sTile[];  // tileC * vecs
+  const uint32_t vecs = profSize / 8;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (uint32_t c0 = 0; c0 < nClusters; c0 += tileC) {
+    const uint32_t nc = min(tileC, nClusters - c0);
+    __syncthreads();
+    for (uint32_t x = threadIdx.x; x < nc * vecs; x += blockDim.x) {
+      const uint32_t c = x / vecs, v = x - c * vecs;
+      sTile[x] = __ldg(reinterpret_cast<const uint4*>(profiles + size_t(clusters[c0 + c]) * profSize) + v);
+    }
+    __syncthreads();
+    for (uint32_t r = blockIdx.x * warps + warp; r < nReads; r += gridDim.x * warps) {
+      const uint32_t ir = reads[r];
+      const uint4* pr = reinterpret_cast<const uint4*>(profiles + size_t(ir) * profSize);
+      uint4 mine[VPL];
+#pragma unroll
+      for (int x = 0; x < VPL; ++x) mine[x] = __ldg(pr + lane + 32 * x);
+      const uint32_t lr = uint32_t(seqs.offsets[ir + 1] - seqs.offsets[ir]);
+      for (uint32_t g = 0; g < nc; g += 32) {  // 32 clusters at a time: 32 independent partial sums per lane
+        uint32_t part[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          uint32_t acc = 0;
+          if (g + c < nc) {
+            const uint4* pc = sTile + size_t(g + c) * vecs;
+#pragma unroll
+            for (int x = 0; x < VPL; ++x) acc = minSum8(mine[x], pc[lane + 32 * x], acc);
+          }
+          part[c] = (acc & 0xffffu) + (acc >> 16);
+        }
+        // transpose-reduce: 31 shuffles turn 32 per-lane partials into one total per lane
+        // (lane L ends up with the sum for cluster g + L)
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const uint32_t send = upper ? part[i] : part[i + off];
+            const uint32_t keepv = upper ? part[i + off] : part[i];
+            part[i] = keepv + __shfl_xor_sync(FULL, send, off);
+          }
+        }
+        const uint32_t cc = g + lane;
+        if (cc < nc) {  // 32 results -> one coalesced write
+          const uint32_t ic = clusters[c0 + cc];
+          const uint32_t lc = uint32_t(seqs.offsets[ic + 1] - seqs.offsets[ic]);
+          const uint32_t minLen = lr < lc ? lr : lc;
+          const size_t o = size_t(r) * nClusters + c0 + cc;
+          sharedOut[o] = part[0];
+          fracOut[o] = (minLen >= kLen) ? double(part[0]) / double(minLen - kLen + 1) : 0.0;
+        }
+      }
+    }
+  }
+}
+
+template <int VPL>
+static int gridLaunch(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nReads, const uint32_t* dClusters,
+                      uint32_t nClusters, uint32_t* dShared, double* dFrac) {
+  const size_t profBytes = size_t(ctx->profSize) * 2;
+  uint32_t tileC = uint32_t((200u << 10) / profBytes);
+  if (tileC > nClusters) tileC = nClusters;
+  const size_t smem = size_t(tileC) * profBytes;
+  SD_CUDA(ctx, cudaFuncSetAttribute(kmerCompareGridKernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const uint32_t ctasPerSM = smem > (100u << 10) ? 1 : 2;
+  // one CTA per SM when the tile fills shared memory: make it 16 warps to keep the ALU pipe fed
+  kmerCompareGridKernel<VPL><<<ctx->numSMs * ctasPerSM, ctasPerSM == 1 ? 512 : 256, smem, ctx->stream>>>(
+      sd_dev_seqs(ctx), ctx->dProfiles, ctx->profSize, ctx->profK, dReads, nReads, dClusters, nClusters, tileC, dShared, dFrac);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  return SDGPU_OK;
+}
+
 static int compareLaunch(sdgpu_ctx* ctx, const uint32_t* dA, const uint32_t* dB, uint64_t nPairs, uint32_t nCols,
                          uint32_t* dShared, double* dFrac) {
+  if (nCols) {  // dense grid: use the tiled kernel when a profile splits evenly over the lanes
+    const uint32_t vecs = ctx->profSize / 8, nReads = uint32_t(nPairs / nCols);
+    if (vecs % 32 == 0 && size_t(ctx->profSize) * 2 <= (200u << 10)) {
+      switch (vecs / 32) {
+        case 1: return gridLaunch<1>(ctx, dA, nReads, dB, nCols, dShared, dFrac);
+        case 2: return gridLaunch<2>(ctx, dA, nReads, dB, nCols, dShared, dFrac);
+        case 4: return gridLaunch<4>(ctx, dA, nReads, dB, nCols, dShared, dFrac);
+        case 8: return gridLaunch<8>(ctx, dA, nReads, dB, nCols, dShared, dFrac);
+        case 16: return gridLaunch<16>(ctx, dA, nReads, dB, nCols, dShared, dFrac);
+        default: break;
+      }
+    }
+  }
   uint64_t ctas = (nPairs + 3) / 4;
   const uint64_t maxGrid = uint64_t(ctx->numSMs) * 16;
   if (ctas > maxGrid) ctas = maxGrid;
