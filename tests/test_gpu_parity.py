@@ -326,3 +326,55 @@ def test_wide_reads_strip_mined(oracle):
         want, wg = oracle.align_profile_batch(params, bases, q, offsets, refIdx, readIdx, _abi.USING_QUALITY, gapCap=64)
         H.assert_comparisons_equal(got, want)
         assert np.array_equal(gg, wg)
+
+
+def test_random_parameter_fuzz(oracle):
+    """Differential fuzz over the whole parameter space of the boundary: random gap penalties (all ten,
+    including extend > open and zeros), random score matrices (asymmetric, positive mismatches),
+    random quality thresholds / windows / flags, ragged related and unrelated sequences."""
+    from seekdeep_b200.scoring import GapScoringParameters, SubstituteMatrix
+    rng = np.random.default_rng(20261019)
+    for trial in range(24):
+        gp = GapScoringParameters(*[int(x) for x in rng.integers(0, 9, 10)])
+        m = np.full((128, 128), int(rng.integers(-4, 0)), np.int32)
+        letters = b"ACGTN"
+        sub = rng.integers(-4, 5, (5, 5))
+        for a in range(5):
+            for b in range(5):
+                m[letters[a], letters[b]] = sub[a, b]
+            m[letters[a], letters[a]] = int(rng.integers(1, 5))
+        params = make_params(gaps=gp, scoring=SubstituteMatrix(m), primaryQual=int(rng.integers(0, 41)),
+                             secondaryQual=int(rng.integers(0, 41)), qualThresWindow=int(rng.integers(0, 6)),
+                             countEndGaps=bool(rng.integers(2)), weighHomopolymers=bool(rng.integers(2)))
+        alpha = np.frombuffer(b"ACGT" * 6 + b"N", dtype=np.uint8)
+        seqs = []
+        for fam in range(3):
+            root = H.rand_seq(rng, int(rng.integers(5, 140)), alpha)
+            seqs.append(root)
+            for _ in range(6):
+                seqs.append(H.mutate(rng, root, int(rng.integers(0, 5)), int(rng.integers(0, 3)), int(rng.integers(0, 3)),
+                                     hp=bool(rng.integers(2))))
+        quals = [rng.integers(0, 42, len(s)).astype(np.uint8) for s in seqs]
+        bases, q, offsets = np.concatenate(seqs), np.concatenate(quals), np.zeros(len(seqs) + 1, np.uint64)
+        offsets[1:] = np.cumsum([len(s) for s in seqs])
+        cnts = rng.integers(1, 9, len(seqs)).astype(np.float64)
+        n = 150
+        refIdx = rng.integers(0, len(seqs), n).astype(np.uint32)
+        readIdx = rng.integers(0, len(seqs), n).astype(np.uint32)
+        flags = int(rng.integers(0, 8))
+        kmer = dict(kLength=int(rng.integers(2, 8)), runCutOff=int(rng.integers(0, 6)), kmersByPosition=bool(rng.integers(2)),
+                    expandKmerPos=bool(rng.integers(2)), expandKmerSize=int(rng.integers(0, 4)))
+        for mode in (1, 0):  # int32 pass, then automatic (packed fp16 whenever its range check allows)
+            with GpuAligner(params) as al:
+                al.set_kernel(mode)
+                al.upload_seqs(bases, q, offsets, cnts)
+                al.index_kmers(**kmer)
+                got, gg = al.align_profile(refIdx, readIdx, checkKmer=bool(flags & 1), usingQuality=bool(flags & 2),
+                                           doingMatchQuality=bool(flags & 4), gapCap=30)
+            if mode == 1:
+                km = oracle.index_kmers(bases, offsets, cnts, kmer["kLength"], kmer["runCutOff"], kmer["kmersByPosition"],
+                                        kmer["expandKmerPos"], kmer["expandKmerSize"])
+                want, wg = oracle.align_profile_batch(params, bases, q, offsets, refIdx, readIdx, flags, kmaps=km, gapCap=30)
+                oracle.free_kmaps(km)
+            H.assert_comparisons_equal(got, want)
+            assert np.array_equal(gg, wg), (trial, mode)
