@@ -12,6 +12,8 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "sdgpu_internal.cuh"
 
 namespace {
@@ -308,7 +310,8 @@ int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   const size_t smem = size_t(warpsPerCta) * profSize * 2;
   SD_CUDA(ctx, cudaFuncSetAttribute(kmerProfileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   uint32_t grid = (nSeqs + warpsPerCta - 1) / warpsPerCta;
-  const uint32_t maxGrid = uint32_t(ctx->numSMs) * 32;
+  const char* capEnv = getenv("SD_KPROF_GRIDCAP");
+  const uint32_t maxGrid = uint32_t(ctx->numSMs) * (capEnv ? uint32_t(atoi(capEnv)) : 32u);
   if (grid > maxGrid) grid = maxGrid;
   kmerProfileKernel<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, top, profSize, ctx->dProfiles);
   SD_CUDA(ctx, cudaGetLastError());
