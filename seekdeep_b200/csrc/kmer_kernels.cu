@@ -310,8 +310,7 @@ int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   const size_t smem = size_t(warpsPerCta) * profSize * 2;
   SD_CUDA(ctx, cudaFuncSetAttribute(kmerProfileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   uint32_t grid = (nSeqs + warpsPerCta - 1) / warpsPerCta;
-  const char* capEnv = getenv("SD_KPROF_GRIDCAP");
-  const uint32_t maxGrid = uint32_t(ctx->numSMs) * (capEnv ? uint32_t(atoi(capEnv)) : 32u);
+  const uint32_t maxGrid = uint32_t(ctx->numSMs) * 32;  // (swept 8..unbounded on B200: no effect beyond 16)
   if (grid > maxGrid) grid = maxGrid;
   kmerProfileKernel<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, top, profSize, ctx->dProfiles);
   SD_CUDA(ctx, cudaGetLastError());

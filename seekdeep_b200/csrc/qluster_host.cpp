@@ -249,7 +249,6 @@ class Runner {
   std::vector<uint32_t> prevWindow;   // store indices of the previous iteration's window
   std::vector<uint8_t> inPrevWindow;  // by store index
   static constexpr uint32_t BATCH = 1u << 21;
-  std::vector<uint64_t> maskBuf;
   std::vector<sdgpu_comparison> cmpBuf;
   std::vector<sdgpu_gap> gapBuf;
   double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0, tIndex = 0;
