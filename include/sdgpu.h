@@ -204,6 +204,30 @@ int sdgpu_set_pass_table(sdgpu_ctx* ctx, const sdgpu_iter_par* lines, uint32_t n
 int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,
                      uint32_t flags, uint64_t* passMaskOut);
 
+/* Chimera probe: the per-(parent, candidate) part of collapser::markChimeras
+ * (clusterDown.cpp:566-577; options clusterDownSetUp.cpp:372-381).  Per pair i the call runs
+ * alignCacheGlobal(parent, candidate) + profileAlignment(parent, candidate, checkKmer,
+ * usingQuality, matchQuality), takes the mismatches markChimeras keeps (all of them if
+ * keepLowQualityMismatches, else every class but low-quality), and profiles the alignment
+ * columns before the first kept mismatch ("front") and after the last one ("back") against
+ * chiOverlap (chiOpts_.chiOverlap_, passErrorProfile semantics; stopCheck/smallCutoff/onPerId
+ * ignored).  Only this 32-byte record per pair returns to the host. */
+typedef struct sdgpu_chimera_probe {
+  int32_t alnScore;
+  uint32_t keptMismatches; /* mismatches markChimeras looks at */
+  uint32_t numGaps;        /* counted gap runs of the whole alignment */
+  uint32_t firstPos;       /* candidate (read) base position of the first kept mismatch */
+  uint32_t lastPos;        /* ... of the last kept mismatch */
+  uint32_t firstAlnPos;    /* alignment columns of the two */
+  uint32_t lastAlnPos;
+  uint32_t flags;          /* SDGPU_CHI_* */
+} sdgpu_chimera_probe;
+#define SDGPU_CHI_FRONT_PASS 1u /* columns [0, firstAlnPos) pass chiOverlap */
+#define SDGPU_CHI_BACK_PASS 2u  /* columns (lastAlnPos, alnLen) pass chiOverlap */
+int sdgpu_chimera_probe_pairs(sdgpu_ctx* ctx, const uint32_t* parentIdx, const uint32_t* candIdx,
+                              uint32_t nPairs, uint32_t flags, const sdgpu_iter_par* chiOverlap,
+                              int keepLowQualityMismatches, sdgpu_chimera_probe* out);
+
 /* All-vs-all alignment of the sequences listed in seqIdx (NULL: the whole store): the pair list
  * is the upper triangle (i < j) in row-major order, ref = seqIdx[i], read = seqIdx[j]; the call
  * computes pairs [firstPair, firstPair + nPairs) of it, so disjoint blocks can run on different

@@ -12,8 +12,11 @@
  * the unchanged sequential logic from a pair cache — the same "lookup-or-compute" contract
  * aligner::alignCacheGlobal already has (clusterDown.cpp:694, 739).
  *
+ * With opts.markChimeras the run ends with collapser::markChimeras (:566-577) on the sorted
+ * clusters, every (parent, candidate) probe of it computed in one sdgpu_chimera_probe_pairs batch.
+ *
  * Out of scope here (left to the caller, as in the reference): FASTQ parsing, Illumina sample
- * filtering / down-sampling (:83-181), chimera marking (:566-598), output files.
+ * filtering / down-sampling (:83-181), cluster renaming, output files.
  */
 #ifndef SDGPU_QLUSTER_H_
 #define SDGPU_QLUSTER_H_
@@ -40,6 +43,16 @@ typedef struct sdq_opts {
   uint32_t leaveOutSinglets; /* --leaveOutSinglets */
   uint32_t dontRecalLowFreq; /* --dontRecalLowFreqMismatchAndReRun */
   uint32_t smallReadSize;    /* reads with len <= this are dropped (clusterDown.cpp:269) */
+  /* chimera marking: pars_.chiOpts_ (clusterDownSetUp.cpp:372-381; clusterDown.cpp:566-577) */
+  uint32_t markChimeras;         /* checkChimeras_ (qluster: on unless --noMarkChimeras) */
+  uint32_t chiKeepLowQual;       /* keepLowQaulityMismatches_ (--chiKeepLowQaulityMismatches) */
+  uint32_t chiRunCutOff;         /* candidates with cnt_ <= this are not examined (njhseq default 1) */
+  uint32_t chiOverlapSizeCutoff; /* overLapSizeCutoff_: bases a parent must explain (njhseq default 5) */
+  uint32_t chiPosSpacing;        /* posSpacing_ (--chiPosSpacing) */
+  uint32_t reserved;
+  double chiParentFreqs;         /* parentFreqs_ (--parFreqs, 2) */
+  sdq_iter_par chiOverlap;       /* chiOverlap_ (njhseq: oneBaseIndel 2, twoBaseIndel 1, lowKmer 1;
+                                    qluster sets largeBaseIndel .99, clusterDown.cpp:572) */
 } sdq_opts;
 
 typedef struct sdq_result sdq_result;
@@ -53,6 +66,8 @@ typedef struct sdq_stats {
   uint64_t cellUpdates;     /* DP cells of all of the above */
   uint64_t gpuBatches;      /* alignment kernel launches */
   uint64_t onDemandPairs;   /* pairs computed outside the speculative batches */
+  uint64_t chimeraPairs;    /* (parent, candidate) probes of markChimeras */
+  uint64_t chimericClusters;
   double secondsGpu;        /* wall time inside sdgpu_align_profile calls */
   double secondsTotal;
   double msResident;        /* CUDA-event time on the ctx stream from "unique reads resident in HBM" to the end */
@@ -70,6 +85,10 @@ uint32_t sdq_num_clusters(const sdq_result* r);
 uint32_t sdq_cluster_len(const sdq_result* r, uint32_t c);
 double sdq_cluster_cnt(const sdq_result* r, uint32_t c);
 int sdq_cluster_seq(const sdq_result* r, uint32_t c, uint8_t* seq, uint8_t* qual);
+/* 1 if markChimeras flagged cluster c (seqBase_.markAsChimeric()); parents[2] = cluster indices of
+ * the parent explaining its front and the one explaining its back, positions[2] = the candidate
+ * base positions of the two crossover mismatches (the columns of chiParentsInfo.txt, :578-581) */
+int sdq_cluster_chimeric(const sdq_result* r, uint32_t c, uint32_t* parents, uint32_t* positions);
 /* final cluster index of every input read (UINT32_MAX: dropped as a small read) */
 int sdq_membership(const sdq_result* r, uint32_t* clusterOfRead);
 

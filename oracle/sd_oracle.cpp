@@ -321,9 +321,16 @@ static void handleGapCounting(const GapEvent& g, const std::string& withGap, con
 
 // njhseq aligner::profileAlignment (reference call sites clusterDown.cpp:696,741;
 // ControlBencher.hpp:118; PairedReadProcessor.cpp:336) + comparison::setEventBaseIdentity.
+// The (start, stop) column window and the per-mismatch records (`mismatches_`: alignment column,
+// read base position, class) are what collapser::markChimeras asks of it.
+struct MismatchEv {
+  uint32_t alnPos, seqBasePos;
+  int cls;  // 1 = high quality, 2 = low quality, 3 = low k-mer
+};
 static void profileAlignment(const sdgpu_params& P, const KMaps* km, const uint8_t* A, const uint8_t* qA,
                              uint32_t la, const uint8_t* B, const uint8_t* qB, uint32_t lb, const Gapped& ga,
-                             const Gapped& gb, uint32_t flags, sdgpu_comparison& c) {
+                             const Gapped& gb, uint32_t flags, sdgpu_comparison& c, uint32_t start = 0,
+                             uint32_t stop = UINT32_MAX, std::vector<MismatchEv>* events = nullptr) {
   const bool checkKmer = flags & SDGPU_CHECK_KMER, usingQuality = flags & SDGPU_USING_QUALITY,
              matchQuality = flags & SDGPU_MATCH_QUALITY;
   const std::string& sa = ga.seq;
@@ -348,6 +355,7 @@ static void profileAlignment(const sdgpu_params& P, const KMaps* km, const uint8
         ++i;
         ++off;
       }
+      if (g.startPos < start || g.startPos >= stop) continue;
       const bool endGap = (g.startPos + g.size >= len) || g.startPos == 0;
       if (endGap) {
         (inA ? endA : endB) += g.size;
@@ -362,17 +370,23 @@ static void profileAlignment(const sdgpu_params& P, const KMaps* km, const uint8
       }
       continue;
     }
+    if (i < start || i >= stop) continue;
     const uint32_t pa = i - firstOffset, pb = i - secondOffset;
     if (P.scoreMat[size_t(uint8_t(sa[i]) & 127) * SDGPU_MAT_DIM + (uint8_t(sb[i]) & 127)] < 0) {
       bool hq = true;
       if (usingQuality) hq = checkQual(qA, la, pa, P) && checkQual(qB, lb, pb, P);
+      int cls;
       if (!hq) {
         ++c.lqMismatches;
+        cls = 2;
       } else if (checkKmer && (isLowFreqAt(km, A, la, pa) || isLowFreqAt(km, B, lb, pb))) {
         ++c.lowKmerMismatches;
+        cls = 3;
       } else {
         ++c.hqMismatches;
+        cls = 1;
       }
+      if (events) events->push_back(MismatchEv{i, pb, cls});
     } else {
       if (matchQuality && !(checkQual(qA, la, pa, P) && checkQual(qB, lb, pb, P))) {
         ++c.lowQualityMatches;
@@ -427,6 +441,8 @@ struct Clus {
   bool remove = false, needCons = false;
   double avgErr = 0;
   std::unordered_map<uint32_t, sdgpu_comparison> prev;
+  bool chimeric = false;  // seqBase_.markAsChimeric()
+  uint32_t chiParent[2] = {0, 0}, chiPos[2] = {0, 0};
 };
 
 static double averageErrorRate(const std::vector<uint8_t>& q) {
@@ -453,6 +469,43 @@ static bool passErrorCheck(const sdo_iter_par& it, const sdgpu_comparison& g) {
   return it.oneBaseIndel >= g.oneBaseIndel && it.twoBaseIndel >= g.twoBaseIndel &&
          it.largeBaseIndel >= g.largeBaseIndel && it.hqMismatches >= double(g.hqMismatches) &&
          it.lqMismatches >= double(g.lqMismatches) && it.lowKmerMismatches >= double(g.lowKmerMismatches);
+}
+
+// The per-(parent, candidate) step of collapser::markChimeras (call site clusterDown.cpp:576,
+// options clusterDownSetUp.cpp:372-381): global alignment, errorProfile with mismatch records,
+// low-quality mismatches dropped unless keepLowQaulityMismatches_, then the columns before the
+// first and after the last remaining mismatch re-profiled and judged against chiOverlap_.
+static void chimeraProbe(const sdgpu_params& P, const KMaps* km, const uint8_t* A, const uint8_t* qA, uint32_t la,
+                         const uint8_t* B, const uint8_t* qB, uint32_t lb, uint32_t flags,
+                         const sdo_iter_par& chiOverlap, bool keepLq, std::vector<Cell>& mat,
+                         sdgpu_chimera_probe& out) {
+  AlnResult aln;
+  Gapped ga, gb;
+  sdgpu_comparison c;
+  std::memset(&c, 0, sizeof(c));
+  std::memset(&out, 0, sizeof(out));
+  runNeedleSave(P, A, la, B, lb, mat, aln);
+  rearrangeGlobal(A, qA, la, B, qB, lb, aln, ga, gb);
+  std::vector<MismatchEv> ev;
+  profileAlignment(P, km, A, qA, la, B, qB, lb, ga, gb, flags, c, 0, UINT32_MAX, &ev);
+  if (!keepLq) ev.erase(std::remove_if(ev.begin(), ev.end(), [](const MismatchEv& e) { return e.cls == 2; }), ev.end());
+  out.alnScore = aln.score;
+  out.keptMismatches = uint32_t(ev.size());
+  out.numGaps = c.numGaps;
+  if (ev.empty()) return;
+  out.firstPos = ev.front().seqBasePos;
+  out.lastPos = ev.back().seqBasePos;
+  out.firstAlnPos = ev.front().alnPos;
+  out.lastAlnPos = ev.back().alnPos;
+  sdo_iter_par t = chiOverlap;
+  t.onPerId = 0;
+  sdgpu_comparison w;
+  std::memset(&w, 0, sizeof(w));
+  profileAlignment(P, km, A, qA, la, B, qB, lb, ga, gb, flags, w, 0, out.firstAlnPos);
+  if (passErrorCheck(t, w)) out.flags |= SDGPU_CHI_FRONT_PASS;
+  std::memset(&w, 0, sizeof(w));
+  profileAlignment(P, km, A, qA, la, B, qB, lb, ga, gb, flags, w, out.lastAlnPos + 1, UINT32_MAX);
+  if (passErrorCheck(t, w)) out.flags |= SDGPU_CHI_BACK_PASS;
 }
 
 struct CharCounter {  // njhseq charCounter restricted to what consensus building uses
@@ -660,6 +713,44 @@ struct Engine {
   }
 
   // njhseq collapser::runFullClustering (reference call sites clusterDown.cpp:488-518).
+  // collapser::markChimeras(clusters, alignerObj, chiOpts_) (clusterDown.cpp:566-577).  `cs` is
+  // sorted by total count; candidates start at the third cluster; a parent must be at least
+  // parentFreqs_ times as abundant; a candidate is chimeric when one parent explains its front
+  // up to a mismatch that lies behind the last mismatch against another parent explaining its back.
+  void markChimeras(std::vector<Clus>& cs) {
+    if (cs.size() <= 2) return;
+    const uint32_t flags = SDGPU_USING_QUALITY;  // profileAlignment(parent, sub, false, true, false)
+    for (size_t sub = 2; sub < cs.size(); ++sub) {
+      Clus& cand = cs[sub];
+      if (cand.cnt <= double(O.chiRunCutOff)) continue;
+      std::multimap<uint32_t, uint32_t> front, back;  // read position of the mismatch -> parent
+      for (size_t par = 0; par < sub; ++par) {
+        const Clus& parent = cs[par];
+        if (parent.cnt / cand.cnt < O.chiParentFreqs) continue;
+        sdgpu_chimera_probe pr;
+        chimeraProbe(P, nullptr, reinterpret_cast<const uint8_t*>(parent.seq.data()), parent.qual.data(),
+                     uint32_t(parent.seq.size()), reinterpret_cast<const uint8_t*>(cand.seq.data()), cand.qual.data(),
+                     uint32_t(cand.seq.size()), flags, O.chiOverlap, O.chiKeepLowQual != 0, mat, pr);
+        ++nAlign;
+        nCells += uint64_t(parent.seq.size()) * cand.seq.size();
+        if (pr.keptMismatches == 0) continue;
+        const uint32_t lb = uint32_t(cand.seq.size());
+        if ((pr.flags & SDGPU_CHI_FRONT_PASS) && pr.firstPos >= O.chiOverlapSizeCutoff) front.emplace(pr.firstPos, uint32_t(par));
+        if ((pr.flags & SDGPU_CHI_BACK_PASS) && lb - 1 - pr.lastPos >= O.chiOverlapSizeCutoff) back.emplace(pr.lastPos, uint32_t(par));
+      }
+      for (const auto& f : front) {
+        for (const auto& b : back) {
+          if (cand.chimeric) break;
+          if (f.second != b.second && f.first > b.first && f.first - b.first >= O.chiPosSpacing) {
+            cand.chimeric = true;
+            cand.chiParent[0] = f.second, cand.chiPos[0] = f.first;
+            cand.chiParent[1] = b.second, cand.chiPos[1] = b.first;
+          }
+        }
+      }
+    }
+  }
+
   void runFullClustering(std::vector<Clus>& cs, const sdo_iter_par* its, uint32_t nIts) {
     for (uint32_t i = 0; i < nIts; ++i) {
       cs.erase(std::remove_if(cs.begin(), cs.end(), [](const Clus& c) { return c.remove; }), cs.end());
@@ -861,6 +952,7 @@ sdo_qluster_result* sdo_qluster(const sdgpu_params* p, const sdo_qluster_opts* o
     for (uint32_t u : clusters[c].members)
       for (uint32_t r : E.uniq[u].inputIdx) res->membership[r] = c;
   for (Clus& c : clusters) c.prev.clear();
+  if (o->markChimeras) E.markChimeras(clusters);  // clusterDown.cpp:566-577
   res->clusters = std::move(clusters);
   res->nAlign = E.nAlign;
   res->nCells = E.nCells;
@@ -878,6 +970,27 @@ void sdo_qluster_cluster_seq(const sdo_qluster_result* r, uint32_t c, uint8_t* s
   const Clus& cl = r->clusters[c];
   if (seq) std::memcpy(seq, cl.seq.data(), cl.seq.size());
   if (qual) std::memcpy(qual, cl.qual.data(), cl.qual.size());
+}
+int sdo_qluster_cluster_chimeric(const sdo_qluster_result* r, uint32_t c, uint32_t* parents, uint32_t* positions) {
+  const Clus& cl = r->clusters[c];
+  if (cl.chimeric && parents) parents[0] = cl.chiParent[0], parents[1] = cl.chiParent[1];
+  if (cl.chimeric && positions) positions[0] = cl.chiPos[0], positions[1] = cl.chiPos[1];
+  return cl.chimeric ? 1 : 0;
+}
+int sdo_chimera_probe_batch(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8_t* bases, const uint8_t* quals,
+                            const uint64_t* offsets, const uint32_t* parentIdx, const uint32_t* candIdx,
+                            uint32_t nPairs, uint32_t flags, const sdo_iter_par* chiOverlap,
+                            int keepLowQualityMismatches, sdgpu_chimera_probe* out) {
+  if (!p || !bases || !offsets || !parentIdx || !candIdx || !out || !chiOverlap) return SDGPU_E_ARG;
+  std::vector<Cell> mat;
+  for (uint32_t i = 0; i < nPairs; ++i) {
+    const uint64_t oa = offsets[parentIdx[i]], ob = offsets[candIdx[i]];
+    const uint32_t la = uint32_t(offsets[parentIdx[i] + 1] - oa), lb = uint32_t(offsets[candIdx[i] + 1] - ob);
+    if (la == 0 || lb == 0) return SDGPU_E_ARG;
+    chimeraProbe(*p, kmaps ? kmaps->km : nullptr, bases + oa, quals ? quals + oa : nullptr, la, bases + ob,
+                 quals ? quals + ob : nullptr, lb, flags, *chiOverlap, keepLowQualityMismatches != 0, mat, out[i]);
+  }
+  return SDGPU_OK;
 }
 void sdo_qluster_membership(const sdo_qluster_result* r, uint32_t* clusterOfRead) {
   std::memcpy(clusterOfRead, r->membership.data(), r->membership.size() * sizeof(uint32_t));

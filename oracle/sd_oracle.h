@@ -4,7 +4,7 @@
  * TEST INFRASTRUCTURE ONLY.  This directory is the checker for the CUDA hot path: a plain,
  * single-threaded CPU restatement of the njhseq algorithms SeekDeep's qluster calls
  * (aligner::alignCacheGlobal / alignCalc::runNeedleSave, aligner::profileAlignment,
- * kmerInfo::compareKmers, indexKmers, collapser::runFullClustering).  Only tests/,
+ * kmerInfo::compareKmers, indexKmers, collapser::runFullClustering, collapser::markChimeras).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  * Nothing under seekdeep_b200/ links, includes or calls it.
  *
@@ -79,6 +79,15 @@ typedef struct sdo_qluster_opts {
   uint32_t leaveOutSinglets;
   uint32_t dontRecalLowFreq;/* dontRecalLowFreqMismatchAndReRun */
   uint32_t smallReadSize;
+  /* chimera marking, chiOpts_ (clusterDownSetUp.cpp:372-381; clusterDown.cpp:566-577) */
+  uint32_t markChimeras;         /* checkChimeras_ */
+  uint32_t chiKeepLowQual;       /* keepLowQaulityMismatches_ */
+  uint32_t chiRunCutOff;         /* candidates with cnt_ <= this are skipped */
+  uint32_t chiOverlapSizeCutoff; /* overLapSizeCutoff_ */
+  uint32_t chiPosSpacing;        /* posSpacing_ */
+  uint32_t reserved;
+  double chiParentFreqs;         /* parentFreqs_ */
+  sdo_iter_par chiOverlap;       /* chiOverlap_ */
 } sdo_qluster_opts;
 
 typedef struct sdo_qluster_result sdo_qluster_result;
@@ -98,6 +107,14 @@ uint64_t sdo_qluster_num_cells(const sdo_qluster_result* r);
 uint32_t sdo_qluster_cluster_len(const sdo_qluster_result* r, uint32_t c);
 double sdo_qluster_cluster_cnt(const sdo_qluster_result* r, uint32_t c);
 void sdo_qluster_cluster_seq(const sdo_qluster_result* r, uint32_t c, uint8_t* seq, uint8_t* qual);
+/* 1 if cluster c was marked chimeric; parents[2] / positions[2] = (front parent, back parent)
+ * cluster indices and the candidate base positions of the two crossover mismatches */
+int sdo_qluster_cluster_chimeric(const sdo_qluster_result* r, uint32_t c, uint32_t* parents, uint32_t* positions);
+/* collapser::markChimeras' per-pair probe over a packed store (checks sdgpu_chimera_probe_pairs) */
+int sdo_chimera_probe_batch(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8_t* bases, const uint8_t* quals,
+                            const uint64_t* offsets, const uint32_t* parentIdx, const uint32_t* candIdx,
+                            uint32_t nPairs, uint32_t flags, const sdo_iter_par* chiOverlap,
+                            int keepLowQualityMismatches, sdgpu_chimera_probe* out);
 /* membership: for each input read, the final cluster index (UINT32_MAX: dropped as small read) */
 void sdo_qluster_membership(const sdo_qluster_result* r, uint32_t* clusterOfRead);
 

@@ -55,6 +55,10 @@ GAP_DTYPE = _np.dtype([("pos", "<u4"), ("size", "<u4"), ("gapInA", "<u4")])
 PAIR_SUMMARY_DTYPE = _np.dtype([("alnScore", "<i4"), ("hqMismatches", "<u2"), ("lqMismatches", "<u2"),
                                 ("lowKmerMismatches", "<u2"), ("numGaps", "<u2"), ("oneBaseIndel", "<f4"),
                                 ("twoBaseIndel", "<f4"), ("largeBaseIndel", "<f4"), ("eventBasedIdentity", "<f4")])
+CHIMERA_PROBE_DTYPE = _np.dtype([("alnScore", "<i4")] + [(n, "<u4") for n in (
+    "keptMismatches", "numGaps", "firstPos", "lastPos", "firstAlnPos", "lastAlnPos", "flags")])
+CHI_FRONT_PASS, CHI_BACK_PASS = 1, 2
+assert CHIMERA_PROBE_DTYPE.itemsize == 32
 assert PAIR_SUMMARY_DTYPE.itemsize == 28
 assert COMPARISON_DTYPE.itemsize == C.sizeof(Comparison) == 104
 assert GAP_DTYPE.itemsize == C.sizeof(Gap) == 12
@@ -83,6 +87,7 @@ SIGNATURES = {
     "sdgpu_align_profile": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_set_pass_table": (C.c_int, [_ctx, C.c_void_p, C.c_uint32]),
     "sdgpu_align_pass": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "sdgpu_chimera_probe_pairs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]),
     "sdgpu_kmer_compare_all_dev": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "sdgpu_all_vs_all": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
     "sdgpu_align_pass_submit": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),

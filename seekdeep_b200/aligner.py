@@ -198,6 +198,19 @@ class GpuAligner:
         self._check(self._lib.sdgpu_align_pass(self._ctx, _ptr(refIdx), _ptr(readIdx), len(refIdx), flags, _ptr(out)))
         return out
 
+    def chimera_probe(self, parentIdx, candIdx, chiOverlap, keepLowQualityMismatches=False, checkKmer=False,
+                      usingQuality=True):
+        """collapser::markChimeras' per-(parent, candidate) probe (clusterDown.cpp:576): CHIMERA_PROBE_DTYPE[nPairs].
+        `chiOverlap` is an IterPar-like object / ctypes struct holding chiOpts_.chiOverlap_'s thresholds."""
+        parentIdx = np.ascontiguousarray(parentIdx, np.uint32)
+        candIdx = np.ascontiguousarray(candIdx, np.uint32)
+        flags = (_abi.CHECK_KMER if checkKmer else 0) | (_abi.USING_QUALITY if usingQuality else 0)
+        out = np.zeros(len(parentIdx), _abi.CHIMERA_PROBE_DTYPE)
+        self._check(self._lib.sdgpu_chimera_probe_pairs(self._ctx, _ptr(parentIdx), _ptr(candIdx), len(parentIdx), flags,
+                                                        C.cast(C.pointer(chiOverlap), C.c_void_p),
+                                                        int(keepLowQualityMismatches), _ptr(out)))
+        return out
+
     def all_vs_all(self, seqIdx=None, n=None, firstPair=0, nPairs=None, checkKmer=False, usingQuality=True):
         """Upper-triangle all-vs-all alignment (config 3).  Returns PAIR_SUMMARY_DTYPE[nPairs] for the pair
         block [firstPair, firstPair + nPairs) in row-major (i < j) order."""

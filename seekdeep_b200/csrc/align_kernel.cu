@@ -65,6 +65,9 @@ struct AlignArgs {
   const sdgpu_iter_par* lines;  // par-file lines for the verdict mask (device)
   uint32_t nLines;
   uint64_t* passOut;   // per pair: bit l = passes line l (or NULL)
+  sdgpu_chimera_probe* chiOut;  // per pair: markChimeras' front/back probe (or NULL)
+  sdgpu_iter_par chiPar;        // chiOpts_.chiOverlap_
+  uint32_t chiKeepLq;           // chiOpts_.keepLowQaulityMismatches_
 };
 
 enum { ST_D = 0, ST_U = 1, ST_L = 2 };
@@ -113,16 +116,20 @@ struct BitsH2 {
 };
 
 // njhseq seqInfo::checkQual (strictly-greater thresholds, trailing window stops before the last base)
-__device__ bool checkQualDev(const uint8_t* q, int len, int pos, const DevScoring& sc) {
-  if (int(q[pos]) <= sc.primaryQual) return false;
-  const int lower = pos > sc.window ? pos - sc.window : 0;
+__device__ __forceinline__ bool checkQualDev(const uint8_t* q, int len, int pos, int primaryQual, int secondaryQual,
+                                             int window) {
+  if (int(q[pos]) <= primaryQual) return false;
+  const int lower = pos > window ? pos - window : 0;
   for (int i = lower; i < pos; ++i)
-    if (int(q[i]) <= sc.secondaryQual) return false;
+    if (int(q[i]) <= secondaryQual) return false;
   int higher = len - 1;
-  if (pos + sc.window + 1 < len) higher = pos + sc.window + 1;
+  if (pos + window + 1 < len) higher = pos + window + 1;
   for (int i = pos + 1; i < higher; ++i)
-    if (int(q[i]) <= sc.secondaryQual) return false;
+    if (int(q[i]) <= secondaryQual) return false;
   return true;
+}
+__device__ __forceinline__ bool checkQualDev(const uint8_t* q, int len, int pos, const DevScoring& sc) {
+  return checkQualDev(q, len, pos, sc.primaryQual, sc.secondaryQual, sc.window);
 }
 
 // KmerMaps::isKmerLowFrequency for the k-mer centred on base p (clamped to the sequence)
@@ -159,6 +166,123 @@ struct PairView {
   const uint8_t *cA, *cB, *qA, *qB;
 };
 
+// njhseq aligner::handleGapCountingInA/InB weight of one gap run: 1, or for a homopolymer run
+// under weighHomopolymers |gapSide - baseSide| / (gapSide + baseSide) over the flanking run
+__device__ double gapWeightDev(const uint8_t* gA, const uint8_t* gB, int alnLen, int startPos, int size, bool inA) {
+  const uint8_t* gs = inA ? gA : gB;  // string holding the '-' run
+  const uint8_t* os = inA ? gB : gA;  // string holding the gapped bases
+  const int base = os[startPos];
+  for (int x = 1; x < size; ++x)
+    if (os[startPos + x] != base) return 1.0;
+  double gapSide = 0, baseSide = size;
+  for (int cur = startPos + size; cur < alnLen && gs[cur] == base; ++cur) gapSide += 1;
+  for (int cur = 1; cur <= startPos && gs[startPos - cur] == base; ++cur) gapSide += 1;
+  for (int cur = startPos + size; cur < alnLen && os[cur] == base; ++cur) baseSide += 1;
+  for (int cur = 1; cur <= startPos && os[startPos - cur] == base; ++cur) baseSide += 1;
+  return fabs(gapSide - baseSide) / (gapSide + baseSide);
+}
+
+// collapser::markChimeras' per-(parent, candidate) probe on the traced alignment: first / last
+// kept mismatch and the errorProfiles of the columns before the first and after the last one,
+// judged against chiOverlap.  The windows hold no kept mismatch by construction, so their
+// profiles are the low-quality mismatches and the counted gap runs that fall inside them.
+// (compiled only into the CHI instantiations of the int32 kernels, so the probe's doubles do not
+// cost the collapse loop's kernels registers)
+struct ChiArgs {
+  int primaryQual, secondaryQual, window, countEndGaps, weighHomopolymers;
+  uint32_t flags, chiKeepLq;
+  DevKmerIndex idx;
+  sdgpu_chimera_probe* chiOut;
+  double one, two, large, hq, lq, lk;  // chiOverlap thresholds
+};
+__device__ __forceinline__ void chimeraProbeDev(const ChiArgs& a, const PairView& pv, const uint8_t* gA, const uint8_t* gB,
+                                             int alnLen, int alnStart, const uint32_t* gapRecs, int nRecs,
+                                             const int* sTab, int score, int lane) {
+  const ChiArgs& sc = a;
+  const bool checkKmer = (a.flags & SDGPU_CHECK_KMER) != 0;
+  const bool usingQuality = (a.flags & SDGPU_USING_QUALITY) != 0;
+  const unsigned ltMask = (1u << lane) - 1u;
+  int baseA = 0, baseB = 0;
+  int firstCol = -1, lastCol = -1, firstPos = 0, lastPos = 0;
+  unsigned kept = 0, lqFront = 0, lqBack = 0;
+  for (int cs = 0; cs < alnLen; cs += 32) {
+    const int k = cs + lane;
+    const bool inb = k < alnLen;
+    const int ca = inb ? int(gA[k]) : SDGPU_GAP_CODE;
+    const int cb = inb ? int(gB[k]) : SDGPU_GAP_CODE;
+    const unsigned hasA = __ballot_sync(FULL, inb && ca != SDGPU_GAP_CODE);
+    const unsigned hasB = __ballot_sync(FULL, inb && cb != SDGPU_GAP_CODE);
+    int cls = 0;  // 1 = hq, 2 = lq, 3 = lowKmer
+    const int pa = baseA + __popc(hasA & ltMask), pb = baseB + __popc(hasB & ltMask);
+    if (inb && ca != SDGPU_GAP_CODE && cb != SDGPU_GAP_CODE && sTab[ca * SDGPU_MAX_SYMBOLS + cb] < 0) {
+      bool good = true;
+      if (usingQuality)
+        good = checkQualDev(pv.qA, pv.la, pa, sc.primaryQual, sc.secondaryQual, sc.window) &&
+               checkQualDev(pv.qB, pv.lb, pb, sc.primaryQual, sc.secondaryQual, sc.window);
+      if (!good) {
+        cls = 2;
+      } else if (checkKmer && (lowFreqDev(a.idx, pv.cA, pv.la, pa) || lowFreqDev(a.idx, pv.cB, pv.lb, pb))) {
+        cls = 3;
+      } else {
+        cls = 1;
+      }
+    }
+    const unsigned lqMask = __ballot_sync(FULL, cls == 2);
+    const unsigned keptMask = a.chiKeepLq ? __ballot_sync(FULL, cls != 0) : __ballot_sync(FULL, cls == 1 || cls == 3);
+    const unsigned dropLq = a.chiKeepLq ? 0u : lqMask;  // mismatches markChimeras does not look at
+    if (keptMask) {
+      const int f = __ffs(keptMask) - 1, l = 31 - __clz(keptMask);
+      if (firstCol < 0) {
+        firstCol = cs + f;
+        firstPos = __shfl_sync(FULL, pb, f);
+        lqFront += __popc(dropLq & ((1u << f) - 1u));
+      }
+      lastCol = cs + l;
+      lastPos = __shfl_sync(FULL, pb, l);
+      lqBack = __popc(dropLq & ~((2u << l) - 1u));
+      kept += __popc(keptMask);
+    } else {
+      if (firstCol < 0) lqFront += __popc(dropLq);
+      lqBack += __popc(dropLq);
+    }
+    baseA += __popc(hasA);
+    baseB += __popc(hasB);
+  }
+  // counted gap runs, by window
+  double oneF = 0, twoF = 0, largeF = 0, oneB = 0, twoB = 0, largeB = 0;
+  unsigned numGaps = 0;
+  for (int r = nRecs - 1; r >= 0; --r) {
+    const int startPos = int(gapRecs[3 * r + 0]) - alnStart;
+    const int size = int(gapRecs[3 * r + 1]);
+    const bool inA = (gapRecs[3 * r + 2] & 1u) != 0;
+    const bool endGap = (startPos + size >= alnLen) || startPos == 0;
+    if (endGap && !sc.countEndGaps) continue;
+    ++numGaps;
+    const bool front = firstCol >= 0 && startPos < firstCol, back = lastCol >= 0 && startPos > lastCol;
+    if (!front && !back) continue;
+    const double wgt = sc.weighHomopolymers ? gapWeightDev(gA, gB, alnLen, startPos, size, inA) : 1.0;
+    if (front) (size >= 3 ? largeF : (size == 2 ? twoF : oneF)) += wgt;
+    if (back) (size >= 3 ? largeB : (size == 2 ? twoB : oneB)) += wgt;
+  }
+  if (lane == 0) {
+    sdgpu_chimera_probe o;
+    o.alnScore = score;
+    o.keptMismatches = kept;
+    o.numGaps = numGaps;
+    o.firstPos = uint32_t(firstPos);
+    o.lastPos = uint32_t(lastPos);
+    o.firstAlnPos = uint32_t(firstCol < 0 ? 0 : firstCol);
+    o.lastAlnPos = uint32_t(lastCol < 0 ? 0 : lastCol);
+    o.flags = 0;
+    if (kept) {
+      const bool base = a.hq >= 0.0 && a.lk >= 0.0;
+      if (base && a.one >= oneF && a.two >= twoF && a.large >= largeF && a.lq >= double(lqFront)) o.flags |= SDGPU_CHI_FRONT_PASS;
+      if (base && a.one >= oneB && a.two >= twoB && a.large >= largeB && a.lq >= double(lqBack)) o.flags |= SDGPU_CHI_BACK_PASS;
+    }
+    a.chiOut[pv.pair] = o;
+  }
+}
+
 // Traceback (njhseq runNeedleSave's pointer walk + gapInfo records), gapped strings
 // (rearrangeGlobal), errorProfile (profileAlignment + setEventBaseIdentity), verdict mask
 // (passErrorProfile) and outputs for one pair; warp-cooperative, `bits` reads the forward
@@ -166,7 +290,7 @@ struct PairView {
 // SCORE_FROM_PATH: the caller did not keep the DP's corner value; the score is re-derived as the
 // score of the traced alignment (substitution scores of the aligned columns minus each gap run's
 // open + extends under the ten position-dependent penalties), which equals it by construction.
-template <bool SCORE_FROM_PATH, class Bits>
+template <bool SCORE_FROM_PATH, bool CHI, class Bits>
 __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView& pv, int score, uint8_t* alnA,
                            uint8_t* alnB, uint32_t* gapRecs, const int* sTab, int lane) {
   const DevScoring& sc = a.sc;
@@ -326,22 +450,7 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
       (inA ? regA : regB) += size;
     }
     ++numGaps;
-    double wgt = 1.0;
-    if (sc.weighHomopolymers) {
-      const uint8_t* gs = inA ? gA : gB;  // string holding the '-' run
-      const uint8_t* os = inA ? gB : gA;  // string holding the gapped bases
-      const int base = os[startPos];
-      bool homo = true;
-      for (int x = 1; x < size; ++x) homo = homo && (os[startPos + x] == base);
-      if (homo) {
-        double gapSide = 0, baseSide = size;
-        for (int cur = startPos + size; cur < alnLen && gs[cur] == base; ++cur) gapSide += 1;
-        for (int cur = 1; cur <= startPos && gs[startPos - cur] == base; ++cur) gapSide += 1;
-        for (int cur = startPos + size; cur < alnLen && os[cur] == base; ++cur) baseSide += 1;
-        for (int cur = 1; cur <= startPos && os[startPos - cur] == base; ++cur) baseSide += 1;
-        wgt = fabs(gapSide - baseSide) / (gapSide + baseSide);
-      }
-    }
+    const double wgt = sc.weighHomopolymers ? gapWeightDev(gA, gB, alnLen, startPos, size, inA) : 1.0;
     if (size >= 3) {
       large += wgt;
     } else if (size == 2) {
@@ -352,6 +461,15 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
   }
 
   if (SCORE_FROM_PATH) score = int(warpSum(unsigned(matchSum))) - gapCost;
+  if constexpr (CHI) {
+    ChiArgs ca;
+    ca.primaryQual = sc.primaryQual, ca.secondaryQual = sc.secondaryQual, ca.window = sc.window;
+    ca.countEndGaps = sc.countEndGaps, ca.weighHomopolymers = sc.weighHomopolymers;
+    ca.flags = a.flags, ca.chiKeepLq = a.chiKeepLq, ca.idx = a.idx, ca.chiOut = a.chiOut;
+    ca.one = a.chiPar.oneBaseIndel, ca.two = a.chiPar.twoBaseIndel, ca.large = a.chiPar.largeBaseIndel;
+    ca.hq = a.chiPar.hqMismatches, ca.lq = a.chiPar.lqMismatches, ca.lk = a.chiPar.lowKmerMismatches;
+    chimeraProbeDev(ca, pv, gA, gB, alnLen, alnStart, gapRecs, int(nRecs), sTab, score, lane);
+  }
 
   // comparison::passErrorProfile against every par-file line at once: lane l judges lines l and
   // l + 32, two ballots give the 64-bit verdict mask the host collapse loop consumes
@@ -431,7 +549,7 @@ __device__ __forceinline__ PairView viewOf(const AlignArgs& a, uint32_t pair) {
 // strip-mined in blocks of 32*C; lane 31 leaves its per-row toRight / toDiag in an edge buffer and
 // lane 0 of the next block picks them up instead of the closed-form column-0 boundary.
 // =====================================================================================
-template <int C, bool WIDE>
+template <int C, bool WIDE, bool CHI>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const AlignArgs a) {
   using Bits = BitsI32<C>;
   constexpr int CW = Bits::CW;
@@ -562,7 +680,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
       }
       __syncwarp();
     }
-    finishPair<false>(a, Bits{ptrWords, size_t(a.blockWords)}, viewOf(a, pair), score, alnA, alnB, gapRecs, sTab, lane);
+    finishPair<false, CHI>(a, Bits{ptrWords, size_t(a.blockWords)}, viewOf(a, pair), score, alnA, alnB, gapRecs, sTab, lane);
   }
 }
 
@@ -708,8 +826,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernelH2(const
     // The shorter pair's registers keep running on padding rows, so the corner values are not kept:
     // each pair's score is re-derived from its traced alignment (finishPair<true>).
     // (views are re-read here so their eight pointers do not stay live across the DP loop)
-    finishPair<true>(a, Bits{ptrWords, 0}, viewOf(a, 2 * item), 0, alnA, alnB, gapRecs, sTab, lane);
-    if (haveY) finishPair<true>(a, Bits{ptrWords, 1}, viewOf(a, 2 * item + 1), 0, alnA, alnB, gapRecs, sTab, lane);
+    finishPair<true, false>(a, Bits{ptrWords, 0}, viewOf(a, 2 * item), 0, alnA, alnB, gapRecs, sTab, lane);
+    if (haveY) finishPair<true, false>(a, Bits{ptrWords, 1}, viewOf(a, 2 * item + 1), 0, alnA, alnB, gapRecs, sTab, lane);
   }
 }
 
@@ -762,14 +880,15 @@ int launchKernel(sdgpu_ctx* ctx, Kernel kernel, AlignArgs& args, uint32_t workIt
   return SDGPU_OK;
 }
 
-template <int C>
+template <int C, bool CHI = false>
 int launchI32(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
-  return launchKernel(ctx, alignProfileKernel<C, false>, args, args.nPairs, BitsI32<C>::CW, maxLenA, maxLenB);
+  return launchKernel(ctx, alignProfileKernel<C, false, CHI>, args, args.nPairs, BitsI32<C>::CW, maxLenA, maxLenB);
 }
+template <bool CHI = false>
 int launchWide(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
   constexpr int C = 16;
   const uint32_t nBlocks = (maxLenB + 32 * C - 1) / (32 * C);
-  return launchKernel(ctx, alignProfileKernel<C, true>, args, args.nPairs, BitsI32<C>::CW, maxLenA, maxLenB, nBlocks);
+  return launchKernel(ctx, alignProfileKernel<C, true, CHI>, args, args.nPairs, BitsI32<C>::CW, maxLenA, maxLenB, nBlocks);
 }
 template <int C>
 int launchH2(sdgpu_ctx* ctx, AlignArgs& args, uint32_t maxLenA, uint32_t maxLenB) {
@@ -799,7 +918,7 @@ bool halfRangeOk(const sdgpu_ctx* ctx, uint32_t maxLenA, uint32_t cols) {
 
 int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx, uint32_t nPairs,
                     uint32_t flags, sdgpu_comparison* dOut, sdgpu_gap* dGaps, uint32_t gapCap, uint32_t maxLenA,
-                    uint32_t maxLenB, uint64_t* dPassOut) {
+                    uint32_t maxLenB, uint64_t* dPassOut, const SdChimeraReq* chi) {
   if (nPairs == 0) return SDGPU_OK;
   if ((flags & SDGPU_CHECK_KMER) && !ctx->haveIndex)
     return sd_fail(ctx, SDGPU_E_STATE, "SDGPU_CHECK_KMER requires sdgpu_build_kmer_index first");
@@ -818,8 +937,16 @@ int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dRe
   args.lines = ctx->dLines;
   args.nLines = ctx->nLines;
   args.passOut = dPassOut;
+  args.chiOut = chi ? chi->dOut : nullptr;
+  args.chiPar = chi ? chi->overlap : sdgpu_iter_par{};
+  args.chiKeepLq = chi ? chi->keepLq : 0u;
   if (dPassOut && ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
   const uint32_t needC = (maxLenB + 31) / 32;
+  if (chi) {  // chimera probes: a few thousand pairs per sample, int32 kernels with the probe compiled in
+    ctx->lastKernelWasH2 = false;
+    if (needC > 16) return launchWide<true>(ctx, args, maxLenA, maxLenB);
+    return needC <= 8 ? launchI32<8, true>(ctx, args, maxLenA, maxLenB) : launchI32<16, true>(ctx, args, maxLenA, maxLenB);
+  }
   if (needC > 16) {  // reads wider than 512 columns: strip-mined int32 pass
     if (ctx->forceKernel == 2) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "packed fp16 alignment kernel not applicable to this launch");
     ctx->lastKernelWasH2 = false;

@@ -155,6 +155,8 @@ struct Clus {
   double cnt = 0;
   uint32_t firstId = 0;   // cluster::firstReadName_ stand-in (tie-break of the sort)
   uint32_t storeIdx = 0;  // device sequence-store entry (verdict-equivalent to (seq, qual))
+  bool chimeric = false;  // seqBase_.markAsChimeric()
+  uint32_t chiParent[2] = {0, 0}, chiPos[2] = {0, 0};
   std::vector<uint32_t> members;
   bool remove = false, needCons = false;
   double avgErr = 0;
@@ -757,6 +759,67 @@ class Runner {
 
 }  // namespace
 
+// collapser::markChimeras(clusters, alignerObj, chiOpts_) (clusterDown.cpp:566-577) on the final,
+// count-sorted clusters.  Which (parent, candidate) pairs are examined depends only on the counts,
+// so all probes go to the GPU as one batch; the crossover search over the returned 32-byte
+// records stays here.
+static int markChimeras(sdgpu_ctx* ctx, const sdq_opts& O, ClusVec& cs, sdq_stats& st) {
+  const size_t n = cs.size();
+  if (n <= 2) return SDGPU_OK;
+  std::vector<uint32_t> parentIdx, candIdx;
+  std::vector<uint32_t> firstPair(n + 1, 0);
+  for (size_t sub = 2; sub < n; ++sub) {
+    firstPair[sub] = uint32_t(parentIdx.size());
+    if (cs[sub].cnt <= double(O.chiRunCutOff)) continue;
+    for (size_t par = 0; par < sub; ++par) {
+      if (cs[par].cnt / cs[sub].cnt < O.chiParentFreqs) continue;
+      parentIdx.push_back(cs[par].storeIdx);
+      candIdx.push_back(cs[sub].storeIdx);
+    }
+  }
+  firstPair[n] = uint32_t(parentIdx.size());
+  for (size_t sub = 0; sub < 2; ++sub) firstPair[sub] = 0;
+  st.chimeraPairs = parentIdx.size();
+  if (parentIdx.empty()) return SDGPU_OK;
+  std::vector<sdgpu_chimera_probe> probes(parentIdx.size());
+  // profileAlignment(parent, candidate, false, true, false)
+  if (sdgpu_chimera_probe_pairs(ctx, parentIdx.data(), candIdx.data(), uint32_t(parentIdx.size()), SDGPU_USING_QUALITY,
+                                &O.chiOverlap, int(O.chiKeepLowQual), probes.data()))
+    return SDGPU_E_CUDA;
+  std::vector<std::pair<uint32_t, uint32_t>> front, back;  // (candidate base position, parent)
+  for (size_t sub = 2; sub < n; ++sub) {
+    Clus& cand = cs[sub];
+    if (cand.cnt <= double(O.chiRunCutOff)) continue;
+    front.clear();
+    back.clear();
+    const uint32_t lb = uint32_t(cand.seq.size());
+    uint32_t x = firstPair[sub];
+    for (size_t par = 0; par < sub; ++par) {
+      if (cs[par].cnt / cand.cnt < O.chiParentFreqs) continue;
+      const sdgpu_chimera_probe& pr = probes[x++];
+      if (pr.keptMismatches == 0) continue;
+      if ((pr.flags & SDGPU_CHI_FRONT_PASS) && pr.firstPos >= O.chiOverlapSizeCutoff) front.emplace_back(pr.firstPos, uint32_t(par));
+      if ((pr.flags & SDGPU_CHI_BACK_PASS) && lb - 1 - pr.lastPos >= O.chiOverlapSizeCutoff) back.emplace_back(pr.lastPos, uint32_t(par));
+    }
+    // multimap order: by position, insertion order among equal positions
+    auto byPos = [](const std::pair<uint32_t, uint32_t>& a, const std::pair<uint32_t, uint32_t>& b) { return a.first < b.first; };
+    std::stable_sort(front.begin(), front.end(), byPos);
+    std::stable_sort(back.begin(), back.end(), byPos);
+    for (const auto& f : front) {
+      for (const auto& b : back) {
+        if (cand.chimeric) break;
+        if (f.second != b.second && f.first > b.first && f.first - b.first >= O.chiPosSpacing) {
+          cand.chimeric = true;
+          cand.chiParent[0] = f.second, cand.chiPos[0] = f.first;
+          cand.chiParent[1] = b.second, cand.chiPos[1] = b.first;
+          ++st.chimericClusters;
+        }
+      }
+    }
+  }
+  return SDGPU_OK;
+}
+
 struct sdq_result {
   std::vector<Clus> pool;  // storage of every cluster object of the run
   ClusVec clusters;        // the final clusters, sorted
@@ -920,6 +983,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     for (uint32_t u : clusters[c].members)
       for (uint32_t r : R.uniq[u].inputIdx) res->membership[r] = c;
   }
+  if (opts->markChimeras && markChimeras(ctx, *opts, clusters, R.st)) return bail(R.fail(SDGPU_E_CUDA));  // :566-577
   uint64_t launches1 = 0, cells1 = 0;
   float msResident = 0;
   if (sdgpu_timer_stop(ctx, &msResident)) return bail(R.fail(SDGPU_E_CUDA));
@@ -960,6 +1024,14 @@ int sdq_cluster_seq(const sdq_result* r, uint32_t c, uint8_t* seq, uint8_t* qual
   if (seq) std::memcpy(seq, cl.seq.data(), cl.seq.size());
   if (qual) std::memcpy(qual, cl.qual.data(), cl.qual.size());
   return SDGPU_OK;
+}
+
+int sdq_cluster_chimeric(const sdq_result* r, uint32_t c, uint32_t* parents, uint32_t* positions) {
+  if (!r || c >= r->clusters.size()) return 0;
+  const Clus& cl = r->clusters[c];
+  if (cl.chimeric && parents) parents[0] = cl.chiParent[0], parents[1] = cl.chiParent[1];
+  if (cl.chimeric && positions) positions[0] = cl.chiPos[0], positions[1] = cl.chiPos[1];
+  return cl.chimeric ? 1 : 0;
 }
 
 int sdq_membership(const sdq_result* r, uint32_t* clusterOfRead) {

@@ -437,6 +437,40 @@ int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* rea
   return SDGPU_OK;
 }
 
+int sdgpu_chimera_probe_pairs(sdgpu_ctx* ctx, const uint32_t* parentIdx, const uint32_t* candIdx, uint32_t nPairs,
+                              uint32_t flags, const sdgpu_iter_par* chiOverlap, int keepLowQualityMismatches,
+                              sdgpu_chimera_probe* out) {
+  if (!ctx || !chiOverlap || (nPairs && (!parentIdx || !candIdx || !out))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  if (nPairs == 0) return SDGPU_OK;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  uint32_t maxA = 0, maxB = 0;
+  for (uint32_t x = 0; x < nPairs; ++x) {
+    if (parentIdx[x] >= nSeqs || candIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "pair index out of range");
+    maxA = std::max<uint32_t>(maxA, uint32_t(ctx->hOffsets[parentIdx[x] + 1] - ctx->hOffsets[parentIdx[x]]));
+    maxB = std::max<uint32_t>(maxB, uint32_t(ctx->hOffsets[candIdx[x] + 1] - ctx->hOffsets[candIdx[x]]));
+  }
+  const uint64_t bytesIdx = uint64_t(nPairs) * 4, bytesOut = uint64_t(nPairs) * sizeof(sdgpu_chimera_probe);
+  int rc = sd_ensure_stage(ctx, bytesOut + 2 * bytesIdx + 256);
+  if (rc) return rc;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->dStage);
+  SdChimeraReq req;
+  req.dOut = reinterpret_cast<sdgpu_chimera_probe*>(base);
+  req.overlap = *chiOverlap;
+  req.keepLq = keepLowQualityMismatches ? 1u : 0u;
+  uint32_t* dRef = reinterpret_cast<uint32_t*>(base + bytesOut);
+  uint32_t* dRead = dRef + nPairs;
+  SD_CUDA(ctx, cudaMemcpyAsync(dRef, parentIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(dRead, candIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  rc = sd_launch_align(ctx, dRef, dRead, nPairs, flags, nullptr, nullptr, 0, maxA, maxB, nullptr, &req);
+  if (rc) return rc;
+  SD_CUDA(ctx, cudaMemcpyAsync(out, req.dOut, bytesOut, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->h2dBytes += 2 * bytesIdx;
+  ctx->d2hBytes += bytesOut;
+  return SDGPU_OK;
+}
+
 int sdgpu_align_pass_submit(sdgpu_ctx* ctx, int slot, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,
                             uint32_t flags) {
   if (!ctx || slot < 0 || slot > 1 || !nPairs || !refIdx || !readIdx) return sd_fail(ctx, SDGPU_E_ARG, "bad argument");

@@ -124,9 +124,15 @@ DevSeqs sd_dev_seqs(const sdgpu_ctx* ctx);
 DevKmerIndex sd_dev_index(const sdgpu_ctx* ctx);
 
 // align_kernel.cu
+struct SdChimeraReq {  // sdgpu_chimera_probe_pairs: per-pair probe output + chiOpts_
+  sdgpu_chimera_probe* dOut;
+  sdgpu_iter_par overlap;
+  uint32_t keepLq;
+};
 int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx, uint32_t nPairs,
                     uint32_t flags, sdgpu_comparison* dOut, sdgpu_gap* dGaps, uint32_t gapCap,
-                    uint32_t maxLenA, uint32_t maxLenB, uint64_t* dPassOut = nullptr);
+                    uint32_t maxLenA, uint32_t maxLenB, uint64_t* dPassOut = nullptr,
+                    const SdChimeraReq* chi = nullptr);
 // kmer_kernels.cu
 int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, uint32_t kLen, uint32_t runCutOff,
                         int byPos, int expandPos, uint32_t expandSize);

@@ -24,12 +24,15 @@ class IterParC(C.Structure):
 class QlusterOptsC(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("kLen", "runCutOff", "kmersByPosition", "expandKmerPos", "expandKmerSize",
                                           "checkKmers", "startWithSingles", "leaveOutSinglets", "dontRecalLowFreq",
-                                          "smallReadSize")]
+                                          "smallReadSize", "markChimeras", "chiKeepLowQual", "chiRunCutOff",
+                                          "chiOverlapSizeCutoff", "chiPosSpacing", "reserved")] + \
+               [("chiParentFreqs", C.c_double), ("chiOverlap", IterParC)]
 
 
 class StatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("inputReads", "uniqueSeqs", "finalClusters", "pairsComputed", "pairsConsumed",
-                                          "consensusAligns", "cellUpdates", "gpuBatches", "onDemandPairs")] + \
+                                          "consensusAligns", "cellUpdates", "gpuBatches", "onDemandPairs",
+                                          "chimeraPairs", "chimericClusters")] + \
                [("secondsGpu", C.c_double), ("secondsTotal", C.c_double), ("msResident", C.c_double)]
 
 
@@ -47,11 +50,24 @@ class QlusterPars:
     leaveOutSinglets: bool = False
     dontRecalLowFreqMismatchAndReRun: bool = False
     smallReadSize: int = 18  # 2 * kLength (clusterDownSetUp.cpp:406)
+    # pars_.chiOpts_ (clusterDownSetUp.cpp:372-381): on unless --noMarkChimeras, parentFreqs 2
+    markChimeras: bool = True
+    parFreqs: float = 2.0
+    chiKeepLowQaulityMismatches: bool = False
+    chiPosSpacing: int = 1
+    chiRunCutOff: int = 1
+    chiOverlapSizeCutoff: int = 5
+    # chiOverlap_: njhseq's ChimeraOpts defaults + `largeBaseIndel_ = .99` (clusterDown.cpp:572)
+    chiOverlap: tuple = (2.0, 1.0, 0.99, 0.0, 0.0, 1.0)  # one, two, large indel; hq, lq, lowKmer mismatches
 
     def to_c(self):
+        o = self.chiOverlap
         return QlusterOptsC(self.kLength, self.runCutOff, int(self.kmersByPosition), int(self.expandKmerPos),
                             self.expandKmerSize, int(self.checkKmers), int(self.startWithSingles),
-                            int(self.leaveOutSinglets), int(self.dontRecalLowFreqMismatchAndReRun), self.smallReadSize)
+                            int(self.leaveOutSinglets), int(self.dontRecalLowFreqMismatchAndReRun), self.smallReadSize,
+                            int(self.markChimeras), int(self.chiKeepLowQaulityMismatches), self.chiRunCutOff,
+                            self.chiOverlapSizeCutoff, self.chiPosSpacing, 0, float(self.parFreqs),
+                            IterParC(0, 0, o[0], o[1], o[2], o[3], o[4], o[5], 0, 0, 0.0))
 
 
 def iter_pars_to_c(iters):
@@ -85,6 +101,8 @@ def _bind(lib):
     lib.sdq_cluster_cnt.argtypes = [v, C.c_uint32]
     lib.sdq_cluster_seq.argtypes = [v, C.c_uint32, v, v]
     lib.sdq_membership.argtypes = [v, v]
+    lib.sdq_cluster_chimeric.restype = C.c_int
+    lib.sdq_cluster_chimeric.argtypes = [v, C.c_uint32, v, v]
     _bound = True
 
 
@@ -110,20 +128,7 @@ def qluster(aligner: GpuAligner, bases, quals, offsets, pars: QlusterPars = None
     if rc != _abi.OK:
         raise SdgpuError(rc, (lib.sdq_last_error() or b"").decode())
     try:
-        st = StatsC()
-        lib.sdq_get_stats(h, C.byref(st))
-        res = {"stats": {k: getattr(st, k) for k, _ in StatsC._fields_}, "clusters": []}
-        if want_clusters:
-            for c in range(lib.sdq_num_clusters(h)):
-                ln = lib.sdq_cluster_len(h, c)
-                s = np.zeros(ln, np.uint8)
-                q = np.zeros(ln, np.uint8)
-                lib.sdq_cluster_seq(h, c, _ptr(s), _ptr(q))
-                res["clusters"].append((s.tobytes().decode(), q, lib.sdq_cluster_cnt(h, c)))
-        mem = np.zeros(n, np.uint32)
-        lib.sdq_membership(h, _ptr(mem))
-        res["membership"] = mem
-        return res
+        return _result_to_dict(lib, h, n, want_clusters)
     finally:
         lib.sdq_free(h)
 
@@ -139,6 +144,11 @@ def _result_to_dict(lib, h, n, want_clusters):
             q = np.zeros(ln, np.uint8)
             lib.sdq_cluster_seq(h, c, _ptr(s), _ptr(q))
             res["clusters"].append((s.tobytes().decode(), q, lib.sdq_cluster_cnt(h, c)))
+    res["chimeras"] = {}  # cluster -> (frontParent, backParent, frontPos, backPos), chiParentsInfo.txt's columns
+    for c in range(lib.sdq_num_clusters(h)):
+        par, pos = (C.c_uint32 * 2)(), (C.c_uint32 * 2)()
+        if lib.sdq_cluster_chimeric(h, c, par, pos):
+            res["chimeras"][c] = (par[0], par[1], pos[0], pos[1])
     mem = np.zeros(n, np.uint32)
     lib.sdq_membership(h, _ptr(mem))
     res["membership"] = mem
@@ -184,3 +194,13 @@ def qluster_many(params, samples, device=0, nWorkers=2, pars: QlusterPars = None
 def shard_samples(nSamples, rank, world):
     """Static round-robin of independent samples over ranks (no data-path collective)."""
     return list(range(rank, nSamples, world))
+
+
+def shard_pair_blocks(totalPairs, rank, world):
+    """Contiguous block [firstPair, firstPair + nPairs) of an all-vs-all pair list for this rank
+    (sdgpu_all_vs_all's firstPair / nPairs): blocks are disjoint, cover every pair once and differ
+    by at most one pair; sequences are replicated, results stay on the rank that computed them
+    (no data-path collective)."""
+    base, extra = divmod(int(totalPairs), int(world))
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)

@@ -145,3 +145,27 @@ PARAM_SETS = {
 
 def params_for(name):
     return make_params(**PARAM_SETS[name])
+
+
+def chimera_sample(rng, length=200, nDiff=8, counts=(60, 45, 8, 6), qual=38):
+    """Reads of two parents, their crossover (front of parent 0, back of parent 1) and a one-SNP
+    variant of parent 0, all error-free at high quality: (bases, quals, offsets, seqs)."""
+    p0 = rand_seq(rng, length)
+    p1 = p0.copy()
+    pos = np.sort(rng.choice(np.arange(10, length - 10), nDiff, replace=False))
+    for x in pos:
+        p1[x] = BASES[(list(BASES).index(p1[x]) + 1 + int(rng.integers(3))) % 4]
+    cut = int((pos[nDiff // 2 - 1] + pos[nDiff // 2]) // 2)
+    chi = np.concatenate([p0[:cut], p1[cut:]])
+    var = p0.copy()
+    x = int(pos[-1]) + 3
+    var[x] = BASES[(list(BASES).index(var[x]) + 1) % 4]
+    seqs = []
+    for s, c in zip((p0, p1, chi, var), counts):
+        seqs += [s] * c
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]
+    offsets = np.zeros(len(seqs) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    bases = np.concatenate(seqs)
+    return bases, np.full(len(bases), qual, np.uint8), offsets, (p0, p1, chi, var), cut

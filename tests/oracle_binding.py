@@ -13,17 +13,8 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "_build", "libsdoracle.so")
 
 
-class IterParC(C.Structure):
-    _fields_ = [("stopCheck", C.c_uint32), ("smallCutoff", C.c_uint32), ("oneBaseIndel", C.c_double),
-                ("twoBaseIndel", C.c_double), ("largeBaseIndel", C.c_double), ("hqMismatches", C.c_double),
-                ("lqMismatches", C.c_double), ("lowKmerMismatches", C.c_double), ("onPerId", C.c_uint32),
-                ("onHqPerId", C.c_uint32), ("perId", C.c_double)]
-
-
-class QlusterOptsC(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("kLen", "runCutOff", "kmersByPosition", "expandKmerPos", "expandKmerSize",
-                                          "checkKmers", "startWithSingles", "leaveOutSinglets", "dontRecalLowFreq",
-                                          "smallReadSize")]
+# POD layouts are shared with the product's headers (include/sdgpu_qluster.h ≙ oracle/sd_oracle.h)
+from seekdeep_b200.qluster import IterParC, QlusterOptsC  # noqa: E402
 
 
 def iter_pars_to_c(iters):
@@ -71,6 +62,11 @@ class Oracle:
         lib.sdo_qluster_cluster_cnt.argtypes = [v, C.c_uint32]
         lib.sdo_qluster_cluster_seq.argtypes = [v, C.c_uint32, v, v]
         lib.sdo_qluster_membership.argtypes = [v, v]
+        lib.sdo_qluster_cluster_chimeric.restype = C.c_int
+        lib.sdo_qluster_cluster_chimeric.argtypes = [v, C.c_uint32, v, v]
+        lib.sdo_chimera_probe_batch.restype = C.c_int
+        lib.sdo_chimera_probe_batch.argtypes = [C.POINTER(_abi.Params), v, v, v, v, v, v, C.c_uint32, C.c_uint32,
+                                                C.POINTER(IterParC), C.c_int, v]
 
     # one pair, strings in
     def align_global(self, params, a, b, gapCap=64):
@@ -110,6 +106,20 @@ class Oracle:
                                               _p(readIdx), n, flags, _p(out), _p(gaps), gapCap)
         assert rc == 0
         return (out, gaps) if gapCap else out
+
+    def chimera_probe_batch(self, params, bases, quals, offsets, parentIdx, candIdx, chiOverlap, keepLowQual=False,
+                            flags=_abi.USING_QUALITY, kmaps=None):
+        bases = np.ascontiguousarray(bases, np.uint8)
+        quals = None if quals is None else np.ascontiguousarray(quals, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        parentIdx = np.ascontiguousarray(parentIdx, np.uint32)
+        candIdx = np.ascontiguousarray(candIdx, np.uint32)
+        out = np.zeros(len(parentIdx), _abi.CHIMERA_PROBE_DTYPE)
+        rc = self.lib.sdo_chimera_probe_batch(C.byref(params), kmaps, _p(bases), _p(quals), _p(offsets), _p(parentIdx),
+                                              _p(candIdx), len(parentIdx), flags, C.byref(chiOverlap),
+                                              int(keepLowQual), _p(out))
+        assert rc == 0
+        return out
 
     def index_kmers(self, bases, offsets, cnts, kLen, runCutOff, byPos=True, expandPos=False, expandSize=0, seqIdx=None):
         bases = np.ascontiguousarray(bases, np.uint8)
@@ -152,6 +162,11 @@ class Oracle:
                 q = np.zeros(ln, np.uint8)
                 self.lib.sdo_qluster_cluster_seq(h, c, _p(s), _p(q))
                 res["clusters"].append((s.tobytes().decode(), q, self.lib.sdo_qluster_cluster_cnt(h, c)))
+            res["chimeras"] = {}
+            for c in range(nc):
+                par, pos = (C.c_uint32 * 2)(), (C.c_uint32 * 2)()
+                if self.lib.sdo_qluster_cluster_chimeric(h, c, par, pos):
+                    res["chimeras"][c] = (par[0], par[1], pos[0], pos[1])
             mem = np.zeros(n, np.uint32)
             self.lib.sdo_qluster_membership(h, _p(mem))
             res["membership"] = mem

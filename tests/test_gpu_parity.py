@@ -378,3 +378,31 @@ def test_random_parameter_fuzz(oracle):
                 oracle.free_kmaps(km)
             H.assert_comparisons_equal(got, want)
             assert np.array_equal(gg, wg), (trial, mode)
+
+
+@pytest.mark.parametrize("pname", ["qluster", "degenHomopolymer", "countEnds", "asym"])
+@pytest.mark.parametrize("length", [90, 250, 300, 600])
+def test_chimera_probe_matches_oracle(oracle, pname, length):
+    """sdgpu_chimera_probe_pairs vs the oracle's markChimeras probe (windowed profileAlignment):
+    kept-mismatch counts, first/last positions and the front/back chiOverlap verdicts, with and
+    without low-quality mismatches kept, loose and strict overlap thresholds."""
+    from seekdeep_b200.qluster import IterParC
+    rng = np.random.default_rng(length + len(pname))
+    bases, quals, offsets, cnts, _, _ = H.make_store(rng, 40, length, lowFrac=0.25)
+    n = 600
+    par = rng.integers(0, 40, n).astype(np.uint32)
+    cand = rng.integers(0, 40, n).astype(np.uint32)
+    params = H.params_for(pname)
+    seen = set()
+    with GpuAligner(params) as al:
+        al.upload_seqs(bases, quals, offsets, cnts)
+        for ov in (IterParC(0, 0, 2.0, 1.0, 0.99, 0.0, 0.0, 1.0, 0, 0, 0.0), IterParC(0, 0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0, 0, 0.0),
+                   IterParC(0, 0, 0.6, 5.0, 5.0, 0.0, 3.0, 0.0, 0, 0, 0.0)):
+            for keep in (False, True):
+                got = al.chimera_probe(par, cand, ov, keepLowQualityMismatches=keep)
+                want = oracle.chimera_probe_batch(params, bases, quals, offsets, par, cand, ov, keepLowQual=keep)
+                for name in got.dtype.names:
+                    bad = np.nonzero(got[name] != want[name])[0]
+                    assert bad.size == 0, f"{name} keep={keep}: pair {bad[0]} got {got[name][bad[0]]} want {want[name][bad[0]]}"
+                seen |= set(np.unique(got["flags"]).tolist())
+    assert seen == {0, 1, 2, 3}  # every verdict combination was exercised

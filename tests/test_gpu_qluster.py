@@ -13,9 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def oracle_opts(p: sd.QlusterPars):
-    return oracle_binding.QlusterOptsC(p.kLength, p.runCutOff, int(p.kmersByPosition), int(p.expandKmerPos),
-                                       p.expandKmerSize, int(p.checkKmers), int(p.startWithSingles),
-                                       int(p.leaveOutSinglets), int(p.dontRecalLowFreqMismatchAndReRun), p.smallReadSize)
+    return p.to_c()  # sdo_qluster_opts has sdq_opts' layout
 
 
 def assert_same(got, want):
@@ -23,6 +21,7 @@ def assert_same(got, want):
     assert np.array_equal(got["membership"], want["membership"])
     for (gs, gq, gc), (ws, wq, wc) in zip(got["clusters"], want["clusters"]):
         assert gs == ws and gc == wc and np.array_equal(gq, wq)
+    assert got["chimeras"] == want["chimeras"]
 
 
 def run_pair(oracle, params, pars, iters, bases, quals, offsets, init=None):
@@ -133,3 +132,29 @@ def test_config1_full_size_properties():
         src = which[mem == ci]
         assert (src == hs[s]).mean() > 0.90  # a 1-SNP neighbour's erroneous reads can land here legitimately
     assert a["stats"]["uniqueSeqs"] == len({x.tobytes() for x in seqs})
+
+
+def test_mark_chimeras_matches_oracle(oracle):
+    """collapser::markChimeras at the end of the run: the crossover of two abundant parents is
+    flagged with the same parents / positions as the oracle, noisy reads included."""
+    from tests import helpers as H
+    rng = np.random.default_rng(21)
+    bases, quals, offsets, (p0, p1, chi, var), cut = H.chimera_sample(rng, length=240, counts=(300, 220, 40, 25))
+    # sequencing noise on top: substitutions at low quality
+    bases = bases.copy()
+    quals = quals.copy()
+    hit = rng.random(len(bases)) < 0.003
+    bases[hit] = H.BASES[rng.integers(0, 4, int(hit.sum()))]
+    quals[hit] = rng.integers(2, 15, int(hit.sum()))
+    its = CollapseIterations.gen_illumina_default_pars(100)
+    for pars in (sd.QlusterPars(), sd.QlusterPars(chiKeepLowQaulityMismatches=True, chiPosSpacing=3),
+                 sd.QlusterPars(markChimeras=False), sd.QlusterPars(parFreqs=1.0, chiRunCutOff=0)):
+        got, want = run_pair(oracle, sd.make_params(), pars, its, bases, quals, offsets)
+        assert_same(got, want)
+        if pars.markChimeras:
+            assert got["stats"]["chimeraPairs"] > 0
+            flagged = [got["clusters"][c][0] for c in got["chimeras"]]
+            assert bytes(chi).decode() in flagged
+            assert got["stats"]["chimericClusters"] == len(got["chimeras"])
+        else:
+            assert got["chimeras"] == {} and got["stats"]["chimeraPairs"] == 0

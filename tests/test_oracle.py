@@ -184,3 +184,52 @@ def test_identity_fields(oracle):
     assert comp.overLappingEvents == ev
     assert comp.eventBasedIdentity == comp.highQualityMatches / ev
     assert comp.basesInAln == len(read)
+
+
+def test_mark_chimeras_crossover(oracle):
+    """Two abundant parents, their crossover and a one-SNP variant: only the crossover is flagged,
+    with (front parent, back parent) and crossover mismatch positions that bracket the cut."""
+    import seekdeep_b200 as sd
+    from seekdeep_b200.iterpars import CollapseIterations
+    rng = np.random.default_rng(11)
+    bases, quals, offsets, (p0, p1, chi, var), cut = H.chimera_sample(rng)
+    its = CollapseIterations.gen_illumina_default_pars(100)
+    pars = sd.QlusterPars()
+    res = oracle.qluster(sd.make_params(), pars.to_c(), its.iters, its.iters, bases, quals, offsets)
+    seqs = [c[0] for c in res["clusters"]]
+    assert seqs == [bytes(s).decode() for s in (p0, p1, chi, var)]
+    assert list(res["chimeras"]) == [2]
+    front, back, fpos, bpos = res["chimeras"][2]
+    assert (front, back) == (0, 1) and bpos < cut <= fpos
+    off = sd.QlusterPars(markChimeras=False)
+    assert oracle.qluster(sd.make_params(), off.to_c(), its.iters, its.iters, bases, quals, offsets)["chimeras"] == {}
+    # a parent must be parFreqs times as abundant as the candidate
+    strict = sd.QlusterPars(parFreqs=7.0)
+    assert oracle.qluster(sd.make_params(), strict.to_c(), its.iters, its.iters, bases, quals, offsets)["chimeras"] == {}
+
+
+def test_chimera_probe_windows(oracle):
+    """Front / back windows of the probe: low-quality mismatches are dropped from the kept list but
+    still judged by chiOverlap's lqMismatches; gaps inside a window use its indel thresholds."""
+    from seekdeep_b200.qluster import IterParC
+    p = make_params()
+    a = "ACGTTGCAAGCTAGCTTAGGCTAACGTAGCTAGGATCCATGCAAGT"
+    b = list(a)
+    b[8] = "C"    # low quality mismatch (front window)
+    b[20] = "A"   # kept mismatch
+    b[35] = "G"   # kept mismatch
+    b = "".join(b)
+    qa = np.full(len(a), 38, np.uint8)
+    qb = qa.copy()
+    qb[8] = 5
+    bases = np.frombuffer((a + b).encode(), np.uint8)
+    quals = np.concatenate([qa, qb])
+    offsets = np.array([0, len(a), 2 * len(a)], np.uint64)
+    ov = IterParC(0, 0, 2.0, 1.0, 0.99, 0.0, 0.0, 1.0, 0, 0, 0.0)
+    pr = oracle.chimera_probe_batch(p, bases, quals, offsets, [0], [1], ov)[0]
+    assert (pr["keptMismatches"], pr["firstPos"], pr["lastPos"]) == (2, 20, 35)
+    assert pr["flags"] == 2          # the low-quality mismatch fails the front window, the back passes
+    ov.lqMismatches = 1.0
+    assert oracle.chimera_probe_batch(p, bases, quals, offsets, [0], [1], ov)[0]["flags"] == 3
+    keep = oracle.chimera_probe_batch(p, bases, quals, offsets, [0], [1], ov, keepLowQual=True)[0]
+    assert (keep["keptMismatches"], keep["firstPos"], keep["flags"]) == (3, 8, 3)
