@@ -114,6 +114,78 @@ __global__ void __launch_bounds__(256) kmerProfileKernel(DevSeqs seqs, uint32_t 
   }
 }
 
+// ACGT-only fast path of the profile build (every code < 4): a lane takes 4*W consecutive start
+// positions, fetches the 4*W + kLen - 1 codes they cover as W + 3 aligned words, realigns them with
+// funnel shifts and squeezes each word's four codes into one byte (first base most significant),
+// so every k-mer id is a 2*kLen-bit field of one 64-bit register: per sequence the LSU sees
+// W + 3 word loads per lane instead of two byte loads per position.
+template <int W>
+__device__ __forceinline__ void profileLane4(const uint32_t* codeWords, uint64_t off, uint32_t base, uint32_t len,
+                                             uint32_t nk, uint32_t kLen, uint32_t mask, uint32_t lane, uint32_t* mine) {
+  const uint32_t p0 = base + lane * 4 * W;
+  if (p0 >= nk) return;
+  const uint64_t b = off + p0;
+  const uint32_t mis = uint32_t(b & 3);
+  const uint64_t firstWord = b >> 2, endWord = (off + len + 3) >> 2;  // words holding this sequence's codes
+  uint32_t w[W + 3];
+#pragma unroll
+  for (int j = 0; j < W + 3; ++j) w[j] = (firstWord + j < endWord) ? __ldg(codeWords + firstWord + j) : 0u;
+  uint64_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < W + 2; ++j) {
+    const uint32_t r = __funnelshift_r(w[j], w[j + 1], 8 * mis) & 0x03030303u;
+    bits = (bits << 8) | ((r * 0x40100401u) >> 24);  // c0<<6 | c1<<4 | c2<<2 | c3
+  }
+  constexpr int T = 4 * (W + 2);  // codes held in `bits`; code i sits at bit 2*(T-1-i)
+#pragma unroll
+  for (int i = 0; i < 4 * W; ++i) {
+    if (p0 + i < nk) {
+      const uint32_t id = uint32_t(bits >> (2 * (T - i - int(kLen)))) & mask;
+      atomicAdd(&mine[id >> 1], 1u << (16 * (id & 1)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 6) kmerProfileKernel4(DevSeqs seqs, uint32_t kLen, uint32_t profSize,
+                                                             uint16_t* profiles) {
+  extern __shared__ uint4 sProfVec[];
+  const uint32_t warpInCta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warpsPerCta = blockDim.x >> 5;
+  const uint32_t vecs = profSize / 8;
+  uint4* mineVec = sProfVec + warpInCta * vecs;
+  uint32_t* mine = reinterpret_cast<uint32_t*>(mineVec);
+  const uint32_t* codeWords = reinterpret_cast<const uint32_t*>(seqs.codes);  // cudaMalloc'd: aligned
+  const uint32_t mask = (1u << (2 * kLen)) - 1u;
+  for (uint32_t x = lane; x < vecs; x += 32) mineVec[x] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  for (uint32_t s = blockIdx.x * warpsPerCta + warpInCta; s < seqs.n; s += gridDim.x * warpsPerCta) {
+    const uint64_t off = seqs.offsets[s];
+    const uint32_t len = uint32_t(seqs.offsets[s + 1] - off);
+    if (len >= kLen) {
+      const uint32_t nk = len - kLen + 1;
+      for (uint32_t base = 0; base < nk; base += 512) {
+        const uint32_t rem = nk - base;
+        if (rem <= 128) {
+          profileLane4<1>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
+        } else if (rem <= 256) {
+          profileLane4<2>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
+        } else if (rem <= 384) {
+          profileLane4<3>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
+        } else {
+          profileLane4<4>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
+        }
+      }
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(profiles + size_t(s) * profSize);
+    for (uint32_t x = lane; x < vecs; x += 32) {  // write out and leave the histogram zeroed for the next sequence
+      dst[x] = mineVec[x];
+      mineVec[x] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+  }
+}
+
 __device__ __forceinline__ uint32_t minSum8(const uint4& p, const uint4& q, uint32_t acc) {
   acc = __vadd2(acc, __vminu2(p.x, q.x));
   acc = __vadd2(acc, __vminu2(p.y, q.y));
@@ -307,12 +379,18 @@ int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   for (uint32_t x = 0; x + 1 < kLen; ++x) top *= sigma;
   uint32_t warpsPerCta = uint32_t((200u << 10) / (size_t(profSize) * 2));  // stay under the 227 KB shared-memory limit
   warpsPerCta = warpsPerCta < 1 ? 1 : (warpsPerCta > 8 ? 8 : warpsPerCta);
+  const bool acgtOnly = sigma <= 4 && kLen <= 8 && profSize == (1u << (2 * kLen));  // codes 0..3: 2-bit fast path
   const size_t smem = size_t(warpsPerCta) * profSize * 2;
-  SD_CUDA(ctx, cudaFuncSetAttribute(kmerProfileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  SD_CUDA(ctx, cudaFuncSetAttribute(acgtOnly ? (const void*)kmerProfileKernel4 : (const void*)kmerProfileKernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   uint32_t grid = (nSeqs + warpsPerCta - 1) / warpsPerCta;
   const uint32_t maxGrid = uint32_t(ctx->numSMs) * 32;  // (swept 8..unbounded on B200: no effect beyond 16)
   if (grid > maxGrid) grid = maxGrid;
-  kmerProfileKernel<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, top, profSize, ctx->dProfiles);
+  if (acgtOnly) {
+    kmerProfileKernel4<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, profSize, ctx->dProfiles);
+  } else {
+    kmerProfileKernel<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, top, profSize, ctx->dProfiles);
+  }
   SD_CUDA(ctx, cudaGetLastError());
   ++ctx->launches;
   return SDGPU_OK;

@@ -406,3 +406,35 @@ def test_chimera_probe_matches_oracle(oracle, pname, length):
                     assert bad.size == 0, f"{name} keep={keep}: pair {bad[0]} got {got[name][bad[0]]} want {want[name][bad[0]]}"
                 seen |= set(np.unique(got["flags"]).tolist())
     assert seen == {0, 1, 2, 3}  # every verdict combination was exercised
+
+
+def test_kmer_profiles_ragged_lengths_both_paths(oracle):
+    """Profile build over lengths 1..1300 (one to four words per lane, several 512-position rounds,
+    sequences shorter than k) for the ACGT-only 2-bit path and, with an N in the store, the general
+    sigma^k path: self-comparison must equal len-k+1 and random pairs must match the oracle."""
+    rng = np.random.default_rng(77)
+    lens = np.concatenate([np.arange(1, 40), rng.integers(40, 700, 60), [127, 128, 129, 131, 132, 133, 256, 257, 259, 260,
+                                                                        384, 385, 388, 389, 511, 512, 513, 516, 517, 1023, 1300]])
+    for withN in (False, True):
+        seqs = [H.rand_seq(rng, int(n)) for n in lens]
+        rel = [H.mutate(rng, s, 3, 1, 1) for s in seqs[40:80]]  # related copies: many shared k-mers
+        seqs = seqs + rel
+        if withN:
+            seqs[50] = seqs[50].copy()
+            seqs[50][len(seqs[50]) // 2] = ord("N")
+        b, q, off = pack_seqs([s.tobytes() for s in seqs], [np.zeros(len(s), np.uint8) for s in seqs])
+        n = len(seqs)
+        with GpuAligner(make_params()) as al:
+            al.upload_seqs(b, q, off)
+            for k in (2, 4, 5, 6, 7) if not withN else (3, 5):
+                al.build_kmer_profiles(k)
+                me = np.arange(n, dtype=np.uint32)
+                shared, frac = al.compare_kmers(me, me)
+                L = np.array([len(s) for s in seqs])
+                assert np.array_equal(shared, np.where(L >= k, L - k + 1, 0))
+                a = np.concatenate([rng.integers(0, n, 300), np.arange(40, 80)]).astype(np.uint32)
+                c = np.concatenate([rng.integers(0, n, 300), np.arange(len(lens), len(lens) + 40)]).astype(np.uint32)
+                shared, frac = al.compare_kmers(a, c)
+                for i in range(len(a)):
+                    ws, wf = oracle.kmer_compare(seqs[a[i]].tobytes(), seqs[c[i]].tobytes(), k)
+                    assert shared[i] == ws and frac[i] == wf, (withN, k, i, len(seqs[a[i]]), len(seqs[c[i]]))
