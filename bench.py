@@ -244,7 +244,8 @@ def main():
             "steps": K, "warmup": args.warmup, "ms_per_step": res_ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": dict(workload_config(nReads), unique_seqs=stats["uniqueSeqs"], final_clusters=stats["finalClusters"],
-                           pairs_computed_per_step=stats["pairsComputed"], consensus_aligns_per_step=stats["consensusAligns"]),
+                           pairs_computed_per_step=stats["pairsComputed"], consensus_aligns_per_step=stats["consensusAligns"],
+                           chimera_probes_per_step=stats["chimeraPairs"], chimeric_clusters=stats["chimericClusters"]),
             "gcups": cellsAll / (res_ms_max * 1e-3) / 1e9,
             "e2e": {"value": readsAll * K / (wall_ms_max * 1e-3), "unit": "reads/s",
                     "h2d_bytes_per_step": int(prof["h2dBytes"] // K), "d2h_bytes_per_step": int(prof["d2hBytes"] // K) + d2h_result,
