@@ -277,6 +277,13 @@ int sdgpu_counters(sdgpu_ctx* ctx, uint64_t* kernelLaunches, uint64_t* cellUpdat
  * sdgpu_last_kernel reports which one the last launch used (1 or 2).  For tests / profiling. */
 int sdgpu_set_kernel(sdgpu_ctx* ctx, int mode);
 int sdgpu_last_kernel(sdgpu_ctx* ctx);
+/* Banded first pass.  mode 0 (default): every launch of at least 64 pairs first runs a 64-diagonal
+ * banded forward pass; a pair whose banded score exceeds the best score any alignment leaving the
+ * band could reach (maxSub x the diagonal moves left to it, gap penalties being >= 0) provably has
+ * its full-matrix optimum, traceback and errorProfile inside the band and is finished there; all
+ * other pairs are recomputed by the full-matrix kernel in the same call.  Results are identical to
+ * mode 1 (full-matrix kernels only) by construction; sdgpu_set_kernel(1|2) also turns the band off. */
+int sdgpu_set_band(sdgpu_ctx* ctx, int mode);
 
 /* Measurement bookkeeping for bench.py: with profiling enabled every alignment-kernel launch is
  * bracketed by CUDA events on the ctx stream; sdgpu_profile_read sums them (optionally resets). */
@@ -284,8 +291,12 @@ typedef struct sdgpu_profile {
   double alignKernelMs;        /* sum of per-launch device time of the alignment kernel */
   uint64_t alignKernelLaunches;
   uint64_t kernelLaunches;     /* all kernels this library launched on the ctx */
-  uint64_t cellUpdates;        /* DP cells computed by those launches */
+  uint64_t cellUpdates;        /* sum of lenA x lenB over the pairs those launches finished (the GCUPS numerator) */
   uint64_t h2dBytes, d2hBytes; /* bytes the library copied across PCIe */
+  uint64_t evaluatedCells;     /* DP cells the kernels really evaluated (band cells + full matrices of the rest) */
+  uint64_t bandCells;          /* ... of which inside banded passes */
+  uint64_t bandCertifiedCells; /* sum of lenA x lenB over the pairs finished by the banded pass */
+  double bandKernelMs;         /* part of alignKernelMs spent in banded passes */
 } sdgpu_profile;
 int sdgpu_profile_enable(sdgpu_ctx* ctx, int on);
 int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset);

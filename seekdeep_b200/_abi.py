@@ -103,6 +103,7 @@ SIGNATURES = {
     "sdgpu_counters": (C.c_int, [_ctx, _u64p, _u64p]),
     "sdgpu_set_kernel": (C.c_int, [_ctx, C.c_int]),
     "sdgpu_last_kernel": (C.c_int, [_ctx]),
+    "sdgpu_set_band": (C.c_int, [_ctx, C.c_int]),
     "sdgpu_profile_enable": (C.c_int, [_ctx, C.c_int]),
     "sdgpu_profile_read": (C.c_int, [_ctx, C.c_void_p, C.c_int]),
     "sdgpu_measure_int32_peak": (C.c_int, [_ctx, C.c_int, _f64p]),

@@ -233,10 +233,16 @@ class GpuAligner:
     def profile_enable(self, on=True):
         self._check(self._lib.sdgpu_profile_enable(self._ctx, int(on)))
 
+    def set_band(self, mode):
+        """0 = banded first pass + exact redo (default), 1 = full-matrix kernels only."""
+        self._check(self._lib.sdgpu_set_band(self._ctx, int(mode)))
+
     def profile_read(self, reset=True):
         class Prof(C.Structure):
             _fields_ = [("alignKernelMs", C.c_double), ("alignKernelLaunches", C.c_uint64), ("kernelLaunches", C.c_uint64),
-                        ("cellUpdates", C.c_uint64), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64)]
+                        ("cellUpdates", C.c_uint64), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
+                        ("evaluatedCells", C.c_uint64), ("bandCells", C.c_uint64), ("bandCertifiedCells", C.c_uint64),
+                        ("bandKernelMs", C.c_double)]
         p = Prof()
         self._check(self._lib.sdgpu_profile_read(self._ctx, C.byref(p), int(reset)))
         return {k: getattr(p, k) for k, _ in Prof._fields_}

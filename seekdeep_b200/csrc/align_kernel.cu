@@ -34,6 +34,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 
 #include "sdgpu_internal.cuh"
 
@@ -65,6 +66,10 @@ struct AlignArgs {
   const sdgpu_iter_par* lines;  // par-file lines for the verdict mask (device)
   uint32_t nLines;
   uint64_t* passOut;   // per pair: bit l = passes line l (or NULL)
+  const uint32_t* pairMap;   // redo pass: work item -> pair index (or NULL: identity)
+  const uint32_t* nWorkDev;  // redo pass: number of work items, read on the device (or NULL: nPairs)
+  uint32_t* redo;            // banded pass: pairs whose band could not be certified
+  int maxSub;                // largest substitution score (certificate bound)
   sdgpu_chimera_probe* chiOut;  // per pair: markChimeras' front/back probe (or NULL)
   sdgpu_iter_par chiPar;        // chiOpts_.chiOverlap_
   uint32_t chiKeepLq;           // chiOpts_.keepLowQaulityMismatches_
@@ -112,6 +117,23 @@ struct BitsH2 {
     const int inWord = (C - wi * CPW) < CPW ? (C - wi * CPW) : CPW;
     const unsigned w = __ldcg(words + (size_t(t - 1) * CW + wi) * 32 + lj);
     return ~(w >> (16 * half + 16 - 5 * inWord + 5 * k)) & 31u;  // bit 0 = first inserted
+  }
+};
+
+// banded forward pass: lane = (offset - dlo) / 2, one cell per lane per anti-diagonal, six
+// anti-diagonals (30 bits) per word, first cell in the highest bits
+struct BitsBand {
+  const unsigned* words;
+  int dlo;
+  int aBase;  // first anti-diagonal of the pass (1 or 2: the one on which lanes meet their even offset)
+  __device__ __forceinline__ unsigned operator()(int i, int j) const {
+    const int st = i + j - aBase;
+    int ln = (j - i - dlo) >> 1;
+    ln = ln < 0 ? 0 : (ln > 31 ? 31 : ln);  // speculative traceback lanes may look outside the band; their result is discarded
+    const int g = st / 6, k = st - g * 6;
+    const unsigned w = __ldcg(words + size_t(g) * 32 + ln);
+    const unsigned gb = ~(w >> (5 * (5 - k))) & 31u;
+    return __brev(gb) >> 27;
   }
 };
 
@@ -571,11 +593,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernel(const A
   const DevScoring& sc = a.sc;
   const int dInt = sc.go - sc.ge;
 
+  const uint32_t nWork = a.nWorkDev ? *a.nWorkDev : a.nPairs;
   for (;;) {
     uint32_t pair = 0;
     if (lane == 0) pair = atomicAdd(&a.work[0], 1u);
     pair = __shfl_sync(FULL, pair, 0);
-    if (pair >= a.nPairs) break;
+    if (pair >= nWork) break;
+    if (a.pairMap) pair = a.pairMap[pair];
     const PairView pv = viewOf(a, pair);
     const int la = pv.la, lb = pv.lb;
     const uint8_t *cA = pv.cA, *cB = pv.cB;
@@ -721,16 +745,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernelH2(const
 
   const DevScoring& sc = a.sc;
   const int dInt = sc.go - sc.ge;
-  const uint32_t nItems = (a.nPairs + 1) / 2;
+  const uint32_t nWork = a.nWorkDev ? *a.nWorkDev : a.nPairs;
+  const uint32_t nItems = (nWork + 1) / 2;
 
   for (;;) {
     uint32_t item = 0;
     if (lane == 0) item = atomicAdd(&a.work[0], 1u);
     item = __shfl_sync(FULL, item, 0);
     if (item >= nItems) break;
-    const bool haveY = 2 * item + 1 < a.nPairs;
-    const PairView px = viewOf(a, 2 * item);
-    const PairView py = viewOf(a, haveY ? 2 * item + 1 : 2 * item);
+    const bool haveY = 2 * item + 1 < nWork;
+    const uint32_t pairX = a.pairMap ? a.pairMap[2 * item] : 2 * item;
+    const uint32_t pairY = haveY ? (a.pairMap ? a.pairMap[2 * item + 1] : 2 * item + 1) : pairX;
+    const PairView px = viewOf(a, pairX);
+    const PairView py = viewOf(a, pairY);
     const int laM = max(px.la, py.la), lbM = max(px.lb, py.lb);
 
     __half2 U[C], T[C];
@@ -826,14 +853,186 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernelH2(const
     // The shorter pair's registers keep running on padding rows, so the corner values are not kept:
     // each pair's score is re-derived from its traced alignment (finishPair<true>).
     // (views are re-read here so their eight pointers do not stay live across the DP loop)
-    finishPair<true, false>(a, Bits{ptrWords, 0}, viewOf(a, 2 * item), 0, alnA, alnB, gapRecs, sTab, lane);
-    if (haveY) finishPair<true, false>(a, Bits{ptrWords, 1}, viewOf(a, 2 * item + 1), 0, alnA, alnB, gapRecs, sTab, lane);
+    finishPair<true, false>(a, Bits{ptrWords, 0}, viewOf(a, pairX), 0, alnA, alnB, gapRecs, sTab, lane);
+    if (haveY) finishPair<true, false>(a, Bits{ptrWords, 1}, viewOf(a, pairY), 0, alnA, alnB, gapRecs, sTab, lane);
+  }
+}
+
+// =====================================================================================
+// Banded first pass.  Most (cluster, read) pairs of a collapse are near-identical, so the optimal
+// alignment hugs the main diagonal.  This kernel evaluates only the 64 diagonals (offsets j - i)
+// centred between the two corner diagonals, anti-diagonal by anti-diagonal: lane l owns offsets
+// dlo + 2l and dlo + 2l + 1 and updates one cell per step; the up / left inputs come from its own
+// previous cell or, every other step, from one neighbour (one shuffle per step).  Same recurrence,
+// same decision bits, out-of-band inputs = -inf.
+// Exactness: the banded optimum S_w is reached by a real alignment, so S_w <= S_opt.  An alignment
+// that touches offset hi + 1 has at least hi + 1 more right than down moves, hence at most
+// lb - hi - 1 diagonal moves and (gap penalties being >= 0) a score <= maxSub * (lb - hi - 1);
+// likewise maxSub * (la + lo - 1) below the band.  If S_w exceeds both bounds, every optimal
+// alignment -- and every tie the traceback's decision bits could see along it -- lies inside the
+// band, where banded and full values coincide: score, path and errorProfile are the full DP's.
+// Otherwise the pair goes to the redo list and the full-matrix kernel recomputes it.
+// =====================================================================================
+constexpr int BAND_NEG = -(1 << 28);
+constexpr int BAND_MAX_DIFF = 30;  // |lb - la| beyond which the 64-diagonal band is not tried
+
+struct BandLane {  // one lane's running state: two offsets, outputs of its previous cell, bit accumulator
+  int Tp0, Tp1;             // toDiag of the previous cell on offset d0 / d0 + 1
+  int lastDown, lastRight;  // toDown / toRight of the cell this lane updated one step ago
+  uint32_t acc;
+};
+
+// One cell update.  ODD: the lane's odd offset d0 + 1 (inputs: left from its own previous cell, up from
+// the right neighbour), else d0 (left from the left neighbour, up from its own previous cell).
+// GEN: general step with border rows / columns, last-row / last-column penalties and cells outside
+// the matrix; !GEN: interior step (every lane's cell has 2 <= i < la, 2 <= j < lb).
+template <bool ODD, bool GEN>
+__device__ __forceinline__ void bandCell(BandLane& st, int i, int j, int lane, int la, int lb, int s,
+                                         const DevScoring& sc, int dInt) {
+  int recv = ODD ? __shfl_down_sync(FULL, st.lastDown, 1) : __shfl_up_sync(FULL, st.lastRight, 1);
+  if (ODD ? (lane == 31) : (lane == 0)) recv = BAND_NEG;  // beyond the band
+  if (GEN && !(i >= 1 && i <= la && j >= 1 && j <= lb)) {
+    st.acc <<= 5;
+    return;
+  }
+  int Lin = ODD ? st.lastRight : recv;  // toRight of (i, j-1): offset d-1
+  int Uin = ODD ? recv : st.lastDown;   // toDown of (i-1, j): offset d+1
+  int Tin = ODD ? st.Tp1 : st.Tp0;      // toDiag of (i-1, j-1): same offset, two steps ago
+  int gorow = sc.go, drow = dInt, gocol = sc.go, dcol = dInt;
+  if (GEN) {
+    if (i == la) gorow = sc.goRR, drow = sc.goRR - sc.geRR;
+    if (j == lb) gocol = sc.goRQ, dcol = sc.goRQ - sc.geRQ;
+    if (i == 1) {  // row 0 border (njhseq's i == 1 case)
+      const int r0 = -sc.goLR - (j - 1) * sc.geLR;
+      Uin = r0 - gocol;
+      Tin = (j == 1) ? 0 : r0 + sc.geLR;
+    }
+    if (j == 1) {  // column 0 border (njhseq's j == 1 case)
+      const int c0 = -sc.goLQ - (i - 1) * sc.geLQ;
+      Lin = c0 - gorow;
+      if (i != 1) Tin = c0 + sc.geLQ;
+    }
+  }
+  uint32_t acc = st.acc;
+  const int D = Tin + s;
+  const int W = max(Lin, D);
+  const int d1 = Lin - D;
+  acc = __funnelshift_l(uint32_t(d1), acc, 1);
+  const int T = max(Uin, W);
+  const int d2 = Uin - W;
+  acc = __funnelshift_l(uint32_t(d2), acc, 1);
+  st.lastDown = __viaddmax_s32(Uin, dcol, W) - gocol;
+  acc = __funnelshift_l(uint32_t(d2 + dcol), acc, 1);
+  const int tt = __viaddmax_s32(Lin, drow, D);
+  acc = __funnelshift_l(uint32_t(d1 + drow), acc, 1);
+  st.lastRight = max(Uin, tt) - gorow;
+  acc = __funnelshift_l(uint32_t(Uin - tt), acc, 1);
+  st.acc = acc;
+  if (ODD) {
+    st.Tp1 = T;
+  } else {
+    st.Tp0 = T;
+  }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignBandKernel(const AlignArgs a) {
+  __shared__ int sTab[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];
+  for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS; x += blockDim.x) sTab[x] = a.sc.score[x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warpInCta = threadIdx.x >> 5;
+  const size_t warpGlobal = size_t(blockIdx.x) * WARPS_PER_CTA + warpInCta;
+  uint8_t* slab = a.scratch + warpGlobal * a.slabBytes;
+  uint32_t* ptrWords = reinterpret_cast<uint32_t*>(slab);
+  uint8_t* alnA = slab + a.ptrBytes;
+  uint8_t* alnB = alnA + a.maxAln;
+  uint32_t* gapRecs = reinterpret_cast<uint32_t*>(alnB + a.maxAln);
+  const DevScoring& sc = a.sc;
+  const int dInt = sc.go - sc.ge;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.work[5] = a.nPairs;  // read back with the redo count
+
+  for (;;) {
+    uint32_t pair = 0;
+    if (lane == 0) pair = atomicAdd(&a.work[0], 1u);
+    pair = __shfl_sync(FULL, pair, 0);
+    if (pair >= a.nPairs) break;
+    const PairView pv = viewOf(a, pair);
+    const int la = pv.la, lb = pv.lb;
+    const uint8_t *cA = pv.cA, *cB = pv.cB;
+    const int diff = lb - la;
+    bool certified = false;
+    int score = 0;
+    const int dlo = (diff - 63) >> 1;        // floor: the band [dlo, dlo + 63] is centred between offsets 0 and diff
+    const int aBase = 2 - ((2 - dlo) & 1);   // lanes meet their even offset d0 on anti-diagonals aBase, aBase + 2, ...
+    if (diff >= -BAND_MAX_DIFF && diff <= BAND_MAX_DIFF) {
+      const int d0 = dlo + 2 * lane;
+      // step pair p: anti-diagonals aBase + 2p (offset d0) and aBase + 2p + 1 (offset d0 + 1); both cells
+      // of a lane sit in row i = I0 - lane + p, columns j = i + d0 and j + 1
+      const int I0 = (aBase - dlo) >> 1;
+      const int nPairSteps = (la + lb - aBase) / 2 + 1;
+      const int nWords = (nPairSteps + 2) / 3;
+      // interior pairs: for every lane 2 <= i <= la - 1 and 2 <= j, j + 1 <= lb - 1
+      const int pBodyStart = max(max(33 - I0, 2 - I0 - dlo), 0);
+      const int pBodyEnd = min(la - I0, lb - 32 - I0 - dlo);  // exclusive
+      BandLane st{0, 0, BAND_NEG, BAND_NEG, 0u};
+      uint32_t* dst = ptrWords + lane;
+      int i = I0 - lane, j = i + d0;
+      for (int w = 0; w < nWords; ++w, dst += 32) {
+        st.acc = 0;
+        const int p = 3 * w;
+        if (p >= pBodyStart && p + 3 <= pBodyEnd) {
+          int bCode = int(__ldg(cB + j - 1));
+#pragma unroll
+          for (int k = 0; k < 3; ++k, ++i, ++j) {
+            const int* rowTab = sTab + int(__ldg(cA + i - 1)) * SDGPU_MAX_SYMBOLS;
+            const int bNext = int(__ldg(cB + j));
+            bandCell<false, false>(st, i, j, lane, la, lb, rowTab[bCode], sc, dInt);
+            bandCell<true, false>(st, i, j + 1, lane, la, lb, rowTab[bNext], sc, dInt);
+            bCode = bNext;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k, ++i, ++j) {
+            const bool rowIn = i >= 1 && i <= la;
+            const int* rowTab = sTab + (rowIn ? int(__ldg(cA + i - 1)) : 0) * SDGPU_MAX_SYMBOLS;
+            const int s0 = rowTab[(j >= 1 && j <= lb) ? int(__ldg(cB + j - 1)) : 0];
+            const int s1 = rowTab[(j + 1 >= 1 && j + 1 <= lb) ? int(__ldg(cB + j)) : 0];
+            bandCell<false, true>(st, i, j, lane, la, lb, s0, sc, dInt);
+            bandCell<true, true>(st, i, j + 1, lane, la, lb, s1, sc, dInt);
+          }
+        }
+        *dst = st.acc;
+      }
+      const int cornerOdd = (diff - dlo) & 1;
+      score = __shfl_sync(FULL, cornerOdd ? st.Tp1 : st.Tp0, (diff - dlo) >> 1);  // toDiag of (la, lb)
+      const int hi = dlo + 63;
+      const long long ubHigh = (hi + 1 <= lb) ? (long long)a.maxSub * (lb - hi - 1) : LLONG_MIN;
+      const long long ubLow = (1 - dlo <= la) ? (long long)a.maxSub * (la + dlo - 1) : LLONG_MIN;
+      certified = (long long)score > (ubHigh > ubLow ? ubHigh : ubLow);
+      // cells of the band that lie inside the matrix (what this pass actually evaluated)
+      unsigned cells = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int d = d0 + e;
+        const int n = min(la, lb - d) - max(1, 1 - d) + 1;
+        cells += n > 0 ? unsigned(n) : 0u;
+      }
+      cells = warpSum(cells);
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.work + 6), (unsigned long long)cells);
+    }
+    __syncwarp();
+    if (certified) {
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.work + 8), (unsigned long long)la * (unsigned long long)lb);
+      finishPair<false, false>(a, BitsBand{ptrWords, dlo, aBase}, pv, score, alnA, alnB, gapRecs, sTab, lane);
+    } else if (lane == 0) {
+      a.redo[atomicAdd(&a.work[4], 1u)] = pair;
+    }
   }
 }
 
 template <class Kernel>
 int launchKernel(sdgpu_ctx* ctx, Kernel kernel, AlignArgs& args, uint32_t workItems, int CW, uint32_t maxLenA,
-                 uint32_t maxLenB, uint32_t nBlocks = 1) {
+                 uint32_t maxLenB, uint32_t nBlocks = 1, uint64_t bandBitBytes = 0) {
   int ctasPerSM = 0;
   SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kernel, WARPS_PER_CTA * 32, 0));
   if (ctasPerSM < 1) ctasPerSM = 1;
@@ -841,7 +1040,7 @@ int launchKernel(sdgpu_ctx* ctx, Kernel kernel, AlignArgs& args, uint32_t workIt
   const uint32_t needCtas = (workItems + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   if (grid > needCtas) grid = needCtas;
   const uint64_t maxSteps = uint64_t(maxLenA) + 31;
-  const uint64_t blockBytes = maxSteps * CW * 128;
+  const uint64_t blockBytes = bandBitBytes ? bandBitBytes : maxSteps * CW * 128;
   if (blockBytes * nBlocks >= (1ull << 32)) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "alignment too large (traceback bits >= 4 GiB per pair)");
   args.blockWords = blockBytes / 4;
   args.ptrBytes = uint32_t(blockBytes * nBlocks);
@@ -868,6 +1067,8 @@ int launchKernel(sdgpu_ctx* ctx, Kernel kernel, AlignArgs& args, uint32_t workIt
       ctx->evPool.resize(old + 256, nullptr);
       for (size_t x = old; x < ctx->evPool.size(); ++x) SD_CUDA(ctx, cudaEventCreate(&ctx->evPool[x]));
     }
+    if (ctx->evBand.size() < ctx->evPool.size() / 2) ctx->evBand.resize(ctx->evPool.size() / 2, 0);
+    ctx->evBand[ctx->evUsed / 2] = bandBitBytes ? 1 : 0;
     e0 = ctx->evPool[ctx->evUsed++];
     e1 = ctx->evPool[ctx->evUsed++];
     SD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
@@ -941,7 +1142,49 @@ int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dRe
   args.chiPar = chi ? chi->overlap : sdgpu_iter_par{};
   args.chiKeepLq = chi ? chi->keepLq : 0u;
   if (dPassOut && ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
+  args.pairMap = nullptr;
+  args.nWorkDev = nullptr;
+  args.redo = nullptr;
+  args.maxSub = 0;
   const uint32_t needC = (maxLenB + 31) / 32;
+  // Banded first pass + exact redo of the uncertified pairs (see alignBandKernel).  Not used when a
+  // test pins a specific full-matrix kernel, for chimera probes, or when the last banded launches
+  // sent most of their pairs to the redo list (dissimilar sequences); then it is re-tried every 16th launch.
+  bool band = ctx->bandMode == 0 && ctx->forceKernel == 0 && !chi && nPairs >= 64 && maxLenA + maxLenB <= 16384;
+  if (band) {
+    const DevScoring& s = ctx->scoring;
+    int maxSub = INT_MIN, maxAbs = 0;
+    for (int x = 0; x < ctx->nSym; ++x)
+      for (int y = 0; y < ctx->nSym; ++y) {
+        const int v = s.score[x * SDGPU_MAX_SYMBOLS + y];
+        maxSub = std::max(maxSub, v);
+        maxAbs = std::max(maxAbs, std::abs(v));
+      }
+    const int pens[10] = {s.go, s.ge, s.goLQ, s.geLQ, s.goRQ, s.geRQ, s.goLR, s.geLR, s.goRR, s.geRR};
+    for (int v : pens) maxAbs = std::max(maxAbs, v);  // penalties are validated >= 0 at set_params
+    band = maxSub > 0 && maxAbs <= 4096;
+    args.maxSub = maxSub;
+  }
+  if (band && ctx->hBandStat[1] >= 64 && 2ull * ctx->hBandStat[0] > ctx->hBandStat[1] && ++ctx->bandSkipped < 16) band = false;
+  if (band) {
+    ctx->bandSkipped = 0;
+    if (nPairs > ctx->redoCap) {
+      if (ctx->dRedo) cudaFree(ctx->dRedo);
+      ctx->dRedo = nullptr;
+      ctx->redoCap = 0;
+      SD_CUDA(ctx, cudaMalloc(&ctx->dRedo, size_t(nPairs) * sizeof(uint32_t)));
+      ctx->redoCap = nPairs;
+    }
+    args.redo = ctx->dRedo;
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->dWork + 4, 0, sizeof(uint32_t), ctx->stream));
+    const uint64_t bitBytes = (uint64_t(maxLenA + maxLenB) / 6 + 2) * 128;
+    int rc = launchKernel(ctx, alignBandKernel, args, nPairs, 0, maxLenA, maxLenB, 1, bitBytes);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(ctx->hBandStat, ctx->dWork + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    args.redo = nullptr;
+    args.pairMap = ctx->dRedo;  // the full-matrix kernels below run over the redo list only
+    args.nWorkDev = ctx->dWork + 4;
+  }
   if (chi) {  // chimera probes: a few thousand pairs per sample, int32 kernels with the probe compiled in
     ctx->lastKernelWasH2 = false;
     if (needC > 16) return launchWide<true>(ctx, args, maxLenA, maxLenB);

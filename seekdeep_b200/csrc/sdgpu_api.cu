@@ -144,10 +144,12 @@ int sdgpu_create(int device, const sdgpu_params* params, sdgpu_ctx** out) {
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->dWork, 64)) != cudaSuccess || (e = cudaMemset(ctx->dWork, 0, 64)) != cudaSuccess) {
+      (e = cudaMalloc(&ctx->dWork, 64)) != cudaSuccess || (e = cudaMemset(ctx->dWork, 0, 64)) != cudaSuccess ||
+      (e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->hBandStat), 2 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) {
     ctx->err = std::string("sdgpu_create: ") + cudaGetErrorString(e);
     return bail(SDGPU_E_CUDA);
   }
+  ctx->hBandStat[0] = ctx->hBandStat[1] = 0;
   ctx->params = *params;
   for (int x = 0; x < 256; ++x) ctx->codeOf[x] = -1;
   // fixed head of the alphabet so that codes are stable across runs
@@ -175,6 +177,8 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   cudaFree(ctx->dProfiles);
   cudaFree(ctx->dScratch);
   cudaFree(ctx->dWork);
+  cudaFree(ctx->dRedo);
+  if (ctx->hBandStat) cudaFreeHost(ctx->hBandStat);
   cudaFree(ctx->dStage);
   cudaFree(ctx->dLines);
   cudaFree(ctx->dIdxWork);
@@ -534,6 +538,12 @@ int sdgpu_set_kernel(sdgpu_ctx* ctx, int mode) {
 
 int sdgpu_last_kernel(sdgpu_ctx* ctx) { return ctx ? (ctx->lastKernelWasH2 ? 2 : 1) : 0; }
 
+int sdgpu_set_band(sdgpu_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return sd_fail(ctx, SDGPU_E_ARG, "sdgpu_set_band: mode must be 0 (automatic) or 1 (off)");
+  ctx->bandMode = mode;
+  return SDGPU_OK;
+}
+
 int sdgpu_profile_enable(sdgpu_ctx* ctx, int on) {
   if (!ctx) return SDGPU_E_ARG;
   ctx->timeKernels = on != 0;
@@ -548,11 +558,19 @@ int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset) {
     float ms = 0;
     SD_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evPool[x], ctx->evPool[x + 1]));
     ctx->alignMs += ms;
+    if (ctx->evBand[x / 2]) ctx->bandMs += ms;
   }
   ctx->evUsed = 0;
-  uint64_t cells = 0;
+  uint64_t cells = 0, band[2] = {0, 0};
   SD_CUDA(ctx, cudaMemcpy(&cells, ctx->dWork + 2, 8, cudaMemcpyDeviceToHost));
+  SD_CUDA(ctx, cudaMemcpy(band, ctx->dWork + 6, 16, cudaMemcpyDeviceToHost));
+  // cells actually evaluated = all la*lb of the finished pairs, minus those the banded pass certified,
+  // plus the band cells it evaluated (certified or not)
+  out->bandCells = band[0] - ctx->bandCells;
+  out->bandCertifiedCells = band[1] - ctx->bandCertCells;
+  out->evaluatedCells = (cells - ctx->cells) - out->bandCertifiedCells + out->bandCells;
   out->alignKernelMs = ctx->alignMs;
+  out->bandKernelMs = ctx->bandMs;
   out->alignKernelLaunches = ctx->alignLaunches;
   out->kernelLaunches = ctx->launches;
   out->cellUpdates = cells - ctx->cells;
@@ -560,9 +578,12 @@ int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset) {
   out->d2hBytes = ctx->d2hBytes;
   if (reset) {
     ctx->alignMs = 0;
+    ctx->bandMs = 0;
     ctx->alignLaunches = 0;
     ctx->launches = 0;
     ctx->cells = cells;
+    ctx->bandCells = band[0];
+    ctx->bandCertCells = band[1];
     ctx->h2dBytes = ctx->d2hBytes = 0;
   }
   return SDGPU_OK;

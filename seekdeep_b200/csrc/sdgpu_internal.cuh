@@ -96,12 +96,20 @@ struct sdgpu_ctx {
   bool timeKernels = false;
   std::vector<cudaEvent_t> evPool;
   size_t evUsed = 0;
-  double alignMs = 0;
+  std::vector<uint8_t> evBand;  // per event pair: 1 = banded pass
+  double alignMs = 0, bandMs = 0;
   uint64_t alignLaunches = 0;
   uint64_t h2dBytes = 0, d2hBytes = 0;
   // alignment kernel selection: 0 = automatic, 1 = int32 only, 2 = packed fp16 only (tests)
   int forceKernel = 0;
   bool lastKernelWasH2 = false;
+  // banded first pass (align_kernel.cu): 0 = automatic, 1 = off; redo list + its async read-back
+  int bandMode = 0;
+  uint32_t* dRedo = nullptr;
+  uint32_t redoCap = 0;
+  uint32_t* hBandStat = nullptr;  // pinned: [0] = redo count of the last banded launch, [1] = its pair count
+  uint32_t bandSkipped = 0;       // launches since banding was last tried while it was not paying off
+  uint64_t bandCells = 0, bandCertCells = 0, bandRedo = 0, bandPairs = 0;  // read-back baselines for profile_read
   // bookkeeping
   uint64_t launches = 0, cells = 0;
   std::string err;

@@ -438,3 +438,50 @@ def test_kmer_profiles_ragged_lengths_both_paths(oracle):
                 for i in range(len(a)):
                     ws, wf = oracle.kmer_compare(seqs[a[i]].tobytes(), seqs[c[i]].tobytes(), k)
                     assert shared[i] == ws and frac[i] == wf, (withN, k, i, len(seqs[a[i]]), len(seqs[c[i]]))
+
+
+@pytest.mark.parametrize("pname", ["qluster", "allEndsCost", "allEndsFree", "asym", "countEnds", "degenHomopolymer"])
+def test_banded_pass_is_exact(oracle, pname):
+    """The banded first pass + redo must return exactly what the full-matrix kernels and the oracle
+    return: near-identical pairs (certified in the band), pairs with indels of 1..45 bases and length
+    differences beyond the band (redone), low-complexity sequences where ties abound."""
+    rng = np.random.default_rng(len(pname) * 7 + 3)
+    seqs = []
+    root = H.rand_seq(rng, 280)
+    lowc = np.frombuffer(("ACACACACAC" * 8 + "AAAAAAAAAATTTTTTTTTT" * 6 + "GATTACA" * 12).encode(), np.uint8).copy()
+    for base in (root, lowc):
+        seqs.append(base)
+        for _ in range(40):  # SNP / small-indel relatives
+            seqs.append(H.mutate(rng, base, int(rng.integers(0, 8)), int(rng.integers(0, 2)), int(rng.integers(0, 2)), hp=True))
+        for size in (1, 5, 12, 20, 27, 30, 31, 33, 38, 45):  # one long deletion / insertion at a random place
+            p = int(rng.integers(20, len(base) - 60))
+            seqs.append(np.concatenate([base[:p], base[p + size:]]))
+            seqs.append(np.concatenate([base[:p], H.rand_seq(rng, size), base[p:]]))
+        for shift in (3, 17, 29, 40):  # end-shifted copies: long end gaps
+            seqs.append(base[shift:])
+            seqs.append(np.concatenate([H.rand_seq(rng, shift), base]))
+    quals = [H.rand_quals(rng, len(s)) for s in seqs]
+    bases, q, offsets = pack_seqs([s.tobytes() for s in seqs], quals)
+    n = len(seqs)
+    refIdx, readIdx = [a.ravel().astype(np.uint32) for a in np.meshgrid(np.arange(n), np.arange(n))]
+    params = H.params_for(pname)
+    with GpuAligner(params) as al:
+        al.upload_seqs(bases, q, offsets)
+        al.profile_enable(True)
+        al.profile_read(reset=True)
+        got, gg = al.align_profile(refIdx, readIdx, usingQuality=True, gapCap=12)
+        prof = al.profile_read()
+        al.set_band(1)
+        full, fg = al.align_profile(refIdx, readIdx, usingQuality=True, gapCap=12)
+        profFull = al.profile_read()
+    assert prof["bandCertifiedCells"] > 0.15 * prof["cellUpdates"]     # the band finished a good share ...
+    assert prof["bandCertifiedCells"] < prof["cellUpdates"]            # ... and some pairs were redone in full
+    assert prof["evaluatedCells"] < prof["cellUpdates"] and profFull["evaluatedCells"] == profFull["cellUpdates"]
+    assert profFull["bandCells"] == 0
+    for name in got.dtype.names:
+        assert np.array_equal(got[name], full[name]), name
+    assert np.array_equal(gg, fg)
+    sel = rng.choice(len(refIdx), 1500, replace=False)
+    want, wg = oracle.align_profile_batch(params, bases, q, offsets, refIdx[sel], readIdx[sel], _abi.USING_QUALITY, gapCap=12)
+    H.assert_comparisons_equal(got[sel], want)
+    assert np.array_equal(gg[sel], wg)
