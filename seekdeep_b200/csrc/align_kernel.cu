@@ -70,6 +70,7 @@ struct AlignArgs {
   const uint32_t* nWorkDev;  // redo pass: number of work items, read on the device (or NULL: nPairs)
   uint32_t* redo;            // banded pass: pairs whose band could not be certified
   int maxSub;                // largest substitution score (certificate bound)
+  int minRight, minDown;     // cheapest gap column in the ref / in the read away from the right ends
   sdgpu_chimera_probe* chiOut;  // per pair: markChimeras' front/back probe (or NULL)
   sdgpu_iter_par chiPar;        // chiOpts_.chiOverlap_
   uint32_t chiKeepLq;           // chiOpts_.keepLowQaulityMismatches_
@@ -866,9 +867,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignProfileKernelH2(const
 // previous cell or, every other step, from one neighbour (one shuffle per step).  Same recurrence,
 // same decision bits, out-of-band inputs = -inf.
 // Exactness: the banded optimum S_w is reached by a real alignment, so S_w <= S_opt.  An alignment
-// that touches offset hi + 1 has at least hi + 1 more right than down moves, hence at most
-// lb - hi - 1 diagonal moves and (gap penalties being >= 0) a score <= maxSub * (lb - hi - 1);
-// likewise maxSub * (la + lo - 1) below the band.  If S_w exceeds both bounds, every optimal
+// that touches offset hi + 1 has at least hi + 1 right moves, hence at most lb - hi - 1 diagonal
+// moves, and pays at least the cheapest non-right-end gap column for each of them: its score is
+// <= maxSub * (lb - hi - 1) - minRight * (hi + 1); likewise below the band with la, lo and minDown.  If S_w exceeds both bounds, every optimal
 // alignment -- and every tie the traceback's decision bits could see along it -- lies inside the
 // band, where banded and full values coincide: score, path and errorProfile are the full DP's.
 // Otherwise the pair goes to the redo list and the full-matrix kernel recomputes it.
@@ -1006,8 +1007,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignBandKernel(const Alig
       const int cornerOdd = (diff - dlo) & 1;
       score = __shfl_sync(FULL, cornerOdd ? st.Tp1 : st.Tp0, (diff - dlo) >> 1);  // toDiag of (la, lb)
       const int hi = dlo + 63;
-      const long long ubHigh = (hi + 1 <= lb) ? (long long)a.maxSub * (lb - hi - 1) : LLONG_MIN;
-      const long long ubLow = (1 - dlo <= la) ? (long long)a.maxSub * (la + dlo - 1) : LLONG_MIN;
+      // (a path that touches offset hi + 1 does so above the last row, so its >= hi + 1 right moves are
+      //  left-end or interior gap columns and cost at least minRight each; same below the band)
+      const long long ubHigh = (hi + 1 <= lb) ? (long long)a.maxSub * (lb - hi - 1) - (long long)a.minRight * (hi + 1) : LLONG_MIN;
+      const long long ubLow = (1 - dlo <= la) ? (long long)a.maxSub * (la + dlo - 1) - (long long)a.minDown * (1 - dlo) : LLONG_MIN;
       certified = (long long)score > (ubHigh > ubLow ? ubHigh : ubLow);
       // cells of the band that lie inside the matrix (what this pass actually evaluated)
       unsigned cells = 0;
@@ -1145,7 +1148,7 @@ int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dRe
   args.pairMap = nullptr;
   args.nWorkDev = nullptr;
   args.redo = nullptr;
-  args.maxSub = 0;
+  args.maxSub = args.minRight = args.minDown = 0;
   const uint32_t needC = (maxLenB + 31) / 32;
   // Banded first pass + exact redo of the uncertified pairs (see alignBandKernel).  Not used when a
   // test pins a specific full-matrix kernel, for chimera probes, or when the last banded launches
@@ -1164,6 +1167,8 @@ int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dRe
     for (int v : pens) maxAbs = std::max(maxAbs, v);  // penalties are validated >= 0 at set_params
     band = maxSub > 0 && maxAbs <= 4096;
     args.maxSub = maxSub;
+    args.minRight = std::min(std::min(s.go, s.ge), std::min(s.goLR, s.geLR));
+    args.minDown = std::min(std::min(s.go, s.ge), std::min(s.goLQ, s.geLQ));
   }
   if (band && ctx->hBandStat[1] >= 64 && 2ull * ctx->hBandStat[0] > ctx->hBandStat[1] && ++ctx->bandSkipped < 16) band = false;
   if (band) {

@@ -253,7 +253,7 @@ class Runner {
   static constexpr uint32_t BATCH = 1u << 21;
   std::vector<sdgpu_comparison> cmpBuf;
   std::vector<sdgpu_gap> gapBuf;
-  double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0, tIndex = 0;
+  double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0, tIndex = 0, tSubmit = 0;
   uint64_t keptVersions = 0, skippedScans = 0;
   bool orderDirty = true;
   // symbols of the consensus counters (bases + '-'), ASCII order kept for njhseq's tie rule
@@ -345,6 +345,7 @@ class Runner {
       const double t0 = nowSec();
       int r = sdgpu_align_pass_submit(R.ctx_, cur, a[cur].data(), b[cur].data(), uint32_t(a[cur].size()), R.flags());
       R.st.secondsGpu += nowSec() - t0;
+      R.tSubmit += nowSec() - t0;
       if (r) {
         rc = R.fail(r);
         return;
@@ -997,8 +998,8 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   res->stats.cellUpdates = cells1 - cells0;
   res->stats.secondsTotal = nowSec() - tStart;
   if (getenv("SDQ_TIMING")) {
-    fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f sort %.3f index %.3f lines %zu\n",
-            res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSpec, R.tInsert, R.tPass, R.tCons, R.tSort, R.tIndex, R.lines.size());
+    fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f (submit %.3f, %llu batches) spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f sort %.3f index %.3f lines %zu\n",
+            res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSubmit, (unsigned long long)R.st.gpuBatches, R.tSpec, R.tInsert, R.tPass, R.tCons, R.tSort, R.tIndex, R.lines.size());
     fprintf(stderr, "[sdq] consensus updates kept on the device version: %llu, store entries: %u (unique reads %u), scans skipped %llu\n",
             (unsigned long long)R.keptVersions, R.storeSize, nU, (unsigned long long)R.skippedScans);
   }
