@@ -22,6 +22,7 @@
 //     lists returned) and re-reads the consensus off the counters (integer sums: exact).
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -307,25 +308,90 @@ class Runner {
   // Streams (cluster, read) pairs to the GPU in chunks through the two asynchronous slots of
   // sdgpu_align_pass_submit/_wait: while the GPU aligns chunk k the host files chunk k-1's
   // verdict masks into the reads' rows and lists chunk k+1.
+  // One helper thread files verdict masks into the reads' rows while this thread lists the next
+  // chunk: a chunk never splits a read's pairs (endRead), so the rows the helper writes belong to
+  // reads listed earlier than any row the lister is looking at.
+  struct Filer {
+    struct Job {
+      ClusVec* cs;
+      const std::vector<uint32_t>*a, *owner;
+      const uint64_t* masks;
+      uint32_t n;
+    };
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Job> queue;
+    size_t done = 0, posted = 0;
+    bool stop = false;
+    double busy = 0;
+    void start() {
+      if (th.joinable()) return;
+      th = std::thread([this] {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+          cv.wait(lk, [this] { return stop || done < posted; });
+          if (done >= posted && stop) return;
+          const Job j = queue[done];
+          lk.unlock();
+          const double t0 = nowSec();
+          for (uint32_t i = 0; i < j.n; ++i) (*j.cs)[(*j.owner)[i]].row.insert((*j.a)[i], j.masks[i]);
+          const double dt = nowSec() - t0;
+          lk.lock();
+          busy += dt;
+          ++done;
+          cv.notify_all();
+        }
+      });
+    }
+    size_t post(const Job& j) {
+      std::lock_guard<std::mutex> lk(mu);
+      queue.push_back(j);
+      ++posted;
+      cv.notify_all();
+      return posted;
+    }
+    void waitFor(size_t ticket) {  // until job number `ticket` (1-based) has been filed
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return done >= ticket; });
+    }
+    ~Filer() {
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+        cv.notify_all();
+      }
+      if (th.joinable()) th.join();
+    }
+  };
+  Filer filer;
+
   struct PassPipe {
     Runner& R;
     ClusVec& cs;
-    std::vector<uint32_t> a[2], b[2], owner[2];
+    struct Buf {
+      std::vector<uint32_t> a, b, owner;
+      void clear() { a.clear(), b.clear(), owner.clear(); }
+    };
+    Buf cur, flight[2];
     bool inflight[2] = {false, false};
-    int cur = 0;
+    size_t ticket[2] = {0, 0};  // filer job still reading flight[s] / the slot's pinned masks
+    int next = 0;
     int rc = 0;
     uint32_t chunk;
-    PassPipe(Runner& r, ClusVec& c) : R(r), cs(c), chunk(g_chunkPairs ? g_chunkPairs : BATCH / 2) {}
+    PassPipe(Runner& r, ClusVec& c) : R(r), cs(c), chunk(g_chunkPairs ? g_chunkPairs : BATCH / 2) { R.filer.start(); }
     void push(uint32_t clusStore, uint32_t readStore, uint32_t ownerPos) {
-      a[cur].push_back(clusStore);
-      b[cur].push_back(readStore);
-      owner[cur].push_back(ownerPos);
-      if (a[cur].size() >= chunk) flush();
+      cur.a.push_back(clusStore);
+      cur.b.push_back(readStore);
+      cur.owner.push_back(ownerPos);
     }
-    void drain(int s) {
+    void endRead() {  // chunk boundaries fall between reads
+      if (cur.a.size() >= chunk) flush();
+    }
+    void drain(int s) {  // wait for the GPU, hand the masks to the filer
       const uint64_t* masks = nullptr;
       uint32_t n = 0;
-      double t0 = nowSec();
+      const double t0 = nowSec();
       int r = sdgpu_align_pass_wait(R.ctx_, s, &masks, &n);
       R.st.secondsGpu += nowSec() - t0;
       inflight[s] = false;
@@ -333,34 +399,37 @@ class Runner {
         rc = R.fail(r);
         return;
       }
-      t0 = nowSec();
-      for (uint32_t i = 0; i < n; ++i) cs[owner[s][i]].row.insert(a[s][i], masks[i]);
-      R.tInsert += nowSec() - t0;
-      a[s].clear();
-      b[s].clear();
-      owner[s].clear();
+      ticket[s] = R.filer.post(Filer::Job{&cs, &flight[s].a, &flight[s].owner, masks, n});
     }
     void flush() {
-      if (rc || a[cur].empty()) return;
+      if (rc || cur.a.empty()) return;
+      const int s = next;
+      if (inflight[s]) drain(s);
+      if (rc) return;
+      R.filer.waitFor(ticket[s]);  // its buffers and the slot's pinned masks are about to be reused
+      flight[s].clear();
+      std::swap(flight[s], cur);
       const double t0 = nowSec();
-      int r = sdgpu_align_pass_submit(R.ctx_, cur, a[cur].data(), b[cur].data(), uint32_t(a[cur].size()), R.flags());
+      int r = sdgpu_align_pass_submit(R.ctx_, s, flight[s].a.data(), flight[s].b.data(), uint32_t(flight[s].a.size()), R.flags());
       R.st.secondsGpu += nowSec() - t0;
       R.tSubmit += nowSec() - t0;
       if (r) {
         rc = R.fail(r);
         return;
       }
-      inflight[cur] = true;
+      inflight[s] = true;
       ++R.st.gpuBatches;
-      R.st.pairsComputed += a[cur].size();
-      const int other = cur ^ 1;
+      R.st.pairsComputed += flight[s].a.size();
+      const int other = s ^ 1;
       if (inflight[other]) drain(other);
-      cur = other;
+      next = other;
     }
     int finish() {
       flush();
       for (int s = 0; s < 2; ++s)
         if (inflight[s]) drain(s);
+      R.filer.waitFor(std::max(ticket[0], ticket[1]));
+      R.tInsert = R.filer.busy;
       return rc;
     }
   };
@@ -402,6 +471,7 @@ class Runner {
             pipe.push(cs[cp].storeIdx, read.storeIdx, rp);
           }
         }
+        pipe.endRead();
         read.rowSerial = serial;
       }
       for (uint32_t s : prevWindow) inPrevWindow[s] = 0;
@@ -442,6 +512,7 @@ class Runner {
           for (size_t r2 = rp + 1; r2-- > 0;) {
             if (cs[r2].remove || r2 == cp || cs[r2].row.find(clus.storeIdx)) continue;
             pipe.push(clus.storeIdx, cs[r2].storeIdx, uint32_t(r2));
+            pipe.endRead();
             ++st.onDemandPairs;
           }
           int rc = pipe.finish();
