@@ -78,6 +78,14 @@ class Row {
     vals_[h] = v;
     ++n_;
   }
+  // make room for `extra` more entries in one step (instead of doubling through 64, 128, 256 ...)
+  void reserve(uint32_t extra) {
+    const uint64_t need = (uint64_t(n_) + extra) * 3;
+    uint64_t cap = keys_.empty() ? 64u : keys_.size();
+    if (!keys_.empty() && need <= cap * 2) return;
+    while (need > cap * 2) cap <<= 1;
+    regrow(uint32_t(cap));
+  }
   void clear() {
     std::vector<uint32_t>().swap(keys_);
     std::vector<uint64_t>().swap(vals_);
@@ -101,8 +109,8 @@ class Row {
   }
 
  private:
-  void grow() {
-    const uint32_t cap = keys_.empty() ? 64u : uint32_t(keys_.size()) * 2u;
+  void grow() { regrow(keys_.empty() ? 64u : uint32_t(keys_.size()) * 2u); }
+  void regrow(uint32_t cap) {
     std::vector<uint32_t> k(cap, EMPTY);
     std::vector<uint64_t> v(cap);
     k.swap(keys_);
@@ -117,6 +125,29 @@ class Row {
   uint32_t n_ = 0, mask_ = 0;
   uint64_t or_ = 0;
 };
+
+// Splits [0, n) over a few short-lived host threads (the prep phases before the GPU has work:
+// hashing, per-unique median qualities, packing, cluster pool set-up are all per-item independent).
+template <class Fn>
+static void parallelFor(size_t n, Fn fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t T = std::min<size_t>(hw ? hw : 1, 8);
+  if (n < 4096) T = 1;
+  if (T <= 1) {
+    fn(size_t(0), n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (n + T - 1) / T;
+  for (size_t t = 0; t < T; ++t) {
+    const size_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back([=] { fn(lo, hi); });
+  }
+  for (auto& x : th) x.join();
+}
+
+static const bool g_verboseTiming = getenv("SDQ_TIMING") && atoi(getenv("SDQ_TIMING")) > 1;
 
 struct Uniq {  // one exact-unique input sequence; its store index is its position in `uniq`
   std::string seq;
@@ -459,6 +490,7 @@ class Runner {
       for (uint32_t rp = uint32_t(cs.size()); rp-- > 0;) {  // same order as the pass below
         Clus& read = cs[rp];
         if (read.remove) continue;
+        const size_t before = pipe.cur.a.size();
         if (read.rowSerial + 1 == serial) {  // row complete for the previous window: only new entries
           for (uint32_t cp : fresh) {
             if (cp == rp) continue;
@@ -471,6 +503,7 @@ class Runner {
             pipe.push(cs[cp].storeIdx, read.storeIdx, rp);
           }
         }
+        if (pipe.cur.a.size() > before) read.row.reserve(uint32_t(pipe.cur.a.size() - before));
         pipe.endRead();
         read.rowSerial = serial;
       }
@@ -480,8 +513,11 @@ class Runner {
         prevWindow.push_back(cs[elig[w]].storeIdx);
         inPrevWindow[cs[elig[w]].storeIdx] = 1;
       }
+      const double tList = nowSec() - tt0;
       int rc = pipe.finish();
       tSpec += nowSec() - tt0;  // listing + GPU + filing, overlapped
+      if (g_verboseTiming && nowSec() - tt0 > 0.01)
+        fprintf(stderr, "[sdq]   line %d: %zu live, window %u, spec %.3f s (until last submit %.3f)\n", line, alive, wn, nowSec() - tt0, tList);
       if (rc) return rc;
     }
     tt0 = nowSec();
@@ -933,31 +969,41 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   // exact-sequence dedupe in first-seen order (clusterDown.cpp:272-288; hashing instead of the
   // reference's O(N*U) scan, same result)
   {
-    // open addressing on a 64-bit hash of the bases; equal hashes are confirmed byte for byte
+    // 64-bit hash of the bases, all reads in parallel; open addressing, equal hashes confirmed byte for byte
+    std::vector<uint64_t> readHash(n);
+    parallelFor(n, [&](size_t lo, size_t hi) {
+      for (size_t r = lo; r < hi; ++r) {
+        const uint32_t len = uint32_t(offsets[r + 1] - offsets[r]);
+        const uint8_t* p = bases + offsets[r];
+        uint64_t h = 0x9e3779b97f4a7c15ull ^ len;
+        uint32_t i = 0;
+        for (; i + 8 <= len; i += 8) {
+          uint64_t w;
+          std::memcpy(&w, p + i, 8);
+          h = (h ^ w) * 0xff51afd7ed558ccdull;
+          h ^= h >> 32;
+        }
+        for (; i < len; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+        readHash[r] = h ^ (h >> 29);
+      }
+    });
     size_t cap = 1024;
     while (cap < size_t(n) * 2 + 16) cap <<= 1;
     std::vector<uint32_t> table(cap, UINT32_MAX);
-    std::vector<uint64_t> hashes;
-    hashes.reserve(n);
+    std::vector<uint32_t> firstRead;  // unique -> its first read (the bytes are materialised afterwards, in parallel)
+    firstRead.reserve(n);
+    R.uniq.reserve(n);
     for (uint32_t r = 0; r < n; ++r) {
       const uint32_t len = uint32_t(offsets[r + 1] - offsets[r]);
       if (len <= opts->smallReadSize) continue;
       const uint8_t* p = bases + offsets[r];
-      uint64_t h = 0x9e3779b97f4a7c15ull ^ len;
-      uint32_t i = 0;
-      for (; i + 8 <= len; i += 8) {
-        uint64_t w;
-        std::memcpy(&w, p + i, 8);
-        h = (h ^ w) * 0xff51afd7ed558ccdull;
-        h ^= h >> 32;
-      }
-      for (; i < len; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
-      h ^= h >> 29;
+      const uint64_t h = readHash[r];
       size_t slot = size_t(h) & (cap - 1);
       uint32_t found = UINT32_MAX;
       while (table[slot] != UINT32_MAX) {
         const uint32_t u = table[slot];
-        if (hashes[u] == h && R.uniq[u].seq.size() == len && std::memcmp(R.uniq[u].seq.data(), p, len) == 0) {
+        const uint32_t fr = firstRead[u];
+        if (readHash[fr] == h && uint32_t(offsets[fr + 1] - offsets[fr]) == len && std::memcmp(bases + offsets[fr], p, len) == 0) {
           found = u;
           break;
         }
@@ -966,23 +1012,25 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
       if (found == UINT32_MAX) {
         found = uint32_t(R.uniq.size());
         table[slot] = found;
-        hashes.push_back(h);
+        firstRead.push_back(r);
         R.uniq.emplace_back();
-        R.uniq.back().seq.assign(reinterpret_cast<const char*>(p), len);
       }
       Uniq& u = R.uniq[found];
       u.cnt += 1.0;
       u.inputIdx.push_back(r);
     }
   }
-  // per-base median quality over the members (clusterDown.cpp:293-359, qualRep "median")
-  {
+  // sequence bytes + per-base median quality over the members (clusterDown.cpp:293-359, qualRep "median")
+  parallelFor(R.uniq.size(), [&](size_t lo, size_t hi) {
     std::vector<uint8_t> col;
-    for (Uniq& u : R.uniq) {
-      const size_t len = u.seq.size(), k = u.inputIdx.size();
+    for (size_t x = lo; x < hi; ++x) {
+      Uniq& u = R.uniq[x];
+      const uint32_t fr = u.inputIdx[0];
+      const size_t len = size_t(offsets[fr + 1] - offsets[fr]), k = u.inputIdx.size();
+      u.seq.assign(reinterpret_cast<const char*>(bases + offsets[fr]), len);
       u.qual.resize(len);
       if (k == 1) {
-        std::memcpy(u.qual.data(), quals + offsets[u.inputIdx[0]], len);
+        std::memcpy(u.qual.data(), quals + offsets[fr], len);
         continue;
       }
       col.resize(k);
@@ -992,7 +1040,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
         u.qual[i] = (k % 2) ? col[k / 2] : uint8_t((uint32_t(col[k / 2 - 1]) + col[k / 2]) / 2);
       }
     }
-  }
+  });
   const uint32_t nU = uint32_t(R.uniq.size());
   res->stats.inputReads = n;
   res->stats.uniqueSeqs = nU;
@@ -1003,32 +1051,39 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   }
   // the unique reads become sequence-store entries 0..nU-1
   {
-    std::vector<uint8_t> b, q;
-    std::vector<uint64_t> off{0};
-    std::vector<double> cn;
-    for (const Uniq& u : R.uniq) {
-      b.insert(b.end(), u.seq.begin(), u.seq.end());
-      q.insert(q.end(), u.qual.begin(), u.qual.end());
-      off.push_back(b.size());
-      cn.push_back(u.cnt);
+    std::vector<uint64_t> off(size_t(nU) + 1, 0);
+    std::vector<double> cn(nU);
+    for (uint32_t u = 0; u < nU; ++u) {
+      off[u + 1] = off[u] + R.uniq[u].seq.size();
+      cn[u] = R.uniq[u].cnt;
     }
+    std::vector<uint8_t> b(off[nU]), q(off[nU]);
+    parallelFor(nU, [&](size_t lo, size_t hi) {
+      for (size_t u = lo; u < hi; ++u) {
+        std::memcpy(b.data() + off[u], R.uniq[u].seq.data(), R.uniq[u].seq.size());
+        std::memcpy(q.data() + off[u], R.uniq[u].qual.data(), R.uniq[u].qual.size());
+      }
+    });
     if (sdgpu_upload_seqs(ctx, b.data(), q.data(), off.data(), cn.data(), nU)) return bail(R.fail(SDGPU_E_CUDA));
     R.storeSize = nU;
     if (sdgpu_timer_start(ctx)) return bail(R.fail(SDGPU_E_CUDA));  // inputs are resident from here on
   }
   res->pool.resize(nU);  // never resized again: ClusVec holds pointers into it
   ClusVec clusters;
-  for (uint32_t u = 0; u < nU; ++u) {
-    Clus& c = res->pool[u];
-    clusters.push_back(&c);
-    c.seq = R.uniq[u].seq;
-    c.qual = R.uniq[u].qual;
-    c.cnt = R.uniq[u].cnt;
-    c.firstId = u;
-    c.storeIdx = u;
-    c.members = {u};
-    c.avgErr = averageErrorRate(c.qual);
-  }
+  for (uint32_t u = 0; u < nU; ++u) clusters.push_back(&res->pool[u]);
+  parallelFor(nU, [&](size_t lo, size_t hi) {
+    for (size_t x = lo; x < hi; ++x) {
+      const uint32_t u = uint32_t(x);
+      Clus& c = res->pool[u];
+      c.seq = R.uniq[u].seq;
+      c.qual = R.uniq[u].qual;
+      c.cnt = R.uniq[u].cnt;
+      c.firstId = u;
+      c.storeIdx = u;
+      c.members = {u};
+      c.avgErr = averageErrorRate(c.qual);
+    }
+  });
   const double tPrep = nowSec() - tStart;
   R.dropRemovedAndSort(clusters);     // clusterDown.cpp:389
   int rc = R.buildIndex(clusters);    // clusterDown.cpp:412-417
