@@ -407,6 +407,13 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
   int matchSum = 0;
   int baseA = 0, baseB = 0;
   const unsigned ltMask = (1u << lane) - 1u;
+  // Pass 1 walks the columns 32 at a time and only sorts them into matches and mismatches; the
+  // mismatches' (ref, read) base positions are queued (top of the gap-record area, growing down:
+  // gap runs + mismatches <= columns, so the two never meet).  Pass 2 classifies the queued
+  // mismatches 32 at a time -- quality windows and low-frequency k-mer look-ups run with every lane
+  // busy instead of the one or two lanes that hold a mismatch in a given 32-column chunk.
+  uint32_t* misTop = gapRecs + 3 * (size_t(a.maxAln) + 2);
+  unsigned nMis = 0;
   for (int cs = 0; cs < alnLen; cs += 32) {
     const int k = cs + lane;
     const bool inb = k < alnLen;
@@ -414,36 +421,57 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
     const int cb = inb ? int(gB[k]) : SDGPU_GAP_CODE;
     const unsigned hasA = __ballot_sync(FULL, inb && ca != SDGPU_GAP_CODE);
     const unsigned hasB = __ballot_sync(FULL, inb && cb != SDGPU_GAP_CODE);
-    if (inb && ca != SDGPU_GAP_CODE && cb != SDGPU_GAP_CODE) {
-      const int pa = baseA + __popc(hasA & ltMask), pb = baseB + __popc(hasB & ltMask);
-      const int sub = sTab[ca * SDGPU_MAX_SYMBOLS + cb];
-      if (SCORE_FROM_PATH) matchSum += sub;
-      if (sub < 0) {
-        bool good = true;
-        if (usingQuality) good = checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc);
-        if (!good) {
-          ++lq;
-        } else if (checkKmer && (lowFreqDev(a.idx, cA, la, pa) || lowFreqDev(a.idx, cB, lb, pb))) {
-          ++lk;
-        } else {
-          ++hq;
-        }
-      } else {
-        if (matchQuality && !(checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc))) {
+    const bool both = inb && ca != SDGPU_GAP_CODE && cb != SDGPU_GAP_CODE;
+    const int pa = baseA + __popc(hasA & ltMask), pb = baseB + __popc(hasB & ltMask);
+    const int sub = both ? sTab[ca * SDGPU_MAX_SYMBOLS + cb] : 0;
+    if (SCORE_FROM_PATH) matchSum += sub;
+    const unsigned misMask = __ballot_sync(FULL, both && sub < 0);
+    if (both && sub < 0) {
+      uint32_t* e = misTop - 2 * (nMis + __popc(misMask & ltMask) + 1);
+      e[0] = uint32_t(pa);
+      e[1] = uint32_t(pb);
+    }
+    nMis += __popc(misMask);
+    if (matchQuality) {
+      if (both && sub >= 0) {
+        if (!(checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc))) {
           ++lqM;
         } else {
           ++hqM;
         }
       }
+    } else if (lane == 0) {
+      hqM += __popc(hasA & hasB & ~misMask);
     }
     baseA += __popc(hasA);
     baseB += __popc(hasB);
   }
-  hq = warpSum(hq);
-  lq = warpSum(lq);
-  lk = warpSum(lk);
-  hqM = warpSum(hqM);
-  lqM = warpSum(lqM);
+  __syncwarp();
+  for (unsigned e0 = 0; e0 < nMis; e0 += 32) {
+    const unsigned e = e0 + lane;
+    int cls = 0;  // 1 = high quality, 2 = low quality, 3 = low k-mer
+    if (e < nMis) {
+      const int pa = int(misTop[-2 * int(e + 1)]), pb = int(misTop[-2 * int(e + 1) + 1]);
+      bool good = true;
+      if (usingQuality) good = checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc);
+      if (!good) {
+        cls = 2;
+      } else if (checkKmer && (lowFreqDev(a.idx, cA, la, pa) || lowFreqDev(a.idx, cB, lb, pb))) {
+        cls = 3;
+      } else {
+        cls = 1;
+      }
+    }
+    hq += __popc(__ballot_sync(FULL, cls == 1));
+    lq += __popc(__ballot_sync(FULL, cls == 2));
+    lk += __popc(__ballot_sync(FULL, cls == 3));
+  }
+  if (matchQuality) {
+    hqM = warpSum(hqM);
+    lqM = warpSum(lqM);
+  } else {
+    hqM = __shfl_sync(FULL, hqM, 0);
+  }
 
   // gap runs in forward order (the records are in traceback order); uniform across the warp
   double one = 0, two = 0, large = 0;
@@ -885,14 +913,18 @@ struct BandLane {  // one lane's running state: two offsets, outputs of its prev
 
 // One cell update.  ODD: the lane's odd offset d0 + 1 (inputs: left from its own previous cell, up from
 // the right neighbour), else d0 (left from the left neighbour, up from its own previous cell).
-// GEN: general step with border rows / columns, last-row / last-column penalties and cells outside
-// the matrix; !GEN: interior step (every lane's cell has 2 <= i < la, 2 <= j < lb).
-template <bool ODD, bool GEN>
+// MODE: BODY = interior step (every lane's cell has 2 <= i < la, 2 <= j < lb); HEAD = steps before the
+// body (border rows / columns and cells above / left of the matrix possible, last row / column not);
+// TAIL = steps after it (last-row / last-column penalties and cells below / right of the matrix);
+// GEN = everything (matrices too small to have a body).
+enum { BAND_BODY = 0, BAND_HEAD = 1, BAND_TAIL = 2, BAND_GEN = 3 };
+template <bool ODD, int MODE>
 __device__ __forceinline__ void bandCell(BandLane& st, int i, int j, int lane, int la, int lb, int s,
                                          const DevScoring& sc, int dInt) {
+  constexpr bool LOW = (MODE & BAND_HEAD) != 0, HIGH = (MODE & BAND_TAIL) != 0;
   int recv = ODD ? __shfl_down_sync(FULL, st.lastDown, 1) : __shfl_up_sync(FULL, st.lastRight, 1);
   if (ODD ? (lane == 31) : (lane == 0)) recv = BAND_NEG;  // beyond the band
-  if (GEN && !(i >= 1 && i <= la && j >= 1 && j <= lb)) {
+  if ((LOW && (i < 1 || j < 1)) || (HIGH && (i > la || j > lb))) {
     st.acc <<= 5;
     return;
   }
@@ -900,9 +932,11 @@ __device__ __forceinline__ void bandCell(BandLane& st, int i, int j, int lane, i
   int Uin = ODD ? recv : st.lastDown;   // toDown of (i-1, j): offset d+1
   int Tin = ODD ? st.Tp1 : st.Tp0;      // toDiag of (i-1, j-1): same offset, two steps ago
   int gorow = sc.go, drow = dInt, gocol = sc.go, dcol = dInt;
-  if (GEN) {
+  if (HIGH) {
     if (i == la) gorow = sc.goRR, drow = sc.goRR - sc.geRR;
     if (j == lb) gocol = sc.goRQ, dcol = sc.goRQ - sc.geRQ;
+  }
+  if (LOW) {
     if (i == 1) {  // row 0 border (njhseq's i == 1 case)
       const int r0 = -sc.goLR - (j - 1) * sc.geLR;
       Uin = r0 - gocol;
@@ -933,6 +967,21 @@ __device__ __forceinline__ void bandCell(BandLane& st, int i, int j, int lane, i
     st.Tp1 = T;
   } else {
     st.Tp0 = T;
+  }
+}
+
+// three step pairs (one word of decision bits) outside the body
+template <int MODE>
+__device__ __forceinline__ void bandWordEdge(BandLane& st, int& i, int& j, int lane, int la, int lb, const uint8_t* cA,
+                                             const uint8_t* cB, const int* sTab, const DevScoring& sc, int dInt) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k, ++i, ++j) {
+    const bool rowIn = i >= 1 && i <= la;
+    const int* rowTab = sTab + (rowIn ? int(__ldg(cA + i - 1)) : 0) * SDGPU_MAX_SYMBOLS;
+    const int s0 = rowTab[(j >= 1 && j <= lb) ? int(__ldg(cB + j - 1)) : 0];
+    const int s1 = rowTab[(j + 1 >= 1 && j + 1 <= lb) ? int(__ldg(cB + j)) : 0];
+    bandCell<false, MODE>(st, i, j, lane, la, lb, s0, sc, dInt);
+    bandCell<true, MODE>(st, i, j + 1, lane, la, lb, s1, sc, dInt);
   }
 }
 
@@ -987,20 +1036,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignBandKernel(const Alig
           for (int k = 0; k < 3; ++k, ++i, ++j) {
             const int* rowTab = sTab + int(__ldg(cA + i - 1)) * SDGPU_MAX_SYMBOLS;
             const int bNext = int(__ldg(cB + j));
-            bandCell<false, false>(st, i, j, lane, la, lb, rowTab[bCode], sc, dInt);
-            bandCell<true, false>(st, i, j + 1, lane, la, lb, rowTab[bNext], sc, dInt);
+            bandCell<false, BAND_BODY>(st, i, j, lane, la, lb, rowTab[bCode], sc, dInt);
+            bandCell<true, BAND_BODY>(st, i, j + 1, lane, la, lb, rowTab[bNext], sc, dInt);
             bCode = bNext;
           }
+        } else if (p + 3 <= pBodyEnd) {
+          bandWordEdge<BAND_HEAD>(st, i, j, lane, la, lb, cA, cB, sTab, sc, dInt);
+        } else if (p >= pBodyStart) {
+          bandWordEdge<BAND_TAIL>(st, i, j, lane, la, lb, cA, cB, sTab, sc, dInt);
         } else {
-#pragma unroll
-          for (int k = 0; k < 3; ++k, ++i, ++j) {
-            const bool rowIn = i >= 1 && i <= la;
-            const int* rowTab = sTab + (rowIn ? int(__ldg(cA + i - 1)) : 0) * SDGPU_MAX_SYMBOLS;
-            const int s0 = rowTab[(j >= 1 && j <= lb) ? int(__ldg(cB + j - 1)) : 0];
-            const int s1 = rowTab[(j + 1 >= 1 && j + 1 <= lb) ? int(__ldg(cB + j)) : 0];
-            bandCell<false, true>(st, i, j, lane, la, lb, s0, sc, dInt);
-            bandCell<true, true>(st, i, j + 1, lane, la, lb, s1, sc, dInt);
-          }
+          bandWordEdge<BAND_GEN>(st, i, j, lane, la, lb, cA, cB, sTab, sc, dInt);
         }
         *dst = st.acc;
       }
