@@ -165,6 +165,29 @@ def kmer_roofline(al, bases, quals, offsets, peaks):
     return out
 
 
+def bind_cpus(local, world):
+    """One rank per GPU: keep each rank's host threads (collapse loop, mask filer, prep workers) on its own
+    slice of the cores NVML reports as local to its GPU, so ranks do not migrate across NUMA nodes or pile
+    onto the same cores."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        allowed = sorted(os.sched_getaffinity(0))
+        words = (max(allowed) + 64) // 64
+        sets = []
+        for d in range(world):
+            m = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(d), words)
+            cpus = [64 * w + b for w, x in enumerate(m) for b in range(64) if (x >> b) & 1]
+            sets.append(tuple(c for c in cpus if c in allowed) or tuple(allowed))
+        mine = sets[local]
+        peers = [d for d in range(world) if sets[d] == mine]
+        per = max(1, len(mine) // len(peers))
+        k = peers.index(local)
+        os.sched_setaffinity(0, set(mine[k * per:(k + 1) * per]))
+    except Exception as e:  # binding is an optimisation, never a requirement
+        print(f"[bench] cpu binding skipped: {e}", file=sys.stderr)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -189,6 +212,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        bind_cpus(local, world)
     bases, quals, offsets = make_sample(2 + rank, args.reads)  # one sample per GPU: sharded by sample
     nReads = len(offsets) - 1
     al = sd.GpuAligner(sd.make_params(), device=local)

@@ -149,6 +149,26 @@ static void parallelFor(size_t n, Fn fn) {
 
 static const bool g_verboseTiming = getenv("SDQ_TIMING") && atoi(getenv("SDQ_TIMING")) > 1;
 
+// Items of very different cost (clusters absorbing 1 .. thousands of members): threads pull indices
+// from a shared counter.
+template <class Fn>
+static void parallelForDynamic(size_t n, Fn fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t T = std::min<size_t>(hw ? hw : 1, 4);
+  if (n < 8) T = 1;
+  if (T <= 1) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> nextIdx{0};
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < T; ++t)
+    th.emplace_back([&] {
+      for (size_t i = nextIdx.fetch_add(1); i < n; i = nextIdx.fetch_add(1)) fn(i);
+    });
+  for (auto& x : th) x.join();
+}
+
 struct Uniq {  // one exact-unique input sequence; its store index is its position in `uniq`
   std::string seq;
   std::vector<uint8_t> qual;
@@ -661,11 +681,16 @@ class Runner {
       gapCap *= 8;
     }
     // column counters -> new consensus (ConsensusHelper::increaseCounters / buildConsensus)
+    // (clusters are independent of each other here: a few host threads share the jobs; what must
+    //  stay in job order -- the list of new device versions -- is collected afterwards)
     std::vector<uint32_t> changed;
-    std::string ga, gb;
-    std::vector<uint8_t> gq;
-    bool symOk = true;
-    for (const Job& j : jobs) {
+    enum : uint8_t { OUT_SAME = 0, OUT_UPLOAD = 1, OUT_KEPT = 2, OUT_BAD_SYMBOL = 3 };
+    std::vector<uint8_t> outcome(jobs.size(), OUT_SAME);
+    parallelForDynamic(jobs.size(), [&](size_t jx) {
+      const Job& j = jobs[jx];
+      std::string ga, gb;
+      std::vector<uint8_t> gq;
+      bool symOk = true;
       Clus& cl = cs[j.clus];
       ConsState& S = *cl.cons;
       const std::string& base = S.baseSeq;
@@ -708,8 +733,8 @@ class Runner {
       }
       S.nDone = cl.members.size();
       if (!symOk) {
-        g_err = "more than 18 distinct symbols in consensus columns";
-        return SDGPU_E_ALPHABET;
+        outcome[jx] = OUT_BAD_SYMBOL;
+        return;
       }
       std::string ns;
       std::vector<uint8_t> nq;
@@ -756,13 +781,21 @@ class Runner {
         cl.seq.swap(ns);
         cl.qual.swap(nq);
         if (needUpload) {
-          changed.push_back(j.clus);
+          outcome[jx] = OUT_UPLOAD;
           cl.devSig.swap(newSig);
         } else {
-          ++keptVersions;
+          outcome[jx] = OUT_KEPT;
         }
       }
       cl.avgErr = averageErrorRate(cl.qual);
+    });
+    for (size_t jx = 0; jx < jobs.size(); ++jx) {
+      if (outcome[jx] == OUT_BAD_SYMBOL) {
+        g_err = "more than 18 distinct symbols in consensus columns";
+        return SDGPU_E_ALPHABET;
+      }
+      if (outcome[jx] == OUT_UPLOAD) changed.push_back(jobs[jx].clus);
+      if (outcome[jx] == OUT_KEPT) ++keptVersions;
     }
     // new consensus versions -> device store (append-only; a store index never changes meaning)
     if (!changed.empty()) {
@@ -971,7 +1004,10 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   {
     // 64-bit hash of the bases, all reads in parallel; open addressing, equal hashes confirmed byte for byte
     std::vector<uint64_t> readHash(n);
+    std::mutex seenMu;
+    uint64_t seen[2] = {0, 0};  // 7-bit characters that occur (the consensus counters' symbol slots)
     parallelFor(n, [&](size_t lo, size_t hi) {
+      uint64_t mine[2] = {0, 0};
       for (size_t r = lo; r < hi; ++r) {
         const uint32_t len = uint32_t(offsets[r + 1] - offsets[r]);
         const uint8_t* p = bases + offsets[r];
@@ -985,8 +1021,16 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
         }
         for (; i < len; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
         readHash[r] = h ^ (h >> 29);
+        for (uint32_t x = 0; x < len; ++x) mine[(p[x] >> 6) & 1] |= 1ull << (p[x] & 63);
       }
+      std::lock_guard<std::mutex> lk(seenMu);
+      seen[0] |= mine[0];
+      seen[1] |= mine[1];
     });
+    // every symbol gets its counter slot now, so the threaded consensus rebuild only reads the slot table
+    R.slot('-');
+    for (int c = 0; c < 128; ++c)
+      if ((seen[c >> 6] >> (c & 63)) & 1) R.slot(char(c));
     size_t cap = 1024;
     while (cap < size_t(n) * 2 + 16) cap <<= 1;
     std::vector<uint32_t> table(cap, UINT32_MAX);
