@@ -970,23 +970,40 @@ __device__ __forceinline__ void bandCell(BandLane& st, int i, int j, int lane, i
   }
 }
 
+// Sequences up to BAND_STAGE bases are staged per warp in shared memory as ready-made byte offsets
+// into the score table (ref: code * 64 = its row, read: code * 4 = its column), so a cell's score is
+// one LDS at base + row + column.
+constexpr int BAND_STAGE = 2048;
+struct BandCodes {
+  const uint16_t* rowOff;  // [i-1] -> byte offset of ref base i's row (shared memory, or nullptr)
+  const uint8_t* colOff;   // [j-1] -> byte offset of read base j's column
+  const uint8_t *cA, *cB;  // global codes (sequences too long to stage)
+  const char* tab;         // score table, bytes
+  __device__ __forceinline__ int row(int i) const {
+    return rowOff ? int(rowOff[i - 1]) : int(__ldg(cA + i - 1)) * (SDGPU_MAX_SYMBOLS * 4);
+  }
+  __device__ __forceinline__ int col(int j) const { return rowOff ? int(colOff[j - 1]) : int(__ldg(cB + j - 1)) * 4; }
+  __device__ __forceinline__ int score(int r, int c) const { return *reinterpret_cast<const int*>(tab + r + c); }
+};
+
 // three step pairs (one word of decision bits) outside the body
 template <int MODE>
-__device__ __forceinline__ void bandWordEdge(BandLane& st, int& i, int& j, int lane, int la, int lb, const uint8_t* cA,
-                                             const uint8_t* cB, const int* sTab, const DevScoring& sc, int dInt) {
+__device__ __forceinline__ void bandWordEdge(BandLane& st, int& i, int& j, int lane, int la, int lb, const BandCodes& bc,
+                                             const DevScoring& sc, int dInt) {
 #pragma unroll
   for (int k = 0; k < 3; ++k, ++i, ++j) {
-    const bool rowIn = i >= 1 && i <= la;
-    const int* rowTab = sTab + (rowIn ? int(__ldg(cA + i - 1)) : 0) * SDGPU_MAX_SYMBOLS;
-    const int s0 = rowTab[(j >= 1 && j <= lb) ? int(__ldg(cB + j - 1)) : 0];
-    const int s1 = rowTab[(j + 1 >= 1 && j + 1 <= lb) ? int(__ldg(cB + j)) : 0];
+    const int r = (i >= 1 && i <= la) ? bc.row(i) : 0;
+    const int s0 = bc.score(r, (j >= 1 && j <= lb) ? bc.col(j) : 0);
+    const int s1 = bc.score(r, (j + 1 >= 1 && j + 1 <= lb) ? bc.col(j + 1) : 0);
     bandCell<false, MODE>(st, i, j, lane, la, lb, s0, sc, dInt);
     bandCell<true, MODE>(st, i, j + 1, lane, la, lb, s1, sc, dInt);
   }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignBandKernel(const AlignArgs a) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) alignBandKernel(const AlignArgs a) {
   __shared__ int sTab[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];
+  __shared__ uint16_t sRow[WARPS_PER_CTA][BAND_STAGE];
+  __shared__ uint8_t sCol[WARPS_PER_CTA][BAND_STAGE];
   for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS; x += blockDim.x) sTab[x] = a.sc.score[x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -1008,13 +1025,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignBandKernel(const Alig
     if (pair >= a.nPairs) break;
     const PairView pv = viewOf(a, pair);
     const int la = pv.la, lb = pv.lb;
-    const uint8_t *cA = pv.cA, *cB = pv.cB;
     const int diff = lb - la;
     bool certified = false;
     int score = 0;
     const int dlo = (diff - 63) >> 1;        // floor: the band [dlo, dlo + 63] is centred between offsets 0 and diff
     const int aBase = 2 - ((2 - dlo) & 1);   // lanes meet their even offset d0 on anti-diagonals aBase, aBase + 2, ...
     if (diff >= -BAND_MAX_DIFF && diff <= BAND_MAX_DIFF) {
+      BandCodes bc{nullptr, nullptr, pv.cA, pv.cB, reinterpret_cast<const char*>(sTab)};
+      const bool staged = la <= BAND_STAGE && lb <= BAND_STAGE;
+      if (staged) {
+        for (int x = lane; x < la; x += 32) sRow[warpInCta][x] = uint16_t(int(pv.cA[x]) * (SDGPU_MAX_SYMBOLS * 4));
+        for (int x = lane; x < lb; x += 32) sCol[warpInCta][x] = uint8_t(int(pv.cB[x]) * 4);
+        bc.rowOff = sRow[warpInCta];
+        bc.colOff = sCol[warpInCta];
+      }
+      __syncwarp();
       const int d0 = dlo + 2 * lane;
       // step pair p: anti-diagonals aBase + 2p (offset d0) and aBase + 2p + 1 (offset d0 + 1); both cells
       // of a lane sit in row i = I0 - lane + p, columns j = i + d0 and j + 1
@@ -1024,30 +1049,45 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) alignBandKernel(const Alig
       // interior pairs: for every lane 2 <= i <= la - 1 and 2 <= j, j + 1 <= lb - 1
       const int pBodyStart = max(max(33 - I0, 2 - I0 - dlo), 0);
       const int pBodyEnd = min(la - I0, lb - 32 - I0 - dlo);  // exclusive
+      int wHead = (pBodyStart + 2) / 3, wBody = pBodyEnd > 0 ? pBodyEnd / 3 : 0;  // words [wHead, wBody) are all-interior
+      if (!staged || wBody <= wHead) wHead = wBody = 0;
       BandLane st{0, 0, BAND_NEG, BAND_NEG, 0u};
       uint32_t* dst = ptrWords + lane;
       int i = I0 - lane, j = i + d0;
-      for (int w = 0; w < nWords; ++w, dst += 32) {
-        st.acc = 0;
-        const int p = 3 * w;
-        if (p >= pBodyStart && p + 3 <= pBodyEnd) {
-          int bCode = int(__ldg(cB + j - 1));
-#pragma unroll
-          for (int k = 0; k < 3; ++k, ++i, ++j) {
-            const int* rowTab = sTab + int(__ldg(cA + i - 1)) * SDGPU_MAX_SYMBOLS;
-            const int bNext = int(__ldg(cB + j));
-            bandCell<false, BAND_BODY>(st, i, j, lane, la, lb, rowTab[bCode], sc, dInt);
-            bandCell<true, BAND_BODY>(st, i, j + 1, lane, la, lb, rowTab[bNext], sc, dInt);
-            bCode = bNext;
-          }
-        } else if (p + 3 <= pBodyEnd) {
-          bandWordEdge<BAND_HEAD>(st, i, j, lane, la, lb, cA, cB, sTab, sc, dInt);
-        } else if (p >= pBodyStart) {
-          bandWordEdge<BAND_TAIL>(st, i, j, lane, la, lb, cA, cB, sTab, sc, dInt);
-        } else {
-          bandWordEdge<BAND_GEN>(st, i, j, lane, la, lb, cA, cB, sTab, sc, dInt);
+      if (wBody > wHead) {
+        for (int w = 0; w < wHead; ++w, dst += 32) {  // head: borders possible, last row / column not
+          st.acc = 0;
+          bandWordEdge<BAND_HEAD>(st, i, j, lane, la, lb, bc, sc, dInt);
+          *dst = st.acc;
         }
-        *dst = st.acc;
+        const uint16_t* rp = bc.rowOff + (i - 1);
+        const uint8_t* cp = bc.colOff + (j - 1);
+        int c0 = int(cp[0]);
+        for (int w = wHead; w < wBody; ++w, dst += 32, rp += 3, cp += 3) {  // body: lean cells
+          st.acc = 0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int r = int(rp[k]);
+            const int c1 = int(cp[k + 1]);
+            bandCell<false, BAND_BODY>(st, 0, 0, lane, la, lb, bc.score(r, c0), sc, dInt);
+            bandCell<true, BAND_BODY>(st, 0, 0, lane, la, lb, bc.score(r, c1), sc, dInt);
+            c0 = c1;
+          }
+          *dst = st.acc;
+        }
+        i += 3 * (wBody - wHead);
+        j += 3 * (wBody - wHead);
+        for (int w = wBody; w < nWords; ++w, dst += 32) {  // tail: last row / column, cells past the matrix
+          st.acc = 0;
+          bandWordEdge<BAND_TAIL>(st, i, j, lane, la, lb, bc, sc, dInt);
+          *dst = st.acc;
+        }
+      } else {
+        for (int w = 0; w < nWords; ++w, dst += 32) {
+          st.acc = 0;
+          bandWordEdge<BAND_GEN>(st, i, j, lane, la, lb, bc, sc, dInt);
+          *dst = st.acc;
+        }
       }
       const int cornerOdd = (diff - dlo) & 1;
       score = __shfl_sync(FULL, cornerOdd ? st.Tp1 : st.Tp0, (diff - dlo) >> 1);  // toDiag of (la, lb)
