@@ -33,7 +33,11 @@ sys.path.insert(0, ROOT)
 
 OPS_PER_CELL = 13  # algorithmic INT32 ops of one 3-state affine cell update
 CPU_SAMPLE_READS = 600
-TRAFFIC_BYTES_PER_CELL = 1.40  # measured: (dram__bytes_read.sum + dram__bytes_write.sum) / cells, profiles/r1b_*
+# DRAM bytes per evaluated cell of the dominant kernel (alignBandKernel): its only bulk traffic is the
+# decision-bit slab, 128 B per 6 anti-diagonals x 32 lanes = 12.8 KB for the ~19.2 k band cells of a 300 x 300
+# pair; the ncu --set full capture profiles/r1m_band_kernel_ncu_full.csv shows 3.37 GB written + 0.04 GB read
+# for a launch whose slabs total 3.4 GB (the full-matrix strip kernel measured 1.40 B/cell, profiles/r1b_*)
+TRAFFIC_BYTES_PER_CELL = 0.67
 
 
 def make_sample(seed, nReads):
@@ -282,10 +286,9 @@ def main():
                     "gcups": cellsAll / (wall_ms_max * 1e-3) / 1e9, "ms_per_step": wall_ms_max / K},
             "gpu_launches": int(prof["kernelLaunches"]),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "int32", "kernel": "alignProfileKernel", "achieved": kernel_gcups, "peak": peak_gcups,
+            "roofline": {"bound": "int32", "kernel": "alignBandKernel (+ alignProfileKernel redo)", "achieved": kernel_gcups, "peak": peak_gcups,
                          "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
-                         # dram read+write bytes per launch: bytes/cell from the ncu --set full capture in
-                         # profiles/r1b_align_kernel_ncu_full.csv (35.36 GB for a 2.52e10-cell launch) x cells per launch
+                         # dram read+write bytes per launch: bytes per evaluated cell (see TRAFFIC_BYTES_PER_CELL) x cells per launch
                          "traffic": TRAFFIC_BYTES_PER_CELL * prof["evaluatedCells"] / max(1, prof["alignKernelLaunches"]),
                          "effective_gcups": effective_gcups,
                          "banded_pass": {"share_of_pair_cells_certified": prof["bandCertifiedCells"] / max(1, prof["cellUpdates"]),
@@ -294,7 +297,7 @@ def main():
                                          "band_kernel_gcups": prof["bandCells"] / max(1e-9, prof["bandKernelMs"] * 1e-3) / 1e9,
                                          "full_kernel_ms_per_step": full_ms / K,
                                          "full_kernel_gcups": full_cells / max(1e-9, full_ms * 1e-3) / 1e9},
-                         "algorithmic_hbm_bytes_per_cell": 0.94,
+                         "algorithmic_hbm_bytes_per_cell": 0.67,
                          "launches": int(prof["alignKernelLaunches"]), "avg_launch_ms": prof["alignKernelMs"] / max(1, prof["alignKernelLaunches"]),
                          "kernel_share_of_step": prof["alignKernelMs"] / resident_ms,
                          "peak_source": f"measured on this GPU in this run: {int32_peak / 1e12:.2f} T INT32 thread-instr/s "
