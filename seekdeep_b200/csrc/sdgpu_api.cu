@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "sdgpu_internal.cuh"
 
@@ -237,24 +239,56 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
     if (len > 0x7fffffffu) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "sequence too long");
     maxLen = std::max<uint32_t>(maxLen, uint32_t(len));
   }
-  for (uint64_t x = 0; x < addBases; ++x) {
-    const uint8_t ch = bases[x];
-    int code = ctx->codeOf[ch];
-    if (code < 0) {
-      if (ch >= 128) return sd_fail(ctx, SDGPU_E_ALPHABET, "base outside 7-bit ASCII");
-      if (ctx->nSym >= SDGPU_MAX_SYMBOLS) return sd_fail(ctx, SDGPU_E_ALPHABET, "more than 16 distinct base characters");
-      code = ctx->nSym;
-      ctx->codeOf[ch] = int16_t(code);
-      ctx->charOf[ctx->nSym++] = ch;
-      newSym = true;
+  // translate with the alphabet as it stands, a few threads side by side; only if a character without
+  // a code turns up (first upload with degenerate bases) the sequential pass below assigns codes
+  bool unknown = false;
+  {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const uint64_t T = addBases < (1u << 20) ? 1 : std::min<uint64_t>(hw ? hw : 1, 8);
+    std::vector<int> maxCode(T, -1);
+    std::vector<uint8_t> sawUnknown(T, 0);
+    auto work = [&](uint64_t t) {
+      const uint64_t lo = addBases * t / T, hi = addBases * (t + 1) / T;
+      int mc = -1;
+      bool unk = false;
+      for (uint64_t x = lo; x < hi; ++x) {
+        const int code = ctx->codeOf[bases[x]];
+        unk |= code < 0;
+        mc = std::max(mc, code);
+        hCodes[x] = uint8_t(code);
+      }
+      if (quals) {
+        std::memcpy(hQuals + lo, quals + lo, hi - lo);
+      } else {
+        std::memset(hQuals + lo, 0, hi - lo);
+      }
+      maxCode[t] = mc;
+      sawUnknown[t] = unk;
+    };
+    std::vector<std::thread> th;
+    for (uint64_t t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (uint64_t t = 0; t < T; ++t) {
+      unknown |= sawUnknown[t] != 0;
+      if (maxCode[t] + 1 > ctx->usedSym) ctx->usedSym = maxCode[t] + 1;
     }
-    hCodes[x] = uint8_t(code);
-    if (code + 1 > ctx->usedSym) ctx->usedSym = code + 1;
   }
-  if (quals) {
-    std::memcpy(hQuals, quals, addBases);
-  } else {
-    std::memset(hQuals, 0, addBases);
+  if (unknown) {
+    for (uint64_t x = 0; x < addBases; ++x) {
+      const uint8_t ch = bases[x];
+      int code = ctx->codeOf[ch];
+      if (code < 0) {
+        if (ch >= 128) return sd_fail(ctx, SDGPU_E_ALPHABET, "base outside 7-bit ASCII");
+        if (ctx->nSym >= SDGPU_MAX_SYMBOLS) return sd_fail(ctx, SDGPU_E_ALPHABET, "more than 16 distinct base characters");
+        code = ctx->nSym;
+        ctx->codeOf[ch] = int16_t(code);
+        ctx->charOf[ctx->nSym++] = ch;
+        newSym = true;
+      }
+      hCodes[x] = uint8_t(code);
+      if (code + 1 > ctx->usedSym) ctx->usedSym = code + 1;
+    }
   }
   if (newSym && (rc = refreshScoring(ctx))) return rc;
   // grow device arrays
