@@ -20,6 +20,8 @@
 //   * consensus rebuilding keeps the per-column counters of a cluster while its base sequence
 //     stays the same, aligns only the newly absorbed members (one GPU batch per iteration, gap
 //     lists returned) and re-reads the consensus off the counters (integer sums: exact).
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -128,9 +130,22 @@ class Row {
 
 // Splits [0, n) over a few short-lived host threads (the prep phases before the GPU has work:
 // hashing, per-unique median qualities, packing, cluster pool set-up are all per-item independent).
+// host threads this process may use: the CPUs it is allowed on (ranks sharing a node are pinned to their
+// own core slices), not the machine's core count
+static unsigned allowedCpus() {
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+    const int n = CPU_COUNT(&set);
+    if (n > 0) return unsigned(n);
+  }
+  const unsigned hw = std::thread::hardware_concurrency();
+  return hw ? hw : 1;
+}
+
 template <class Fn>
 static void parallelFor(size_t n, Fn fn) {
-  unsigned hw = std::thread::hardware_concurrency();
+  const unsigned hw = allowedCpus();
   size_t T = std::min<size_t>(hw ? hw : 1, 8);
   if (n < 4096) T = 1;
   if (T <= 1) {
@@ -153,7 +168,7 @@ static const bool g_verboseTiming = getenv("SDQ_TIMING") && atoi(getenv("SDQ_TIM
 // from a shared counter.
 template <class Fn>
 static void parallelForDynamic(size_t n, Fn fn) {
-  unsigned hw = std::thread::hardware_concurrency();
+  const unsigned hw = allowedCpus();
   size_t T = std::min<size_t>(hw ? hw : 1, 4);
   if (n < 8) T = 1;
   if (T <= 1) {
