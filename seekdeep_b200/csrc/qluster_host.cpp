@@ -167,9 +167,9 @@ static const bool g_verboseTiming = getenv("SDQ_TIMING") && atoi(getenv("SDQ_TIM
 // Items of very different cost (clusters absorbing 1 .. thousands of members): threads pull indices
 // from a shared counter.
 template <class Fn>
-static void parallelForDynamic(size_t n, Fn fn) {
+static void parallelForDynamic(size_t n, Fn fn, size_t maxThreads = 4) {
   const unsigned hw = allowedCpus();
-  size_t T = std::min<size_t>(hw ? hw : 1, 4);
+  size_t T = std::min<size_t>(hw ? hw : 1, maxThreads);
   if (n < 8) T = 1;
   if (T <= 1) {
     for (size_t i = 0; i < n; ++i) fn(i);
@@ -1079,9 +1079,13 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
       u.inputIdx.push_back(r);
     }
   }
+  const double tDedupe = nowSec() - tStart;
   // sequence bytes + per-base median quality over the members (clusterDown.cpp:293-359, qualRep "median")
-  parallelFor(R.uniq.size(), [&](size_t lo, size_t hi) {
+  // (abundant sequences come first and cost the most: blocks of 256 uniques are handed out dynamically)
+  parallelForDynamic((R.uniq.size() + 255) / 256, [&](size_t blk) {
     std::vector<uint8_t> col;
+    std::vector<uint32_t> hist;
+    const size_t lo = blk * 256, hi = std::min(R.uniq.size(), lo + 256);
     for (size_t x = lo; x < hi; ++x) {
       Uniq& u = R.uniq[x];
       const uint32_t fr = u.inputIdx[0];
@@ -1092,14 +1096,42 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
         std::memcpy(u.qual.data(), quals + offsets[fr], len);
         continue;
       }
-      col.resize(k);
+      if (k < 16) {
+        col.resize(k);
+        for (size_t i = 0; i < len; ++i) {
+          for (size_t m = 0; m < k; ++m) col[m] = quals[offsets[u.inputIdx[m]] + i];
+          std::sort(col.begin(), col.end());
+          u.qual[i] = (k % 2) ? col[k / 2] : uint8_t((uint32_t(col[k / 2 - 1]) + col[k / 2]) / 2);
+        }
+        continue;
+      }
+      // many members: per-column histograms filled member by member (sequential reads), medians read off them
+      hist.assign(len * 256, 0);
+      for (size_t m = 0; m < k; ++m) {
+        const uint8_t* q = quals + offsets[u.inputIdx[m]];
+        for (size_t i = 0; i < len; ++i) ++hist[i * 256 + q[i]];
+      }
+      const size_t r1 = (k % 2) ? k / 2 : k / 2 - 1, r2 = k / 2;  // order statistics (0-based) the median needs
       for (size_t i = 0; i < len; ++i) {
-        for (size_t m = 0; m < k; ++m) col[m] = quals[offsets[u.inputIdx[m]] + i];
-        std::sort(col.begin(), col.end());
-        u.qual[i] = (k % 2) ? col[k / 2] : uint8_t((uint32_t(col[k / 2 - 1]) + col[k / 2]) / 2);
+        const uint32_t* h = hist.data() + i * 256;
+        size_t seen = 0;
+        uint32_t v1 = 0, v2 = 0;
+        bool got1 = false;
+        for (uint32_t v = 0; v < 256; ++v) {
+          seen += h[v];
+          if (!got1 && seen > r1) {
+            v1 = v;
+            got1 = true;
+          }
+          if (seen > r2) {
+            v2 = v;
+            break;
+          }
+        }
+        u.qual[i] = (k % 2) ? uint8_t(v1) : uint8_t((v1 + v2) / 2);
       }
     }
-  });
+  }, 8);
   const uint32_t nU = uint32_t(R.uniq.size());
   res->stats.inputReads = n;
   res->stats.uniqueSeqs = nU;
@@ -1108,6 +1140,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     *out = res;
     return SDGPU_OK;
   }
+  const double tMedian = nowSec() - tStart;
   // the unique reads become sequence-store entries 0..nU-1
   {
     std::vector<uint64_t> off(size_t(nU) + 1, 0);
@@ -1127,6 +1160,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     R.storeSize = nU;
     if (sdgpu_timer_start(ctx)) return bail(R.fail(SDGPU_E_CUDA));  // inputs are resident from here on
   }
+  const double tUpload = nowSec() - tStart;
   res->pool.resize(nU);  // never resized again: ClusVec holds pointers into it
   ClusVec clusters;
   for (uint32_t u = 0; u < nU; ++u) clusters.push_back(&res->pool[u]);
@@ -1144,6 +1178,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     }
   });
   const double tPrep = nowSec() - tStart;
+  if (g_verboseTiming) fprintf(stderr, "[sdq]   prep: dedupe %.3f median %.3f pack+upload %.3f pool %.3f\n", tDedupe, tMedian - tDedupe, tUpload - tMedian, tPrep - tUpload);
   R.dropRemovedAndSort(clusters);     // clusterDown.cpp:389
   int rc = R.buildIndex(clusters);    // clusterDown.cpp:412-417
   if (rc) return bail(rc);
