@@ -1282,7 +1282,7 @@ int sdq_run_many(int device, const sdgpu_params* params, const sdq_opts* opts, c
   std::mutex errMutex;
   std::string firstErr;
   auto worker = [&]() {
-    g_chunkPairs = nWorkers > 1 ? (getenv("SDQ_WORKER_CHUNK") ? uint32_t(atoi(getenv("SDQ_WORKER_CHUNK"))) : (1u << 16)) : 0u;
+    g_chunkPairs = nWorkers > 1 ? (getenv("SDQ_WORKER_CHUNK") ? uint32_t(atoi(getenv("SDQ_WORKER_CHUNK"))) : (1u << 18)) : 0u;
     sdgpu_ctx* ctx = nullptr;
     int rc = sdgpu_create(device, params, &ctx);
     if (rc) {
