@@ -485,3 +485,77 @@ def test_banded_pass_is_exact(oracle, pname):
     want, wg = oracle.align_profile_batch(params, bases, q, offsets, refIdx[sel], readIdx[sel], _abi.USING_QUALITY, gapCap=12)
     H.assert_comparisons_equal(got[sel], want)
     assert np.array_equal(gg[sel], wg)
+
+
+def test_banded_pass_edge_geometries(oracle):
+    """Band edge cases: 1..40-base sequences (no interior steps at all), length differences around the
+    +-30 limit, near-identical 2.5 kb pairs (longer than the shared-memory staging: general cells with global
+    loads), and a launch of dissimilar pairs followed by similar ones (the skip-the-band heuristic)."""
+    rng = np.random.default_rng(99)
+    params = H.params_for("qluster")
+    seqs = [H.rand_seq(rng, int(n)) for n in list(range(1, 41)) + [64, 65, 66, 97, 128]]
+    base = H.rand_seq(rng, 200)
+    for d in (28, 29, 30, 31, 32, 40):          # length difference at / beyond the band's limit
+        seqs.append(base[d:])
+        seqs.append(np.concatenate([base, H.rand_seq(rng, d)]))
+    seqs.append(base)
+    long0 = H.rand_seq(rng, 2500)
+    seqs += [long0, H.mutate(rng, long0, 9, 1, 1), H.mutate(rng, long0, 3, 0, 2), long0[7:]]
+    quals = [H.rand_quals(rng, len(s)) for s in seqs]
+    bases, q, offsets = pack_seqs([s.tobytes() for s in seqs], quals)
+    n = len(seqs)
+    nShort = n - 4
+    refIdx, readIdx = [a.ravel().astype(np.uint32) for a in np.meshgrid(np.arange(nShort), np.arange(nShort))]
+    longPairs = np.array([(i, j) for i in range(nShort, n) for j in range(nShort, n)], np.uint32)
+    longPairs = np.tile(longPairs, (5, 1))      # >= 64 pairs so the launch takes the banded pass
+    for ri, rj, mostlyCertified in ((refIdx, readIdx, False), (longPairs[:, 0].copy(), longPairs[:, 1].copy(), True)):
+        with GpuAligner(params) as al:  # fresh ctx each: the first launch's many redo pairs would switch the band off
+            al.upload_seqs(bases, q, offsets)
+            al.profile_enable(True)
+            al.profile_read(reset=True)
+            got, gg = al.align_profile(ri, rj, usingQuality=True, gapCap=16)
+            prof = al.profile_read()
+        assert prof["bandCells"] > 0
+        want, wg = oracle.align_profile_batch(params, bases, q, offsets, ri, rj, _abi.USING_QUALITY, gapCap=16)
+        H.assert_comparisons_equal(got, want)
+        assert np.array_equal(gg, wg)
+        if mostlyCertified:  # the 2.5 kb relatives all certify
+            assert prof["bandCertifiedCells"] > 0.9 * prof["cellUpdates"]
+    with GpuAligner(params) as al:
+        al.profile_enable(True)
+        # dissimilar launches switch the band off for the following ones, a similar launch gets it back later
+        unrel = [H.rand_seq(rng, 150) for _ in range(40)]
+        b2, q2, o2 = pack_seqs([s.tobytes() for s in unrel], [H.rand_quals(rng, 150) for _ in unrel])
+        al.upload_seqs(b2, q2, o2)
+        ri, rj = [a.ravel().astype(np.uint32) for a in np.meshgrid(np.arange(40), np.arange(40))]
+        keep = ri != rj
+        ri, rj = ri[keep], rj[keep]
+        want = oracle.align_profile_batch(params, b2, q2, o2, ri, rj, _abi.USING_QUALITY)
+        sawSkip = False
+        for _ in range(4):
+            al.profile_read(reset=True)
+            got = al.align_profile(ri, rj, usingQuality=True)
+            sawSkip |= al.profile_read()["bandCells"] == 0
+            H.assert_comparisons_equal(got, want)
+        assert sawSkip
+
+
+def test_band_not_used_when_bound_is_unsound(oracle):
+    """maxSub <= 0 (no positive score) or penalties beyond 4096: the certificate does not apply, the
+    launch must go straight to the full-matrix kernels and still match the oracle."""
+    rng = np.random.default_rng(5)
+    bases, quals, offsets, cnts, _, _ = H.make_store(rng, 24, 120)
+    ri = rng.integers(0, 24, 300).astype(np.uint32)
+    rj = rng.integers(0, 24, 300).astype(np.uint32)
+    from seekdeep_b200.scoring import SubstituteMatrix
+    for kw in (dict(scoring=SubstituteMatrix.create_degen_score_matrix_case_insensitive(0, -3)),
+               dict(gaps=GapScoringParameters(5000, 1, 5000, 1, 0, 0, 5000, 1, 0, 0))):
+        params = make_params(**kw)
+        with GpuAligner(params) as al:
+            al.upload_seqs(bases, quals, offsets, cnts)
+            al.profile_enable(True)
+            al.profile_read(reset=True)
+            got = al.align_profile(ri, rj, usingQuality=True)
+            assert al.profile_read()["bandCells"] == 0
+        want = oracle.align_profile_batch(params, bases, quals, offsets, ri, rj, _abi.USING_QUALITY)
+        H.assert_comparisons_equal(got, want)
