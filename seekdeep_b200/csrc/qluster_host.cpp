@@ -122,10 +122,10 @@ class Row {
     for (size_t i = 0; i < k.size(); ++i)
       if (k[i] != EMPTY) insert(k[i], v[i]);
   }
+  uint64_t or_ = 0;  // (summary words first: they share the owning cluster's first cache line)
+  uint32_t n_ = 0, mask_ = 0;
   std::vector<uint32_t> keys_;
   std::vector<uint64_t> vals_;
-  uint32_t n_ = 0, mask_ = 0;
-  uint64_t or_ = 0;
 };
 
 // Splits [0, n) over a few short-lived host threads (the prep phases before the GPU has work:
@@ -216,19 +216,21 @@ struct ConsState {  // column counters of one cluster against one base sequence
   std::map<uint32_t, Col> beginningGap;
 };
 
-struct Clus {
+// The per-iteration loops walk every live cluster but mostly look at a handful of scalars: those come
+// first, together with the row's summary words, so that one 64-byte line per cluster serves them.
+struct alignas(64) Clus {
+  double cnt = 0;
+  double avgErr = 0;
+  uint64_t rowSerial = 0;  // iteration serial at which `row` was complete for that window
+  uint32_t storeIdx = 0;   // device sequence-store entry (verdict-equivalent to (seq, qual))
+  uint32_t firstId = 0;    // cluster::firstReadName_ stand-in (tie-break of the sort)
+  bool remove = false, needCons = false;
+  bool chimeric = false;   // seqBase_.markAsChimeric()
+  Row row;                 // verdicts of this cluster *as the read* against larger clusters
   std::string seq;
   std::vector<uint8_t> qual;
-  double cnt = 0;
-  uint32_t firstId = 0;   // cluster::firstReadName_ stand-in (tie-break of the sort)
-  uint32_t storeIdx = 0;  // device sequence-store entry (verdict-equivalent to (seq, qual))
-  bool chimeric = false;  // seqBase_.markAsChimeric()
-  uint32_t chiParent[2] = {0, 0}, chiPos[2] = {0, 0};
   std::vector<uint32_t> members;
-  bool remove = false, needCons = false;
-  double avgErr = 0;
-  Row row;                 // verdicts of this cluster *as the read* against larger clusters
-  uint64_t rowSerial = 0;  // iteration serial at which `row` was complete for that window
+  uint32_t chiParent[2] = {0, 0}, chiPos[2] = {0, 0};
   std::vector<uint8_t> devSig;  // checkQual outcome per base of the device version (empty: exact copy)
   std::unique_ptr<ConsState> cons;
 };
