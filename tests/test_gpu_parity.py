@@ -559,3 +559,44 @@ def test_band_not_used_when_bound_is_unsound(oracle):
             assert al.profile_read()["bandCells"] == 0
         want = oracle.align_profile_batch(params, bases, quals, offsets, ri, rj, _abi.USING_QUALITY)
         H.assert_comparisons_equal(got, want)
+
+
+def test_banded_vs_full_matrix_fuzz():
+    """Certificate stress test without the oracle: random gap penalties (zeros included), match / mismatch
+    scores, lengths, divergence and indel sizes; the banded pass + redo must reproduce the full-matrix
+    kernels field for field, gap lists included, and must actually certify pairs in most configurations."""
+    from seekdeep_b200.scoring import SubstituteMatrix
+    rng = np.random.default_rng(2026)
+    usedBand = 0
+    for trial in range(240):
+        L = int(rng.choice([40, 90, 150, 250, 300, 420, 700]))
+        g = [int(x) for x in rng.integers(0, 9, 10)]
+        for k in (0, 2, 4, 6, 8):  # extend <= open keeps the parameter sets realistic
+            g[k + 1] = min(g[k + 1], g[k])
+        match, mismatch = int(rng.integers(1, 6)), -int(rng.integers(1, 7))
+        params = make_params(gaps=GapScoringParameters(*g), scoring=SubstituteMatrix.create_degen_score_matrix_case_insensitive(match, mismatch),
+                             weighHomopolymers=bool(rng.integers(2)), countEndGaps=bool(rng.integers(2)))
+        root = H.rand_seq(rng, L)
+        seqs = [root]
+        for _ in range(23):
+            s = H.mutate(rng, root, int(rng.integers(0, 1 + L // 12)), int(rng.integers(0, 3)), int(rng.integers(0, 3)), hp=bool(rng.integers(2)))
+            if rng.random() < 0.3:  # one long indel
+                p, size = int(rng.integers(5, max(6, len(s) - 40))), int(rng.integers(2, 36))
+                s = np.concatenate([s[:p], s[p + size:]]) if rng.random() < 0.5 else np.concatenate([s[:p], H.rand_seq(rng, size), s[p:]])
+            seqs.append(s)
+        quals = [H.rand_quals(rng, len(s)) for s in seqs]
+        bases, q, offsets = pack_seqs([s.tobytes() for s in seqs], quals)
+        ri, rj = [a.ravel().astype(np.uint32) for a in np.meshgrid(np.arange(24), np.arange(24))]
+        with GpuAligner(params) as al:
+            al.upload_seqs(bases, q, offsets)
+            al.profile_enable(True)
+            al.profile_read(reset=True)
+            got, gg = al.align_profile(ri, rj, usingQuality=True, gapCap=16)
+            usedBand += al.profile_read()["bandCertifiedCells"] > 0
+            al.set_band(1)
+            full, fg = al.align_profile(ri, rj, usingQuality=True, gapCap=16)
+        for name in got.dtype.names:
+            bad = np.nonzero(got[name] != full[name])[0]
+            assert bad.size == 0, (trial, name, g, match, mismatch, L, int(ri[bad[0]]), int(rj[bad[0]]))
+        assert np.array_equal(gg, fg), (trial, g, match, mismatch, L)
+    assert usedBand >= 160
