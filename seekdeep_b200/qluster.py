@@ -145,10 +145,11 @@ def _result_to_dict(lib, h, n, want_clusters):
             lib.sdq_cluster_seq(h, c, _ptr(s), _ptr(q))
             res["clusters"].append((s.tobytes().decode(), q, lib.sdq_cluster_cnt(h, c)))
     res["chimeras"] = {}  # cluster -> (frontParent, backParent, frontPos, backPos), chiParentsInfo.txt's columns
-    for c in range(lib.sdq_num_clusters(h)):
+    if st.chimericClusters:  # (a per-cluster ctypes call: only worth it when something was flagged)
         par, pos = (C.c_uint32 * 2)(), (C.c_uint32 * 2)()
-        if lib.sdq_cluster_chimeric(h, c, par, pos):
-            res["chimeras"][c] = (par[0], par[1], pos[0], pos[1])
+        for c in range(lib.sdq_num_clusters(h)):
+            if lib.sdq_cluster_chimeric(h, c, par, pos):
+                res["chimeras"][c] = (par[0], par[1], pos[0], pos[1])
     mem = np.zeros(n, np.uint32)
     lib.sdq_membership(h, _ptr(mem))
     res["membership"] = mem
