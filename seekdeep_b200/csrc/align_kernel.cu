@@ -22,7 +22,12 @@
 //   per-column registers, first row/column through the initial register state and lane 0's
 //   boundary feed.
 //
-// Two forward passes share the traceback / errorProfile code:
+// Three forward passes share the traceback / errorProfile code:
+//   alignBandKernel          first pass of every launch of >= 64 pairs: 64 diagonals, anti-diagonal
+//                            by anti-diagonal, one cell per lane per step; a pair is finished here
+//                            only if its banded score proves the full-matrix optimum and traceback
+//                            lie inside the band (see the comment above the kernel), otherwise it is
+//                            queued for one of the two full-matrix passes below.
 //   alignProfileKernel<C>    one pair per warp, int32 lanes: maxima (two of them fused add+max)
 //                            and funnel shifts on the ALU pipe, differences on the FMA pipe.
 //   alignProfileKernelH2<C>  TWO pairs per warp in the halves of __half2 registers.  Every DP

@@ -20,6 +20,10 @@
 //   * consensus rebuilding keeps the per-column counters of a cluster while its base sequence
 //     stays the same, aligns only the newly absorbed members (one GPU batch per iteration, gap
 //     lists returned) and re-reads the consensus off the counters (integer sums: exact).
+// Host threads: the main thread runs the sequential logic and lists pairs; one helper thread per
+// run files returned verdict masks into the reads' rows; short-lived worker threads share the
+// per-item independent phases (read hashing, per-unique median qualities, packing, cluster pool
+// set-up, consensus counter updates).  None of them changes an order the results depend on.
 #include <sched.h>
 
 #include <algorithm>
