@@ -384,7 +384,7 @@ int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   SD_CUDA(ctx, cudaFuncSetAttribute(acgtOnly ? (const void*)kmerProfileKernel4 : (const void*)kmerProfileKernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   uint32_t grid = (nSeqs + warpsPerCta - 1) / warpsPerCta;
-  const uint32_t maxGrid = uint32_t(ctx->numSMs) * 32;  // (swept 8..unbounded on B200: no effect beyond 16)
+  const uint32_t maxGrid = uint32_t(ctx->numSMs) * 32;  // (swept 6..1000 CTAs per SM on B200: 32-64 is best, 6 costs 5 %)
   if (grid > maxGrid) grid = maxGrid;
   if (acgtOnly) {
     kmerProfileKernel4<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, profSize, ctx->dProfiles);
