@@ -51,7 +51,9 @@ def workload_config(nReads):
                         "homopolymer indels, Illumina par table (illumina_lkmer1, 22 iterations x 3 passes) — BASELINE configs[1]",
             "reads_per_sample": nReads, "samples_per_gpu_per_step": 1, "stopCheck": 100, "gap": "5,1 left 5,1 right 0,0",
             "qualThres": "25,20", "kLength": 9,
-            "l2": "no flush: every alignment launch streams its own traceback-bit slabs (>200 MB per launch, above the 126 MB L2)"}
+            "per_rank_sample": "identical copy of the seed-2 sample on every rank (fixed per-GPU work)",
+            "l2": "no flush: a step streams 107 MB of sequences plus 330 MB of pair lists and verdict masks through ~70 "
+                  "alignment launches and rewrites the 60 MB of per-warp decision-bit slabs in each, far beyond the 126 MB L2"}
 
 
 class ClockSampler(threading.Thread):
@@ -217,7 +219,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         bind_cpus(local, world)
-    bases, quals, offsets = make_sample(2 + rank, args.reads)  # one sample per GPU: sharded by sample
+    # one sample per GPU per step, sharded by sample; every rank gets its own copy of the SAME sample so that
+    # per-GPU work is exactly fixed as N grows (weak scaling) and the step time is not set by whichever rank drew
+    # the heaviest random sample
+    bases, quals, offsets = make_sample(2, args.reads)
     nReads = len(offsets) - 1
     al = sd.GpuAligner(sd.make_params(), device=local)
     al.profile_enable(True)
