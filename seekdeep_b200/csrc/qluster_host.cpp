@@ -148,10 +148,10 @@ static unsigned allowedCpus() {
 }
 
 template <class Fn>
-static void parallelFor(size_t n, Fn fn) {
+static void parallelFor(size_t n, Fn fn, size_t minItemsPerThread = 512) {
   const unsigned hw = allowedCpus();
   size_t T = std::min<size_t>(hw ? hw : 1, 8);
-  if (n < 4096) T = 1;
+  T = std::min(T, std::max<size_t>(1, n / minItemsPerThread));
   if (T <= 1) {
     fn(size_t(0), n);
     return;
@@ -865,7 +865,21 @@ class Runner {
       return clusLess(*a.c, *b.c);
     };
     if (!std::is_sorted(keys.begin(), keys.end(), less)) {
-      std::sort(keys.begin(), keys.end(), less);
+      // the order is total (first id breaks every tie), so chunk sorts + merges give std::sort's result
+      const size_t n = keys.size();
+      const size_t T = n >= (1u << 15) ? std::min<size_t>(allowedCpus(), 4) : 1;
+      if (T > 1) {
+        std::vector<size_t> cut(T + 1);
+        for (size_t t = 0; t <= T; ++t) cut[t] = n * t / T;
+        parallelFor(T, [&](size_t lo, size_t hi) {
+          for (size_t t = lo; t < hi; ++t) std::sort(keys.begin() + cut[t], keys.begin() + cut[t + 1], less);
+        }, 1);
+        for (size_t width = 1; width < T; width *= 2)
+          for (size_t t = 0; t + width < T; t += 2 * width)
+            std::inplace_merge(keys.begin() + cut[t], keys.begin() + cut[t + width], keys.begin() + cut[std::min(T, t + 2 * width)], less);
+      } else {
+        std::sort(keys.begin(), keys.end(), less);
+      }
       for (size_t i = 0; i < v.size(); ++i) v[i] = keys[i].c;
     }
     tSort += nowSec() - t0;
@@ -899,22 +913,24 @@ class Runner {
     } tick{tIndex, t0};
     std::vector<uint32_t> idx(cs.size());
     std::vector<double> cnts(cs.size());
-    std::vector<uint32_t> order(cs.size());
-    for (uint32_t i = 0; i < cs.size(); ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cs[x].storeIdx < cs[y].storeIdx; });
+    std::vector<std::pair<uint32_t, double>> byStore(cs.size());  // store order = sequential reads on the device
+    for (uint32_t i = 0; i < cs.size(); ++i) byStore[i] = {cs[i].storeIdx, cs[i].cnt};
+    std::sort(byStore.begin(), byStore.end(), [](const std::pair<uint32_t, double>& x, const std::pair<uint32_t, double>& y) { return x.first < y.first; });
     for (uint32_t i = 0; i < cs.size(); ++i) {
-      idx[i] = cs[order[i]].storeIdx;
-      cnts[i] = cs[order[i]].cnt;
+      idx[i] = byStore[i].first;
+      cnts[i] = byStore[i].second;
     }
     int rc = sdgpu_update_cnts(ctx_, idx.data(), cnts.data(), uint32_t(idx.size()));
     if (rc) return fail(rc);
     rc = sdgpu_build_kmer_index(ctx_, idx.data(), uint32_t(idx.size()), O.kLen, O.runCutOff, int(O.kmersByPosition),
                                 int(O.expandKmerPos), O.expandKmerSize);
     if (rc) return fail(rc);
-    for (Clus& c : cs) {  // verdicts depend on the index through lowKmerMismatches
-      c.row.clear();
-      c.rowSerial = 0;
-    }
+    parallelFor(cs.size(), [&](size_t lo, size_t hi) {  // verdicts depend on the index through lowKmerMismatches
+      for (size_t i = lo; i < hi; ++i) {
+        cs[i].row.clear();
+        cs[i].rowSerial = 0;
+      }
+    });
     return 0;
   }
 };
