@@ -920,11 +920,15 @@ class Runner {
       idx[i] = byStore[i].first;
       cnts[i] = byStore[i].second;
     }
+    const double tA = nowSec();
     int rc = sdgpu_update_cnts(ctx_, idx.data(), cnts.data(), uint32_t(idx.size()));
     if (rc) return fail(rc);
+    const double tB = nowSec();
     rc = sdgpu_build_kmer_index(ctx_, idx.data(), uint32_t(idx.size()), O.kLen, O.runCutOff, int(O.kmersByPosition),
                                 int(O.expandKmerPos), O.expandKmerSize);
     if (rc) return fail(rc);
+    const double tC = nowSec();
+    if (g_verboseTiming) fprintf(stderr, "[sdq]   index: gather+sort %.3f update_cnts %.3f build %.3f\n", tA - t0, tB - tA, tC - tB);
     parallelFor(cs.size(), [&](size_t lo, size_t hi) {  // verdicts depend on the index through lowKmerMismatches
       for (size_t i = lo; i < hi; ++i) {
         cs[i].row.clear();

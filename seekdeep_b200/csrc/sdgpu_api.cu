@@ -99,6 +99,11 @@ static int refreshScoring(sdgpu_ctx* ctx) {
   return SDGPU_OK;
 }
 
+__global__ void scatterCntsKernel(const uint32_t* idx, const double* vals, uint32_t n, double* cnts) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < n) cnts[idx[x]] = vals[x];
+}
+
 static int validateParams(sdgpu_ctx* ctx, const sdgpu_params* p) {
   const int32_t* g = reinterpret_cast<const int32_t*>(&p->gaps);
   for (int x = 0; x < 10; ++x)
@@ -345,14 +350,26 @@ int sdgpu_update_cnts(sdgpu_ctx* ctx, const uint32_t* seqIdx, const double* cnts
   if (!ctx || (n && (!seqIdx || !cnts))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
-  // contiguous runs become one copy each; cluster lists are short, so this stays cheap
-  for (uint32_t x = 0; x < n;) {
+  for (uint32_t x = 0; x < n; ++x)
     if (seqIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "sequence index out of range");
-    uint32_t y = x + 1;
-    while (y < n && seqIdx[y] == seqIdx[y - 1] + 1 && seqIdx[y] < nSeqs) ++y;
-    SD_CUDA(ctx, cudaMemcpyAsync(ctx->dCnts + seqIdx[x], cnts + x, size_t(y - x) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    x = y;
-  }
+  if (n == 0) return SDGPU_OK;
+  // one staged copy + a scatter kernel (after a collapse the live clusters' store indices are scattered:
+  // per-run copies meant ~20 000 tiny transfers)
+  const uint64_t bytes = uint64_t(n) * 12;
+  int rc = sd_ensure_pinned(ctx, bytes);
+  if (rc) return rc;
+  if ((rc = sd_ensure_stage(ctx, bytes + 256))) return rc;
+  double* hVals = reinterpret_cast<double*>(ctx->hPinned);
+  uint32_t* hIdx = reinterpret_cast<uint32_t*>(hVals + n);
+  std::memcpy(hVals, cnts, size_t(n) * 8);
+  std::memcpy(hIdx, seqIdx, size_t(n) * 4);
+  double* dVals = reinterpret_cast<double*>(ctx->dStage);
+  uint32_t* dIdx = reinterpret_cast<uint32_t*>(dVals + n);
+  SD_CUDA(ctx, cudaMemcpyAsync(dVals, hVals, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  scatterCntsKernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dIdx, dVals, n, ctx->dCnts);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  ctx->h2dBytes += bytes;
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SDGPU_OK;
 }
