@@ -913,13 +913,16 @@ class Runner {
     } tick{tIndex, t0};
     std::vector<uint32_t> idx(cs.size());
     std::vector<double> cnts(cs.size());
-    std::vector<std::pair<uint32_t, double>> byStore(cs.size());  // store order = sequential reads on the device
-    for (uint32_t i = 0; i < cs.size(); ++i) byStore[i] = {cs[i].storeIdx, cs[i].cnt};
-    std::sort(byStore.begin(), byStore.end(), [](const std::pair<uint32_t, double>& x, const std::pair<uint32_t, double>& y) { return x.first < y.first; });
-    for (uint32_t i = 0; i < cs.size(); ++i) {
-      idx[i] = byStore[i].first;
-      cnts[i] = byStore[i].second;
-    }
+    // store order (sequential reads on the device): store indices are unique, so one pass over a
+    // store-sized table replaces a sort
+    std::vector<double> byStore(storeSize, -1.0);
+    for (uint32_t i = 0; i < cs.size(); ++i) byStore[cs[i].storeIdx] = cs[i].cnt;
+    uint32_t m = 0;
+    for (uint32_t sIdx = 0; sIdx < storeSize; ++sIdx)
+      if (byStore[sIdx] >= 0) {
+        idx[m] = sIdx;
+        cnts[m++] = byStore[sIdx];
+      }
     const double tA = nowSec();
     int rc = sdgpu_update_cnts(ctx_, idx.data(), cnts.data(), uint32_t(idx.size()));
     if (rc) return fail(rc);
