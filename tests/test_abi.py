@@ -65,3 +65,18 @@ def test_product_does_not_reference_oracle():
                 if re.search(r"oracle|sdo_|libsdoracle", txt):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_headers_compile_as_c99_and_cxx():
+    """include/*.h are the drop-in boundary: plain C (no C++-isms) and usable from C++."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for hdr in ("sdgpu.h", "sdgpu_qluster.h"):
+        for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c"], ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++"]):
+            r = subprocess.run(cmd + [os.path.join(inc, hdr)], capture_output=True, text=True)
+            assert r.returncode == 0, f"{' '.join(cmd)} {hdr}:\n{r.stderr}"
+
+
+def test_cxx_example_builds_against_the_library():
+    import __graft_entry__ as g
+    assert os.path.exists(g.build_example())

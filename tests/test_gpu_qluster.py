@@ -158,3 +158,35 @@ def test_mark_chimeras_matches_oracle(oracle):
             assert got["stats"]["chimericClusters"] == len(got["chimeras"])
         else:
             assert got["chimeras"] == {} and got["stats"]["chimeraPairs"] == 0
+
+
+def test_cxx_caller_matches_python_api(tmp_path):
+    """examples/qluster_cabi.cpp (C++ straight onto the C ABI, its own parameter set-up) must print the same
+    clusters the Python wrapper returns for the same packed sample."""
+    import subprocess
+    import __graft_entry__ as g
+    from tests import helpers as H
+    exe = g.build_example()
+    rng = np.random.default_rng(33)
+    bases, quals, offsets, (p0, p1, chi, var), cut = H.chimera_sample(rng, length=220, counts=(200, 150, 30, 20))
+    bases = bases.copy()
+    quals = quals.copy()
+    hit = rng.random(len(bases)) < 0.004
+    bases[hit] = H.BASES[rng.integers(0, 4, int(hit.sum()))]
+    quals[hit] = rng.integers(2, 15, int(hit.sum()))
+    path = tmp_path / "sample.bin"
+    with open(path, "wb") as f:
+        f.write(np.uint32(len(offsets) - 1).tobytes())
+        f.write(np.ascontiguousarray(offsets, np.uint64).tobytes())
+        f.write(bases.tobytes())
+        f.write(quals.tobytes())
+    r = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = [line.split("\t") for line in r.stdout.strip().splitlines()]
+    with sd.GpuAligner(sd.make_params()) as al:
+        want = sd.qluster(al, bases, quals, offsets)
+    assert len(got) == len(want["clusters"])
+    for c, (cnt, chim, seq) in enumerate(got):
+        assert float(cnt) == want["clusters"][c][2] and seq == want["clusters"][c][0]
+        assert (chim == "1") == (c in want["chimeras"])
+    assert any(chim == "1" for _, chim, _ in got)
