@@ -80,3 +80,50 @@ def test_headers_compile_as_c99_and_cxx():
 def test_cxx_example_builds_against_the_library():
     import __graft_entry__ as g
     assert os.path.exists(g.build_example())
+
+
+def test_python_struct_layouts_match_the_headers(tmp_path):
+    """sizeof / offsetof of the PODs as the C compiler sees them vs the ctypes / numpy mirrors."""
+    import subprocess
+    import numpy as np
+    import importlib
+    Q = importlib.import_module("seekdeep_b200.qluster")  # (the package also exports a function of that name)
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "sdgpu_qluster.h"
+#define S(t) printf(#t " %zu\n", sizeof(t))
+#define O(t, f) printf(#t "." #f " %zu\n", offsetof(t, f))
+int main(void) {
+  S(sdgpu_params); S(sdgpu_gap); S(sdgpu_comparison); S(sdgpu_iter_par); S(sdgpu_pair_summary); S(sdgpu_chimera_probe);
+  S(sdgpu_profile); S(sdq_opts); S(sdq_stats);
+  O(sdgpu_comparison, oneBaseIndel); O(sdgpu_comparison, queryCoverage); O(sdgpu_iter_par, perId);
+  O(sdq_opts, markChimeras); O(sdq_opts, chiParentFreqs); O(sdq_opts, chiOverlap);
+  O(sdq_stats, chimeraPairs); O(sdq_stats, secondsGpu); O(sdq_stats, msResident);
+  O(sdgpu_chimera_probe, flags); O(sdgpu_profile, evaluatedCells); O(sdgpu_profile, bandKernelMs);
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip().splitlines())
+    c = {k: int(v) for k, v in out.items()}
+    assert c["sdgpu_params"] == C.sizeof(_abi.Params) and c["sdgpu_gap"] == C.sizeof(_abi.Gap)
+    assert c["sdgpu_comparison"] == C.sizeof(_abi.Comparison) == _abi.COMPARISON_DTYPE.itemsize
+    assert c["sdgpu_comparison.oneBaseIndel"] == _abi.COMPARISON_DTYPE.fields["oneBaseIndel"][1]
+    assert c["sdgpu_comparison.queryCoverage"] == _abi.COMPARISON_DTYPE.fields["queryCoverage"][1]
+    assert c["sdgpu_iter_par"] == C.sizeof(Q.IterParC) and c["sdgpu_iter_par.perId"] == Q.IterParC.perId.offset
+    assert c["sdgpu_pair_summary"] == _abi.PAIR_SUMMARY_DTYPE.itemsize
+    assert c["sdgpu_chimera_probe"] == _abi.CHIMERA_PROBE_DTYPE.itemsize
+    assert c["sdgpu_chimera_probe.flags"] == _abi.CHIMERA_PROBE_DTYPE.fields["flags"][1]
+    assert c["sdq_opts"] == C.sizeof(Q.QlusterOptsC)
+    for f in ("markChimeras", "chiParentFreqs", "chiOverlap"):
+        assert c["sdq_opts." + f] == getattr(Q.QlusterOptsC, f).offset, f
+    assert c["sdq_stats"] == C.sizeof(Q.StatsC)
+    for f in ("chimeraPairs", "secondsGpu", "msResident"):
+        assert c["sdq_stats." + f] == getattr(Q.StatsC, f).offset, f
+    # sdgpu_profile is mirrored inside GpuAligner.profile_read: 6 x 8 bytes + 3 x 8 + 8
+    assert c["sdgpu_profile"] == 80 and c["sdgpu_profile.evaluatedCells"] == 48 and c["sdgpu_profile.bandKernelMs"] == 72
+    assert np.dtype(np.uint64).itemsize == 8
