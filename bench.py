@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OPS_PER_CELL = 13  # algorithmic INT32 ops of one 3-state affine cell update
-CPU_SAMPLE_READS = 600
+CPU_SAMPLE_READS = int(os.environ.get("SD_BENCH_CPU_READS", 600))  # reads of the bounded CPU sample (tests shrink it)
 # DRAM bytes per evaluated cell of the dominant kernel (alignBandKernel): its only bulk traffic is the
 # decision-bit slab, 128 B per 6 anti-diagonals x 32 lanes = 12.8 KB for the ~19.2 k band cells of a 300 x 300
 # pair; the ncu --set full capture profiles/r1m_band_kernel_ncu_full.csv shows 3.37 GB written + 0.04 GB read

@@ -50,3 +50,28 @@ def test_matrices():
     assert np.array_equal(d, d.T)
     p = make_params(scoring=SubstituteMatrix(d))
     assert p.scoreMat[ord("R") * 128 + ord("G")] == 2
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) on a shrunken sample: one JSON
+    line with the contract keys, `impl`, a `cpu_baseline` describing the run and a zero-copy `e2e`."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SD_BENCH_CPU_READS="40")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "qluster_reads_per_s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # other ranks of a torchrun launch exit 0 without work
+    r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=600)
+    assert r2.returncode == 0 and r2.stdout.strip() == ""

@@ -233,3 +233,28 @@ def test_chimera_probe_windows(oracle):
     assert oracle.chimera_probe_batch(p, bases, quals, offsets, [0], [1], ov)[0]["flags"] == 3
     keep = oracle.chimera_probe_batch(p, bases, quals, offsets, [0], [1], ov, keepLowQual=True)[0]
     assert (keep["keptMismatches"], keep["firstPos"], keep["flags"]) == (3, 8, 3)
+
+
+def test_mark_chimeras_options(oracle):
+    """The visible chimera options (clusterDownSetUp.cpp:372-381) each switch the flag as their help text
+    says: a candidate at or below runCutOff is not examined, posSpacing demands that much shared sequence
+    between the two crossover mismatches, overLapSizeCutoff demands that many explained bases at each end."""
+    import seekdeep_b200 as sd
+    from seekdeep_b200.iterpars import CollapseIterations
+    rng = np.random.default_rng(12)
+    bases, quals, offsets, (p0, p1, chi, var), cut = H.chimera_sample(rng, length=160, nDiff=6, counts=(40, 30, 6, 4))
+    its = CollapseIterations.gen_illumina_default_pars(100)
+
+    def run(**kw):
+        return oracle.qluster(sd.make_params(), sd.QlusterPars(**kw).to_c(), its.iters, its.iters, bases, quals, offsets)["chimeras"]
+
+    base = run()
+    assert list(base) == [2]
+    front, back, fpos, bpos = base[2]
+    assert run(chiRunCutOff=6) == {}                       # the crossover has 6 reads: not examined
+    assert run(chiRunCutOff=5) == base
+    assert run(chiPosSpacing=fpos - bpos) == base          # exactly the shared stretch between the mismatches
+    assert run(chiPosSpacing=fpos - bpos + 1) == {}
+    assert run(chiOverlapSizeCutoff=bpos + 2) == base or run(chiOverlapSizeCutoff=bpos + 2) == {}  # depends on which end is shorter
+    assert run(chiOverlapSizeCutoff=161) == {}             # nobody can explain more bases than the read has
+    assert run(parFreqs=5.0) == base and run(parFreqs=5.01) == {}  # 30 reads / 6 reads = 5: parent 1 just qualifies
