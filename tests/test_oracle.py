@@ -258,3 +258,41 @@ def test_mark_chimeras_options(oracle):
     assert run(chiOverlapSizeCutoff=bpos + 2) == base or run(chiOverlapSizeCutoff=bpos + 2) == {}  # depends on which end is shorter
     assert run(chiOverlapSizeCutoff=161) == {}             # nobody can explain more bases than the read has
     assert run(parFreqs=5.0) == base and run(parFreqs=5.01) == {}  # 30 reads / 6 reads = 5: parent 1 just qualifies
+
+
+def _pack_reads(reads):
+    seqs = [np.frombuffer(s.encode(), np.uint8) for s, _ in reads]
+    quals = [np.asarray(q, np.uint8) for _, q in reads]
+    offsets = np.zeros(len(seqs) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    return np.concatenate(seqs), np.concatenate(quals), offsets
+
+
+def test_consensus_quality_and_majority_rules(oracle):
+    """Hand-derived consensus cases (baseCluster::calculateConsensus as restated): the winning base of a column
+    keeps the quality sum of ITS reads divided by the column's total count; an insertion carried by a minority
+    of the reads does not enter the consensus."""
+    import seekdeep_b200 as sd
+    from seekdeep_b200.iterpars import CollapseIterations
+    rng = np.random.default_rng(8)
+    A = "".join(rng.choice(list("ACGT"), 60))
+    p = 30
+    sub = A[:p] + ("C" if A[p] != "C" else "G") + A[p + 1:]
+    hi = [38] * 60
+    lowAtP = hi[:p] + [10] + hi[p + 1:]
+    reads = [(A, hi)] * 3 + [(sub, lowAtP)] * 2
+    bases, quals, offsets = _pack_reads(reads)
+    its = CollapseIterations.gen_illumina_default_pars(100)
+    res = oracle.qluster(sd.make_params(), sd.QlusterPars(markChimeras=False).to_c(), its.iters, its.iters, bases, quals, offsets)
+    assert len(res["clusters"]) == 1                      # the low-quality mismatch is forgiven from the third line on
+    seq, q, cnt = res["clusters"][0]
+    assert seq == A and cnt == 5.0
+    expect = np.full(60, 38, np.uint8)
+    expect[p] = (3 * 38) // 5                             # 114 / 5 = 22: quality of the A reads over all five reads
+    assert np.array_equal(q, expect)
+    # a one-base insertion in 2 of 7 reads: merged (1-base indel allowed), not adopted (5 reads do not have it)
+    ins = A[:20] + ("A" if A[20] != "A" and A[19] != "A" else "C") + A[20:]
+    reads = [(A, hi)] * 5 + [(ins, [38] * 61)] * 2
+    bases, quals, offsets = _pack_reads(reads)
+    res = oracle.qluster(sd.make_params(), sd.QlusterPars(markChimeras=False).to_c(), its.iters, its.iters, bases, quals, offsets)
+    assert [(c[0], c[2]) for c in res["clusters"]] == [(A, 7.0)]
