@@ -296,3 +296,39 @@ def test_consensus_quality_and_majority_rules(oracle):
     bases, quals, offsets = _pack_reads(reads)
     res = oracle.qluster(sd.make_params(), sd.QlusterPars(markChimeras=False).to_c(), its.iters, its.iters, bases, quals, offsets)
     assert [(c[0], c[2]) for c in res["clusters"]] == [(A, 7.0)]
+
+
+def test_stop_check_and_small_cutoff_semantics(oracle):
+    """collapseWithParameters as restated: a read looks at the first `stopCheck` live candidates only (largest
+    first), and a cluster is a candidate only if its count exceeds `smallCutoff` (par-file columns 1 and 2,
+    clusterDownSetUp.cpp:63-84)."""
+    import seekdeep_b200 as sd
+    from seekdeep_b200.iterpars import CollapseIterations, IterPar
+    rng = np.random.default_rng(17)
+    haps = ["".join(rng.choice(list("ACGT"), 80)) for _ in range(4)]
+    hi = [38] * 80
+    reads = []
+    for h, n in zip(haps, (40, 30, 20, 10)):
+        reads += [(h, hi)] * n
+    # three reads of the smallest haplotype with one low-quality error each (distinct positions)
+    noisy = []
+    for p in (10, 40, 70):
+        s = haps[3][:p] + ("A" if haps[3][p] != "A" else "C") + haps[3][p + 1:]
+        noisy.append((s, hi[:p] + [8] + hi[p + 1:]))
+    bases, quals, offsets = _pack_reads(reads + noisy)
+
+    def line(stopCheck, smallCutoff):
+        return IterPar(stopCheck=stopCheck, smallCutoff=smallCutoff, oneBaseIndel=0, twoBaseIndel=0, largeBaseIndel=0,
+                       hqMismatches=0, lqMismatches=1, lowKmerMismatches=0)
+
+    def run(stopCheck, smallCutoff):
+        its = [line(stopCheck, smallCutoff)]
+        pars = sd.QlusterPars(markChimeras=False, checkKmers=False)
+        r = oracle.qluster(sd.make_params(), pars.to_c(), its, its, bases, quals, offsets)
+        return sorted((c[2] for c in r["clusters"]), reverse=True)
+
+    assert run(100, 0) == [40.0, 30.0, 20.0, 13.0]               # every noisy read finds its haplotype
+    assert run(3, 0) == [40.0, 30.0, 20.0, 10.0, 1.0, 1.0, 1.0]   # ... but it is the 4th candidate: out of reach
+    assert run(4, 0) == [40.0, 30.0, 20.0, 13.0]
+    assert run(100, 10) == [40.0, 30.0, 20.0, 10.0, 1.0, 1.0, 1.0]  # count 10 does not exceed smallCutoff 10
+    assert run(100, 9) == [40.0, 30.0, 20.0, 13.0]
