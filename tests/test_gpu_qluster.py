@@ -190,3 +190,35 @@ def test_cxx_caller_matches_python_api(tmp_path):
         assert float(cnt) == want["clusters"][c][2] and seq == want["clusters"][c][0]
         assert (chim == "1") == (c in want["chimeras"])
     assert any(chim == "1" for _, chim, _ in got)
+
+
+def test_stop_check_small_cutoff_and_consensus_micro_cases(oracle):
+    """The hand-derived oracle micro-cases (tests/test_oracle.py) through the GPU-driven loop: stopCheck windows of
+    3 / 4 candidates, smallCutoff 9 / 10, the consensus quality rule and the minority insertion."""
+    from seekdeep_b200.iterpars import IterPar
+    from tests.test_oracle import _pack_reads
+    rng = np.random.default_rng(17)
+    haps = ["".join(rng.choice(list("ACGT"), 80)) for _ in range(4)]
+    hi = [38] * 80
+    reads = []
+    for h, n in zip(haps, (40, 30, 20, 10)):
+        reads += [(h, hi)] * n
+    for p in (10, 40, 70):
+        s = haps[3][:p] + ("A" if haps[3][p] != "A" else "C") + haps[3][p + 1:]
+        reads.append((s, hi[:p] + [8] + hi[p + 1:]))
+    bases, quals, offsets = _pack_reads(reads)
+    pars = sd.QlusterPars(markChimeras=False, checkKmers=False)
+    for stopCheck, smallCutoff, expect in ((100, 0, 4), (3, 0, 7), (4, 0, 4), (100, 10, 7), (100, 9, 4)):
+        iters = CollapseIterations([IterPar(stopCheck=stopCheck, smallCutoff=smallCutoff, lqMismatches=1)])
+        got, want = run_pair(oracle, sd.make_params(), pars, iters, bases, quals, offsets)
+        assert_same(got, want)
+        assert len(got["clusters"]) == expect, (stopCheck, smallCutoff)
+    A = haps[0][:60]
+    p = 30
+    sub = A[:p] + ("C" if A[p] != "C" else "G") + A[p + 1:]
+    q60 = [38] * 60
+    bases, quals, offsets = _pack_reads([(A, q60)] * 3 + [(sub, q60[:p] + [10] + q60[p + 1:])] * 2)
+    its = CollapseIterations.gen_illumina_default_pars(100)
+    got, want = run_pair(oracle, sd.make_params(), sd.QlusterPars(markChimeras=False), its, bases, quals, offsets)
+    assert_same(got, want)
+    assert len(got["clusters"]) == 1 and got["clusters"][0][1][p] == 22 and got["clusters"][0][2] == 5.0
