@@ -275,8 +275,8 @@ def main():
         # pairs / kernel time) is reported beside it as "effective"
         kernel_gcups = prof["evaluatedCells"] / (prof["alignKernelMs"] * 1e-3) / 1e9
         effective_gcups = prof["cellUpdates"] / (prof["alignKernelMs"] * 1e-3) / 1e9
-        full_ms = prof["alignKernelMs"] - prof["bandKernelMs"]
-        full_cells = prof["evaluatedCells"] - prof["bandCells"]
+        full_ms = prof["alignKernelMs"] - prof["bandKernelMs"] - prof["screenKernelMs"]
+        full_cells = prof["evaluatedCells"] - prof["bandCells"] - prof["screenCells"]
         K = args.steps
         line = {
             "metric": "qluster_reads_per_s", "value": readsAll * K / (res_ms_max * 1e-3), "unit": "reads/s", "n_gpus": world,
@@ -302,6 +302,10 @@ def main():
                                          "band_kernel_gcups": prof["bandCells"] / max(1e-9, prof["bandKernelMs"] * 1e-3) / 1e9,
                                          "full_kernel_ms_per_step": full_ms / K,
                                          "full_kernel_gcups": full_cells / max(1e-9, full_ms * 1e-3) / 1e9},
+                         "screen_pass": {"pairs_per_step": prof["screenPairs"] / K, "share_of_pairs_finished": prof["screenCertified"] / max(1, prof["screenPairs"]),
+                                         "kernel_ms_per_step": prof["screenKernelMs"] / K,
+                                         "gcups": prof["screenCells"] / max(1e-9, prof["screenKernelMs"] * 1e-3) / 1e9,
+                                         "cells_per_step": prof["screenCells"] / K},
                          "algorithmic_hbm_bytes_per_cell": 0.67,
                          "launches": int(prof["alignKernelLaunches"]), "avg_launch_ms": prof["alignKernelMs"] / max(1, prof["alignKernelLaunches"]),
                          "kernel_share_of_step": prof["alignKernelMs"] / resident_ms,

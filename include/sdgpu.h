@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SDGPU_ABI_VERSION 1
+#define SDGPU_ABI_VERSION 2
 #define SDGPU_MAT_DIM 128 /* substitution matrix is indexed by 7-bit ASCII, like njhseq's mat_[127][127] */
 
 /* return codes */
@@ -204,6 +204,22 @@ int sdgpu_set_pass_table(sdgpu_ctx* ctx, const sdgpu_iter_par* lines, uint32_t n
 int sdgpu_align_pass(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,
                      uint32_t flags, uint64_t* passMaskOut);
 
+/* The collapse loop's own pair shape: every read of readIdx[] against every cluster of
+ * clusterIdx[] (collapser::collapseWithParameters compares each live read with the first
+ * stopCheck clusters of the sorted list; clusterDown.cpp:488-518).  Per (read r, cluster c) with
+ * readIdx[r] != clusterIdx[c] the call runs alignCacheGlobal(cluster, read) + profileAlignment +
+ * passErrorProfile against every line of the pass table, exactly like sdgpu_align_pass -- but the
+ * pair list is generated on the device and only the pairs whose verdict mask is NOT zero come back,
+ * as (read ordinal, cluster ordinal, mask) records in no particular order.  A pair that is absent
+ * from the records failed every line.  *hits stays valid until the next call on ctx. */
+typedef struct sdgpu_grid_hit {
+  uint32_t read;    /* ordinal into readIdx[] */
+  uint32_t cluster; /* ordinal into clusterIdx[] */
+  uint64_t mask;    /* bit l set <=> the pair's errorProfile passes line l */
+} sdgpu_grid_hit;
+int sdgpu_align_pass_grid(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uint32_t nClusters, const uint32_t* readIdx,
+                          uint32_t nReads, uint32_t flags, const sdgpu_grid_hit** hits, uint64_t* nHits);
+
 /* Chimera probe: the per-(parent, candidate) part of collapser::markChimeras
  * (clusterDown.cpp:566-577; options clusterDownSetUp.cpp:372-381).  Per pair i the call runs
  * alignCacheGlobal(parent, candidate) + profileAlignment(parent, candidate, checkKmer,
@@ -285,6 +301,16 @@ int sdgpu_last_kernel(sdgpu_ctx* ctx);
  * mode 1 (full-matrix kernels only) by construction; sdgpu_set_kernel(1|2) also turns the band off. */
 int sdgpu_set_band(sdgpu_ctx* ctx, int mode);
 
+/* Screen pass in front of the verdict-mask calls (sdgpu_align_pass*, sdgpu_align_pass_grid).  For a pair
+ * of equal-length sequences the gapless alignment is scored and profiled in one linear scan, and a
+ * score-only banded DP under a perturbed scoring (every score x K, every gap open cheaper by 1, K larger
+ * than any path's move count) decides whether that gapless alignment is the UNIQUE optimum: it is iff the
+ * perturbed optimum equals K x its score and the score exceeds what any path leaving the band could reach.
+ * Then traceback and errorProfile are the gapless ones whatever the tie rules, and the verdict mask of
+ * the scan is exact; every other pair goes on to the bit-recording passes unchanged.  mode 0 (default):
+ * on whenever applicable; 1: off.  Results are identical either way. */
+int sdgpu_set_screen(sdgpu_ctx* ctx, int mode);
+
 /* Measurement bookkeeping for bench.py: with profiling enabled every alignment-kernel launch is
  * bracketed by CUDA events on the ctx stream; sdgpu_profile_read sums them (optionally resets). */
 typedef struct sdgpu_profile {
@@ -297,6 +323,11 @@ typedef struct sdgpu_profile {
   uint64_t bandCells;          /* ... of which inside banded passes */
   uint64_t bandCertifiedCells; /* sum of lenA x lenB over the pairs finished by the banded pass */
   double bandKernelMs;         /* part of alignKernelMs spent in banded passes */
+  double screenKernelMs;       /* part of alignKernelMs spent in the screen pass (scan + score-only DP) */
+  uint64_t screenPairs;        /* pairs the screen pass looked at */
+  uint64_t screenCertified;    /* ... of which it finished (gapless alignment proved to be the unique optimum) */
+  uint64_t screenCells;        /* DP cells the score-only pass evaluated (included in evaluatedCells) */
+  uint64_t screenCertCells;    /* sum of lenA x lenB over the pairs the screen finished (included in cellUpdates) */
 } sdgpu_profile;
 int sdgpu_profile_enable(sdgpu_ctx* ctx, int on);
 int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset);

@@ -68,6 +68,7 @@ typedef struct sdq_stats {
   uint64_t onDemandPairs;   /* pairs computed outside the speculative batches */
   uint64_t chimeraPairs;    /* (parent, candidate) probes of markChimeras */
   uint64_t chimericClusters;
+  uint64_t passingPairs;    /* computed comparisons whose verdict mask was not zero (the only ones that cross PCIe) */
   double secondsGpu;        /* wall time inside sdgpu_align_profile calls */
   double secondsTotal;
   double msResident;        /* CUDA-event time on the ctx stream from "unique reads resident in HBM" to the end */
@@ -85,6 +86,12 @@ uint32_t sdq_num_clusters(const sdq_result* r);
 uint32_t sdq_cluster_len(const sdq_result* r, uint32_t c);
 double sdq_cluster_cnt(const sdq_result* r, uint32_t c);
 int sdq_cluster_seq(const sdq_result* r, uint32_t c, uint8_t* seq, uint8_t* qual);
+/* All final clusters in one call (the result a caller writes out, clusterDown.cpp:886-913): consensus bases
+ * and qualities concatenated in cluster order, offsets[nClusters + 1], cnts[nClusters] (seqBase_.cnt_).
+ * sdq_clusters_total_len gives the size of the two byte buffers.  Any output pointer may be NULL.
+ * (sdq_cluster_len / _cnt return 0 for a NULL result or an index out of range.) */
+uint64_t sdq_clusters_total_len(const sdq_result* r);
+int sdq_clusters_packed(const sdq_result* r, uint8_t* bases, uint8_t* quals, uint64_t* offsets, double* cnts);
 /* 1 if markChimeras flagged cluster c (seqBase_.markAsChimeric()); parents[2] = cluster indices of
  * the parent explaining its front and the one explaining its back, positions[2] = the candidate
  * base positions of the two crossover mismatches (the columns of chiParentsInfo.txt, :578-581) */

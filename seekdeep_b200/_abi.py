@@ -58,6 +58,8 @@ PAIR_SUMMARY_DTYPE = _np.dtype([("alnScore", "<i4"), ("hqMismatches", "<u2"), ("
 CHIMERA_PROBE_DTYPE = _np.dtype([("alnScore", "<i4")] + [(n, "<u4") for n in (
     "keptMismatches", "numGaps", "firstPos", "lastPos", "firstAlnPos", "lastAlnPos", "flags")])
 CHI_FRONT_PASS, CHI_BACK_PASS = 1, 2
+GRID_HIT_DTYPE = _np.dtype([("read", "<u4"), ("cluster", "<u4"), ("mask", "<u8")])
+assert GRID_HIT_DTYPE.itemsize == 16
 assert CHIMERA_PROBE_DTYPE.itemsize == 32
 assert PAIR_SUMMARY_DTYPE.itemsize == 28
 assert COMPARISON_DTYPE.itemsize == C.sizeof(Comparison) == 104
@@ -87,6 +89,8 @@ SIGNATURES = {
     "sdgpu_align_profile": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_set_pass_table": (C.c_int, [_ctx, C.c_void_p, C.c_uint32]),
     "sdgpu_align_pass": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "sdgpu_align_pass_grid": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), _u64p]),
+    "sdgpu_set_screen": (C.c_int, [_ctx, C.c_int]),
     "sdgpu_chimera_probe_pairs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]),
     "sdgpu_kmer_compare_all_dev": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "sdgpu_all_vs_all": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),

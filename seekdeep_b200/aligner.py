@@ -198,6 +198,24 @@ class GpuAligner:
         self._check(self._lib.sdgpu_align_pass(self._ctx, _ptr(refIdx), _ptr(readIdx), len(refIdx), flags, _ptr(out)))
         return out
 
+    def align_pass_grid(self, clusterIdx, readIdx, checkKmer=False, usingQuality=True):
+        """Every read against every cluster (the collapse loop's pair shape; a sequence is never compared with
+        itself): GRID_HIT_DTYPE records (read ordinal, cluster ordinal, mask) of the non-zero verdict masks only."""
+        clusterIdx = np.ascontiguousarray(clusterIdx, np.uint32)
+        readIdx = np.ascontiguousarray(readIdx, np.uint32)
+        flags = (_abi.CHECK_KMER if checkKmer else 0) | (_abi.USING_QUALITY if usingQuality else 0)
+        hits, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.sdgpu_align_pass_grid(self._ctx, _ptr(clusterIdx), len(clusterIdx), _ptr(readIdx), len(readIdx),
+                                                    flags, C.byref(hits), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, _abi.GRID_HIT_DTYPE)
+        buf = (C.c_uint8 * (n.value * 16)).from_address(hits.value)
+        return np.frombuffer(buf, _abi.GRID_HIT_DTYPE).copy()
+
+    def set_screen(self, mode):
+        """0 = screen pass in front of the verdict-mask launches (default), 1 = off."""
+        self._check(self._lib.sdgpu_set_screen(self._ctx, int(mode)))
+
     def chimera_probe(self, parentIdx, candIdx, chiOverlap, keepLowQualityMismatches=False, checkKmer=False,
                       usingQuality=True):
         """collapser::markChimeras' per-(parent, candidate) probe (clusterDown.cpp:576): CHIMERA_PROBE_DTYPE[nPairs].
@@ -242,7 +260,8 @@ class GpuAligner:
             _fields_ = [("alignKernelMs", C.c_double), ("alignKernelLaunches", C.c_uint64), ("kernelLaunches", C.c_uint64),
                         ("cellUpdates", C.c_uint64), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
                         ("evaluatedCells", C.c_uint64), ("bandCells", C.c_uint64), ("bandCertifiedCells", C.c_uint64),
-                        ("bandKernelMs", C.c_double)]
+                        ("bandKernelMs", C.c_double), ("screenKernelMs", C.c_double), ("screenPairs", C.c_uint64),
+                        ("screenCertified", C.c_uint64), ("screenCells", C.c_uint64), ("screenCertCells", C.c_uint64)]
         p = Prof()
         self._check(self._lib.sdgpu_profile_read(self._ctx, C.byref(p), int(reset)))
         return {k: getattr(p, k) for k, _ in Prof._fields_}

@@ -53,8 +53,7 @@ struct AlignArgs {
   DevScoring sc;
   DevSeqs seqs;
   DevKmerIndex idx;
-  const uint32_t* refIdx;
-  const uint32_t* readIdx;
+  DevPairSrc src;
   uint32_t nPairs;
   uint32_t flags;
   sdgpu_comparison* out;
@@ -71,6 +70,7 @@ struct AlignArgs {
   const sdgpu_iter_par* lines;  // par-file lines for the verdict mask (device)
   uint32_t nLines;
   uint64_t* passOut;   // per pair: bit l = passes line l (or NULL)
+  DevHits hits;        // grid launches: (read, cluster, mask) records of the non-zero masks (recs may be NULL)
   const uint32_t* pairMap;   // redo pass: work item -> pair index (or NULL: identity)
   const uint32_t* nWorkDev;  // redo pass: number of work items, read on the device (or NULL: nPairs)
   uint32_t* redo;            // banded pass: pairs whose band could not be certified
@@ -143,45 +143,9 @@ struct BitsBand {
   }
 };
 
-// njhseq seqInfo::checkQual (strictly-greater thresholds, trailing window stops before the last base)
-__device__ __forceinline__ bool checkQualDev(const uint8_t* q, int len, int pos, int primaryQual, int secondaryQual,
-                                             int window) {
-  if (int(q[pos]) <= primaryQual) return false;
-  const int lower = pos > window ? pos - window : 0;
-  for (int i = lower; i < pos; ++i)
-    if (int(q[i]) <= secondaryQual) return false;
-  int higher = len - 1;
-  if (pos + window + 1 < len) higher = pos + window + 1;
-  for (int i = pos + 1; i < higher; ++i)
-    if (int(q[i]) <= secondaryQual) return false;
-  return true;
-}
-__device__ __forceinline__ bool checkQualDev(const uint8_t* q, int len, int pos, const DevScoring& sc) {
-  return checkQualDev(q, len, pos, sc.primaryQual, sc.secondaryQual, sc.window);
-}
-
-// KmerMaps::isKmerLowFrequency for the k-mer centred on base p (clamped to the sequence)
-__device__ bool lowFreqDev(const DevKmerIndex& idx, const uint8_t* codes, int len, int p) {
-  const int k = int(idx.kLen);
-  if (k == 0 || len < k) return false;
-  int start = p >= k / 2 ? p - k / 2 : 0;
-  if (start + k > len) start = len - k;
-  uint64_t key = 0;
-  for (int x = 0; x < k; ++x) key = (key << 4) | codes[start + x];
-  if (idx.byPos) key |= uint64_t(start) << 48;
-  uint32_t lo = 0, hi = idx.n;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (idx.keys[mid] < key) {
-      lo = mid + 1;
-    } else {
-      hi = mid;
-    }
-  }
-  const uint32_t cnt = (lo < idx.n && idx.keys[lo] == key) ? idx.counts[lo] : 0u;
-  return cnt <= idx.runCutOff;
-}
-
+// Quality windows (seqInfo::checkQual) and low-frequency k-mer look-ups (KmerMaps::isKmerLowFrequency) are not
+// evaluated per mismatch here: both are properties of one base of one stored sequence, kept as per-base flag
+// bytes next to the codes (SD_FLAG_QUAL_OK written at upload, SD_FLAG_LOW_KMER at every index build).
 __device__ __forceinline__ unsigned warpSum(unsigned v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -192,6 +156,7 @@ struct PairView {
   uint32_t pair;
   int la, lb;
   const uint8_t *cA, *cB, *qA, *qB;
+  const uint8_t *fA, *fB;  // per-base SD_FLAG_* bytes
 };
 
 // njhseq aligner::handleGapCountingInA/InB weight of one gap run: 1, or for a homopolymer run
@@ -243,13 +208,11 @@ __device__ __forceinline__ void chimeraProbeDev(const ChiArgs& a, const PairView
     int cls = 0;  // 1 = hq, 2 = lq, 3 = lowKmer
     const int pa = baseA + __popc(hasA & ltMask), pb = baseB + __popc(hasB & ltMask);
     if (inb && ca != SDGPU_GAP_CODE && cb != SDGPU_GAP_CODE && sTab[ca * SDGPU_MAX_SYMBOLS + cb] < 0) {
-      bool good = true;
-      if (usingQuality)
-        good = checkQualDev(pv.qA, pv.la, pa, sc.primaryQual, sc.secondaryQual, sc.window) &&
-               checkQualDev(pv.qB, pv.lb, pb, sc.primaryQual, sc.secondaryQual, sc.window);
+      const unsigned fa = pv.fA[pa], fb = pv.fB[pb];
+      const bool good = !usingQuality || (fa & fb & SD_FLAG_QUAL_OK);
       if (!good) {
         cls = 2;
-      } else if (checkKmer && (lowFreqDev(a.idx, pv.cA, pv.la, pa) || lowFreqDev(a.idx, pv.cB, pv.lb, pb))) {
+      } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
         cls = 3;
       } else {
         cls = 1;
@@ -323,7 +286,7 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
                            uint8_t* alnB, uint32_t* gapRecs, const int* sTab, int lane) {
   const DevScoring& sc = a.sc;
   const int la = pv.la, lb = pv.lb;
-  const uint8_t *cA = pv.cA, *cB = pv.cB, *qA = pv.qA, *qB = pv.qB;
+  const uint8_t *cA = pv.cA, *cB = pv.cB, *fA = pv.fA, *fB = pv.fB;
   const uint32_t pair = pv.pair;
   // ------------------------------------------------------------------ traceback
   int i = la, j = lb;
@@ -439,7 +402,7 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
     nMis += __popc(misMask);
     if (matchQuality) {
       if (both && sub >= 0) {
-        if (!(checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc))) {
+        if (!(fA[pa] & fB[pb] & SD_FLAG_QUAL_OK)) {
           ++lqM;
         } else {
           ++hqM;
@@ -457,11 +420,11 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
     int cls = 0;  // 1 = high quality, 2 = low quality, 3 = low k-mer
     if (e < nMis) {
       const int pa = int(misTop[-2 * int(e + 1)]), pb = int(misTop[-2 * int(e + 1) + 1]);
-      bool good = true;
-      if (usingQuality) good = checkQualDev(qA, la, pa, sc) && checkQualDev(qB, lb, pb, sc);
+      const unsigned fa = fA[pa], fb = fB[pb];
+      const bool good = !usingQuality || (fa & fb & SD_FLAG_QUAL_OK);
       if (!good) {
         cls = 2;
-      } else if (checkKmer && (lowFreqDev(a.idx, cA, la, pa) || lowFreqDev(a.idx, cB, lb, pb))) {
+      } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
         cls = 3;
       } else {
         cls = 1;
@@ -529,7 +492,7 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
 
   // comparison::passErrorProfile against every par-file line at once: lane l judges lines l and
   // l + 32, two ballots give the 64-bit verdict mask the host collapse loop consumes
-  if (a.passOut) {
+  if (a.passOut || a.hits.recs) {
     const unsigned events = hqM + lqM + hq + lq + lk + numGaps;
     const double id = events ? double(hqM + lqM) / double(events) : 0.0;
     const double idHq = events ? double(hqM + lqM + lq + lk) / double(events) : 0.0;
@@ -549,7 +512,11 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
       }
       halves[h] = __ballot_sync(FULL, pass);
     }
-    if (lane == 0) a.passOut[pair] = (uint64_t(halves[1]) << 32) | halves[0];
+    if (lane == 0) {
+      const uint64_t mask = (uint64_t(halves[1]) << 32) | halves[0];
+      if (a.passOut) a.passOut[pair] = mask;
+      if (a.hits.recs && mask) sd_emit_hit(a.src, a.hits, pair, mask);
+    }
   }
   if (lane == 0) {
     atomicAdd(reinterpret_cast<unsigned long long*>(a.work + 2), (unsigned long long)la * (unsigned long long)lb);
@@ -589,7 +556,8 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
 __device__ __forceinline__ PairView viewOf(const AlignArgs& a, uint32_t pair) {
   PairView pv;
   pv.pair = pair;
-  const uint32_t ia = a.refIdx[pair], ib = a.readIdx[pair];
+  uint32_t ia, ib;
+  sd_pair_of(a.src, pair, ia, ib);
   const uint64_t offA = a.seqs.offsets[ia], offB = a.seqs.offsets[ib];
   pv.la = int(a.seqs.offsets[ia + 1] - offA);
   pv.lb = int(a.seqs.offsets[ib + 1] - offB);
@@ -597,6 +565,8 @@ __device__ __forceinline__ PairView viewOf(const AlignArgs& a, uint32_t pair) {
   pv.cB = a.seqs.codes + offB;
   pv.qA = a.seqs.quals + offA;
   pv.qB = a.seqs.quals + offB;
+  pv.fA = a.seqs.flags + offA;
+  pv.fB = a.seqs.flags + offB;
   return pv;
 }
 
@@ -1021,13 +991,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) alignBandKernel(const A
   uint32_t* gapRecs = reinterpret_cast<uint32_t*>(alnB + a.maxAln);
   const DevScoring& sc = a.sc;
   const int dInt = sc.go - sc.ge;
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.work[5] = a.nPairs;  // read back with the redo count
+  const uint32_t nWork = a.nWorkDev ? *a.nWorkDev : a.nPairs;  // behind the screen pass: its redo list
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.work[SD_W_BAND_PAIRS] = nWork;  // read back with the redo count
 
   for (;;) {
     uint32_t pair = 0;
     if (lane == 0) pair = atomicAdd(&a.work[0], 1u);
     pair = __shfl_sync(FULL, pair, 0);
-    if (pair >= a.nPairs) break;
+    if (pair >= nWork) break;
+    if (a.pairMap) pair = a.pairMap[pair];
     const PairView pv = viewOf(a, pair);
     const int la = pv.la, lb = pv.lb;
     const int diff = lb - la;
@@ -1210,36 +1182,103 @@ bool halfRangeOk(const sdgpu_ctx* ctx, uint32_t maxLenA, uint32_t cols) {
 
 }  // namespace
 
-int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx, uint32_t nPairs,
-                    uint32_t flags, sdgpu_comparison* dOut, sdgpu_gap* dGaps, uint32_t gapCap, uint32_t maxLenA,
-                    uint32_t maxLenB, uint64_t* dPassOut, const SdChimeraReq* chi) {
+static int ensureU32(sdgpu_ctx* ctx, uint32_t** buf, uint32_t* cap, uint32_t need) {
+  if (need <= *cap) return SDGPU_OK;
+  if (*buf) {
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(*buf);
+  }
+  *buf = nullptr;
+  *cap = 0;
+  const uint32_t n = std::max<uint32_t>(need, 1u << 16);
+  SD_CUDA(ctx, cudaMalloc(buf, size_t(n) * sizeof(uint32_t)));
+  *cap = n;
+  return SDGPU_OK;
+}
+
+int sd_launch_align(sdgpu_ctx* ctx, const SdAlignReq& req) {
+  const uint32_t nPairs = req.nPairs, flags = req.flags, maxLenA = req.maxLenA, maxLenB = req.maxLenB;
+  const SdChimeraReq* chi = req.chi;
   if (nPairs == 0) return SDGPU_OK;
   if ((flags & SDGPU_CHECK_KMER) && !ctx->haveIndex)
     return sd_fail(ctx, SDGPU_E_STATE, "SDGPU_CHECK_KMER requires sdgpu_build_kmer_index first");
+  const bool wantMask = req.dPassOut != nullptr || req.hits.recs != nullptr;
+  if (wantMask && ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
+  {  // the int32 passes keep every DP value far inside int32 (the fp16 and banded passes check their own ranges)
+    const DevScoring& s = ctx->scoring;
+    int64_t maxAbs = 0;
+    for (int x = 0; x < ctx->nSym; ++x)
+      for (int y = 0; y < ctx->nSym; ++y) maxAbs = std::max<int64_t>(maxAbs, std::abs(int(s.score[x * SDGPU_MAX_SYMBOLS + y])));
+    const int64_t maxPen = std::max({s.go, s.ge, s.goLQ, s.geLQ, s.goRQ, s.geRQ, s.goLR, s.geLR, s.goRR, s.geRR});
+    const int64_t worst = maxAbs * std::min(maxLenA, maxLenB) + maxPen * (int64_t(maxLenA) + maxLenB + 2);
+    if (worst >= (int64_t(1) << 30)) return sd_fail(ctx, SDGPU_E_OVERFLOW, "penalties x lengths overflow the 32-bit DP values");
+  }
   AlignArgs args;
   args.sc = ctx->scoring;
   args.seqs = sd_dev_seqs(ctx);
   args.idx = sd_dev_index(ctx);
-  args.refIdx = dRefIdx;
-  args.readIdx = dReadIdx;
+  args.src = req.src;
   args.nPairs = nPairs;
   args.flags = flags;
-  args.out = dOut;
-  args.gapsOut = dGaps;
-  args.gapCap = gapCap;
+  args.out = req.dOut;
+  args.gapsOut = req.dGaps;
+  args.gapCap = req.gapCap;
   args.work = ctx->dWork;
   args.lines = ctx->dLines;
   args.nLines = ctx->nLines;
-  args.passOut = dPassOut;
+  args.passOut = req.dPassOut;
+  args.hits = req.hits;
   args.chiOut = chi ? chi->dOut : nullptr;
   args.chiPar = chi ? chi->overlap : sdgpu_iter_par{};
   args.chiKeepLq = chi ? chi->keepLq : 0u;
-  if (dPassOut && ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
   args.pairMap = nullptr;
   args.nWorkDev = nullptr;
   args.redo = nullptr;
   args.maxSub = args.minRight = args.minDown = 0;
   const uint32_t needC = (maxLenB + 31) / 32;
+  const bool gridSrc = req.src.clus != nullptr;
+  // Screen pass (screen_kernel.cu): verdict-mask launches only.  A grid launch always starts with its scan
+  // kernel, which at least lists the pairs that are not a cluster against itself.
+  const bool maskOnly = wantMask && !req.dOut && !req.dGaps && !chi;
+  SdScreenArgs scr{};
+  const bool screen = maskOnly && ctx->screenMode == 0 && ctx->bandMode == 0 && ctx->forceKernel == 0 && nPairs >= 64 &&
+                      sd_screen_plan(ctx, maxLenA, maxLenB, &scr);
+  bool behindScreen = false;
+  if (screen || gridSrc) {
+    int rc = ensureU32(ctx, &ctx->dRedo, &ctx->redoCap, nPairs);
+    if (rc) return rc;
+    if (screen && nPairs > ctx->screenItemsCap) {
+      if (ctx->dScreenItems) {
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->dScreenItems);
+      }
+      ctx->dScreenItems = nullptr;
+      ctx->screenItemsCap = 0;
+      const uint64_t cap = std::max<uint64_t>(nPairs, 1u << 16);
+      SD_CUDA(ctx, cudaMalloc(&ctx->dScreenItems, 3 * cap * sizeof(SdScreenItem)));
+      ctx->screenItemsCap = cap;
+    }
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->dWork + SD_W_SCAN, 0, 8 * sizeof(uint32_t), ctx->stream));
+    scr.sc = ctx->scoring;
+    scr.seqs = args.seqs;
+    scr.idx = args.idx;
+    scr.src = req.src;
+    scr.nPairs = nPairs;
+    scr.flags = flags;
+    scr.lines = ctx->dLines;
+    scr.nLines = ctx->nLines;
+    scr.passOut = req.dPassOut;
+    scr.hits = req.hits;
+    scr.items = ctx->dScreenItems;
+    scr.redo = ctx->dRedo;
+    scr.work = ctx->dWork;
+    scr.screenOn = screen ? 1 : 0;
+    if ((rc = sd_launch_screen(ctx, scr))) return rc;
+    if (screen) ctx->screenPairs += nPairs;
+    args.pairMap = ctx->dRedo;  // everything below runs over the screen's redo list
+    args.nWorkDev = ctx->dWork + SD_W_BIN0 + 3;
+    behindScreen = true;
+  }
   // Banded first pass + exact redo of the uncertified pairs (see alignBandKernel).  Not used when a
   // test pins a specific full-matrix kernel, for chimera probes, or when the last banded launches
   // sent most of their pairs to the redo list (dissimilar sequences); then it is re-tried every 16th launch.
@@ -1260,25 +1299,30 @@ int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dRe
     args.minRight = std::min(std::min(s.go, s.ge), std::min(s.goLR, s.geLR));
     args.minDown = std::min(std::min(s.go, s.ge), std::min(s.goLQ, s.geLQ));
   }
-  if (band && ctx->hBandStat[1] >= 64 && 2ull * ctx->hBandStat[0] > ctx->hBandStat[1] && ++ctx->bandSkipped < 16) band = false;
+  // (the statistics of the last banded launch are only looked at once their copy has landed; behind the
+  //  screen pass the band sees the pairs with gaps, which is what it is for: no skipping there)
+  if (band && !behindScreen && ctx->bandStatEv && cudaEventQuery(ctx->bandStatEv) == cudaSuccess && ctx->hBandStat[1] >= 64 &&
+      2ull * ctx->hBandStat[0] > ctx->hBandStat[1] && ++ctx->bandSkipped < 16)
+    band = false;
+  cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
   if (band) {
-    ctx->bandSkipped = 0;
-    if (nPairs > ctx->redoCap) {
-      if (ctx->dRedo) cudaFree(ctx->dRedo);
-      ctx->dRedo = nullptr;
-      ctx->redoCap = 0;
-      SD_CUDA(ctx, cudaMalloc(&ctx->dRedo, size_t(nPairs) * sizeof(uint32_t)));
-      ctx->redoCap = nPairs;
-    }
-    args.redo = ctx->dRedo;
-    SD_CUDA(ctx, cudaMemsetAsync(ctx->dWork + 4, 0, sizeof(uint32_t), ctx->stream));
-    const uint64_t bitBytes = (uint64_t(maxLenA + maxLenB) / 6 + 2) * 128;
-    int rc = launchKernel(ctx, alignBandKernel, args, nPairs, 0, maxLenA, maxLenB, 1, bitBytes);
+    uint32_t** redoBuf = behindScreen ? &ctx->dRedo2 : &ctx->dRedo;
+    int rc = ensureU32(ctx, redoBuf, behindScreen ? &ctx->redo2Cap : &ctx->redoCap, nPairs);
     if (rc) return rc;
-    SD_CUDA(ctx, cudaMemcpyAsync(ctx->hBandStat, ctx->dWork + 4, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!behindScreen) ctx->bandSkipped = 0;
+    args.redo = *redoBuf;
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->dWork + SD_W_REDO, 0, sizeof(uint32_t), ctx->stream));
+    const uint64_t bitBytes = (uint64_t(maxLenA + maxLenB) / 6 + 2) * 128;
+    rc = launchKernel(ctx, alignBandKernel, args, nPairs, 0, maxLenA, maxLenB, 1, bitBytes);
+    if (rc) return rc;
+    if (!behindScreen) {
+      if (!ctx->bandStatEv) SD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->bandStatEv, cudaEventDisableTiming));
+      SD_CUDA(ctx, cudaMemcpyAsync(ctx->hBandStat, ctx->dWork + SD_W_REDO, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      SD_CUDA(ctx, cudaEventRecord(ctx->bandStatEv, ctx->stream));
+    }
     args.redo = nullptr;
-    args.pairMap = ctx->dRedo;  // the full-matrix kernels below run over the redo list only
-    args.nWorkDev = ctx->dWork + 4;
+    args.pairMap = *redoBuf;  // the full-matrix kernels below run over the redo list only
+    args.nWorkDev = ctx->dWork + SD_W_REDO;
   }
   if (chi) {  // chimera probes: a few thousand pairs per sample, int32 kernels with the probe compiled in
     ctx->lastKernelWasH2 = false;

@@ -56,6 +56,63 @@ __global__ void kmerKeysKernel(DevSeqs seqs, const uint32_t* seqIdx, const uint6
   }
 }
 
+// first key of every position of a by-position table: posStart[p] = lower_bound(keys, p << 48), p = 0 .. nPos
+__global__ void kmerPosStartKernel(const uint64_t* keys, uint32_t n, uint32_t nPos, uint32_t* posStart) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > nPos) return;
+  const uint64_t key = uint64_t(p) << 48;
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (keys[mid] < key) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  posStart[p] = lo;
+}
+
+// SD_FLAG_LOW_KMER of every base of sequences [firstSeq, firstSeq + nSeqs): one warp per sequence.  This is
+// the look-up aligner::profileAlignment makes per would-be high-quality mismatch (kMaps_.isKmerLowFrequency on
+// the k-mer centred on the base), made once per base and index build instead of once per mismatch and pair.
+__global__ void __launch_bounds__(256) lowKmerFlagKernel(DevSeqs seqs, DevKmerIndex idx, uint32_t firstSeq, uint32_t nSeqs,
+                                                        uint8_t* flags) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= nSeqs) return;
+  const uint32_t s = firstSeq + warp;
+  const uint64_t off = seqs.offsets[s];
+  const int len = int(seqs.offsets[s + 1] - off);
+  const uint8_t* c = seqs.codes + off;
+  for (int p = int(lane); p < len; p += 32) {
+    const bool low = sd_low_freq(idx, c, len, p);
+    flags[off + p] = uint8_t((flags[off + p] & SD_FLAG_QUAL_OK) | (low ? SD_FLAG_LOW_KMER : 0u));
+  }
+}
+
+// SD_FLAG_QUAL_OK of every base: njhseq seqInfo::checkQual (strictly-greater thresholds, trailing window stops
+// before the last base); clears SD_FLAG_LOW_KMER (set again by lowKmerFlagKernel when an index exists)
+__global__ void __launch_bounds__(256) qualFlagKernel(DevSeqs seqs, uint32_t firstSeq, uint32_t nSeqs, int primaryQual,
+                                                     int secondaryQual, int window, uint8_t* flags) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= nSeqs) return;
+  const uint32_t s = firstSeq + warp;
+  const uint64_t off = seqs.offsets[s];
+  const int len = int(seqs.offsets[s + 1] - off);
+  const uint8_t* q = seqs.quals + off;
+  for (int pos = int(lane); pos < len; pos += 32) {
+    bool ok = int(q[pos]) > primaryQual;
+    const int lower = pos > window ? pos - window : 0;
+    for (int i = lower; ok && i < pos; ++i) ok = int(q[i]) > secondaryQual;
+    int higher = len - 1;
+    if (pos + window + 1 < len) higher = pos + window + 1;
+    for (int i = pos + 1; ok && i < higher; ++i) ok = int(q[i]) > secondaryQual;
+    flags[off + pos] = ok ? uint8_t(SD_FLAG_QUAL_OK) : uint8_t(0);
+  }
+}
+
 __global__ void kmerLookupKernel(DevKmerIndex idx, const uint64_t* keys, uint32_t n, uint32_t* out) {
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= n) return;
@@ -230,6 +287,24 @@ __global__ void kmerCompareKernel(DevSeqs seqs, const uint16_t* profiles, uint32
 
 }  // namespace
 
+int sd_refresh_qual_flags(sdgpu_ctx* ctx, uint32_t firstSeq, uint32_t nSeqs) {
+  if (nSeqs == 0) return SDGPU_OK;
+  const DevScoring& s = ctx->scoring;
+  qualFlagKernel<<<(nSeqs + 7) / 8, 256, 0, ctx->stream>>>(sd_dev_seqs(ctx), firstSeq, nSeqs, s.primaryQual, s.secondaryQual, s.window,
+                                                         ctx->dFlags);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  return SDGPU_OK;
+}
+
+int sd_refresh_kmer_flags(sdgpu_ctx* ctx, uint32_t firstSeq, uint32_t nSeqs) {
+  if (nSeqs == 0 || !ctx->haveIndex) return SDGPU_OK;
+  lowKmerFlagKernel<<<(nSeqs + 7) / 8, 256, 0, ctx->stream>>>(sd_dev_seqs(ctx), sd_dev_index(ctx), firstSeq, nSeqs, ctx->dFlags);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  return SDGPU_OK;
+}
+
 int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, uint32_t kLen, uint32_t runCutOff,
                         int byPos, int expandPos, uint32_t expandSize) {
   if (kLen == 0 || kLen > 12) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "k-mer index supports 1 <= kLen <= 12");
@@ -246,13 +321,15 @@ int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, 
     start[n + 1] = start[n] + (byPos ? expandedBefore(nk, e) : nk);
   }
   const uint64_t total = start[nIdx];
-  if (total >= (1ull << 32)) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "k-mer index too large (>= 2^32 occurrences)");
+  // (the sort / reduce below take a 32-bit signed item count)
+  if (total >= (1ull << 31)) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "k-mer index too large (>= 2^31 occurrences)");
   ctx->nIdx = 0;
+  ctx->idxNPos = 0;
   ctx->idxK = kLen;
   ctx->idxRunCutOff = runCutOff;
   ctx->idxByPos = byPos ? 1 : 0;
   ctx->haveIndex = true;
-  if (total == 0) return SDGPU_OK;
+  if (total == 0) return sd_refresh_kmer_flags(ctx, 0, nSeqs);
 
   // one grow-only work arena per ctx: cudaMalloc/cudaFree of GB-sized buffers cost (variable)
   // hundreds of milliseconds and the index is rebuilt in every qluster run
@@ -320,8 +397,23 @@ int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, 
   SD_CUDA_C(cudaMemcpyAsync(ctx->dIdxCnts, dWIn, size_t(numRuns) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   SD_CUDA_C(cudaStreamSynchronize(ctx->stream));
   ctx->nIdx = numRuns;
+  if (byPos) {  // first key of every position: look-ups search one position's keys only
+    const uint32_t nPos = ctx->maxLen + e + 1;
+    if (nPos + 1 > ctx->idxPosCap) {
+      if (ctx->dIdxPosStart) cudaFree(ctx->dIdxPosStart);
+      ctx->dIdxPosStart = nullptr;
+      ctx->idxPosCap = 0;
+      SD_CUDA_C(cudaMalloc(&ctx->dIdxPosStart, (size_t(nPos) + 1) * 4));
+      ctx->idxPosCap = nPos + 1;
+    }
+    kmerPosStartKernel<<<(nPos + 256) / 256, 256, 0, ctx->stream>>>(ctx->dIdxKeys, numRuns, nPos, ctx->dIdxPosStart);
+    SD_CUDA_C(cudaGetLastError());
+    ++ctx->launches;
+    ctx->idxNPos = nPos;
+  }
 #undef SD_CUDA_C
-  return SDGPU_OK;
+  // the low-frequency flag of every base of the store against the new table
+  return sd_refresh_kmer_flags(ctx, 0, nSeqs);
 }
 
 int sd_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers, const uint32_t* positions, uint32_t n,

@@ -9,19 +9,23 @@
 //     answers the same pair for every later iteration;
 //   * before an iteration's sequential pass, every (cluster, read) pair the pass can ask for —
 //     each live read against the first stopCheck(+1) eligible clusters, the "window" — that the
-//     read's row does not hold yet goes to the GPU in large batches.  A read whose row was
-//     complete for the previous window only needs the window's new entries;
-//   * verdicts live in per-read rows keyed by the cluster's sequence-store index.  A store index
-//     names one immutable (sequence, quality) version, so a cached verdict is a pure function of
-//     its key (+ the k-mer index, on whose rebuild all rows are dropped) — the same transparency
-//     njhseq's previousErrorChecks_ / alnHolder_ caches have.  A cluster whose consensus moved
+//     read is not covered for yet goes to the GPU as a (reads x clusters) grid: only the two index
+//     lists travel up (sdgpu_align_pass_grid generates the pairs on the device) and only the pairs
+//     whose verdict mask is not zero travel back.  A read that was covered for the previous window
+//     only needs the window's new entries;
+//   * non-zero verdicts live in per-read rows keyed by the cluster's sequence-store index; a pair
+//     the read is covered for and whose key is absent failed every line.  Coverage is a pair of
+//     serial numbers: the read has been judged against every window since `coverStart`, the cluster
+//     version was last in a window at `lastIn`.  A store index names one immutable (sequence,
+//     quality) version, so a cached verdict is a pure function of its key (+ the k-mer index, on
+//     whose rebuild all rows are dropped) — the same transparency njhseq's previousErrorChecks_ /
+//     alnHolder_ caches have.  A cluster whose consensus moved
 //     only in quality values keeps its device version as long as seqInfo::checkQual gives the
 //     same answer at every base: qualities enter an errorProfile only through checkQual;
 //   * consensus rebuilding keeps the per-column counters of a cluster while its base sequence
 //     stays the same, aligns only the newly absorbed members (one GPU batch per iteration, gap
 //     lists returned) and re-reads the consensus off the counters (integer sums: exact).
-// Host threads: the main thread runs the sequential logic and lists pairs; one helper thread per
-// run files returned verdict masks into the reads' rows; short-lived worker threads share the
+// Host threads: the main thread runs the sequential logic; short-lived worker threads share the
 // per-item independent phases (read hashing, per-unique median qualities, packing, cluster pool
 // set-up, consensus counter updates).  None of them changes an order the results depend on.
 #include <sched.h>
@@ -225,7 +229,8 @@ struct ConsState {  // column counters of one cluster against one base sequence
 struct alignas(64) Clus {
   double cnt = 0;
   double avgErr = 0;
-  uint64_t rowSerial = 0;  // iteration serial at which `row` was complete for that window
+  uint64_t rowSerial = 0;  // iteration serial at which the read was last judged against the whole window
+  uint64_t coverStart = 0; // ... and the first of the unbroken run of iterations that ends there (0: none)
   uint32_t storeIdx = 0;   // device sequence-store entry (verdict-equivalent to (seq, qual))
   uint32_t firstId = 0;    // cluster::firstReadName_ stand-in (tie-break of the sort)
   bool remove = false, needCons = false;
@@ -323,6 +328,8 @@ class Runner {
   uint64_t serial = 0;                // iteration counter across the three clustering runs
   std::vector<uint32_t> prevWindow;   // store indices of the previous iteration's window
   std::vector<uint8_t> inPrevWindow;  // by store index
+  std::vector<uint64_t> lastIn;       // by store index: latest iteration serial whose window held this version
+  std::vector<uint64_t> onDemandAt;   // by store index: iteration serial in which it was judged on demand
   static constexpr uint32_t BATCH = 1u << 21;
   std::vector<sdgpu_comparison> cmpBuf;
   std::vector<sdgpu_gap> gapBuf;
@@ -377,134 +384,30 @@ class Runner {
       }
   }
 
-  // Streams (cluster, read) pairs to the GPU in chunks through the two asynchronous slots of
-  // sdgpu_align_pass_submit/_wait: while the GPU aligns chunk k the host files chunk k-1's
-  // verdict masks into the reads' rows and lists chunk k+1.
-  // One helper thread files verdict masks into the reads' rows while this thread lists the next
-  // chunk: a chunk never splits a read's pairs (endRead), so the rows the helper writes belong to
-  // reads listed earlier than any row the lister is looking at.
-  struct Filer {
-    struct Job {
-      ClusVec* cs;
-      const std::vector<uint32_t>*a, *owner;
-      const uint64_t* masks;
-      uint32_t n;
-    };
-    std::thread th;
-    std::mutex mu;
-    std::condition_variable cv;
-    std::vector<Job> queue;
-    size_t done = 0, posted = 0;
-    bool stop = false;
-    double busy = 0;
-    void start() {
-      if (th.joinable()) return;
-      th = std::thread([this] {
-        std::unique_lock<std::mutex> lk(mu);
-        for (;;) {
-          cv.wait(lk, [this] { return stop || done < posted; });
-          if (done >= posted && stop) return;
-          const Job j = queue[done];
-          lk.unlock();
-          const double t0 = nowSec();
-          for (uint32_t i = 0; i < j.n; ++i) (*j.cs)[(*j.owner)[i]].row.insert((*j.a)[i], j.masks[i]);
-          const double dt = nowSec() - t0;
-          lk.lock();
-          busy += dt;
-          ++done;
-          cv.notify_all();
-        }
-      });
-    }
-    size_t post(const Job& j) {
-      std::lock_guard<std::mutex> lk(mu);
-      queue.push_back(j);
-      ++posted;
-      cv.notify_all();
-      return posted;
-    }
-    void waitFor(size_t ticket) {  // until job number `ticket` (1-based) has been filed
-      std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return done >= ticket; });
-    }
-    ~Filer() {
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        stop = true;
-        cv.notify_all();
-      }
-      if (th.joinable()) th.join();
-    }
-  };
-  Filer filer;
-
-  struct PassPipe {
-    Runner& R;
-    ClusVec& cs;
-    struct Buf {
-      std::vector<uint32_t> a, b, owner;
-      void clear() { a.clear(), b.clear(), owner.clear(); }
-    };
-    Buf cur, flight[2];
-    bool inflight[2] = {false, false};
-    size_t ticket[2] = {0, 0};  // filer job still reading flight[s] / the slot's pinned masks
-    int next = 0;
-    int rc = 0;
-    uint32_t chunk;
-    PassPipe(Runner& r, ClusVec& c) : R(r), cs(c), chunk(g_chunkPairs ? g_chunkPairs : BATCH / 2) { R.filer.start(); }
-    void push(uint32_t clusStore, uint32_t readStore, uint32_t ownerPos) {
-      cur.a.push_back(clusStore);
-      cur.b.push_back(readStore);
-      cur.owner.push_back(ownerPos);
-    }
-    void endRead() {  // chunk boundaries fall between reads
-      if (cur.a.size() >= chunk) flush();
-    }
-    void drain(int s) {  // wait for the GPU, hand the masks to the filer
-      const uint64_t* masks = nullptr;
-      uint32_t n = 0;
-      const double t0 = nowSec();
-      int r = sdgpu_align_pass_wait(R.ctx_, s, &masks, &n);
-      R.st.secondsGpu += nowSec() - t0;
-      inflight[s] = false;
-      if (r) {
-        rc = R.fail(r);
-        return;
-      }
-      ticket[s] = R.filer.post(Filer::Job{&cs, &flight[s].a, &flight[s].owner, masks, n});
-    }
-    void flush() {
-      if (rc || cur.a.empty()) return;
-      const int s = next;
-      if (inflight[s]) drain(s);
-      if (rc) return;
-      R.filer.waitFor(ticket[s]);  // its buffers and the slot's pinned masks are about to be reused
-      flight[s].clear();
-      std::swap(flight[s], cur);
-      const double t0 = nowSec();
-      int r = sdgpu_align_pass_submit(R.ctx_, s, flight[s].a.data(), flight[s].b.data(), uint32_t(flight[s].a.size()), R.flags());
-      R.st.secondsGpu += nowSec() - t0;
-      R.tSubmit += nowSec() - t0;
-      if (r) {
-        rc = R.fail(r);
-        return;
-      }
-      inflight[s] = true;
-      ++R.st.gpuBatches;
-      R.st.pairsComputed += flight[s].a.size();
-      const int other = s ^ 1;
-      if (inflight[other]) drain(other);
-      next = other;
-    }
-    int finish() {
-      flush();
-      for (int s = 0; s < 2; ++s)
-        if (inflight[s]) drain(s);
-      R.filer.waitFor(std::max(ticket[0], ticket[1]));
-      R.tInsert = R.filer.busy;
-      return rc;
-    }
-  };
+  // One (reads x clusters) grid on the GPU; the non-zero verdict masks are filed into the reads' rows.
+  // readPos[r] is the position in `cs` of the read behind readStore[r].
+  int gridPass(ClusVec& cs, const std::vector<uint32_t>& clusStore, const std::vector<uint32_t>& readStore,
+               const std::vector<uint32_t>& readPos) {
+    if (clusStore.empty() || readStore.empty()) return 0;
+    const sdgpu_grid_hit* hits = nullptr;
+    uint64_t nHits = 0;
+    const double t0 = nowSec();
+    int rc = sdgpu_align_pass_grid(ctx_, clusStore.data(), uint32_t(clusStore.size()), readStore.data(), uint32_t(readStore.size()),
+                                   flags(), &hits, &nHits);
+    st.secondsGpu += nowSec() - t0;
+    if (rc) return fail(rc);
+    ++st.gpuBatches;
+    st.pairsComputed += uint64_t(clusStore.size()) * readStore.size();
+    const double t1 = nowSec();
+    for (uint64_t i = 0; i < nHits; ++i) cs[readPos[hits[i].read]].row.insert(clusStore[hits[i].cluster], hits[i].mask);
+    tInsert += nowSec() - t1;
+    st.passingPairs += nHits;
+    return 0;
+  }
+  // has `read` been judged against cluster version `s` (so that an absent row entry means "fails every line")?
+  bool covered(const Clus& read, uint32_t s) const {
+    return (read.coverStart != 0 && lastIn[s] >= read.coverStart) || onDemandAt[s] == serial;
+  }
 
   // njhseq collapser::collapseWithParameters + findMatch for one par-file line
   int collapseWithParameters(ClusVec& cs, const sdq_iter_par& it, int line) {
@@ -521,55 +424,56 @@ class Runner {
     const uint32_t wn = uint32_t(std::min<uint64_t>(elig.size(), uint64_t(it.stopCheck) + 1));
     std::vector<uint8_t> inWindow(cs.size(), 0);
     {
-      std::vector<uint32_t> fresh;
       if (inPrevWindow.size() < storeSize) inPrevWindow.resize(storeSize, 0);
+      if (lastIn.size() < storeSize) lastIn.resize(storeSize, 0);
+      if (onDemandAt.size() < storeSize) onDemandAt.resize(storeSize, 0);
+      std::vector<uint32_t> window, fresh;  // store indices: the whole window / its entries the previous one lacked
       for (uint32_t w = 0; w < wn; ++w) {
         inWindow[elig[w]] = 1;
-        if (!inPrevWindow[cs[elig[w]].storeIdx]) fresh.push_back(elig[w]);
+        const uint32_t sIdx = cs[elig[w]].storeIdx;
+        window.push_back(sIdx);
+        if (!inPrevWindow[sIdx]) fresh.push_back(sIdx);
       }
-      PassPipe pipe(*this, cs);
+      // reads covered for the previous window only need the fresh entries; the others the whole window
+      std::vector<uint32_t> fullStore, fullPos, incStore, incPos;
       for (uint32_t rp = uint32_t(cs.size()); rp-- > 0;) {  // same order as the pass below
         Clus& read = cs[rp];
         if (read.remove) continue;
-        const size_t before = pipe.cur.a.size();
-        if (read.rowSerial + 1 == serial) {  // row complete for the previous window: only new entries
-          for (uint32_t cp : fresh) {
-            if (cp == rp) continue;
-            pipe.push(cs[cp].storeIdx, read.storeIdx, rp);
-          }
+        if (read.coverStart != 0 && read.rowSerial + 1 == serial) {
+          incStore.push_back(read.storeIdx);
+          incPos.push_back(rp);
         } else {
-          for (uint32_t w = 0; w < wn; ++w) {
-            const uint32_t cp = elig[w];
-            if (cp == rp || read.row.find(cs[cp].storeIdx)) continue;
-            pipe.push(cs[cp].storeIdx, read.storeIdx, rp);
-          }
+          fullStore.push_back(read.storeIdx);
+          fullPos.push_back(rp);
+          read.coverStart = serial;
         }
-        if (pipe.cur.a.size() > before) read.row.reserve(uint32_t(pipe.cur.a.size() - before));
-        pipe.endRead();
         read.rowSerial = serial;
       }
       for (uint32_t s : prevWindow) inPrevWindow[s] = 0;
-      prevWindow.clear();
-      for (uint32_t w = 0; w < wn; ++w) {
-        prevWindow.push_back(cs[elig[w]].storeIdx);
-        inPrevWindow[cs[elig[w]].storeIdx] = 1;
+      prevWindow = window;
+      for (uint32_t s : window) {
+        inPrevWindow[s] = 1;
+        lastIn[s] = serial;
       }
       const double tList = nowSec() - tt0;
-      int rc = pipe.finish();
-      tSpec += nowSec() - tt0;  // listing + GPU + filing, overlapped
+      int rc = gridPass(cs, window, fullStore, fullPos);
+      if (!rc) rc = gridPass(cs, fresh, incStore, incPos);
+      tSpec += nowSec() - tt0;  // listing + GPU + filing
       if (g_verboseTiming && nowSec() - tt0 > 0.01)
-        fprintf(stderr, "[sdq]   line %d: %zu live, window %u, spec %.3f s (until last submit %.3f)\n", line, alive, wn, nowSec() - tt0, tList);
+        fprintf(stderr, "[sdq]   line %d: %zu live, window %u (%zu new), %zu reads x window + %zu x new, spec %.3f s (listing %.3f)\n", line,
+                alive, wn, fresh.size(), fullStore.size(), incStore.size(), nowSec() - tt0, tList);
       if (rc) return rc;
     }
     tt0 = nowSec();
     // ---- the sequential pass (smallest cluster first; first passing candidate absorbs it)
     size_t amountAdded = 0;
     bool windowIntact = true;  // no window cluster absorbed yet: every read sees the static window
+    std::vector<uint32_t> odClus(1), odStore, odPos;
     for (size_t rp = cs.size(); rp-- > 0;) {
       Clus& read = cs[rp];
       if (read.remove) continue;
-      // its row holds every window verdict; if none has this line's bit there is nothing to find
-      if (windowIntact && read.rowSerial == serial && !(read.row.orMask() & bit)) {
+      // it has been judged against every window cluster; if no verdict has this line's bit there is nothing to find
+      if (windowIntact && !(read.row.orMask() & bit)) {
         ++skippedScans;
         continue;
       }
@@ -582,22 +486,25 @@ class Runner {
         ++count;
         if (count > it.stopCheck) break;
         const uint64_t* v = read.row.find(clus.storeIdx);
-        if (!v) {
+        if (!v && !covered(read, clus.storeIdx)) {
           // a candidate that slid into the window because earlier ones were absorbed: the reads
-          // still to come will meet it too, so judge it against all of them in one batch
-          PassPipe pipe(*this, cs);
+          // still to come will meet it too, so judge it against all of them in one grid
+          odClus[0] = clus.storeIdx;
+          odStore.clear();
+          odPos.clear();
           for (size_t r2 = rp + 1; r2-- > 0;) {
-            if (cs[r2].remove || r2 == cp || cs[r2].row.find(clus.storeIdx)) continue;
-            pipe.push(clus.storeIdx, cs[r2].storeIdx, uint32_t(r2));
-            pipe.endRead();
-            ++st.onDemandPairs;
+            if (cs[r2].remove || r2 == cp || covered(cs[r2], clus.storeIdx)) continue;
+            odStore.push_back(cs[r2].storeIdx);
+            odPos.push_back(uint32_t(r2));
           }
-          int rc = pipe.finish();
+          st.onDemandPairs += odStore.size();
+          int rc = gridPass(cs, odClus, odStore, odPos);
           if (rc) return rc;
+          onDemandAt[clus.storeIdx] = serial;
           v = read.row.find(clus.storeIdx);
         }
         ++st.pairsConsumed;
-        if (*v & bit) {
+        if (v && (*v & bit)) {
           clus.cnt += read.cnt;
           clus.members.insert(clus.members.end(), read.members.begin(), read.members.end());
           clus.needCons = true;
@@ -842,6 +749,7 @@ class Runner {
         cl.storeIdx = first + uint32_t(i);
         cl.row.clear();  // its verdicts as a read were for the old version
         cl.rowSerial = 0;
+        cl.coverStart = 0;
       }
       storeSize = first + uint32_t(changed.size());
     }
@@ -891,12 +799,6 @@ class Runner {
       if (orderDirty) dropRemovedAndSort(cs);  // counts / members only change when something merged
       orderDirty = false;
       if (cs.size() < 2) break;
-      if ((serial & 7) == 7) {  // forget verdicts against cluster versions that are gone
-        std::vector<uint8_t> live(storeSize, 0);
-        for (const Clus& c : cs) live[c.storeIdx] = 1;
-        for (Clus& c : cs)
-          if (c.row.size() > 256) c.row.prune(live);
-      }
       int rc = collapseWithParameters(cs, its[i], lineOf(its[i]));
       if (rc) return rc;
     }
@@ -936,6 +838,7 @@ class Runner {
       for (size_t i = lo; i < hi; ++i) {
         cs[i].row.clear();
         cs[i].rowSerial = 0;
+        cs[i].coverStart = 0;
       }
     });
     return 0;
@@ -1265,8 +1168,31 @@ int sdq_get_stats(const sdq_result* r, sdq_stats* out) {
 }
 
 uint32_t sdq_num_clusters(const sdq_result* r) { return r ? uint32_t(r->clusters.size()) : 0; }
-uint32_t sdq_cluster_len(const sdq_result* r, uint32_t c) { return uint32_t(r->clusters[c].seq.size()); }
-double sdq_cluster_cnt(const sdq_result* r, uint32_t c) { return r->clusters[c].cnt; }
+uint32_t sdq_cluster_len(const sdq_result* r, uint32_t c) { return (r && c < r->clusters.size()) ? uint32_t(r->clusters[c].seq.size()) : 0u; }
+double sdq_cluster_cnt(const sdq_result* r, uint32_t c) { return (r && c < r->clusters.size()) ? r->clusters[c].cnt : 0.0; }
+
+uint64_t sdq_clusters_total_len(const sdq_result* r) {
+  uint64_t n = 0;
+  if (r)
+    for (const Clus& c : r->clusters) n += c.seq.size();
+  return n;
+}
+
+int sdq_clusters_packed(const sdq_result* r, uint8_t* bases, uint8_t* quals, uint64_t* offsets, double* cnts) {
+  if (!r) return SDGPU_E_ARG;
+  uint64_t off = 0;
+  const size_t n = r->clusters.size();
+  for (size_t c = 0; c < n; ++c) {
+    const Clus& cl = r->clusters[c];
+    if (offsets) offsets[c] = off;
+    if (bases) std::memcpy(bases + off, cl.seq.data(), cl.seq.size());
+    if (quals) std::memcpy(quals + off, cl.qual.data(), cl.qual.size());
+    if (cnts) cnts[c] = cl.cnt;
+    off += cl.seq.size();
+  }
+  if (offsets) offsets[n] = off;
+  return SDGPU_OK;
+}
 
 int sdq_cluster_seq(const sdq_result* r, uint32_t c, uint8_t* seq, uint8_t* qual) {
   if (!r || c >= r->clusters.size()) return SDGPU_E_ARG;

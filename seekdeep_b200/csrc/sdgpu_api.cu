@@ -53,6 +53,7 @@ DevSeqs sd_dev_seqs(const sdgpu_ctx* ctx) {
   DevSeqs s;
   s.codes = ctx->dCodes;
   s.quals = ctx->dQuals;
+  s.flags = ctx->dFlags;
   s.offsets = ctx->dOffsets;
   s.cnts = ctx->dCnts;
   s.n = uint32_t(ctx->hOffsets.size() - 1);
@@ -67,6 +68,8 @@ DevKmerIndex sd_dev_index(const sdgpu_ctx* ctx) {
   k.kLen = ctx->idxK;
   k.runCutOff = ctx->idxRunCutOff;
   k.byPos = ctx->idxByPos;
+  k.posStart = (ctx->idxByPos && ctx->idxNPos) ? ctx->dIdxPosStart : nullptr;
+  k.nPos = ctx->idxNPos;
   return k;
 }
 
@@ -151,7 +154,7 @@ int sdgpu_create(int device, const sdgpu_params* params, sdgpu_ctx** out) {
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
       (e = cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
-      (e = cudaMalloc(&ctx->dWork, 64)) != cudaSuccess || (e = cudaMemset(ctx->dWork, 0, 64)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->dWork, SD_W_WORDS * 4)) != cudaSuccess || (e = cudaMemset(ctx->dWork, 0, SD_W_WORDS * 4)) != cudaSuccess ||
       (e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->hBandStat), 2 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) {
     ctx->err = std::string("sdgpu_create: ") + cudaGetErrorString(e);
     return bail(SDGPU_E_CUDA);
@@ -177,6 +180,8 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dCodes);
   cudaFree(ctx->dQuals);
+  cudaFree(ctx->dFlags);
+  cudaFree(ctx->dIdxPosStart);
   cudaFree(ctx->dOffsets);
   cudaFree(ctx->dCnts);
   cudaFree(ctx->dIdxKeys);
@@ -185,6 +190,15 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   cudaFree(ctx->dScratch);
   cudaFree(ctx->dWork);
   cudaFree(ctx->dRedo);
+  cudaFree(ctx->dRedo2);
+  cudaFree(ctx->dScreenItems);
+  cudaFree(ctx->dGridIdx);
+  for (auto& G : ctx->gridSlots) {
+    if (G.hHits) cudaFreeHost(G.hHits);
+    if (G.hCount) cudaFreeHost(G.hCount);
+    if (G.done) cudaEventDestroy(G.done);
+  }
+  if (ctx->bandStatEv) cudaEventDestroy(ctx->bandStatEv);
   if (ctx->hBandStat) cudaFreeHost(ctx->hBandStat);
   cudaFree(ctx->dStage);
   cudaFree(ctx->dLines);
@@ -210,8 +224,18 @@ int sdgpu_set_params(sdgpu_ctx* ctx, const sdgpu_params* params) {
   if (!ctx || !params) return SDGPU_E_ARG;
   int rc = validateParams(ctx, params);
   if (rc) return rc;
+  const bool qualChanged = params->primaryQual != ctx->params.primaryQual || params->secondaryQual != ctx->params.secondaryQual ||
+                           params->qualThresWindow != ctx->params.qualThresWindow;
   ctx->params = *params;
-  return refreshScoring(ctx);
+  rc = refreshScoring(ctx);
+  if (rc || !qualChanged) return rc;
+  // the per-base checkQual flags follow qScorePars_
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  if ((rc = sd_refresh_qual_flags(ctx, 0, nSeqs))) return rc;
+  if ((rc = sd_refresh_kmer_flags(ctx, 0, nSeqs))) return rc;
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SDGPU_OK;
 }
 
 int sdgpu_get_params(sdgpu_ctx* ctx, sdgpu_params* out) {
@@ -220,15 +244,26 @@ int sdgpu_get_params(sdgpu_ctx* ctx, sdgpu_params* out) {
   return SDGPU_OK;
 }
 
+// `replace`: the new sequences become the whole store (sdgpu_upload_seqs).  Nothing of the ctx changes
+// before the batch has been validated: a rejected call leaves the previous store and alphabet as they were.
 static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
-                      const double* cnts, uint32_t n, uint32_t* firstIndex) {
+                      const double* cnts, uint32_t n, uint32_t* firstIndex, bool replace) {
   if (!ctx || (n && (!bases || !offsets))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
-  const uint32_t oldN = uint32_t(ctx->hOffsets.size() - 1);
+  const uint32_t oldN = replace ? 0u : uint32_t(ctx->hOffsets.size() - 1);
   if (firstIndex) *firstIndex = oldN;
-  if (n == 0) return SDGPU_OK;
+  if (n == 0) {
+    if (replace) {
+      ctx->hOffsets.assign(1, 0);
+      ctx->maxLen = 0;
+      ctx->usedSym = 0;
+      ctx->haveIndex = false;
+      ctx->profSeqs = 0;
+    }
+    return SDGPU_OK;
+  }
   if (offsets[0] != 0) return sd_fail(ctx, SDGPU_E_ARG, "offsets[0] must be 0");
-  const uint64_t oldBases = ctx->hOffsets.back();
+  const uint64_t oldBases = replace ? 0ull : ctx->hOffsets.back();
   const uint64_t addBases = offsets[n];
   // alphabet + code translation on the host (one pass; the store is write-once, read-many)
   int rc = sd_ensure_pinned(ctx, addBases * 2 + 64);
@@ -236,7 +271,8 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
   uint8_t* hCodes = reinterpret_cast<uint8_t*>(ctx->hPinned);
   uint8_t* hQuals = hCodes + addBases;
   bool newSym = false;
-  uint32_t maxLen = ctx->maxLen;
+  uint32_t maxLen = replace ? 0u : ctx->maxLen;
+  int usedSym = replace ? 0 : ctx->usedSym;
   for (uint32_t s = 0; s < n; ++s) {
     if (offsets[s + 1] < offsets[s]) return sd_fail(ctx, SDGPU_E_ARG, "offsets must be non-decreasing");
     const uint64_t len = offsets[s + 1] - offsets[s];
@@ -276,10 +312,20 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
     for (auto& x : th) x.join();
     for (uint64_t t = 0; t < T; ++t) {
       unknown |= sawUnknown[t] != 0;
-      if (maxCode[t] + 1 > ctx->usedSym) ctx->usedSym = maxCode[t] + 1;
+      if (maxCode[t] + 1 > usedSym) usedSym = maxCode[t] + 1;
     }
   }
   if (unknown) {
+    // which characters are new, and do they fit?  (checked before any of them gets a code)
+    bool isNew[256] = {false};
+    int nNew = 0;
+    for (uint64_t x = 0; x < addBases; ++x) {
+      const uint8_t ch = bases[x];
+      if (ctx->codeOf[ch] >= 0 || isNew[ch]) continue;
+      if (ch >= 128) return sd_fail(ctx, SDGPU_E_ALPHABET, "base outside 7-bit ASCII");
+      isNew[ch] = true;
+      if (ctx->nSym + ++nNew > SDGPU_MAX_SYMBOLS) return sd_fail(ctx, SDGPU_E_ALPHABET, "more than 16 distinct base characters");
+    }
     for (uint64_t x = 0; x < addBases; ++x) {
       const uint8_t ch = bases[x];
       int code = ctx->codeOf[ch];
@@ -292,15 +338,25 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
         newSym = true;
       }
       hCodes[x] = uint8_t(code);
-      if (code + 1 > ctx->usedSym) ctx->usedSym = code + 1;
+      if (code + 1 > usedSym) usedSym = code + 1;
     }
   }
   if (newSym && (rc = refreshScoring(ctx))) return rc;
+  ctx->usedSym = usedSym;
+  if (replace) {  // validated: the old store goes
+    ctx->hOffsets.assign(1, 0);
+    ctx->maxLen = 0;
+    ctx->haveIndex = false;
+    ctx->profSeqs = 0;
+  }
   // grow device arrays
-  uint64_t capB = ctx->capBases, capB2 = ctx->capBases;
-  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dCodes), &capB, oldBases + addBases, oldBases))) return rc;
-  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dQuals), &capB2, oldBases + addBases, oldBases))) return rc;
-  ctx->capBases = std::min(capB, capB2);
+  uint64_t capB = ctx->capBases, capB2 = ctx->capBases, capB3 = ctx->capBases;
+  // (64 spare bytes behind the last base, kept at code 0: the score-only screen pass prefetches a few bases
+  //  past the end of a sequence and must find valid codes there)
+  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dCodes), &capB, oldBases + addBases + 64, oldBases))) return rc;
+  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dQuals), &capB2, oldBases + addBases + 64, oldBases))) return rc;
+  if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dFlags), &capB3, oldBases + addBases + 64, oldBases))) return rc;
+  ctx->capBases = std::min(std::min(capB, capB2), capB3);
   const uint64_t needSeqs = uint64_t(oldN) + n + 1;
   uint64_t capO = uint64_t(ctx->capSeqs) * 8, capC = uint64_t(ctx->capSeqs) * 8;
   if ((rc = growDevice(ctx, reinterpret_cast<void**>(&ctx->dOffsets), &capO, needSeqs * 8, (uint64_t(oldN) + 1) * 8))) return rc;
@@ -309,6 +365,7 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
   ctx->h2dBytes += 2 * addBases + (uint64_t(n) + 1) * 8 + uint64_t(n) * 8;
   SD_CUDA(ctx, cudaMemcpyAsync(ctx->dCodes + oldBases, hCodes, addBases, cudaMemcpyHostToDevice, ctx->stream));
   SD_CUDA(ctx, cudaMemcpyAsync(ctx->dQuals + oldBases, hQuals, addBases, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemsetAsync(ctx->dCodes + oldBases + addBases, 0, 64, ctx->stream));
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging is reused below
   ctx->hOffsets.reserve(needSeqs);
   for (uint32_t s = 1; s <= n; ++s) ctx->hOffsets.push_back(oldBases + offsets[s]);
@@ -319,25 +376,23 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
   hC = reinterpret_cast<double*>(ctx->hPinned);
   for (uint32_t s = 0; s < n; ++s) hC[s] = cnts ? cnts[s] : 1.0;
   SD_CUDA(ctx, cudaMemcpyAsync(ctx->dCnts + oldN, hC, uint64_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->maxLen = maxLen;
+  // per-base flags of the new sequences: checkQual outcome, and the low-frequency k-mer bit when a table exists
+  if ((rc = sd_refresh_qual_flags(ctx, oldN, n))) return rc;
+  if ((rc = sd_refresh_kmer_flags(ctx, oldN, n))) return rc;
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return SDGPU_OK;
 }
 
 int sdgpu_upload_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
                       const double* cnts, uint32_t n) {
   if (!ctx) return SDGPU_E_ARG;
-  ctx->hOffsets.assign(1, 0);
-  ctx->maxLen = 0;
-  ctx->usedSym = 0;
-  ctx->haveIndex = false;
-  ctx->profSeqs = 0;
-  return appendImpl(ctx, bases, quals, offsets, cnts, n, nullptr);
+  return appendImpl(ctx, bases, quals, offsets, cnts, n, nullptr, true);
 }
 
 int sdgpu_append_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
                       const double* cnts, uint32_t n, uint32_t* firstIndex) {
-  return appendImpl(ctx, bases, quals, offsets, cnts, n, firstIndex);
+  return appendImpl(ctx, bases, quals, offsets, cnts, n, firstIndex, false);
 }
 
 int sdgpu_num_seqs(sdgpu_ctx* ctx, uint32_t* n) {
@@ -595,6 +650,110 @@ int sdgpu_set_band(sdgpu_ctx* ctx, int mode) {
   return SDGPU_OK;
 }
 
+int sdgpu_set_screen(sdgpu_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return sd_fail(ctx, SDGPU_E_ARG, "sdgpu_set_screen: mode must be 0 (automatic) or 1 (off)");
+  ctx->screenMode = mode;
+  return SDGPU_OK;
+}
+
+// Every read of readIdx[] against every cluster of clusterIdx[]: pair lists are generated on the device in
+// chunks of ~2 M pairs; each chunk's launches append (read, cluster, mask) records of the non-zero masks to one
+// of two mapped pinned buffers, which the host empties while the next chunk runs.
+int sdgpu_align_pass_grid(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uint32_t nClusters, const uint32_t* readIdx,
+                          uint32_t nReads, uint32_t flags, const sdgpu_grid_hit** hits, uint64_t* nHits) {
+  if (!ctx || !hits || !nHits || (nClusters && !clusterIdx) || (nReads && !readIdx)) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  *hits = nullptr;
+  *nHits = 0;
+  ctx->gridHits.clear();
+  if (nClusters == 0 || nReads == 0) return SDGPU_OK;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  uint32_t maxA = 0, maxB = 0;
+  for (uint32_t x = 0; x < nClusters; ++x) {
+    if (clusterIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "cluster index out of range");
+    maxA = std::max<uint32_t>(maxA, uint32_t(ctx->hOffsets[clusterIdx[x] + 1] - ctx->hOffsets[clusterIdx[x]]));
+  }
+  for (uint32_t x = 0; x < nReads; ++x) {
+    if (readIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "read index out of range");
+    maxB = std::max<uint32_t>(maxB, uint32_t(ctx->hOffsets[readIdx[x] + 1] - ctx->hOffsets[readIdx[x]]));
+  }
+  const uint64_t nIdx = uint64_t(nClusters) + nReads;
+  int rc = sd_ensure_pinned(ctx, nIdx * 4);
+  if (rc) return rc;
+  if (nIdx > ctx->gridIdxCap) {
+    if (ctx->dGridIdx) {
+      SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->dGridIdx);
+    }
+    ctx->dGridIdx = nullptr;
+    ctx->gridIdxCap = 0;
+    const uint64_t cap = std::max<uint64_t>(nIdx * 2, 1u << 16);
+    SD_CUDA(ctx, cudaMalloc(&ctx->dGridIdx, cap * 4));
+    ctx->gridIdxCap = cap;
+  }
+  uint32_t* hIdx = reinterpret_cast<uint32_t*>(ctx->hPinned);
+  std::memcpy(hIdx, clusterIdx, size_t(nClusters) * 4);
+  std::memcpy(hIdx + nClusters, readIdx, size_t(nReads) * 4);
+  SD_CUDA(ctx, cudaMemcpyAsync(ctx->dGridIdx, hIdx, nIdx * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2dBytes += nIdx * 4;
+  const uint64_t chunkPairs = 1ull << 21;
+  const uint32_t readsPerChunk = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(nReads, chunkPairs / nClusters)));
+  if (uint64_t(readsPerChunk) * nClusters >= (1ull << 32)) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "more than 2^32 clusters in one grid call");
+  auto drain = [&](sdgpu_ctx::GridSlot& G) -> int {
+    SD_CUDA(ctx, cudaEventSynchronize(G.done));
+    G.busy = false;
+    const uint32_t n = *G.hCount;
+    ctx->gridHits.insert(ctx->gridHits.end(), G.hHits, G.hHits + n);
+    ctx->d2hBytes += uint64_t(n) * sizeof(sdgpu_grid_hit) + 4;
+    return SDGPU_OK;
+  };
+  uint32_t k = 0;
+  for (uint32_t r0 = 0; r0 < nReads; r0 += readsPerChunk, ++k) {
+    const uint32_t nr = std::min(readsPerChunk, nReads - r0);
+    const uint64_t pairs = uint64_t(nr) * nClusters;
+    const int slot = int(k & 1);
+    sdgpu_ctx::GridSlot& G = ctx->gridSlots[slot];
+    if (G.busy && (rc = drain(G))) return rc;
+    if (pairs > G.cap) {
+      if (G.hHits) cudaFreeHost(G.hHits);
+      G.hHits = G.dHits = nullptr;
+      G.cap = 0;
+      const uint64_t cap = std::max<uint64_t>(pairs, 1u << 14);
+      SD_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&G.hHits), cap * sizeof(sdgpu_grid_hit), cudaHostAllocMapped));
+      SD_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&G.dHits), G.hHits, 0));
+      G.cap = cap;
+    }
+    if (!G.hCount) SD_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&G.hCount), 64, cudaHostAllocDefault));
+    if (!G.done) SD_CUDA(ctx, cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->dWork + SD_W_HITS + slot, 0, sizeof(uint32_t), ctx->stream));
+    SdAlignReq req;
+    req.src.clus = ctx->dGridIdx;
+    req.src.reads = ctx->dGridIdx + nClusters + r0;
+    req.src.nClus = nClusters;
+    req.src.readBase = r0;
+    req.nPairs = uint32_t(pairs);
+    req.flags = flags;
+    req.maxLenA = maxA;
+    req.maxLenB = maxB;
+    req.hits.recs = G.dHits;
+    req.hits.count = ctx->dWork + SD_W_HITS + slot;
+    req.hits.cap = uint32_t(std::min<uint64_t>(G.cap, 0xffffffffu));
+    if ((rc = sd_launch_align(ctx, req))) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(G.hCount, ctx->dWork + SD_W_HITS + slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaEventRecord(G.done, ctx->stream));
+    G.busy = true;
+  }
+  // the older slot first
+  for (uint32_t x = 0; x < 2; ++x) {
+    sdgpu_ctx::GridSlot& G = ctx->gridSlots[(k + x) & 1];
+    if (G.busy && (rc = drain(G))) return rc;
+  }
+  *hits = ctx->gridHits.data();
+  *nHits = ctx->gridHits.size();
+  return SDGPU_OK;
+}
+
 int sdgpu_profile_enable(sdgpu_ctx* ctx, int on) {
   if (!ctx) return SDGPU_E_ARG;
   ctx->timeKernels = on != 0;
@@ -609,17 +768,26 @@ int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset) {
     float ms = 0;
     SD_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evPool[x], ctx->evPool[x + 1]));
     ctx->alignMs += ms;
-    if (ctx->evBand[x / 2]) ctx->bandMs += ms;
+    if (ctx->evBand[x / 2] == 1) ctx->bandMs += ms;
+    if (ctx->evBand[x / 2] == 2) ctx->screenMs += ms;
   }
   ctx->evUsed = 0;
-  uint64_t cells = 0, band[2] = {0, 0};
-  SD_CUDA(ctx, cudaMemcpy(&cells, ctx->dWork + 2, 8, cudaMemcpyDeviceToHost));
-  SD_CUDA(ctx, cudaMemcpy(band, ctx->dWork + 6, 16, cudaMemcpyDeviceToHost));
-  // cells actually evaluated = all la*lb of the finished pairs, minus those the banded pass certified,
-  // plus the band cells it evaluated (certified or not)
+  uint64_t cells = 0, band[2] = {0, 0}, scr[2] = {0, 0};
+  uint32_t scrCert = 0;
+  SD_CUDA(ctx, cudaMemcpy(&cells, ctx->dWork + SD_W_CELLS, 8, cudaMemcpyDeviceToHost));
+  SD_CUDA(ctx, cudaMemcpy(band, ctx->dWork + SD_W_BAND_CELLS, 16, cudaMemcpyDeviceToHost));
+  SD_CUDA(ctx, cudaMemcpy(scr, ctx->dWork + SD_W_SCR_CELLS, 16, cudaMemcpyDeviceToHost));
+  SD_CUDA(ctx, cudaMemcpy(&scrCert, ctx->dWork + SD_W_SCR_CERT, 4, cudaMemcpyDeviceToHost));
+  // cells actually evaluated = all la*lb of the finished pairs, minus those the screen and the banded pass
+  // finished, plus the band cells the two really evaluated (certified or not)
   out->bandCells = band[0] - ctx->bandCells;
   out->bandCertifiedCells = band[1] - ctx->bandCertCells;
-  out->evaluatedCells = (cells - ctx->cells) - out->bandCertifiedCells + out->bandCells;
+  out->screenCells = scr[0] - ctx->screenCells;
+  out->screenCertCells = scr[1] - ctx->screenCertCells;
+  out->screenCertified = uint64_t(scrCert) - ctx->screenCert;  // (a 32-bit device counter: read before it wraps)
+  out->screenPairs = ctx->screenPairs;
+  out->screenKernelMs = ctx->screenMs;
+  out->evaluatedCells = (cells - ctx->cells) - out->bandCertifiedCells - out->screenCertCells + out->bandCells + out->screenCells;
   out->alignKernelMs = ctx->alignMs;
   out->bandKernelMs = ctx->bandMs;
   out->alignKernelLaunches = ctx->alignLaunches;
@@ -635,6 +803,11 @@ int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset) {
     ctx->cells = cells;
     ctx->bandCells = band[0];
     ctx->bandCertCells = band[1];
+    ctx->screenCells = scr[0];
+    ctx->screenCertCells = scr[1];
+    ctx->screenCert = scrCert;
+    ctx->screenPairs = 0;
+    ctx->screenMs = 0;
     ctx->h2dBytes = ctx->d2hBytes = 0;
   }
   return SDGPU_OK;
@@ -706,7 +879,7 @@ int sdgpu_counters(sdgpu_ctx* ctx, uint64_t* kernelLaunches, uint64_t* cellUpdat
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   uint64_t cells = 0;
-  SD_CUDA(ctx, cudaMemcpy(&cells, ctx->dWork + 2, 8, cudaMemcpyDeviceToHost));
+  SD_CUDA(ctx, cudaMemcpy(&cells, ctx->dWork + SD_W_CELLS, 8, cudaMemcpyDeviceToHost));
   if (kernelLaunches) *kernelLaunches = ctx->launches;
   if (cellUpdates) *cellUpdates = cells;
   return SDGPU_OK;

@@ -23,13 +23,52 @@ struct DevScoring {
   int16_t score[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];  // [refCode*16 + readCode]
 };
 
+#define SD_FLAG_QUAL_OK 1u   // seqInfo::checkQual(pos, qScorePars_) holds for this base
+#define SD_FLAG_LOW_KMER 2u  // the k-mer centred on this base is low-frequency in the current KmerMaps
+
 struct DevSeqs {
   const uint8_t* codes;  // 1 byte per base, value < 16
   const uint8_t* quals;
+  const uint8_t* flags;  // 1 byte per base: SD_FLAG_* (what an errorProfile needs to know about a mismatching base)
   const uint64_t* offsets;  // n+1
   const double* cnts;
   uint32_t n;
 };
+
+// Where a launch's (ref, read) pairs come from: two explicit index lists, or the (read x cluster)
+// grid of the collapse loop (pair p = r * nClus + c -> ref clus[c], read reads[r]; pairs whose two
+// store indices coincide are skipped: a cluster is never compared with itself).
+struct DevPairSrc {
+  const uint32_t* refIdx;  // list mode
+  const uint32_t* readIdx;
+  const uint32_t* clus;    // grid mode when non-null
+  const uint32_t* reads;
+  uint32_t nClus;
+  uint32_t readBase;       // ordinal of reads[0] in the caller's read list (hit records carry ordinals)
+};
+__device__ __forceinline__ void sd_pair_of(const DevPairSrc& s, uint32_t p, uint32_t& ia, uint32_t& ib) {
+  if (s.clus) {
+    const uint32_t r = p / s.nClus;
+    ia = s.clus[p - r * s.nClus];
+    ib = s.reads[r];
+  } else {
+    ia = s.refIdx[p];
+    ib = s.readIdx[p];
+  }
+}
+// compacted output of a grid launch: one record per pair whose verdict mask is not zero
+struct DevHits {
+  sdgpu_grid_hit* recs;  // may live in mapped pinned host memory
+  uint32_t* count;
+  uint32_t cap;
+};
+__device__ __forceinline__ void sd_emit_hit(const DevPairSrc& s, const DevHits& h, uint32_t p, uint64_t mask) {
+  const uint32_t slot = atomicAdd(h.count, 1u);
+  if (slot < h.cap) {
+    const uint32_t r = p / s.nClus;
+    h.recs[slot] = sdgpu_grid_hit{s.readBase + r, p - r * s.nClus, mask};
+  }
+}
 
 // Sorted positional k-mer table (KmerMaps): key = pos << 48 | 4-bit-coded k-mer.
 struct DevKmerIndex {
@@ -37,6 +76,43 @@ struct DevKmerIndex {
   const uint32_t* counts;
   uint32_t n;
   uint32_t kLen, runCutOff, byPos;
+  const uint32_t* posStart;  // by-position tables: first key of every position (nPos + 1 entries), else NULL
+  uint32_t nPos;
+};
+
+// KmerMaps::isKmerLowFrequency for the k-mer centred on base p (clamped to the sequence): count <= runCutOff
+__device__ __forceinline__ bool sd_low_freq(const DevKmerIndex& idx, const uint8_t* codes, int len, int p) {
+  const int k = int(idx.kLen);
+  if (k == 0 || len < k) return false;
+  int start = p >= k / 2 ? p - k / 2 : 0;
+  if (start + k > len) start = len - k;
+  uint64_t key = 0;
+  for (int x = 0; x < k; ++x) key = (key << 4) | codes[start + x];
+  uint32_t lo = 0, hi = idx.n;
+  if (idx.byPos) {
+    key |= uint64_t(start) << 48;
+    if (idx.posStart) {  // the keys of one position are contiguous
+      lo = idx.posStart[min(uint32_t(start), idx.nPos)];
+      if (uint32_t(start) < idx.nPos) hi = idx.posStart[start + 1];
+    }
+  }
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(idx.keys + mid) < key) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  const uint32_t cnt = (lo < idx.n && __ldg(idx.keys + lo) == key) ? __ldg(idx.counts + lo) : 0u;
+  return cnt <= idx.runCutOff;
+}
+
+// screen_kernel.cu work item
+struct SdScreenItem {  // a pair whose gapless alignment still has to be proved the unique optimum
+  uint32_t pair;
+  int32_t sdiagK;  // K x score of the gapless alignment
+  uint64_t mask;   // its verdict mask
 };
 
 struct sdgpu_ctx {
@@ -54,6 +130,7 @@ struct sdgpu_ctx {
   // sequence store
   uint8_t* dCodes = nullptr;
   uint8_t* dQuals = nullptr;
+  uint8_t* dFlags = nullptr;  // SD_FLAG_* per base
   uint64_t* dOffsets = nullptr;
   double* dCnts = nullptr;
   uint64_t capBases = 0;
@@ -66,6 +143,8 @@ struct sdgpu_ctx {
   uint32_t nIdx = 0, idxK = 0, idxRunCutOff = 0, idxByPos = 0;
   bool haveIndex = false;
   uint32_t idxCapRuns = 0;
+  uint32_t* dIdxPosStart = nullptr;  // by-position index: first key of every position
+  uint32_t idxPosCap = 0, idxNPos = 0;
   void* dIdxWork = nullptr;  // grow-only arena for the index build (keys, weights, CUB temp)
   uint64_t idxWorkBytes = 0;
   // dense k-mer profiles
@@ -109,6 +188,28 @@ struct sdgpu_ctx {
   uint32_t redoCap = 0;
   uint32_t* hBandStat = nullptr;  // pinned: [0] = redo count of the last banded launch, [1] = its pair count
   uint32_t bandSkipped = 0;       // launches since banding was last tried while it was not paying off
+  cudaEvent_t bandStatEv = nullptr;  // completes when hBandStat holds the last banded launch's numbers
+  uint32_t* dRedo2 = nullptr;     // redo list of the banded pass when it runs behind the screen pass
+  uint32_t redo2Cap = 0;
+  // screen pass (screen_kernel.cu): 0 = automatic, 1 = off; band lists
+  int screenMode = 0;
+  SdScreenItem* dScreenItems = nullptr;
+  uint64_t screenItemsCap = 0;  // pairs per list
+  double screenMs = 0;
+  uint64_t screenPairs = 0;
+  uint64_t screenCells = 0, screenCertCells = 0, screenCert = 0;  // read-back baselines for profile_read
+  // sdgpu_align_pass_grid: device copies of the two index lists, two zero-copy hit slots, the result vector
+  uint32_t* dGridIdx = nullptr;
+  uint64_t gridIdxCap = 0;
+  struct GridSlot {
+    sdgpu_grid_hit* hHits = nullptr;  // mapped pinned memory, written by the kernels
+    sdgpu_grid_hit* dHits = nullptr;  // device alias
+    uint32_t* hCount = nullptr;       // pinned
+    uint64_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+  } gridSlots[2];
+  std::vector<sdgpu_grid_hit> gridHits;
   uint64_t bandCells = 0, bandCertCells = 0, bandRedo = 0, bandPairs = 0;  // read-back baselines for profile_read
   // bookkeeping
   uint64_t launches = 0, cells = 0;
@@ -137,13 +238,85 @@ struct SdChimeraReq {  // sdgpu_chimera_probe_pairs: per-pair probe output + chi
   sdgpu_iter_par overlap;
   uint32_t keepLq;
 };
-int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx, uint32_t nPairs,
-                    uint32_t flags, sdgpu_comparison* dOut, sdgpu_gap* dGaps, uint32_t gapCap,
-                    uint32_t maxLenA, uint32_t maxLenB, uint64_t* dPassOut = nullptr,
-                    const SdChimeraReq* chi = nullptr);
+struct SdAlignReq {  // one alignment launch; every pointer is a device pointer
+  DevPairSrc src{};
+  uint32_t nPairs = 0;
+  uint32_t flags = 0;
+  sdgpu_comparison* dOut = nullptr;
+  sdgpu_gap* dGaps = nullptr;
+  uint32_t gapCap = 0;
+  uint32_t maxLenA = 0, maxLenB = 0;
+  uint64_t* dPassOut = nullptr;
+  const SdChimeraReq* chi = nullptr;
+  DevHits hits{};  // grid launches: compacted non-zero verdict masks
+};
+int sd_launch_align(sdgpu_ctx* ctx, const SdAlignReq& req);
+inline int sd_launch_align(sdgpu_ctx* ctx, const uint32_t* dRefIdx, const uint32_t* dReadIdx, uint32_t nPairs,
+                           uint32_t flags, sdgpu_comparison* dOut, sdgpu_gap* dGaps, uint32_t gapCap,
+                           uint32_t maxLenA, uint32_t maxLenB, uint64_t* dPassOut = nullptr,
+                           const SdChimeraReq* chi = nullptr) {
+  SdAlignReq r;
+  r.src.refIdx = dRefIdx;
+  r.src.readIdx = dReadIdx;
+  r.nPairs = nPairs;
+  r.flags = flags;
+  r.dOut = dOut;
+  r.dGaps = dGaps;
+  r.gapCap = gapCap;
+  r.maxLenA = maxLenA;
+  r.maxLenB = maxLenB;
+  r.dPassOut = dPassOut;
+  r.chi = chi;
+  return sd_launch_align(ctx, r);
+}
+
+// screen_kernel.cu: the screen pass in front of the verdict-mask launches
+struct SdScreenArgs {
+  DevScoring sc;
+  DevSeqs seqs;
+  DevKmerIndex idx;
+  DevPairSrc src;
+  uint32_t nPairs;
+  uint32_t flags;
+  const sdgpu_iter_par* lines;
+  uint32_t nLines;
+  uint64_t* passOut;
+  DevHits hits;
+  SdScreenItem* items;  // three lists of nPairs entries: bands of 16 / 32 / 64 diagonals
+  uint32_t* redo;       // pairs left to the bit-recording kernels
+  uint32_t* work;       // ctx->dWork (SD_W_* words)
+  int K;                // perturbation scale: a power of two above the move count of any path
+  int maxSub;
+  long long bandSlack[3];  // a pair whose deficit maxSub*L - S_diag is below bandSlack[b] cannot be beaten outside band b
+  int screenOn;         // 0: the scan only lists the non-self pairs of a grid launch
+};
+bool sd_screen_plan(const sdgpu_ctx* ctx, uint32_t maxLenA, uint32_t maxLenB, SdScreenArgs* out);
+int sd_launch_screen(sdgpu_ctx* ctx, SdScreenArgs& args);
+
+// words of ctx->dWork (uint32 indices; 64-bit counters sit on even indices)
+enum {
+  SD_W_NEXT = 0,           // work counter of the running alignment kernel
+  SD_W_CELLS = 2,          // u64, cumulative: sum of lenA x lenB over finished pairs
+  SD_W_REDO = 4,           // banded pass: pairs it could not certify
+  SD_W_BAND_PAIRS = 5,     // banded pass: pairs it looked at
+  SD_W_BAND_CELLS = 6,     // u64, cumulative
+  SD_W_BAND_CERTCELLS = 8, // u64, cumulative
+  SD_W_SCAN = 16,          // screen scan: work counter
+  SD_W_BIN0 = 17,          // 17..19: entries of the three band lists, 20: entries of the screen's redo list
+  SD_W_DP0 = 21,           // 21..23: work counters of the three score-only DP launches
+  SD_W_SCR_CELLS = 24,     // u64, cumulative: band cells the score-only DP evaluated
+  SD_W_SCR_CERTCELLS = 26, // u64, cumulative: lenA x lenB of the pairs the screen finished
+  SD_W_SCR_CERT = 28,      // cumulative: pairs the screen finished
+  SD_W_HITS = 30,          // 30, 31: hit counters of the two grid slots
+  SD_W_WORDS = 64
+};
+
 // kmer_kernels.cu
 int sd_build_kmer_index(sdgpu_ctx* ctx, const uint32_t* hSeqIdx, uint32_t nIdx, uint32_t kLen, uint32_t runCutOff,
                         int byPos, int expandPos, uint32_t expandSize);
+// per-base flags of store sequences [firstSeq, firstSeq + nSeqs): checkQual outcome / low-frequency k-mer
+int sd_refresh_qual_flags(sdgpu_ctx* ctx, uint32_t firstSeq, uint32_t nSeqs);
+int sd_refresh_kmer_flags(sdgpu_ctx* ctx, uint32_t firstSeq, uint32_t nSeqs);
 int sd_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers, const uint32_t* positions, uint32_t n,
                          uint32_t* countsOut);
 int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen);

@@ -32,7 +32,7 @@ class QlusterOptsC(C.Structure):
 class StatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("inputReads", "uniqueSeqs", "finalClusters", "pairsComputed", "pairsConsumed",
                                           "consensusAligns", "cellUpdates", "gpuBatches", "onDemandPairs",
-                                          "chimeraPairs", "chimericClusters")] + \
+                                          "chimeraPairs", "chimericClusters", "passingPairs")] + \
                [("secondsGpu", C.c_double), ("secondsTotal", C.c_double), ("msResident", C.c_double)]
 
 
@@ -101,6 +101,10 @@ def _bind(lib):
     lib.sdq_cluster_cnt.argtypes = [v, C.c_uint32]
     lib.sdq_cluster_seq.argtypes = [v, C.c_uint32, v, v]
     lib.sdq_membership.argtypes = [v, v]
+    lib.sdq_clusters_total_len.restype = C.c_uint64
+    lib.sdq_clusters_total_len.argtypes = [v]
+    lib.sdq_clusters_packed.restype = C.c_int
+    lib.sdq_clusters_packed.argtypes = [v, v, v, v, v]
     lib.sdq_cluster_chimeric.restype = C.c_int
     lib.sdq_cluster_chimeric.argtypes = [v, C.c_uint32, v, v]
     _bound = True
@@ -137,13 +141,18 @@ def _result_to_dict(lib, h, n, want_clusters):
     st = StatsC()
     lib.sdq_get_stats(h, C.byref(st))
     res = {"stats": {k: getattr(st, k) for k, _ in StatsC._fields_}, "clusters": []}
-    if want_clusters:
-        for c in range(lib.sdq_num_clusters(h)):
-            ln = lib.sdq_cluster_len(h, c)
-            s = np.zeros(ln, np.uint8)
-            q = np.zeros(ln, np.uint8)
-            lib.sdq_cluster_seq(h, c, _ptr(s), _ptr(q))
-            res["clusters"].append((s.tobytes().decode(), q, lib.sdq_cluster_cnt(h, c)))
+    # every consensus sequence, its qualities and its count in one call (sdq_clusters_packed)
+    nc = lib.sdq_num_clusters(h)
+    tot = lib.sdq_clusters_total_len(h)
+    pb, pq = np.zeros(tot, np.uint8), np.zeros(tot, np.uint8)
+    po, pc = np.zeros(nc + 1, np.uint64), np.zeros(nc, np.float64)
+    lib.sdq_clusters_packed(h, _ptr(pb), _ptr(pq), _ptr(po), _ptr(pc))
+    res["packed"] = {"bases": pb, "quals": pq, "offsets": po, "cnts": pc}
+    if want_clusters:  # per-cluster Python objects (tests); the packed arrays above are the bulk form
+        blob = pb.tobytes().decode()
+        for c in range(nc):
+            lo, hi = int(po[c]), int(po[c + 1])
+            res["clusters"].append((blob[lo:hi], pq[lo:hi].copy(), float(pc[c])))
     res["chimeras"] = {}  # cluster -> (frontParent, backParent, frontPos, backPos), chiParentsInfo.txt's columns
     if st.chimericClusters:  # (a per-cluster ctypes call: only worth it when something was flagged)
         par, pos = (C.c_uint32 * 2)(), (C.c_uint32 * 2)()

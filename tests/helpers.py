@@ -169,3 +169,18 @@ def chimera_sample(rng, length=200, nDiff=8, counts=(60, 45, 8, 6), qual=38):
     offsets[1:] = np.cumsum([len(s) for s in seqs])
     bases = np.concatenate(seqs)
     return bases, np.full(len(bases), qual, np.uint8), offsets, (p0, p1, chi, var), cut
+
+
+def masks_from_comparisons(comps, iters):
+    """comparison::passErrorProfile of every par line applied on the host to errorProfiles
+    (COMPARISON_DTYPE records): the uint64 verdict masks sdgpu_align_pass* must return."""
+    masks = np.zeros(len(comps), np.uint64)
+    for l, it in enumerate(iters):
+        if it.onPerId:
+            ok = (comps["eventBasedIdentityHq"] if it.onHqPerId else comps["eventBasedIdentity"]) >= it.perId
+        else:
+            ok = ((it.oneBaseIndel >= comps["oneBaseIndel"]) & (it.twoBaseIndel >= comps["twoBaseIndel"]) &
+                  (it.largeBaseIndel >= comps["largeBaseIndel"]) & (it.hqMismatches >= comps["hqMismatches"]) &
+                  (it.lqMismatches >= comps["lqMismatches"]) & (it.lowKmerMismatches >= comps["lowKmerMismatches"]))
+        masks |= ok.astype(np.uint64) << np.uint64(l)
+    return masks

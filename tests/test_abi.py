@@ -42,7 +42,7 @@ def test_pod_layouts():
     assert C.sizeof(_abi.GapPars) == 40
     assert C.sizeof(_abi.Params) == 40 + 4 * 128 * 128 + 24
     assert C.sizeof(_abi.Comparison) == 104 and C.sizeof(_abi.Gap) == 12
-    assert _abi.load().sdgpu_abi_version() == 1
+    assert _abi.load().sdgpu_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
@@ -97,11 +97,12 @@ def test_python_struct_layouts_match_the_headers(tmp_path):
 #define O(t, f) printf(#t "." #f " %zu\n", offsetof(t, f))
 int main(void) {
   S(sdgpu_params); S(sdgpu_gap); S(sdgpu_comparison); S(sdgpu_iter_par); S(sdgpu_pair_summary); S(sdgpu_chimera_probe);
-  S(sdgpu_profile); S(sdq_opts); S(sdq_stats);
+  S(sdgpu_profile); S(sdq_opts); S(sdq_stats); S(sdgpu_grid_hit);
   O(sdgpu_comparison, oneBaseIndel); O(sdgpu_comparison, queryCoverage); O(sdgpu_iter_par, perId);
   O(sdq_opts, markChimeras); O(sdq_opts, chiParentFreqs); O(sdq_opts, chiOverlap);
   O(sdq_stats, chimeraPairs); O(sdq_stats, secondsGpu); O(sdq_stats, msResident);
-  O(sdgpu_chimera_probe, flags); O(sdgpu_profile, evaluatedCells); O(sdgpu_profile, bandKernelMs);
+  O(sdgpu_chimera_probe, flags); O(sdgpu_profile, evaluatedCells); O(sdgpu_profile, bandKernelMs); O(sdgpu_profile, screenCertCells);
+  O(sdgpu_grid_hit, mask); O(sdq_stats, passingPairs);
   return 0;
 }
 ''')
@@ -124,6 +125,9 @@ int main(void) {
     assert c["sdq_stats"] == C.sizeof(Q.StatsC)
     for f in ("chimeraPairs", "secondsGpu", "msResident"):
         assert c["sdq_stats." + f] == getattr(Q.StatsC, f).offset, f
-    # sdgpu_profile is mirrored inside GpuAligner.profile_read: 6 x 8 bytes + 3 x 8 + 8
-    assert c["sdgpu_profile"] == 80 and c["sdgpu_profile.evaluatedCells"] == 48 and c["sdgpu_profile.bandKernelMs"] == 72
+    # sdgpu_profile is mirrored inside GpuAligner.profile_read: 15 x 8 bytes
+    assert c["sdgpu_profile"] == 120 and c["sdgpu_profile.evaluatedCells"] == 48 and c["sdgpu_profile.bandKernelMs"] == 72
+    assert c["sdgpu_profile.screenCertCells"] == 112
+    assert c["sdgpu_grid_hit"] == _abi.GRID_HIT_DTYPE.itemsize and c["sdgpu_grid_hit.mask"] == _abi.GRID_HIT_DTYPE.fields["mask"][1]
+    assert c["sdq_stats.passingPairs"] == Q.StatsC.passingPairs.offset
     assert np.dtype(np.uint64).itemsize == 8

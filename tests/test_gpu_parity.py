@@ -156,6 +156,54 @@ def test_append_and_errors():
         assert out["alnLen"][0] == 800 and out["alnLen"][1] == 800
 
 
+def test_rejected_upload_leaves_the_store_and_alphabet_alone(oracle):
+    """A batch that fails validation (17th distinct character, byte >= 128, empty sequence) must not change the
+    ctx: the previous store, its alphabet codes and scoring stay usable and later uploads of characters that
+    the rejected batch introduced still get correct scores."""
+    p = H.params_for("degenHomopolymer")
+    seqs = ["ACGTRYACGTTGCA", "ACGTRYACGATGCA"]
+    b, q, off = pack_seqs(seqs, [np.full(len(s), 35, np.uint8) for s in seqs])
+    with GpuAligner(p) as al:
+        al.upload_seqs(b, q, off)
+        before = al.align_profile([0], [1])
+        many = "ACGTNRYSWKMBDHVXZ"  # 12 new characters on top of A,C,G,T,N,R,Y: the 17th does not fit
+        for bad in (pack_seqs([many], [np.full(len(many), 30, np.uint8)]),
+                    (np.frombuffer(b"ACG\xc8", np.uint8).copy(), np.full(4, 30, np.uint8), np.array([0, 4], np.uint64))):
+            with pytest.raises(SdgpuError) as ei:
+                al.upload_seqs(*bad)
+            assert ei.value.code == _abi.E_ALPHABET
+            with pytest.raises(SdgpuError):
+                al.append_seqs(*bad)
+        with pytest.raises(SdgpuError):
+            al.upload_seqs(np.frombuffer(b"ACGT", np.uint8).copy(), np.full(4, 30, np.uint8), np.array([0, 4, 4], np.uint64))
+        assert al.num_seqs() == 2
+        after = al.align_profile([0], [1])
+        assert after.tobytes() == before.tobytes()
+        # S, W, K were named by the rejected batch: they must score like the matrix says once they do arrive
+        extra = ["ACGTSWACGTKGCA", "ACGTGAACGTTGCA"]
+        al.append_seqs(*pack_seqs(extra, [np.full(14, 35, np.uint8)] * 2))
+        got = al.align_profile([2, 0], [3, 2])
+    allSeqs = seqs + extra
+    bb, qq, oo = pack_seqs(allSeqs, [np.full(len(s), 35, np.uint8) for s in allSeqs])
+    want = oracle.align_profile_batch(p, bb, qq, oo, np.array([2, 0], np.uint32), np.array([3, 2], np.uint32))
+    H.assert_comparisons_equal(got, want)
+
+
+def test_kmer_index_size_limit():
+    """The index build sorts with a signed 32-bit item count: 2^31 or more (position, k-mer) occurrences are refused
+    loudly instead of silently producing an empty table (every mismatch would turn into a lowKmer mismatch)."""
+    rng = np.random.default_rng(3)
+    seqs = [H.rand_seq(rng, 300).tobytes() for _ in range(3000)]
+    b, q, off = pack_seqs(seqs, [np.full(300, 30, np.uint8)] * len(seqs))
+    with GpuAligner(make_params()) as al:
+        al.upload_seqs(b, q, off)
+        with pytest.raises(SdgpuError) as ei:
+            al.index_kmers(9, 1, True, expandKmerPos=True, expandKmerSize=1300)  # 3000 x 292 x ~2600 > 2^31
+        assert ei.value.code == _abi.E_UNSUPPORTED and "2^31" in str(ei.value)
+        al.index_kmers(9, 1, True, expandKmerPos=True, expandKmerSize=2)
+        assert al.kmer_index_lookup([seqs[0][5:14]], [4])[0] >= 1
+
+
 def test_full_size_properties():
     """BASELINE config-2 shaped batch (300 bp) without the oracle: size-independent properties."""
     rng = np.random.default_rng(61)

@@ -105,6 +105,30 @@ def test_qluster_many_equals_single_runs(oracle):
     assert_same(many[0], want)
 
 
+@pytest.mark.parametrize("mode", ["default", "noScreen", "noBand"])
+@pytest.mark.parametrize("name", ["c2_5k", "c1_full", "c2_20k", "c2_20k_hp"])
+def test_qluster_matches_frozen_oracle_at_baseline_sizes(name, mode):
+    """BASELINE config 1 at full size and the config 2 generator at 5k / 20k reads (with and without
+    homopolymer weighting) against the oracle's frozen results (tests/golden/make_qluster_fixtures.py):
+    membership, consensus sequences / qualities / counts, chimera flags bit for bit -- through the screen
+    pass, with it off (banded + full-matrix kernels) and with screen and band off (full-matrix only)."""
+    from tests import golden_fixtures as G
+    if name not in G.NAMES:
+        pytest.skip(f"fixture {name} has not been generated")
+    (bases, q, offsets, params, pars, iters), fx = G.load(name)
+    with sd.GpuAligner(params) as al:
+        if mode != "default":
+            al.set_screen(1)
+        if mode == "noBand":
+            al.set_band(1)
+        al.profile_enable(True)
+        got = sd.qluster(al, bases, q, offsets, pars, iters, want_clusters=False)
+        prof = al.profile_read()
+    G.assert_result_equals_fixture(got, fx)
+    assert (prof["screenCertified"] > 0) == (mode == "default")
+    assert (prof["bandCells"] > 0) == (mode != "noBand")
+
+
 def test_config1_full_size_properties():
     """BASELINE config 1 at full size (10k reads x 250 bp, 20 haplotypes), without the oracle:
     size-independent properties of the collapse — conservation of reads, determinism, exact recovery

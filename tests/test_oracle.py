@@ -332,3 +332,19 @@ def test_stop_check_and_small_cutoff_semantics(oracle):
     assert run(4, 0) == [40.0, 30.0, 20.0, 13.0]
     assert run(100, 10) == [40.0, 30.0, 20.0, 10.0, 1.0, 1.0, 1.0]  # count 10 does not exceed smallCutoff 10
     assert run(100, 9) == [40.0, 30.0, 20.0, 13.0]
+
+
+def test_frozen_qluster_fixtures_match_their_generators():
+    """tests/golden/qluster_*.npz carry the SHA-256 of the input they were computed from: the seeded
+    generators must still reproduce it (otherwise a GPU mismatch would be a generator drift, not a parity failure),
+    and the frozen results must be self-consistent (every read in a cluster, counts add up)."""
+    from tests import golden_fixtures as G
+    assert "c1_full" in G.NAMES and "c2_5k" in G.NAMES
+    for name in G.NAMES:
+        (bases, q, offsets, params, pars, iters), fx = G.load(name)
+        n = len(offsets) - 1
+        mem = fx["membership"]
+        assert len(mem) == n and len(fx["cnts"]) + 1 == len(fx["offsets"])
+        kept = mem != np.uint32(0xFFFFFFFF)
+        assert np.array_equal(np.bincount(mem[kept], minlength=len(fx["cnts"])).astype(np.float64), fx["cnts"])
+        assert fx["offsets"][-1] == len(fx["seqs"]) == len(fx["quals"])
