@@ -60,80 +60,52 @@ double nowSec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Per-read verdict row: cluster store index -> pass mask (tiny open-addressing table).
+// Per-read verdict row: cluster store index -> pass mask.  Only non-zero masks are kept, so a row holds a
+// handful of entries: two live in the object itself, the rest in a small vector; look-ups are linear scans.
 class Row {
  public:
-  static constexpr uint32_t EMPTY = 0xffffffffu;
   const uint64_t* find(uint32_t k) const {
-    if (keys_.empty()) return nullptr;
-    uint32_t h = (k * 2654435761u) & mask_;
-    while (keys_[h] != EMPTY) {
-      if (keys_[h] == k) return &vals_[h];
-      h = (h + 1) & mask_;
-    }
+    for (uint32_t i = 0; i < n_ && i < INLINE; ++i)
+      if (keys_[i] == k) return &vals_[i];
+    for (const auto& e : more_)
+      if (e.first == k) return &e.second;
     return nullptr;
   }
   void insert(uint32_t k, uint64_t v) {
-    if (keys_.empty() || (n_ + 1) * 3 > (mask_ + 1) * 2) grow();
     or_ |= v;
-    uint32_t h = (k * 2654435761u) & mask_;
-    while (keys_[h] != EMPTY) {
-      if (keys_[h] == k) {
-        vals_[h] = v;
+    for (uint32_t i = 0; i < n_ && i < INLINE; ++i)
+      if (keys_[i] == k) {
+        vals_[i] = v;
         return;
       }
-      h = (h + 1) & mask_;
+    for (auto& e : more_)
+      if (e.first == k) {
+        e.second = v;
+        return;
+      }
+    if (n_ < INLINE) {
+      keys_[n_] = k;
+      vals_[n_] = v;
+    } else {
+      more_.emplace_back(k, v);
     }
-    keys_[h] = k;
-    vals_[h] = v;
     ++n_;
   }
-  // make room for `extra` more entries in one step (instead of doubling through 64, 128, 256 ...)
-  void reserve(uint32_t extra) {
-    const uint64_t need = (uint64_t(n_) + extra) * 3;
-    uint64_t cap = keys_.empty() ? 64u : keys_.size();
-    if (!keys_.empty() && need <= cap * 2) return;
-    while (need > cap * 2) cap <<= 1;
-    regrow(uint32_t(cap));
-  }
   void clear() {
-    std::vector<uint32_t>().swap(keys_);
-    std::vector<uint64_t>().swap(vals_);
+    std::vector<std::pair<uint32_t, uint64_t>>().swap(more_);
     n_ = 0;
-    mask_ = 0;
     or_ = 0;
   }
   uint32_t size() const { return n_; }
   uint64_t orMask() const { return or_; }  // superset of every verdict bit held in the row
-  // drop verdicts against cluster versions that no longer exist
-  void prune(const std::vector<uint8_t>& live) {
-    std::vector<uint32_t> k;
-    std::vector<uint64_t> v;
-    k.swap(keys_);
-    v.swap(vals_);
-    n_ = 0;
-    mask_ = 0;
-    or_ = 0;
-    for (size_t i = 0; i < k.size(); ++i)
-      if (k[i] != EMPTY && live[k[i]]) insert(k[i], v[i]);
-  }
 
  private:
-  void grow() { regrow(keys_.empty() ? 64u : uint32_t(keys_.size()) * 2u); }
-  void regrow(uint32_t cap) {
-    std::vector<uint32_t> k(cap, EMPTY);
-    std::vector<uint64_t> v(cap);
-    k.swap(keys_);
-    v.swap(vals_);
-    mask_ = cap - 1;
-    n_ = 0;
-    for (size_t i = 0; i < k.size(); ++i)
-      if (k[i] != EMPTY) insert(k[i], v[i]);
-  }
-  uint64_t or_ = 0;  // (summary words first: they share the owning cluster's first cache line)
-  uint32_t n_ = 0, mask_ = 0;
-  std::vector<uint32_t> keys_;
-  std::vector<uint64_t> vals_;
+  static constexpr uint32_t INLINE = 2;
+  uint64_t or_ = 0;
+  uint32_t n_ = 0;
+  uint32_t keys_[INLINE] = {0, 0};
+  uint64_t vals_[INLINE] = {0, 0};
+  std::vector<std::pair<uint32_t, uint64_t>> more_;
 };
 
 // Splits [0, n) over a few short-lived host threads (the prep phases before the GPU has work:
@@ -229,8 +201,6 @@ struct ConsState {  // column counters of one cluster against one base sequence
 struct alignas(64) Clus {
   double cnt = 0;
   double avgErr = 0;
-  uint64_t rowSerial = 0;  // iteration serial at which the read was last judged against the whole window
-  uint64_t coverStart = 0; // ... and the first of the unbroken run of iterations that ends there (0: none)
   uint32_t storeIdx = 0;   // device sequence-store entry (verdict-equivalent to (seq, qual))
   uint32_t firstId = 0;    // cluster::firstReadName_ stand-in (tie-break of the sort)
   bool remove = false, needCons = false;
@@ -328,6 +298,21 @@ class Runner {
   uint64_t serial = 0;                // iteration counter across the three clustering runs
   std::vector<uint32_t> prevWindow;   // store indices of the previous iteration's window
   std::vector<uint8_t> inPrevWindow;  // by store index
+  uint64_t lastListSerial = 0;        // serial of the latest iteration that listed (judged) every live read
+  // Compact copies, by position in the sorted cluster list, of what the per-iteration loops look at for EVERY
+  // cluster: rebuilt whenever the list is re-sorted, updated in place at the few points an iteration changes
+  // them.  The loops then touch a heavy Clus object only for the few reads that have a passing verdict.
+  struct Pos {
+    double cnt, avgErr;  // sort keys as of the last sort (readVecSorter "totalCount": count desc, average error asc)
+    Clus* c;
+    uint64_t cover;      // first of the unbroken run of iterations in which this read was judged against the whole window (0: none)
+    uint64_t orMask;     // row.orMask()
+    uint32_t store;      // storeIdx
+    uint8_t remove;
+    uint8_t changed;     // absorbed reads since the last sort: its keys / device version may have moved
+  };
+  std::vector<Pos> PR;                // parallel to the cluster list
+  bool posValid = false;              // P matches the list and only `remove` / `changed` entries moved since the last sort
   std::vector<uint64_t> lastIn;       // by store index: latest iteration serial whose window held this version
   std::vector<uint64_t> onDemandAt;   // by store index: iteration serial in which it was judged on demand
   static constexpr uint32_t BATCH = 1u << 21;
@@ -399,26 +384,30 @@ class Runner {
     ++st.gpuBatches;
     st.pairsComputed += uint64_t(clusStore.size()) * readStore.size();
     const double t1 = nowSec();
-    for (uint64_t i = 0; i < nHits; ++i) cs[readPos[hits[i].read]].row.insert(clusStore[hits[i].cluster], hits[i].mask);
+    for (uint64_t i = 0; i < nHits; ++i) {
+      const uint32_t rp = readPos[hits[i].read];
+      cs[rp].row.insert(clusStore[hits[i].cluster], hits[i].mask);
+      PR[rp].orMask |= hits[i].mask;
+    }
     tInsert += nowSec() - t1;
     st.passingPairs += nHits;
     return 0;
   }
   // has `read` been judged against cluster version `s` (so that an absent row entry means "fails every line")?
-  bool covered(const Clus& read, uint32_t s) const {
-    return (read.coverStart != 0 && lastIn[s] >= read.coverStart) || onDemandAt[s] == serial;
+  bool covered(uint64_t coverStart, uint32_t s) const {
+    return (coverStart != 0 && lastIn[s] >= coverStart) || onDemandAt[s] == serial;
   }
 
   // njhseq collapser::collapseWithParameters + findMatch for one par-file line
   int collapseWithParameters(ClusVec& cs, const sdq_iter_par& it, int line) {
     ++serial;
     size_t alive = 0;
-    for (const Clus& c : cs) alive += !c.remove;
+    for (const Pos& x : PR) alive += !x.remove;
     if (alive < 2) return 0;
     const uint64_t bit = 1ull << line;
     std::vector<uint32_t> elig;  // candidate clusters in sorted order (smallCutoff rule)
     for (uint32_t cp = 0; cp < cs.size(); ++cp)
-      if (!cs[cp].remove && cs[cp].cnt > double(it.smallCutoff)) elig.push_back(cp);
+      if (!PR[cp].remove && PR[cp].cnt > double(it.smallCutoff)) elig.push_back(cp);
     // ---- speculative batch: the window = first stopCheck(+1: a read skips itself) candidates
     double tt0 = nowSec();
     const uint32_t wn = uint32_t(std::min<uint64_t>(elig.size(), uint64_t(it.stopCheck) + 1));
@@ -430,25 +419,25 @@ class Runner {
       std::vector<uint32_t> window, fresh;  // store indices: the whole window / its entries the previous one lacked
       for (uint32_t w = 0; w < wn; ++w) {
         inWindow[elig[w]] = 1;
-        const uint32_t sIdx = cs[elig[w]].storeIdx;
+        const uint32_t sIdx = PR[elig[w]].store;
         window.push_back(sIdx);
         if (!inPrevWindow[sIdx]) fresh.push_back(sIdx);
       }
       // reads covered for the previous window only need the fresh entries; the others the whole window
       std::vector<uint32_t> fullStore, fullPos, incStore, incPos;
-      for (uint32_t rp = uint32_t(cs.size()); rp-- > 0;) {  // same order as the pass below
-        Clus& read = cs[rp];
-        if (read.remove) continue;
-        if (read.coverStart != 0 && read.rowSerial + 1 == serial) {
-          incStore.push_back(read.storeIdx);
+      const bool unbroken = lastListSerial + 1 == serial;  // the previous iteration judged every live read
+      for (uint32_t rp = uint32_t(cs.size()); rp-- > 0;) {   // same order as the pass below
+        if (PR[rp].remove) continue;
+        if (unbroken && PR[rp].cover != 0) {
+          incStore.push_back(PR[rp].store);
           incPos.push_back(rp);
         } else {
-          fullStore.push_back(read.storeIdx);
+          fullStore.push_back(PR[rp].store);
           fullPos.push_back(rp);
-          read.coverStart = serial;
+          PR[rp].cover = serial;
         }
-        read.rowSerial = serial;
       }
+      lastListSerial = serial;
       for (uint32_t s : prevWindow) inPrevWindow[s] = 0;
       prevWindow = window;
       for (uint32_t s : window) {
@@ -470,45 +459,49 @@ class Runner {
     bool windowIntact = true;  // no window cluster absorbed yet: every read sees the static window
     std::vector<uint32_t> odClus(1), odStore, odPos;
     for (size_t rp = cs.size(); rp-- > 0;) {
-      Clus& read = cs[rp];
-      if (read.remove) continue;
+      if (PR[rp].remove) continue;
       // it has been judged against every window cluster; if no verdict has this line's bit there is nothing to find
-      if (windowIntact && !(read.row.orMask() & bit)) {
+      if (windowIntact && !(PR[rp].orMask & bit)) {
         ++skippedScans;
         continue;
       }
+      Clus& read = cs[rp];
       uint32_t count = 0;
       for (uint32_t e = 0; e < elig.size(); ++e) {
         const uint32_t cp = elig[e];
-        Clus& clus = cs[cp];
-        if (clus.remove) continue;
+        if (PR[cp].remove) continue;
         if (cp == rp) continue;
         ++count;
         if (count > it.stopCheck) break;
-        const uint64_t* v = read.row.find(clus.storeIdx);
-        if (!v && !covered(read, clus.storeIdx)) {
+        const uint32_t clusStore = PR[cp].store;
+        const uint64_t* v = read.row.find(clusStore);
+        if (!v && !covered(PR[rp].cover, clusStore)) {
+          Clus& clus = cs[cp];
           // a candidate that slid into the window because earlier ones were absorbed: the reads
           // still to come will meet it too, so judge it against all of them in one grid
           odClus[0] = clus.storeIdx;
           odStore.clear();
           odPos.clear();
           for (size_t r2 = rp + 1; r2-- > 0;) {
-            if (cs[r2].remove || r2 == cp || covered(cs[r2], clus.storeIdx)) continue;
-            odStore.push_back(cs[r2].storeIdx);
+            if (PR[r2].remove || r2 == cp || covered(PR[r2].cover, clus.storeIdx)) continue;
+            odStore.push_back(PR[r2].store);
             odPos.push_back(uint32_t(r2));
           }
           st.onDemandPairs += odStore.size();
           int rc = gridPass(cs, odClus, odStore, odPos);
           if (rc) return rc;
           onDemandAt[clus.storeIdx] = serial;
-          v = read.row.find(clus.storeIdx);
+          v = read.row.find(clusStore);
         }
         ++st.pairsConsumed;
         if (v && (*v & bit)) {
+          Clus& clus = cs[cp];
           clus.cnt += read.cnt;
           clus.members.insert(clus.members.end(), read.members.begin(), read.members.end());
           clus.needCons = true;
           read.remove = true;
+          PR[rp].remove = 1;
+          PR[cp].changed = 1;
           read.row.clear();
           read.cons.reset();
           if (inWindow[rp]) windowIntact = false;
@@ -537,8 +530,9 @@ class Runner {
     std::vector<Job> jobs;
     std::vector<uint32_t> a, b;
     for (uint32_t ci = 0; ci < cs.size(); ++ci) {
+      if (PR[ci].remove || !PR[ci].changed) continue;  // (the clusters that absorbed reads in this iteration)
       Clus& cl = cs[ci];
-      if (cl.remove || !cl.needCons) continue;
+      if (!cl.needCons) continue;
       cl.needCons = false;
       if (cl.members.size() <= 1) continue;
       double totalLen = 0, totalCnt = 0;
@@ -748,53 +742,80 @@ class Runner {
         Clus& cl = cs[changed[i]];
         cl.storeIdx = first + uint32_t(i);
         cl.row.clear();  // its verdicts as a read were for the old version
-        cl.rowSerial = 0;
-        cl.coverStart = 0;
+        PR[changed[i]].cover = 0;
+        PR[changed[i]].orMask = 0;
+        PR[changed[i]].store = cl.storeIdx;
       }
       storeSize = first + uint32_t(changed.size());
     }
     return 0;
   }
 
-  // drop absorbed clusters, then readVecSorter "totalCount" (index sort: a Clus is heavy to move)
+  // drop absorbed clusters, then readVecSorter "totalCount".  A Clus is heavy, so the list holds pointers and the
+  // sort works on the compact records of P.  Between two sorts only a few records move -- the clusters that absorbed
+  // reads (new count / average error) and the absorbed ones (gone) -- so the usual call compacts the sorted records,
+  // sorts the few changed ones and merges the two runs; the order is total (first id breaks every tie), hence the
+  // result is std::sort's.
+  static bool posLess(const Pos& a, const Pos& b) {
+    if (a.cnt != b.cnt) return a.cnt > b.cnt;
+    if (a.avgErr != b.avgErr) return a.avgErr < b.avgErr;
+    return clusLess(*a.c, *b.c);
+  }
   void dropRemovedAndSort(ClusVec& cs) {
     const double t0 = nowSec();
     std::vector<Clus*>& v = cs.ptrs();
-    v.erase(std::remove_if(v.begin(), v.end(), [](const Clus* c) { return c->remove; }), v.end());
-    struct Key {  // the two leading sort keys packed contiguously; sequence / first id only on ties
-      double cnt, avgErr;
-      Clus* c;
-    };
-    std::vector<Key> keys(v.size());
-    for (size_t i = 0; i < v.size(); ++i) keys[i] = Key{v[i]->cnt, v[i]->avgErr, v[i]};
-    auto less = [](const Key& a, const Key& b) {
-      if (a.cnt != b.cnt) return a.cnt > b.cnt;
-      if (a.avgErr != b.avgErr) return a.avgErr < b.avgErr;
-      return clusLess(*a.c, *b.c);
-    };
-    if (!std::is_sorted(keys.begin(), keys.end(), less)) {
-      // the order is total (first id breaks every tie), so chunk sorts + merges give std::sort's result
-      const size_t n = keys.size();
-      const size_t T = n >= (1u << 15) ? std::min<size_t>(allowedCpus(), 4) : 1;
-      if (T > 1) {
-        std::vector<size_t> cut(T + 1);
-        for (size_t t = 0; t <= T; ++t) cut[t] = n * t / T;
-        parallelFor(T, [&](size_t lo, size_t hi) {
-          for (size_t t = lo; t < hi; ++t) std::sort(keys.begin() + cut[t], keys.begin() + cut[t + 1], less);
-        }, 1);
-        for (size_t width = 1; width < T; width *= 2)
-          for (size_t t = 0; t + width < T; t += 2 * width)
-            std::inplace_merge(keys.begin() + cut[t], keys.begin() + cut[t + width], keys.begin() + cut[std::min(T, t + 2 * width)], less);
-      } else {
-        std::sort(keys.begin(), keys.end(), less);
+    if (posValid && PR.size() == v.size()) {
+      std::vector<Pos> moved;
+      size_t w = 0;
+      for (size_t i = 0; i < PR.size(); ++i) {
+        if (PR[i].remove) continue;
+        if (PR[i].changed) {
+          Pos x = PR[i];
+          x.cnt = x.c->cnt;
+          x.avgErr = x.c->avgErr;
+          x.changed = 0;
+          moved.push_back(x);
+          continue;
+        }
+        PR[w++] = PR[i];
       }
-      for (size_t i = 0; i < v.size(); ++i) v[i] = keys[i].c;
+      PR.resize(w);
+      if (!moved.empty()) {
+        std::sort(moved.begin(), moved.end(), posLess);
+        std::vector<Pos> out(PR.size() + moved.size());
+        std::merge(PR.begin(), PR.end(), moved.begin(), moved.end(), out.begin(), posLess);
+        PR.swap(out);
+      }
+    } else {  // a new list (start of a clustering run): build the records from the clusters and sort them all
+      v.erase(std::remove_if(v.begin(), v.end(), [](const Clus* c) { return c->remove; }), v.end());
+      PR.resize(v.size());
+      for (size_t i = 0; i < v.size(); ++i) PR[i] = Pos{v[i]->cnt, v[i]->avgErr, v[i], 0, v[i]->row.orMask(), v[i]->storeIdx, 0, 0};
+      if (!std::is_sorted(PR.begin(), PR.end(), posLess)) {
+        const size_t n = PR.size();
+        const size_t T = n >= (1u << 15) ? std::min<size_t>(allowedCpus(), 4) : 1;
+        if (T > 1) {
+          std::vector<size_t> cut(T + 1);
+          for (size_t t = 0; t <= T; ++t) cut[t] = n * t / T;
+          parallelFor(T, [&](size_t lo, size_t hi) {
+            for (size_t t = lo; t < hi; ++t) std::sort(PR.begin() + cut[t], PR.begin() + cut[t + 1], posLess);
+          }, 1);
+          for (size_t width = 1; width < T; width *= 2)
+            for (size_t t = 0; t + width < T; t += 2 * width)
+              std::inplace_merge(PR.begin() + cut[t], PR.begin() + cut[t + width], PR.begin() + cut[std::min(T, t + 2 * width)], posLess);
+        } else {
+          std::sort(PR.begin(), PR.end(), posLess);
+        }
+      }
     }
+    v.resize(PR.size());
+    for (size_t i = 0; i < PR.size(); ++i) v[i] = PR[i].c;
+    posValid = true;
     tSort += nowSec() - t0;
   }
 
   int runFullClustering(ClusVec& cs, const sdq_iter_par* its, uint32_t nIts) {
     orderDirty = true;
+    posValid = false;  // the list may have been re-composed (singletons joining)
     for (uint32_t i = 0; i < nIts; ++i) {
       if (orderDirty) dropRemovedAndSort(cs);  // counts / members only change when something merged
       orderDirty = false;
@@ -837,10 +858,9 @@ class Runner {
     parallelFor(cs.size(), [&](size_t lo, size_t hi) {  // verdicts depend on the index through lowKmerMismatches
       for (size_t i = lo; i < hi; ++i) {
         cs[i].row.clear();
-        cs[i].rowSerial = 0;
-        cs[i].coverStart = 0;
       }
     });
+    for (Pos& x : PR) x.cover = 0, x.orMask = 0;
     return 0;
   }
 };

@@ -193,12 +193,12 @@ def test_kmer_index_size_limit():
     """The index build sorts with a signed 32-bit item count: 2^31 or more (position, k-mer) occurrences are refused
     loudly instead of silently producing an empty table (every mismatch would turn into a lowKmer mismatch)."""
     rng = np.random.default_rng(3)
-    seqs = [H.rand_seq(rng, 300).tobytes() for _ in range(3000)]
+    seqs = [H.rand_seq(rng, 300).tobytes() for _ in range(6000)]
     b, q, off = pack_seqs(seqs, [np.full(300, 30, np.uint8)] * len(seqs))
     with GpuAligner(make_params()) as al:
         al.upload_seqs(b, q, off)
         with pytest.raises(SdgpuError) as ei:
-            al.index_kmers(9, 1, True, expandKmerPos=True, expandKmerSize=1300)  # 3000 x 292 x ~2600 > 2^31
+            al.index_kmers(9, 1, True, expandKmerPos=True, expandKmerSize=1300)  # 6000 x 292 x ~1450 keys > 2^31
         assert ei.value.code == _abi.E_UNSUPPORTED and "2^31" in str(ei.value)
         al.index_kmers(9, 1, True, expandKmerPos=True, expandKmerSize=2)
         assert al.kmer_index_lookup([seqs[0][5:14]], [4])[0] >= 1
