@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the qluster hot path on B200 (driver contract in the task).
 
-Workload = BASELINE.json configs[1]: one synthetic sample, 200k reads x 300 bp
-from 200 haplotypes at 1 % substitutions + homopolymer indels, qluster with the Illumina
-iteration table (etc/SeekDeepParameterFiles/illumina_lkmer1 == genIlluminaDefaultPars(100)),
+Workload (default, `--workload c2`) = BASELINE.json configs[1]: one synthetic sample,
+200k reads x 300 bp from 200 haplotypes at 1 % substitutions + homopolymer indels, qluster with the
+Illumina iteration table (etc/SeekDeepParameterFiles/illumina_lkmer1 == genIlluminaDefaultPars(100)),
 qualities 25/20, gaps 5,1 / left 5,1 / right 0,0, k-mer checks on (k = 9, by position).
 
 A "step" is one full qluster collapse of one sample per GPU: dedupe -> k-mer index -> three
-runFullClustering passes (k-mer prefilter table, affine-gap alignment + traceback, errorProfile,
+runFullClustering passes (k-mer table, screen pass / affine-gap alignment + traceback, errorProfile,
 par-file verdicts on the GPU; the sequential merge/consensus logic on the host, in C++).
 
   value : input reads / s, timed with CUDA events on the library's stream from the moment the
           sample's unique reads are resident in HBM (sdq_stats.msResident)
-  e2e   : input reads / s through the C-ABI call with host buffers (sdq_run wall time: dedupe,
-          uploads, pair lists H2D, verdict masks / gap lists D2H all inside)
+  e2e   : input reads / s through the C-ABI call with host buffers (sdq_run wall time: dedupe, uploads,
+          index lists H2D, hit records / gap lists D2H, and the final clusters -- consensus sequences,
+          qualities, counts, membership -- fetched, all inside)
   gcups : DP cell updates / s (second half of BASELINE.json's metric) over the same step
 Multi-GPU: samples shard over ranks with no data-path collective (one sample per GPU per step,
 weak scaling); only the timings are reduced (MAX) for reporting.
+
+`--workload c5` runs BASELINE configs[4] instead (384 samples x 50k reads x 250 bp sharded over the ranks,
+several worker contexts per GPU through sdq_run_many); `--impl reference` times the CPU restatement of the
+reference (the oracle port; the SeekDeep binary cannot be built here) on a bounded sample of the C2 generator.
 """
 import argparse
 import json
@@ -32,12 +37,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OPS_PER_CELL = 13  # algorithmic INT32 ops of one 3-state affine cell update
-CPU_SAMPLE_READS = int(os.environ.get("SD_BENCH_CPU_READS", 600))  # reads of the bounded CPU sample (tests shrink it)
-# DRAM bytes per evaluated cell of the dominant kernel (alignBandKernel): its only bulk traffic is the
-# decision-bit slab, 128 B per 6 anti-diagonals x 32 lanes = 12.8 KB for the ~19.2 k band cells of a 300 x 300
-# pair; the ncu --set full capture profiles/r1m_band_kernel_ncu_full.csv shows 3.37 GB written + 0.04 GB read
-# for a launch whose slabs total 3.4 GB (the full-matrix strip kernel measured 1.40 B/cell, profiles/r1b_*)
-TRAFFIC_BYTES_PER_CELL = 0.67
+# The CPU arms run the oracle on samples of the SAME generator shrunk to this many reads (the 200k-read sample
+# would take hours per core); the GPU arm runs the identical small samples too (`same_input`).
+CPU_SAMPLE_READS = int(os.environ.get("SD_BENCH_CPU_READS", 200))
+CPU_SAMPLE_SEED0 = 5000
+# DRAM read + write bytes per launch of the dominant kernel (screenDpKernel<8>), from the committed
+# `ncu --set full` capture profiles/r2_screen_dp_kernel_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum of
+# one launch of the bench at full size); None until a capture exists.  The kernel writes no traceback bits: its
+# algorithmic HBM bytes are the two sequences and the 16-byte work item of each pair.
+DP_KERNEL_DRAM_BYTES_PER_LAUNCH = None
+DP_KERNEL_DRAM_SOURCE = "profiles/r2_screen_dp_kernel_ncu_full.csv"
 
 
 def make_sample(seed, nReads):
@@ -46,14 +55,27 @@ def make_sample(seed, nReads):
     return synth.pack(seqs, quals)
 
 
+def make_c5_sample(seed, nReads=50_000):
+    """One sample of BASELINE configs[4]: the C1 generator (20 haplotypes x 250 bp, 0.5 % substitutions) at 50k reads."""
+    from seekdeep_b200 import synth
+    rng = np.random.default_rng(seed)
+    haps = synth.make_haplotypes(rng, 20, 250, 1, 6)
+    seqs, quals, _ = synth.fast_reads(rng, haps, nReads, 0.005)
+    return synth.pack(seqs, quals)
+
+
 def workload_config(nReads):
+    """Identical in both arms.  `reference_arm_sample` says what the CPU arm can afford of this workload."""
     return {"workload": f"SeekDeep qluster single sample, {nReads} reads x 300 bp from 200 haplotypes at 1% error with "
                         "homopolymer indels, Illumina par table (illumina_lkmer1, 22 iterations x 3 passes) — BASELINE configs[1]",
             "reads_per_sample": nReads, "samples_per_gpu_per_step": 1, "stopCheck": 100, "gap": "5,1 left 5,1 right 0,0",
             "qualThres": "25,20", "kLength": 9,
             "per_rank_sample": "identical copy of the seed-2 sample on every rank (fixed per-GPU work)",
-            "l2": "no flush: a step streams 107 MB of sequences plus 330 MB of pair lists and verdict masks through ~70 "
-                  "alignment launches and rewrites the 60 MB of per-warp decision-bit slabs in each, far beyond the 126 MB L2"}
+            "reference_arm_sample": f"the CPU arm (--impl reference, cpu_baseline) runs the same generator shrunk to {CPU_SAMPLE_READS} reads "
+                                    "per sample, one single-threaded qluster per host core; the GPU arm reports the identical small samples "
+                                    "under same_input",
+            "l2": "no flush: a step streams 107 MB of sequences and flags through ~60 grid launches whose pair lists (20.8 M pairs) "
+                  "are generated on the device; inputs are far larger than the 126 MB L2"}
 
 
 class ClockSampler(threading.Thread):
@@ -84,35 +106,43 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_qluster(seed):
+def cpu_qluster(seed, want_result=False):
     """One single-threaded oracle qluster (the CPU restatement of the reference) on a bounded sample."""
     import seekdeep_b200 as sd
     from seekdeep_b200.iterpars import CollapseIterations
     from tests import oracle_binding
-    from tests.test_gpu_qluster import oracle_opts
     o = oracle_binding.load()
     bases, quals, offsets = make_sample(seed, CPU_SAMPLE_READS)
     its = CollapseIterations.gen_illumina_default_pars(100).iters
     t0 = time.perf_counter()
-    r = o.qluster(sd.make_params(), oracle_opts(sd.QlusterPars()), its, its, bases, quals, offsets)
+    r = o.qluster(sd.make_params(), sd.QlusterPars().to_c(), its, its, bases, quals, offsets)
     dt = time.perf_counter() - t0
+    if want_result:
+        return dt, CPU_SAMPLE_READS, r["nCells"], r
     return dt, CPU_SAMPLE_READS, r["nCells"]
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path.  The SeekDeep binary
-    cannot be built here (njhseq un-vendored), so this is the oracle port, parallelised exactly
-    like the reference: one single-threaded qluster per sample, as many concurrent samples as
-    host cores (runMultipleCommands --numThreads, SeekDeepUtilsRunner.cpp:294-356)."""
+    """--impl reference: the reference's CPU implementation of the path.  The SeekDeep binary cannot be built here
+    (njhseq un-vendored), so this is the oracle port, parallelised exactly like the reference: one single-threaded
+    qluster per sample, as many concurrent samples as host cores (runMultipleCommands --numThreads,
+    SeekDeepUtilsRunner.cpp:294-356).  Each step = one bounded sample per core (a few seconds)."""
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     times = []
     with mp.get_context("fork").Pool(cores) as pool:
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(cpu_qluster, [5000 + step * cores + c for c in range(cores)])
+            res = pool.map(cpu_qluster, [CPU_SAMPLE_SEED0 + (step * cores + c) % 64 for c in range(cores)])
             dt = time.perf_counter() - t0
             if step >= args.warmup:
                 times.append((dt, sum(r[1] for r in res), sum(r[2] for r in res)))
@@ -125,10 +155,38 @@ def run_reference(args, rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "gcups": cells / tot / 1e9,
             "config": workload_config(args.reads),
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port",
-                             "sample": f"per step: {cores} concurrent single-threaded oracle qlusters, each on a {CPU_SAMPLE_READS}-read "
-                                       "sample of the same generator (the full 200k-read sample would take hours per core)"},
+                             "sample": f"per step: {cores} concurrent single-threaded oracle qlusters (one per host core), each on a "
+                                       f"{CPU_SAMPLE_READS}-read sample of the C2 generator (seeds {CPU_SAMPLE_SEED0}+); NOT the 200k-read sample, "
+                                       "which would take hours per core"},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def same_input_block(sd, local):
+    """The reference arm's own small samples on the GPU (like-for-like input): reads/s through sdq_run_many with
+    host buffers, and the clusters of the first samples checked against the oracle's in this very run."""
+    from seekdeep_b200.qluster import qluster_many
+    n = 16
+    samples = [make_sample(CPU_SAMPLE_SEED0 + c, CPU_SAMPLE_READS) for c in range(n)]
+    qluster_many(sd.make_params(), samples[:4], device=local, nWorkers=4, want_clusters=False)  # contexts warm
+    t0 = time.perf_counter()
+    rs = qluster_many(sd.make_params(), samples, device=local, nWorkers=4, want_clusters=False)
+    dt = time.perf_counter() - t0
+    checked, cpu_s = 0, 0.0
+    for c in range(2):
+        cdt, _, _, want = cpu_qluster(CPU_SAMPLE_SEED0 + c, want_result=True)
+        cpu_s += cdt
+        got = rs[c]
+        wseq = "".join(s for s, _, _ in want["clusters"])
+        ok = (np.array_equal(got["membership"], want["membership"]) and got["packed"]["bases"].tobytes().decode() == wseq and
+              np.array_equal(got["packed"]["cnts"], np.array([x for _, _, x in want["clusters"]])))
+        if not ok:
+            raise RuntimeError(f"same_input: GPU clusters of sample {c} differ from the oracle's")
+        checked += 1
+    return {"samples": n, "reads_per_sample": CPU_SAMPLE_READS, "value": n * CPU_SAMPLE_READS / dt, "unit": "reads/s", "workers": 4,
+            "ms": dt * 1e3, "oracle_checked_samples": checked, "oracle_reads_per_s_one_core": checked * CPU_SAMPLE_READS / cpu_s,
+            "note": "identical inputs to --impl reference's samples; such small samples are launch- and host-bound on a GPU "
+                    "(59 launches per sample), the number is what the reference arm's ratio can honestly be compared with"}
 
 
 def kmer_roofline(al, bases, quals, offsets, peaks):
@@ -145,11 +203,10 @@ def kmer_roofline(al, bases, quals, offsets, peaks):
     algo = float(lens.sum() + len(lens) * (16 + 1024 * 2))  # codes + offsets in, uint16[4^5] profile out, per read
     gbs = algo / (best * 1e-3) / 1e9
     peak = peaks.get("hbm_gbs", 6650.0)
-    out = {"bound": "hbm", "kernel": "kmerProfileKernel(k=5)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+    out = {"bound": "hbm", "kernel": "kmerProfileKernel4(k=5)", "achieved": gbs, "peak": peak, "unit": "GB/s",
            "frac": gbs / peak, "traffic": None, "ms": best, "algorithmic_bytes": algo,
            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
     # reads x clusters compareKmers grid (every read vs the 100 first sequences), device-resident
-    import ctypes as C
     nR, nC = len(lens), min(100, len(lens))
     dR, dC = al.dev_alloc(nR * 4), al.dev_alloc(nC * 4)
     dS, dF = al.dev_alloc(nR * nC * 4), al.dev_alloc(nR * nC * 8)
@@ -163,7 +220,7 @@ def kmer_roofline(al, bases, quals, offsets, peaks):
     for p in (dR, dC, dS, dF):
         al.dev_free(p)
     algoc = float((nR + nC) * 1024 * 2 + nR * nC * 12)  # (R + C) * P + R * C * 12 B
-    out["compare"] = {"kernel": "kmerCompareKernel(reads x 100 clusters)", "ms": bestc, "pairs_per_s": nR * nC / (bestc * 1e-3),
+    out["compare"] = {"kernel": "kmerCompareGridKernel(reads x 100 clusters)", "ms": bestc, "pairs_per_s": nR * nC / (bestc * 1e-3),
                       "achieved": algoc / (bestc * 1e-3) / 1e9, "unit": "GB/s", "frac": algoc / (bestc * 1e-3) / 1e9 / peak,
                       "algorithmic_bytes": algoc,
                       "note": "cluster tile in shared memory, each read profile fetched from HBM once: HBM traffic is the compulsory "
@@ -172,7 +229,7 @@ def kmer_roofline(al, bases, quals, offsets, peaks):
 
 
 def bind_cpus(local, world):
-    """One rank per GPU: keep each rank's host threads (collapse loop, mask filer, prep workers) on its own
+    """One rank per GPU: keep each rank's host threads (collapse loop, prep / consensus workers) on its own
     slice of the cores NVML reports as local to its GPU, so ranks do not migrate across NUMA nodes or pile
     onto the same cores."""
     try:
@@ -194,14 +251,72 @@ def bind_cpus(local, world):
         print(f"[bench] cpu binding skipped: {e}", file=sys.stderr)
 
 
+def run_c5(args, rank, world, local, torch, dist, sd):
+    """BASELINE configs[4]: 384 samples x 50k reads x 250 bp, sharded over the ranks by sample (static round-robin,
+    SeekDeepUtilsRunner.cpp:294-356 / setUpTarAmpAnalysis.cpp:998-1001), several worker contexts per GPU."""
+    from seekdeep_b200.qluster import qluster_many, shard_samples
+    nSamples = int(os.environ.get("SD_BENCH_C5_SAMPLES", 384))
+    distinct = [make_c5_sample(500 + s) for s in range(4)]  # four seeded samples, replicated (generating 384 takes minutes)
+    mine = [distinct[s % len(distinct)] for s in shard_samples(nSamples, rank, world)]
+    workers = max(1, min(8, host_cores()))
+    params = sd.make_params()
+    reads_mine = sum(len(s[2]) - 1 for s in mine)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        qluster_many(params, mine[:max(workers, 1)], device=local, nWorkers=workers, want_clusters=False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    wall = 0.0
+    cells = launches = 0
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        rs = qluster_many(params, mine, device=local, nWorkers=workers, want_clusters=False)
+        torch.cuda.synchronize()
+        wall += time.perf_counter() - t0
+        cells += sum(r["stats"]["cellUpdates"] for r in rs)
+        launches += sum(r["stats"]["gpuBatches"] for r in rs)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([wall * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(reads_mine), float(cells), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        K = args.steps
+        ms = t.item()
+        v = tot[0].item() * K / (ms * 1e-3)
+        line = {"metric": "qluster_reads_per_s", "value": v, "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": f"Scaling sweep: {nSamples}-sample batch, 50k reads x 250 bp each (C1 generator), qluster — BASELINE configs[4]",
+                           "samples": nSamples, "reads_per_sample": 50000, "worker_contexts_per_gpu": workers,
+                           "distinct_samples": len(distinct), "timing": "host wall clock around sdq_run_many (many concurrent contexts per GPU: "
+                                                                        "no single stream to put CUDA events on), max over ranks",
+                           "l2": "inputs of one step (hundreds of MB per rank) exceed L2"},
+                "gcups": tot[1].item() / (ms * 1e-3) / 1e9,
+                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                        "note": "value IS end to end here: host buffers in, clusters out"},
+                "gpu_launches": int(tot[2].item()), "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sdgpu")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
     ap.add_argument("--reads", type=int, default=int(os.environ.get("SD_BENCH_READS", 200000)), help="reads per sample")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU legs (cpu_baseline, same_input's oracle check)")
     ap.add_argument("--no-multi", action="store_true", help="skip the many-samples-per-GPU throughput measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -219,6 +334,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         bind_cpus(local, world)
+    if args.workload == "c5":
+        run_c5(args, rank, world, local, torch, dist, sd)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # one sample per GPU per step, sharded by sample; every rank gets its own copy of the SAME sample so that
     # per-GPU work is exactly fixed as N grows (weak scaling) and the step time is not set by whichever rank drew
     # the heaviest random sample
@@ -241,13 +361,14 @@ def main():
     sampler.start()
     wall = resident_ms = 0.0
     stats = None
+    d2h_result = 0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        res = sd.qluster(al, bases, quals, offsets, want_clusters=False)
+        res = sd.qluster(al, bases, quals, offsets, want_clusters=False)  # (packed clusters + membership are fetched)
         wall += time.perf_counter() - t0
         stats = res["stats"]
         resident_ms += stats["msResident"]
-        d2h_result = int(res["membership"].nbytes)
+        d2h_result = int(res["membership"].nbytes + sum(a.nbytes for a in res["packed"].values()))
     barrier()
     sampler.stop_flag = True
     sampler.join()
@@ -267,52 +388,57 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        rates = [al.measure_int32_peak(k) for k in range(4)]
-        int32_peak = max(rates)
+        rates = [al.measure_int32_peak(k) for k in range(6)]
+        names = ["add", "max", "fused add-max", "max3", "max+imad (two pipes)", "add-max+imad (two pipes)"]
+        int32_peak = max(rates)  # the best rate of any mix, single-pipe or two-pipe
         peak_gcups = int32_peak / OPS_PER_CELL / 1e9
-        # roofline numerator = cell updates the kernels really evaluated (band cells of the banded first pass,
-        # whole matrices of the pairs redone in full); the GCUPS metric (sum of lenA x lenB over aligned
-        # pairs / kernel time) is reported beside it as "effective"
-        kernel_gcups = prof["evaluatedCells"] / (prof["alignKernelMs"] * 1e-3) / 1e9
+        K = args.steps
+        # dominant kernel: the score-only banded DP of the screen pass (screenDpKernel<2|4|8>)
+        dp_ms = prof["screenKernelMs"] - prof["screenScanMs"]
+        dp_gcups = prof["screenCells"] / max(1e-9, dp_ms * 1e-3) / 1e9
+        # all alignment kernels together: cells really evaluated (screen bands, banded pass, full matrices) per kernel second;
+        # the BASELINE GCUPS metric (sum of lenA x lenB over aligned pairs / kernel time) is "effective"
+        all_gcups = prof["evaluatedCells"] / (prof["alignKernelMs"] * 1e-3) / 1e9
         effective_gcups = prof["cellUpdates"] / (prof["alignKernelMs"] * 1e-3) / 1e9
         full_ms = prof["alignKernelMs"] - prof["bandKernelMs"] - prof["screenKernelMs"]
         full_cells = prof["evaluatedCells"] - prof["bandCells"] - prof["screenCells"]
-        K = args.steps
         line = {
             "metric": "qluster_reads_per_s", "value": readsAll * K / (res_ms_max * 1e-3), "unit": "reads/s", "n_gpus": world,
             "steps": K, "warmup": args.warmup, "ms_per_step": res_ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": dict(workload_config(nReads), unique_seqs=stats["uniqueSeqs"], final_clusters=stats["finalClusters"],
-                           pairs_computed_per_step=stats["pairsComputed"], consensus_aligns_per_step=stats["consensusAligns"],
-                           chimera_probes_per_step=stats["chimeraPairs"], chimeric_clusters=stats["chimericClusters"]),
+            "config": dict(workload_config(nReads)),
+            "run": {"unique_seqs": stats["uniqueSeqs"], "final_clusters": stats["finalClusters"],
+                    "pairs_computed_per_step": stats["pairsComputed"], "passing_pairs_per_step": stats["passingPairs"],
+                    "consensus_aligns_per_step": stats["consensusAligns"], "chimera_probes_per_step": stats["chimeraPairs"],
+                    "chimeric_clusters": stats["chimericClusters"]},
             "gcups": cellsAll / (res_ms_max * 1e-3) / 1e9,
             "e2e": {"value": readsAll * K / (wall_ms_max * 1e-3), "unit": "reads/s",
                     "h2d_bytes_per_step": int(prof["h2dBytes"] // K), "d2h_bytes_per_step": int(prof["d2hBytes"] // K) + d2h_result,
-                    "gcups": cellsAll / (wall_ms_max * 1e-3) / 1e9, "ms_per_step": wall_ms_max / K},
+                    "gcups": cellsAll / (wall_ms_max * 1e-3) / 1e9, "ms_per_step": wall_ms_max / K,
+                    "result_fetched": "membership + packed consensus sequences, qualities, counts (sdq_clusters_packed)"},
             "gpu_launches": int(prof["kernelLaunches"]),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "int32", "kernel": "alignBandKernel (+ alignProfileKernel redo)", "achieved": kernel_gcups, "peak": peak_gcups,
-                         "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
-                         # dram read+write bytes per launch: bytes per evaluated cell (see TRAFFIC_BYTES_PER_CELL) x cells per launch
-                         "traffic": TRAFFIC_BYTES_PER_CELL * prof["evaluatedCells"] / max(1, prof["alignKernelLaunches"]),
-                         "effective_gcups": effective_gcups,
-                         "banded_pass": {"share_of_pair_cells_certified": prof["bandCertifiedCells"] / max(1, prof["cellUpdates"]),
-                                         "evaluated_over_effective_cells": prof["evaluatedCells"] / max(1, prof["cellUpdates"]),
-                                         "band_kernel_ms_per_step": prof["bandKernelMs"] / K,
-                                         "band_kernel_gcups": prof["bandCells"] / max(1e-9, prof["bandKernelMs"] * 1e-3) / 1e9,
-                                         "full_kernel_ms_per_step": full_ms / K,
-                                         "full_kernel_gcups": full_cells / max(1e-9, full_ms * 1e-3) / 1e9},
-                         "screen_pass": {"pairs_per_step": prof["screenPairs"] / K, "share_of_pairs_finished": prof["screenCertified"] / max(1, prof["screenPairs"]),
-                                         "kernel_ms_per_step": prof["screenKernelMs"] / K,
-                                         "gcups": prof["screenCells"] / max(1e-9, prof["screenKernelMs"] * 1e-3) / 1e9,
-                                         "cells_per_step": prof["screenCells"] / K},
-                         "algorithmic_hbm_bytes_per_cell": 0.67,
-                         "launches": int(prof["alignKernelLaunches"]), "avg_launch_ms": prof["alignKernelMs"] / max(1, prof["alignKernelLaunches"]),
-                         "kernel_share_of_step": prof["alignKernelMs"] / resident_ms,
-                         "peak_source": f"measured on this GPU in this run: {int32_peak / 1e12:.2f} T INT32 thread-instr/s "
-                                        f"(add / max / fused add-max / max3 = {', '.join(f'{r / 1e12:.2f}' for r in rates)}) / "
-                                        f"{OPS_PER_CELL} algorithmic ops per cell update",
-                         "single_alu_pipe_peak_gcups": rates[2] / OPS_PER_CELL / 1e9},
+            "roofline": {"bound": "int32", "kernel": "screenDpKernel<2|4|8> (score-only banded DP of the screen pass)",
+                         "achieved": dp_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": dp_gcups / peak_gcups,
+                         "traffic": DP_KERNEL_DRAM_BYTES_PER_LAUNCH, "traffic_source": DP_KERNEL_DRAM_SOURCE,
+                         "ops_per_cell": OPS_PER_CELL, "kernel_ms_per_step": dp_ms / K, "cells_per_step": prof["screenCells"] / K,
+                         "kernel_share_of_step": dp_ms / resident_ms,
+                         "peak_source": f"measured on this GPU in this run: best of six INT32 microbenchmarks = {int32_peak / 1e12:.2f} T thread-instr/s ("
+                                        + ", ".join(f"{n} {r / 1e12:.2f}" for n, r in zip(names, rates)) + f") / {OPS_PER_CELL} algorithmic ops per cell update",
+                         "single_alu_pipe_peak_gcups": rates[2] / OPS_PER_CELL / 1e9,
+                         "all_alignment_kernels": {
+                             "achieved": all_gcups, "frac": all_gcups / peak_gcups, "effective_gcups": effective_gcups,
+                             "kernel_ms_per_step": prof["alignKernelMs"] / K, "kernel_share_of_step": prof["alignKernelMs"] / resident_ms,
+                             "launches": int(prof["alignKernelLaunches"]),
+                             "evaluated_over_effective_cells": prof["evaluatedCells"] / max(1, prof["cellUpdates"]),
+                             "screen_pass": {"pairs_per_step": prof["screenPairs"] / K,
+                                             "share_of_pairs_finished": prof["screenCertified"] / max(1, prof["screenPairs"]),
+                                             "scan_kernel_ms_per_step": prof["screenScanMs"] / K, "dp_kernel_ms_per_step": dp_ms / K},
+                             "banded_pass": {"share_of_pair_cells_certified": prof["bandCertifiedCells"] / max(1, prof["cellUpdates"]),
+                                             "band_kernel_ms_per_step": prof["bandKernelMs"] / K,
+                                             "band_kernel_gcups": prof["bandCells"] / max(1e-9, prof["bandKernelMs"] * 1e-3) / 1e9},
+                             "full_matrix": {"kernel_ms_per_step": full_ms / K,
+                                             "gcups": full_cells / max(1e-9, full_ms * 1e-3) / 1e9}}},
         }
         try:
             line["roofline_kmer"] = kmer_roofline(al, bases, quals, offsets, peaks)
@@ -332,10 +458,14 @@ def main():
                                         "note": "wall time of one sdq_run_many call, worker contexts created inside it"}
             except Exception as e:
                 line["multi_sample"] = {"error": str(e)}
-        if not args.no_cpu:
-            dt, n, c = cpu_qluster(2)
+        if world == 1 and not args.no_cpu:
+            dt, n, c = cpu_qluster(CPU_SAMPLE_SEED0)
             line["cpu_baseline"] = {"value": n / dt, "unit": "reads/s", "cores": 1, "kind": "port", "gcups": c / dt / 1e9,
                                     "sample": f"one single-threaded oracle qluster on a {n}-read sample of the same generator ({dt:.1f} s)"}
+            try:
+                line["same_input"] = same_input_block(sd, local)
+            except Exception as e:
+                line["same_input"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
     al.close()
     if world > 1:

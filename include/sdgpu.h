@@ -328,12 +328,15 @@ typedef struct sdgpu_profile {
   uint64_t screenCertified;    /* ... of which it finished (gapless alignment proved to be the unique optimum) */
   uint64_t screenCells;        /* DP cells the score-only pass evaluated (included in evaluatedCells) */
   uint64_t screenCertCells;    /* sum of lenA x lenB over the pairs the screen finished (included in cellUpdates) */
+  double screenScanMs;         /* part of screenKernelMs spent in the scan kernel (the rest is the score-only DP) */
 } sdgpu_profile;
 int sdgpu_profile_enable(sdgpu_ctx* ctx, int on);
 int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset);
 
-/* Roofline denominator for the alignment kernel: measured thread-level INT32 instructions per
- * second of one kind (0 add, 1 max(+sub), 2 fused add-max VIADDMNMX, 3 max3(+sub)) on this GPU. */
+/* Roofline denominator for the alignment kernels: measured thread-level INT32 instructions per second on this
+ * GPU, of one kind (0 add, 1 max(+sub), 2 fused add-max VIADDMNMX, 3 max3(+sub)) or of a two-pipe mix with both
+ * instructions counted (4: max on the ALU pipe + multiply-add on the FMA pipe, 5: fused add-max + multiply-add --
+ * the mix the DP kernels issue). */
 int sdgpu_measure_int32_peak(sdgpu_ctx* ctx, int which, double* instrPerSec);
 
 #ifdef __cplusplus

@@ -261,7 +261,8 @@ class GpuAligner:
                         ("cellUpdates", C.c_uint64), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
                         ("evaluatedCells", C.c_uint64), ("bandCells", C.c_uint64), ("bandCertifiedCells", C.c_uint64),
                         ("bandKernelMs", C.c_double), ("screenKernelMs", C.c_double), ("screenPairs", C.c_uint64),
-                        ("screenCertified", C.c_uint64), ("screenCells", C.c_uint64), ("screenCertCells", C.c_uint64)]
+                        ("screenCertified", C.c_uint64), ("screenCells", C.c_uint64), ("screenCertCells", C.c_uint64),
+                        ("screenScanMs", C.c_double)]
         p = Prof()
         self._check(self._lib.sdgpu_profile_read(self._ctx, C.byref(p), int(reset)))
         return {k: getattr(p, k) for k, _ in Prof._fields_}

@@ -10,9 +10,31 @@ namespace {
 constexpr int ILP = 8;
 constexpr int ITERS = 4096;
 
-// which: 0 = add (IADD3/VIADD), 1 = max (VIMNMX), 2 = fused add+max (VIADDMNMX), 3 = max3 (VIMNMX3)
+// which: 0 = add (IADD3/VIADD), 1 = max (VIMNMX), 2 = fused add+max (VIADDMNMX), 3 = max3 (VIMNMX3),
+//        4 = max (ALU pipe) interleaved 1:1 with a multiply-add (IMAD, FMA pipe), both counted,
+//        5 = fused add+max (ALU pipe) interleaved 1:1 with IMAD, both counted: the instruction mix of the DP kernels
 template <int WHICH>
 __global__ void __launch_bounds__(256) int32PeakKernel(int* out, int a, int b) {
+  if (WHICH >= 4) {
+    int x[ILP], y[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) x[k] = threadIdx.x + k, y[k] = threadIdx.x - k;
+    int m = (b & 1) | 1;  // a multiplier the compiler cannot see through: the multiply-adds stay IMADs
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+      for (int k = 0; k < ILP; ++k) {
+        if (WHICH == 4) x[k] = max(x[k], b);
+        if (WHICH == 5) x[k] = __viaddmax_s32(x[k], a, b);
+        asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[k]) : "r"(m), "r"(a));
+      }
+      b ^= it;
+    }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) s += x[k] ^ y[k];
+    if (s == 0x7fffffff) out[0] = s;
+    return;
+  }
   int x[ILP];
 #pragma unroll
   for (int k = 0; k < ILP; ++k) x[k] = threadIdx.x + k;
@@ -35,7 +57,7 @@ __global__ void __launch_bounds__(256) int32PeakKernel(int* out, int a, int b) {
 }  // namespace
 
 extern "C" int sdgpu_measure_int32_peak(sdgpu_ctx* ctx, int which, double* instrPerSec) {
-  if (!ctx || !instrPerSec || which < 0 || which > 3) return SDGPU_E_ARG;
+  if (!ctx || !instrPerSec || which < 0 || which > 5) return SDGPU_E_ARG;
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc = sd_ensure_stage(ctx, 256);
   if (rc) return rc;
@@ -48,6 +70,8 @@ extern "C" int sdgpu_measure_int32_peak(sdgpu_ctx* ctx, int which, double* instr
     if (which == 1) int32PeakKernel<1><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
     if (which == 2) int32PeakKernel<2><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
     if (which == 3) int32PeakKernel<3><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
+    if (which == 4) int32PeakKernel<4><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
+    if (which == 5) int32PeakKernel<5><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
     SD_CUDA(ctx, cudaGetLastError());
     SD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     SD_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
@@ -55,8 +79,9 @@ extern "C" int sdgpu_measure_int32_peak(sdgpu_ctx* ctx, int which, double* instr
     SD_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (rep > 0 && ms < best) best = ms;
   }
-  // thread-level instructions of the measured kind (WHICH 1 and 3 also issue one subtract each)
-  const double n = double(grid) * block * double(ITERS) * ILP;
+  // thread-level instructions of the measured kind (WHICH 1 and 3 also issue one subtract each, not counted;
+  // WHICH 4 and 5 count both instructions of each pair)
+  const double n = double(grid) * block * double(ITERS) * ILP * (which >= 4 ? 2.0 : 1.0);
   *instrPerSec = n / (double(best) * 1e-3);
   return SDGPU_OK;
 }

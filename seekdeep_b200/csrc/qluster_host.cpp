@@ -608,22 +608,40 @@ class Runner {
     std::vector<uint32_t> changed;
     enum : uint8_t { OUT_SAME = 0, OUT_UPLOAD = 1, OUT_KEPT = 2, OUT_BAD_SYMBOL = 3 };
     std::vector<uint8_t> outcome(jobs.size(), OUT_SAME);
-    parallelForDynamic(jobs.size(), [&](size_t jx) {
-      const Job& j = jobs[jx];
+    // (a) counting: members are independent and the sums are integers, so a cluster's new members are cut into
+    //     chunks that any thread may take; ungapped members (the rule) are tallied in thread-local columns and
+    //     added to the cluster's counters under its lock, gapped ones go through the lock directly
+    struct Chunk {
+      uint32_t job;
+      size_t m0, m1;
+    };
+    std::vector<Chunk> chunks;
+    for (uint32_t jx = 0; jx < jobs.size(); ++jx) {
+      const size_t mEnd = cs[jobs[jx].clus].members.size();
+      for (size_t m = jobs[jx].firstMember; m < mEnd; m += 512) chunks.push_back(Chunk{jx, m, std::min(mEnd, m + 512)});
+    }
+    std::vector<std::mutex> jobMu(jobs.size());
+    std::vector<uint8_t> jobBad(jobs.size(), 0);
+    parallelForDynamic(chunks.size(), [&](size_t cx) {
+      const Chunk& ch = chunks[cx];
+      const Job& j = jobs[ch.job];
       std::string ga, gb;
       std::vector<uint8_t> gq;
+      std::vector<Col> local;
       bool symOk = true;
       Clus& cl = cs[j.clus];
       ConsState& S = *cl.cons;
       const std::string& base = S.baseSeq;
-      for (size_t m = j.firstMember; m < cl.members.size(); ++m) {
+      for (size_t m = ch.m0; m < ch.m1; ++m) {
         const Uniq& r = uniq[cl.members[m]];
         const uint32_t w = uint32_t(std::llround(r.cnt));
         const std::vector<sdgpu_gap>& gl = gaps[j.firstPair + (m - j.firstMember)];
         if (gl.empty() && r.seq.size() == base.size()) {  // ungapped: column i is base position i
-          for (uint32_t i = 0; i < base.size(); ++i) symOk &= add(S.counters[i], r.seq[i], r.qual[i], w);
+          if (local.empty()) local.assign(base.size(), Col());
+          for (uint32_t i = 0; i < base.size(); ++i) symOk &= add(local[i], r.seq[i], r.qual[i], w);
           continue;
         }
+        std::lock_guard<std::mutex> lk(jobMu[ch.job]);
         ga = base;
         gb = r.seq;
         gq = r.qual;
@@ -653,6 +671,22 @@ class Runner {
           symOk &= add(S.counters[i - offSet], gb[i], gq[i], w);
         }
       }
+      if (!local.empty()) {
+        std::lock_guard<std::mutex> lk(jobMu[ch.job]);
+        for (size_t i = 0; i < local.size(); ++i)
+          for (int x = 0; x < NSYM; ++x) {
+            S.counters[i].cnt[x] += local[i].cnt[x];
+            S.counters[i].qual[x] += local[i].qual[x];
+          }
+      }
+      if (!symOk) jobBad[ch.job] = 1;
+    }, 8);
+    // (b) the new consensus of every cluster, clusters side by side
+    parallelForDynamic(jobs.size(), [&](size_t jx) {
+      const Job& j = jobs[jx];
+      const bool symOk = !jobBad[jx];
+      Clus& cl = cs[j.clus];
+      ConsState& S = *cl.cons;
       S.nDone = cl.members.size();
       if (!symOk) {
         outcome[jx] = OUT_BAD_SYMBOL;

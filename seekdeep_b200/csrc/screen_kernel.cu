@@ -452,7 +452,7 @@ int sd_launch_screen(sdgpu_ctx* ctx, SdScreenArgs& args) {
   };
   int rc = timed(2, [&] { screenScanKernel<<<grid, 128, 0, ctx->stream>>>(args); });
   if (rc || !args.screenOn) return rc;
-  if ((rc = timed(2, [&] { screenDpKernel<2><<<grid, 128, 0, ctx->stream>>>(args, 0); }))) return rc;
-  if ((rc = timed(2, [&] { screenDpKernel<4><<<grid, 128, 0, ctx->stream>>>(args, 1); }))) return rc;
-  return timed(2, [&] { screenDpKernel<8><<<grid, 128, 0, ctx->stream>>>(args, 2); });
+  if ((rc = timed(3, [&] { screenDpKernel<2><<<grid, 128, 0, ctx->stream>>>(args, 0); }))) return rc;
+  if ((rc = timed(3, [&] { screenDpKernel<4><<<grid, 128, 0, ctx->stream>>>(args, 1); }))) return rc;
+  return timed(3, [&] { screenDpKernel<8><<<grid, 128, 0, ctx->stream>>>(args, 2); });
 }

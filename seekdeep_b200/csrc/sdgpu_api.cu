@@ -769,7 +769,8 @@ int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset) {
     SD_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evPool[x], ctx->evPool[x + 1]));
     ctx->alignMs += ms;
     if (ctx->evBand[x / 2] == 1) ctx->bandMs += ms;
-    if (ctx->evBand[x / 2] == 2) ctx->screenMs += ms;
+    if (ctx->evBand[x / 2] >= 2) ctx->screenMs += ms;
+    if (ctx->evBand[x / 2] == 2) ctx->screenScanMs += ms;
   }
   ctx->evUsed = 0;
   uint64_t cells = 0, band[2] = {0, 0}, scr[2] = {0, 0};
@@ -787,6 +788,7 @@ int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset) {
   out->screenCertified = uint64_t(scrCert) - ctx->screenCert;  // (a 32-bit device counter: read before it wraps)
   out->screenPairs = ctx->screenPairs;
   out->screenKernelMs = ctx->screenMs;
+  out->screenScanMs = ctx->screenScanMs;
   out->evaluatedCells = (cells - ctx->cells) - out->bandCertifiedCells - out->screenCertCells + out->bandCells + out->screenCells;
   out->alignKernelMs = ctx->alignMs;
   out->bandKernelMs = ctx->bandMs;
@@ -808,6 +810,7 @@ int sdgpu_profile_read(sdgpu_ctx* ctx, sdgpu_profile* out, int reset) {
     ctx->screenCert = scrCert;
     ctx->screenPairs = 0;
     ctx->screenMs = 0;
+    ctx->screenScanMs = 0;
     ctx->h2dBytes = ctx->d2hBytes = 0;
   }
   return SDGPU_OK;

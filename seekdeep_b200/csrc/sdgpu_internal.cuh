@@ -195,7 +195,7 @@ struct sdgpu_ctx {
   int screenMode = 0;
   SdScreenItem* dScreenItems = nullptr;
   uint64_t screenItemsCap = 0;  // pairs per list
-  double screenMs = 0;
+  double screenMs = 0, screenScanMs = 0;
   uint64_t screenPairs = 0;
   uint64_t screenCells = 0, screenCertCells = 0, screenCert = 0;  // read-back baselines for profile_read
   // sdgpu_align_pass_grid: device copies of the two index lists, two zero-copy hit slots, the result vector

@@ -125,8 +125,8 @@ int main(void) {
     assert c["sdq_stats"] == C.sizeof(Q.StatsC)
     for f in ("chimeraPairs", "secondsGpu", "msResident"):
         assert c["sdq_stats." + f] == getattr(Q.StatsC, f).offset, f
-    # sdgpu_profile is mirrored inside GpuAligner.profile_read: 15 x 8 bytes
-    assert c["sdgpu_profile"] == 120 and c["sdgpu_profile.evaluatedCells"] == 48 and c["sdgpu_profile.bandKernelMs"] == 72
+    # sdgpu_profile is mirrored inside GpuAligner.profile_read: 16 x 8 bytes
+    assert c["sdgpu_profile"] == 128 and c["sdgpu_profile.evaluatedCells"] == 48 and c["sdgpu_profile.bandKernelMs"] == 72
     assert c["sdgpu_profile.screenCertCells"] == 112
     assert c["sdgpu_grid_hit"] == _abi.GRID_HIT_DTYPE.itemsize and c["sdgpu_grid_hit.mask"] == _abi.GRID_HIT_DTYPE.fields["mask"][1]
     assert c["sdq_stats.passingPairs"] == Q.StatsC.passingPairs.offset
