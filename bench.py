@@ -43,9 +43,9 @@ CPU_SAMPLE_READS = int(os.environ.get("SD_BENCH_CPU_READS", 200))
 CPU_SAMPLE_SEED0 = 5000
 # DRAM read + write bytes per launch of the dominant kernel (screenDpKernel<8>), from the committed
 # `ncu --set full` capture profiles/r2_screen_dp_kernel_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum of
-# one launch of the bench at full size); None until a capture exists.  The kernel writes no traceback bits: its
+# one launch of the bench at full size).  The kernel writes no traceback bits: its
 # algorithmic HBM bytes are the two sequences and the 16-byte work item of each pair.
-DP_KERNEL_DRAM_BYTES_PER_LAUNCH = None
+DP_KERNEL_DRAM_BYTES_PER_LAUNCH = 22_322_944  # 22.32 MB read + 768 B written, one screenDpKernel<8> launch of 6.53 ms (~640 k pairs)
 DP_KERNEL_DRAM_SOURCE = "profiles/r2_screen_dp_kernel_ncu_full.csv"
 
 

@@ -14,20 +14,20 @@ constexpr int ITERS = 4096;
 //        4 = max (ALU pipe) interleaved 1:1 with a multiply-add (IMAD, FMA pipe), both counted,
 //        5 = fused add+max (ALU pipe) interleaved 1:1 with IMAD, both counted: the instruction mix of the DP kernels
 template <int WHICH>
-__global__ void __launch_bounds__(256) int32PeakKernel(int* out, int a, int b) {
+__global__ void __launch_bounds__(256) int32PeakKernel(int* out, int a, int b, int m) {
   if (WHICH >= 4) {
+    // each chain alternates the two instruction kinds (x feeds y, y feeds x), so neither the maxima nor the
+    // multiply-adds of consecutive iterations can be merged; m is a run-time 1 the compiler cannot see
     int x[ILP], y[ILP];
 #pragma unroll
     for (int k = 0; k < ILP; ++k) x[k] = threadIdx.x + k, y[k] = threadIdx.x - k;
-    int m = (b & 1) | 1;  // a multiplier the compiler cannot see through: the multiply-adds stay IMADs
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
       for (int k = 0; k < ILP; ++k) {
-        if (WHICH == 4) x[k] = max(x[k], b);
-        if (WHICH == 5) x[k] = __viaddmax_s32(x[k], a, b);
-        asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(y[k]) : "r"(m), "r"(a));
+        if (WHICH == 4) x[k] = max(x[k], y[k]);
+        if (WHICH == 5) x[k] = __viaddmax_s32(x[k], a, y[k]);
+        y[k] = y[k] * m + x[k];
       }
-      b ^= it;
     }
     int s = 0;
 #pragma unroll
@@ -66,12 +66,12 @@ extern "C" int sdgpu_measure_int32_peak(sdgpu_ctx* ctx, int which, double* instr
   for (int rep = 0; rep < 4; ++rep) {
     SD_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     int* o = reinterpret_cast<int*>(ctx->dStage);
-    if (which == 0) int32PeakKernel<0><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
-    if (which == 1) int32PeakKernel<1><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
-    if (which == 2) int32PeakKernel<2><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
-    if (which == 3) int32PeakKernel<3><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
-    if (which == 4) int32PeakKernel<4><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
-    if (which == 5) int32PeakKernel<5><<<grid, block, 0, ctx->stream>>>(o, 3, 5);
+    if (which == 0) int32PeakKernel<0><<<grid, block, 0, ctx->stream>>>(o, 3, 5, ctx->numSMs > 0 ? 1 : 0);
+    if (which == 1) int32PeakKernel<1><<<grid, block, 0, ctx->stream>>>(o, 3, 5, ctx->numSMs > 0 ? 1 : 0);
+    if (which == 2) int32PeakKernel<2><<<grid, block, 0, ctx->stream>>>(o, 3, 5, ctx->numSMs > 0 ? 1 : 0);
+    if (which == 3) int32PeakKernel<3><<<grid, block, 0, ctx->stream>>>(o, 3, 5, ctx->numSMs > 0 ? 1 : 0);
+    if (which == 4) int32PeakKernel<4><<<grid, block, 0, ctx->stream>>>(o, 3, 5, ctx->numSMs > 0 ? 1 : 0);
+    if (which == 5) int32PeakKernel<5><<<grid, block, 0, ctx->stream>>>(o, 3, 5, ctx->numSMs > 0 ? 1 : 0);
     SD_CUDA(ctx, cudaGetLastError());
     SD_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     SD_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
