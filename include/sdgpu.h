@@ -174,9 +174,14 @@ int sdgpu_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers /* n*kLen ASCII
 /* Replaces: kmerInfo(seq, kLen, false) for every stored sequence (extractorPairedEnd.cpp:819,
  * PrimersAndMids.cpp:49-54).  Builds dense 4^kLen count profiles on the device (kLen <= 8). */
 int sdgpu_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen);
-/* Replaces: a.compareKmers(b) -> std::pair<uint32_t,double> (extractorPairedEnd.cpp:820-824)
- * for nPairs (a[i], b[i]) index pairs into the store. */
-int sdgpu_kmer_compare(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs,
+/* Replaces: a.compareKmers(b) -> std::pair<uint32_t,double> and, with revCompB != 0,
+ * a.compareKmersRevComp(b) where b = kmerInfo(seq, kLen, true) (extractorPairedEnd.cpp:819-824: the k-mers of a
+ * against the k-mers of b's reverse complement) for nPairs (a[i], b[i]) index pairs into the store.  shared is a
+ * uint32 count and frac the exact double shared / (min(lenA, lenB) - kLen + 1): both identical to the reference's,
+ * not merely within the 1e-6 bar.  The reverse-complement profiles are derived from the forward ones on first
+ * use; an alphabet holding a character without an IUPAC complement in the same alphabet is refused
+ * (SDGPU_E_ALPHABET). */
+int sdgpu_kmer_compare(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, int revCompB,
                        uint32_t* sharedOut, double* fracOut);
 /* All-pairs form used by the qluster prefilter: every read in reads[] against every cluster
  * in clusters[]; outputs are row-major [nReads][nClusters]. */

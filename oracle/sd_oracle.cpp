@@ -863,6 +863,24 @@ int sdo_kmer_compare(const uint8_t* a, uint32_t lenA, const uint8_t* b, uint32_t
   return SDGPU_OK;
 }
 
+// kmerInfo(seq, kLen, true) + refInfo.compareKmersRevComp(info) (extractorPairedEnd.cpp:819-824): the k-mers of `a`
+// against the k-mers of the reverse complement of `b` (njhseq seqUtil::reverseComplement, IUPAC complements).
+static char complementBase(char c) {
+  switch (c) {
+    case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; case 'N': return 'N';
+    case 'R': return 'Y'; case 'Y': return 'R'; case 'S': return 'S'; case 'W': return 'W'; case 'K': return 'M';
+    case 'M': return 'K'; case 'B': return 'V'; case 'V': return 'B'; case 'D': return 'H'; case 'H': return 'D';
+    case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c'; case 'n': return 'n';
+    default: return c;
+  }
+}
+int sdo_kmer_compare_revcomp(const uint8_t* a, uint32_t lenA, const uint8_t* b, uint32_t lenB, uint32_t kLen,
+                             uint32_t* sharedOut, double* fracOut) {
+  std::vector<uint8_t> rc(lenB);
+  for (uint32_t i = 0; i < lenB; ++i) rc[i] = uint8_t(complementBase(char(b[lenB - 1 - i])));
+  return sdo_kmer_compare(a, lenA, rc.data(), lenB, kLen, sharedOut, fracOut);
+}
+
 // qluster body, following clusterDown.cpp:230-563 (dedupe -> quality rep -> sort -> indexKmers
 // -> singlet split -> runFullClustering x3 -> final sort).
 sdo_qluster_result* sdo_qluster(const sdgpu_params* p, const sdo_qluster_opts* o, const sdo_iter_par* initPars,

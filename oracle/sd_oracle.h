@@ -57,6 +57,10 @@ uint32_t sdo_kmaps_count(const sdo_kmaps* k, const uint8_t* kmer, uint32_t pos);
 int sdo_kmer_compare(const uint8_t* a, uint32_t lenA, const uint8_t* b, uint32_t lenB,
                      uint32_t kLen, uint32_t* sharedOut, double* fracOut);
 
+/* kmerInfo(b, kLen, true) + a.compareKmersRevComp(b) (extractorPairedEnd.cpp:819-824) */
+int sdo_kmer_compare_revcomp(const uint8_t* a, uint32_t lenA, const uint8_t* b, uint32_t lenB,
+                             uint32_t kLen, uint32_t* sharedOut, double* fracOut);
+
 /* ---- qluster (clusterDown.cpp:205-563 call sequence) ---- */
 typedef struct sdo_iter_par { /* one par-file line, etc/SeekDeepParameterFiles/illumina_lkmer1 */
   uint32_t stopCheck;

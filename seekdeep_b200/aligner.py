@@ -118,13 +118,14 @@ class GpuAligner:
         """≙ kmerInfo(seq, kLen, false) for every stored sequence."""
         self._check(self._lib.sdgpu_build_kmer_profiles(self._ctx, kLen))
 
-    def compare_kmers(self, a, b):
-        """≙ [seq[a[i]].compareKmers(seq[b[i]]) for i] -> (shared u32[n], frac f64[n])."""
+    def compare_kmers(self, a, b, revCompB=False):
+        """≙ [seq[a[i]].compareKmers(seq[b[i]]) for i] -> (shared u32[n], frac f64[n]); revCompB:
+        compareKmersRevComp (a's k-mers against the k-mers of b's reverse complement)."""
         a = np.ascontiguousarray(a, np.uint32)
         b = np.ascontiguousarray(b, np.uint32)
         shared = np.zeros(len(a), np.uint32)
         frac = np.zeros(len(a), np.float64)
-        self._check(self._lib.sdgpu_kmer_compare(self._ctx, _ptr(a), _ptr(b), len(a), _ptr(shared), _ptr(frac)))
+        self._check(self._lib.sdgpu_kmer_compare(self._ctx, _ptr(a), _ptr(b), len(a), int(revCompB), _ptr(shared), _ptr(frac)))
         return shared, frac
 
     def compare_kmers_all(self, reads, clusters):

@@ -252,7 +252,20 @@ __device__ __forceinline__ uint32_t minSum8(const uint4& p, const uint4& q, uint
 }
 
 // One warp per pair.  pairs given explicitly (a[], b[]) or as a dense reads x clusters grid.
-__global__ void kmerCompareKernel(DevSeqs seqs, const uint16_t* profiles, uint32_t profSize, uint32_t kLen,
+// kmerInfo(seq, k, true): the reverse-complement map of every sequence = its forward profile permuted by
+// k-mer -> reverse-complement k-mer.  One warp per sequence.
+__global__ void kmerProfileRevKernel(const uint16_t* fwd, const uint32_t* rcIndex, uint32_t size, uint32_t profSize, uint32_t nSeqs,
+                                     uint16_t* rev) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= nSeqs) return;
+  const uint16_t* f = fwd + size_t(warp) * profSize;
+  uint16_t* r = rev + size_t(warp) * profSize;
+  for (uint32_t x = lane; x < size; x += 32) r[rcIndex[x]] = f[x];
+  for (uint32_t x = size + lane; x < profSize; x += 32) r[x] = 0;
+}
+
+__global__ void kmerCompareKernel(DevSeqs seqs, const uint16_t* profiles, const uint16_t* profilesB, uint32_t profSize, uint32_t kLen,
                                   const uint32_t* a, const uint32_t* b, uint64_t nPairs, uint32_t nCols,
                                   uint32_t* sharedOut, double* fracOut) {
   const uint64_t warp0 = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -269,7 +282,7 @@ __global__ void kmerCompareKernel(DevSeqs seqs, const uint16_t* profiles, uint32
       ib = b[p];
     }
     const uint4* pa = reinterpret_cast<const uint4*>(profiles + size_t(ia) * profSize);
-    const uint4* pb = reinterpret_cast<const uint4*>(profiles + size_t(ib) * profSize);
+    const uint4* pb = reinterpret_cast<const uint4*>(profilesB + size_t(ib) * profSize);
     uint32_t acc = 0;
     for (uint32_t x = lane; x < vecs; x += 32) acc = minSum8(__ldg(pa + x), __ldg(pb + x), acc);
     uint32_t sum = (acc & 0xffffu) + (acc >> 16);
@@ -458,6 +471,7 @@ int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   ctx->profK = kLen;
   ctx->profSize = profSize;
   ctx->profSeqs = nSeqs;
+  ctx->profRevValid = false;
   if (nSeqs == 0) return SDGPU_OK;
   const uint64_t need = uint64_t(nSeqs) * profSize * 2;
   if (need > ctx->profCapBytes) {  // keep the buffer across rebuilds: cudaMalloc/cudaFree stall the stream
@@ -570,9 +584,72 @@ static int gridLaunch(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nReads, c
   return SDGPU_OK;
 }
 
+// IUPAC complement of a base character (njhseq seqUtil::reverseComplement); 0 = none
+static uint8_t complementChar(uint8_t c) {
+  switch (c) {
+    case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; case 'N': return 'N';
+    case 'R': return 'Y'; case 'Y': return 'R'; case 'S': return 'S'; case 'W': return 'W'; case 'K': return 'M';
+    case 'M': return 'K'; case 'B': return 'V'; case 'V': return 'B'; case 'D': return 'H'; case 'H': return 'D';
+    case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c'; case 'n': return 'n';
+    default: return 0;
+  }
+}
+
+// Reverse-complement profiles of every profiled sequence, derived from the forward ones (once per profile build).
+static int ensureRevProfiles(sdgpu_ctx* ctx) {
+  if (ctx->profRevValid) return SDGPU_OK;
+  const uint32_t sigma = uint32_t(ctx->usedSym < 4 ? 4 : ctx->usedSym), k = ctx->profK;
+  uint32_t comp[SDGPU_MAX_SYMBOLS];
+  for (uint32_t c = 0; c < sigma; ++c) {
+    const uint8_t cc = complementChar(ctx->charOf[c]);
+    const int code = cc ? ctx->codeOf[cc] : -1;
+    if (code < 0 || uint32_t(code) >= sigma)
+      return sd_fail(ctx, SDGPU_E_ALPHABET, "reverse complement: a stored character has no complement inside the store's alphabet");
+    comp[c] = uint32_t(code);
+  }
+  uint64_t size = 1;
+  for (uint32_t x = 0; x < k; ++x) size *= sigma;
+  std::vector<uint32_t> rc(size);
+  for (uint64_t id = 0; id < size; ++id) {  // id = base-sigma digits, first base most significant
+    uint64_t v = id, out = 0;
+    for (uint32_t x = 0; x < k; ++x) {
+      out = out * sigma + comp[v % sigma];  // last base first, complemented
+      v /= sigma;
+    }
+    rc[id] = uint32_t(out);
+  }
+  if (size > ctx->rcIndexCap) {
+    if (ctx->dRcIndex) cudaFree(ctx->dRcIndex);
+    ctx->dRcIndex = nullptr;
+    ctx->rcIndexCap = 0;
+    SD_CUDA(ctx, cudaMalloc(&ctx->dRcIndex, size * 4));
+    ctx->rcIndexCap = uint32_t(size);
+  }
+  const uint64_t need = uint64_t(ctx->profSeqs) * ctx->profSize * 2;
+  if (need > ctx->profRevCapBytes) {
+    if (ctx->dProfilesRev) cudaFree(ctx->dProfilesRev);
+    ctx->dProfilesRev = nullptr;
+    ctx->profRevCapBytes = 0;
+    SD_CUDA(ctx, cudaMalloc(&ctx->dProfilesRev, need));
+    ctx->profRevCapBytes = need;
+  }
+  SD_CUDA(ctx, cudaMemcpyAsync(ctx->dRcIndex, rc.data(), size * 4, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // rc is a local
+  kmerProfileRevKernel<<<(ctx->profSeqs + 3) / 4, 128, 0, ctx->stream>>>(ctx->dProfiles, ctx->dRcIndex, uint32_t(size), ctx->profSize,
+                                                                       ctx->profSeqs, ctx->dProfilesRev);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  ctx->profRevValid = true;
+  return SDGPU_OK;
+}
+
 static int compareLaunch(sdgpu_ctx* ctx, const uint32_t* dA, const uint32_t* dB, uint64_t nPairs, uint32_t nCols,
-                         uint32_t* dShared, double* dFrac) {
-  if (nCols) {  // dense grid: use the tiled kernel when a profile splits evenly over the lanes
+                         uint32_t* dShared, double* dFrac, int revCompB = 0) {
+  if (revCompB) {
+    int rc = ensureRevProfiles(ctx);
+    if (rc) return rc;
+  }
+  if (nCols && !revCompB) {  // dense grid: use the tiled kernel when a profile splits evenly over the lanes
     const uint32_t vecs = ctx->profSize / 8, nReads = uint32_t(nPairs / nCols);
     if (vecs % 32 == 0 && size_t(ctx->profSize) * 2 <= (200u << 10)) {
       switch (vecs / 32) {
@@ -588,8 +665,8 @@ static int compareLaunch(sdgpu_ctx* ctx, const uint32_t* dA, const uint32_t* dB,
   uint64_t ctas = (nPairs + 3) / 4;
   const uint64_t maxGrid = uint64_t(ctx->numSMs) * 16;
   if (ctas > maxGrid) ctas = maxGrid;
-  kmerCompareKernel<<<uint32_t(ctas), 128, 0, ctx->stream>>>(sd_dev_seqs(ctx), ctx->dProfiles, ctx->profSize, ctx->profK, dA,
-                                                            dB, nPairs, nCols, dShared, dFrac);
+  kmerCompareKernel<<<uint32_t(ctas), 128, 0, ctx->stream>>>(sd_dev_seqs(ctx), ctx->dProfiles, revCompB ? ctx->dProfilesRev : ctx->dProfiles,
+                                                            ctx->profSize, ctx->profK, dA, dB, nPairs, nCols, dShared, dFrac);
   SD_CUDA(ctx, cudaGetLastError());
   ++ctx->launches;
   return SDGPU_OK;
@@ -603,8 +680,8 @@ int sd_kmer_compare_all_dev(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nRe
   return compareLaunch(ctx, dReads, dClusters, nPairs, nClusters, dShared, dFrac);
 }
 
-int sd_kmer_compare_pairs(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, uint32_t* sharedOut,
-                          double* fracOut) {
+int sd_kmer_compare_pairs(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, int revCompB,
+                          uint32_t* sharedOut, double* fracOut) {
   if (!ctx->dProfiles) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_build_kmer_profiles has not been called");
   if (nPairs == 0) return SDGPU_OK;
   for (uint32_t x = 0; x < nPairs; ++x)
@@ -618,7 +695,7 @@ int sd_kmer_compare_pairs(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, 
   uint32_t* dShared = dB + nPairs;
   SD_CUDA(ctx, cudaMemcpyAsync(dA, a, size_t(nPairs) * 4, cudaMemcpyHostToDevice, ctx->stream));
   SD_CUDA(ctx, cudaMemcpyAsync(dB, b, size_t(nPairs) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  rc = compareLaunch(ctx, dA, dB, nPairs, 0, dShared, dFrac);
+  rc = compareLaunch(ctx, dA, dB, nPairs, 0, dShared, dFrac, revCompB);
   if (rc) return rc;
   SD_CUDA(ctx, cudaMemcpyAsync(sharedOut, dShared, size_t(nPairs) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   SD_CUDA(ctx, cudaMemcpyAsync(fracOut, dFrac, size_t(nPairs) * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -187,6 +187,8 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   cudaFree(ctx->dIdxKeys);
   cudaFree(ctx->dIdxCnts);
   cudaFree(ctx->dProfiles);
+  cudaFree(ctx->dProfilesRev);
+  cudaFree(ctx->dRcIndex);
   cudaFree(ctx->dScratch);
   cudaFree(ctx->dWork);
   cudaFree(ctx->dRedo);
@@ -449,11 +451,11 @@ int sdgpu_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   return sd_build_kmer_profiles(ctx, kLen);
 }
 
-int sdgpu_kmer_compare(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, uint32_t* sharedOut,
-                       double* fracOut) {
+int sdgpu_kmer_compare(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, int revCompB,
+                       uint32_t* sharedOut, double* fracOut) {
   if (!ctx || (nPairs && (!a || !b || !sharedOut || !fracOut))) return SDGPU_E_ARG;
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
-  return sd_kmer_compare_pairs(ctx, a, b, nPairs, sharedOut, fracOut);
+  return sd_kmer_compare_pairs(ctx, a, b, nPairs, revCompB, sharedOut, fracOut);
 }
 
 int sdgpu_kmer_compare_all_dev(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nReads, const uint32_t* dClusters,

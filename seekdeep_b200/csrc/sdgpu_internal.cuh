@@ -151,6 +151,11 @@ struct sdgpu_ctx {
   uint16_t* dProfiles = nullptr;
   uint32_t profK = 0, profSize = 0, profSeqs = 0;
   uint64_t profCapBytes = 0;
+  uint16_t* dProfilesRev = nullptr;  // kmerInfo(seq, k, true)'s reverse-complement maps, derived on first use
+  uint64_t profRevCapBytes = 0;
+  bool profRevValid = false;
+  uint32_t* dRcIndex = nullptr;      // k-mer id -> id of its reverse complement
+  uint32_t rcIndexCap = 0;
   // scratch for the alignment kernel (pointer slabs), pair staging, work counter
   uint8_t* dScratch = nullptr;
   uint64_t scratchBytes = 0;
@@ -320,7 +325,7 @@ int sd_refresh_kmer_flags(sdgpu_ctx* ctx, uint32_t firstSeq, uint32_t nSeqs);
 int sd_kmer_index_lookup(sdgpu_ctx* ctx, const uint8_t* kmers, const uint32_t* positions, uint32_t n,
                          uint32_t* countsOut);
 int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen);
-int sd_kmer_compare_pairs(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs,
+int sd_kmer_compare_pairs(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, int revCompB,
                           uint32_t* sharedOut, double* fracOut);
 int sd_kmer_compare_all_dev(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nReads, const uint32_t* dClusters,
                             uint32_t nClusters, uint32_t* dShared, double* dFrac);

@@ -48,6 +48,8 @@ class Oracle:
         lib.sdo_kmaps_count.argtypes = [v, v, C.c_uint32]
         lib.sdo_kmer_compare.restype = C.c_int
         lib.sdo_kmer_compare.argtypes = [v, C.c_uint32, v, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+        lib.sdo_kmer_compare_revcomp.restype = C.c_int
+        lib.sdo_kmer_compare_revcomp.argtypes = lib.sdo_kmer_compare.argtypes
         lib.sdo_qluster.restype = v
         lib.sdo_qluster.argtypes = [C.POINTER(_abi.Params), C.POINTER(QlusterOptsC), v, C.c_uint32, v, C.c_uint32, v, v, v, C.c_uint32]
         lib.sdo_qluster_free.argtypes = [v]
@@ -137,11 +139,11 @@ class Oracle:
         kmer = kmer.encode() if isinstance(kmer, str) else bytes(kmer)
         return self.lib.sdo_kmaps_count(k, kmer, pos)
 
-    def kmer_compare(self, a, b, k):
+    def kmer_compare(self, a, b, k, revCompB=False):
         a = a.encode() if isinstance(a, str) else bytes(a)
         b = b.encode() if isinstance(b, str) else bytes(b)
         s, f = C.c_uint32(), C.c_double()
-        self.lib.sdo_kmer_compare(a, len(a), b, len(b), k, C.byref(s), C.byref(f))
+        (self.lib.sdo_kmer_compare_revcomp if revCompB else self.lib.sdo_kmer_compare)(a, len(a), b, len(b), k, C.byref(s), C.byref(f))
         return s.value, f.value
 
     def qluster(self, params, opts, initPars, pars, bases, quals, offsets):

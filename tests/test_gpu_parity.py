@@ -135,6 +135,39 @@ def test_kmer_compare_matches_oracle(oracle):
                     assert sh[i, j] == ws and fr[i, j] == wf
 
 
+def test_kmer_compare_revcomp_matches_oracle(oracle):
+    """kmerInfo(seq, k, true) + compareKmersRevComp (extractorPairedEnd.cpp:819-824): a's k-mers against the k-mers of
+    b's reverse complement, identical to the oracle (uint32 count, bit-identical double) for A,C,G,T stores, stores
+    with N and IUPAC codes; the forward comparison is untouched; a character without a complement is refused."""
+    rng = np.random.default_rng(31)
+    comp = bytes.maketrans(b"ACGTNRYKM", b"TGCANYRMK")
+    for alphabet, ks in ((b"ACGT", (3, 5, 7)), (b"ACGTN", (4,)), (b"ACGTNRYKM", (3,))):
+        al_ = np.frombuffer(alphabet, np.uint8)
+        seqs = [H.rand_seq(rng, int(n), al_) for n in rng.integers(30, 260, 50)]
+        # mates: reverse complements of mutated copies, so that the rev-comp comparison has something to find
+        seqs += [np.frombuffer(H.mutate(rng, s, 2).tobytes().translate(comp)[::-1], np.uint8) for s in seqs[:30]]
+        b, q, off = pack_seqs([s.tobytes() for s in seqs], [np.zeros(len(s), np.uint8) for s in seqs])
+        a = np.concatenate([np.arange(30), rng.integers(0, len(seqs), 200)]).astype(np.uint32)
+        c = np.concatenate([np.arange(50, 80), rng.integers(0, len(seqs), 200)]).astype(np.uint32)
+        with GpuAligner(make_params()) as al:
+            al.upload_seqs(b, q, off)
+            for k in ks:
+                al.build_kmer_profiles(k)
+                fwd = al.compare_kmers(a, c)
+                rev = al.compare_kmers(a, c, revCompB=True)
+                for i in range(len(a)):
+                    ws, wf = oracle.kmer_compare(seqs[a[i]].tobytes(), seqs[c[i]].tobytes(), k)
+                    rs, rf = oracle.kmer_compare(seqs[a[i]].tobytes(), seqs[c[i]].tobytes(), k, revCompB=True)
+                    assert (fwd[0][i], fwd[1][i]) == (ws, wf) and (rev[0][i], rev[1][i]) == (rs, rf), (alphabet, k, i)
+                assert rev[1][:30].mean() > 0.5 > fwd[1][:30].mean()  # the mates only match in reverse complement
+    with GpuAligner(make_params()) as al:
+        al.upload_seqs(*pack_seqs(["ACGTXACGTT", "ACGTTACGTA"], [np.zeros(10, np.uint8)] * 2))
+        al.build_kmer_profiles(3)
+        with pytest.raises(SdgpuError) as ei:
+            al.compare_kmers([0], [1], revCompB=True)
+        assert ei.value.code == _abi.E_ALPHABET
+
+
 def test_append_and_errors():
     p = make_params()
     with GpuAligner(p) as al:

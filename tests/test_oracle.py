@@ -348,3 +348,12 @@ def test_frozen_qluster_fixtures_match_their_generators():
         kept = mem != np.uint32(0xFFFFFFFF)
         assert np.array_equal(np.bincount(mem[kept], minlength=len(fx["cnts"])).astype(np.float64), fx["cnts"])
         assert fx["offsets"][-1] == len(fx["seqs"]) == len(fx["quals"])
+
+
+def test_compare_kmers_revcomp_micro_cases(oracle):
+    """compareKmersRevComp(a, b) == compareKmers(a, reverseComplement(b)); hand-checked: AAAC vs GTTT."""
+    assert oracle.kmer_compare("AAAC", "GTTT", 2, revCompB=True) == (3, 1.0)   # revcomp(GTTT) = AAAC
+    assert oracle.kmer_compare("AAAC", "GTTT", 2) == (0, 0.0)
+    a, b = "ACGGTTACGATTACA", "TGTAATCGTAACCGT"                               # b = revcomp(a)
+    assert oracle.kmer_compare(a, b, 5, revCompB=True) == oracle.kmer_compare(a, a, 5) == (11, 1.0)
+    assert oracle.kmer_compare("ACGRT", "AYCGT", 3, revCompB=True) == oracle.kmer_compare("ACGRT", "ACGRT", 3)  # R <-> Y
