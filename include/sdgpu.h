@@ -152,6 +152,11 @@ int sdgpu_get_params(sdgpu_ctx* ctx, sdgpu_params* out);          /* e.g. readin
  * returns the index of the first appended sequence in *firstIndex. */
 int sdgpu_upload_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals,
                       const uint64_t* offsets, const double* cnts, uint32_t n);
+/* sdgpu_upload_seqs for sequences that are not packed: sequence s is the lens[s] bytes at seqPtrs[s] (qualities at
+ * qualPtrs[s]; qualPtrs may be NULL: all 0).  Saves the caller a packing pass -- the collapse loop's unique reads are
+ * views into the caller's FASTQ buffers (clusterDown.cpp:272-288 keeps one seqInfo per unique sequence). */
+int sdgpu_upload_seqs_gather(sdgpu_ctx* ctx, const uint8_t* const* seqPtrs, const uint8_t* const* qualPtrs,
+                             const uint32_t* lens, const double* cnts, uint32_t n);
 int sdgpu_append_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals,
                       const uint64_t* offsets, const double* cnts, uint32_t n,
                       uint32_t* firstIndex);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "sdgpu_set_params": (C.c_int, [_ctx, C.POINTER(Params)]),
     "sdgpu_get_params": (C.c_int, [_ctx, C.POINTER(Params)]),
     "sdgpu_upload_seqs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sdgpu_upload_seqs_gather": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_append_seqs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, _u32p]),
     "sdgpu_num_seqs": (C.c_int, [_ctx, _u32p]),
     "sdgpu_update_cnts": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32]),

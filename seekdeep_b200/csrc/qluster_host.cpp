@@ -164,11 +164,28 @@ static void parallelForDynamic(size_t n, Fn fn, size_t maxThreads = 4) {
   for (auto& x : th) x.join();
 }
 
+// A sequence or quality string that lives somewhere else: in the caller's read buffers (unique reads are views
+// of their first read), in the run's quality arena (per-base medians) or in a cluster's own consensus storage.
+struct View {
+  const uint8_t* p = nullptr;
+  uint32_t n = 0;
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  const uint8_t* data() const { return p; }
+  const uint8_t* begin() const { return p; }
+  const uint8_t* end() const { return p + n; }
+  uint8_t operator[](size_t i) const { return p[i]; }
+  bool equals(const void* q, size_t m) const { return m == n && (n == 0 || std::memcmp(p, q, n) == 0); }
+  int compare(const View& o) const {  // std::string::compare on the bytes
+    const int c = std::memcmp(p, o.p, std::min(n, o.n));
+    return c != 0 ? c : (n < o.n ? -1 : (n > o.n ? 1 : 0));
+  }
+};
+
 struct Uniq {  // one exact-unique input sequence; its store index is its position in `uniq`
-  std::string seq;
-  std::vector<uint8_t> qual;
+  View seq, qual;
   double cnt = 0;
-  std::vector<uint32_t> inputIdx;
+  uint32_t inputBegin = 0, inputEnd = 0;  // its input reads: Runner::inputList[inputBegin, inputEnd), ascending
 };
 
 // njhseq charCounter restricted to what consensus building uses, over the few symbols that occur
@@ -206,8 +223,9 @@ struct alignas(64) Clus {
   bool remove = false, needCons = false;
   bool chimeric = false;   // seqBase_.markAsChimeric()
   Row row;                 // verdicts of this cluster *as the read* against larger clusters
-  std::string seq;
-  std::vector<uint8_t> qual;
+  View seq, qual;          // current consensus: its seed read until a consensus rebuild changes it, then own storage
+  std::string ownSeq;
+  std::vector<uint8_t> ownQual;
   std::vector<uint32_t> members;
   uint32_t chiParent[2] = {0, 0}, chiPos[2] = {0, 0};
   std::vector<uint8_t> devSig;  // checkQual outcome per base of the device version (empty: exact copy)
@@ -216,7 +234,8 @@ struct alignas(64) Clus {
 
 // seqInfo::checkQual for every base (strictly-greater thresholds, trailing window stops before
 // the last base) — the only way qualities enter profileAlignment.
-void qualSignature(const std::vector<uint8_t>& q, const sdgpu_params& P, std::vector<uint8_t>& sig) {
+template <class Q>
+void qualSignature(const Q& q, const sdgpu_params& P, std::vector<uint8_t>& sig) {
   const int len = int(q.size()), out = int(P.qualThresWindow);
   sig.assign(q.size(), 0);
   for (int pos = 0; pos < len; ++pos) {
@@ -237,18 +256,19 @@ struct ErrLut {
   }
 };
 
-double averageErrorRate(const std::vector<uint8_t>& q) {
+template <class Q>
+double averageErrorRate(const Q& q) {
   static const ErrLut lut;  // same pow() values, evaluated once
-  if (q.empty()) return 0;
+  if (q.size() == 0) return 0;
   double s = 0;
-  for (uint8_t x : q) s += lut.v[x];
+  for (size_t i = 0; i < q.size(); ++i) s += lut.v[q[i]];
   return s / double(q.size());
 }
 
 bool clusLess(const Clus& a, const Clus& b) {  // readVecSorter "totalCount"
   if (a.cnt != b.cnt) return a.cnt > b.cnt;
   if (a.avgErr != b.avgErr) return a.avgErr < b.avgErr;
-  if (a.seq != b.seq) return a.seq < b.seq;
+  if (const int c = a.seq.compare(b.seq)) return c < 0;
   return a.firstId < b.firstId;
 }
 
@@ -292,6 +312,8 @@ class Runner {
   const sdq_opts& O;
   sdgpu_params P;  // the ctx's scoring / quality parameters (for qualSignature)
   std::vector<Uniq> uniq;
+  std::vector<uint32_t> inputList;   // input read indices grouped by unique sequence
+  std::vector<uint8_t> qualArena;    // per-base median qualities of the unique sequences with several reads
   std::vector<sdq_iter_par> lines;  // distinct par-file lines == bits of a verdict mask
   sdq_stats st{};
   uint32_t storeSize = 0;
@@ -542,20 +564,20 @@ class Runner {
       }
       const double avgLen = totalLen / totalCnt;
       uint32_t baseStore = cl.storeIdx;
-      const std::string* baseSeq = &cl.seq;
+      View baseSeq = cl.seq;
       if (std::fabs(double(cl.seq.size()) - avgLen) > 0.1 * avgLen) {  // restart from the longest member
         size_t biggest = 0;
         for (uint32_t u : cl.members)
           if (uniq[u].seq.size() > biggest) {
             biggest = uniq[u].seq.size();
             baseStore = u;
-            baseSeq = &uniq[u].seq;
+            baseSeq = uniq[u].seq;
           }
       }
-      if (!cl.cons || cl.cons->baseSeq != *baseSeq) {  // new base: counters start over
+      if (!cl.cons || !baseSeq.equals(cl.cons->baseSeq.data(), cl.cons->baseSeq.size())) {  // new base: counters start over
         cl.cons.reset(new ConsState());
-        cl.cons->baseSeq = *baseSeq;
-        cl.cons->counters.assign(baseSeq->size(), Col());
+        cl.cons->baseSeq.assign(reinterpret_cast<const char*>(baseSeq.data()), baseSeq.size());
+        cl.cons->counters.assign(baseSeq.size(), Col());
       }
       cl.cons->baseStore = baseStore;
       Job j{ci, a.size(), cl.cons->nDone};
@@ -643,8 +665,8 @@ class Runner {
         }
         std::lock_guard<std::mutex> lk(jobMu[ch.job]);
         ga = base;
-        gb = r.seq;
-        gq = r.qual;
+        gb.assign(reinterpret_cast<const char*>(r.seq.data()), r.seq.size());
+        gq.assign(r.qual.begin(), r.qual.end());
         for (const sdgpu_gap& g : gl) {  // descending positions
           if (g.gapInA) {
             ga.insert(g.pos, g.size, '-');
@@ -725,8 +747,8 @@ class Runner {
         ns.push_back(bch);
         nq.push_back(uint8_t(q / tot));
       }
-      const bool seqChanged = ns != cl.seq;
-      if (seqChanged || nq != cl.qual) {
+      const bool seqChanged = !cl.seq.equals(ns.data(), ns.size());
+      if (seqChanged || !cl.qual.equals(nq.data(), nq.size())) {
         std::vector<uint8_t> newSig;
         qualSignature(nq, P, newSig);
         bool needUpload = seqChanged;
@@ -734,8 +756,10 @@ class Runner {
           if (cl.devSig.empty()) qualSignature(cl.qual, P, cl.devSig);
           needUpload = newSig != cl.devSig;
         }
-        cl.seq.swap(ns);
-        cl.qual.swap(nq);
+        cl.ownSeq.swap(ns);
+        cl.ownQual.swap(nq);
+        cl.seq = View{reinterpret_cast<const uint8_t*>(cl.ownSeq.data()), uint32_t(cl.ownSeq.size())};
+        cl.qual = View{cl.ownQual.data(), uint32_t(cl.ownQual.size())};
         if (needUpload) {
           outcome[jx] = OUT_UPLOAD;
           cl.devSig.swap(newSig);
@@ -1035,7 +1059,8 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     size_t cap = 1024;
     while (cap < size_t(n) * 2 + 16) cap <<= 1;
     std::vector<uint32_t> table(cap, UINT32_MAX);
-    std::vector<uint32_t> firstRead;  // unique -> its first read (the bytes are materialised afterwards, in parallel)
+    std::vector<uint32_t> firstRead;  // unique -> its first read
+    std::vector<uint32_t> uniqOfRead(n, UINT32_MAX);
     firstRead.reserve(n);
     R.uniq.reserve(n);
     for (uint32_t r = 0; r < n; ++r) {
@@ -1060,41 +1085,60 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
         firstRead.push_back(r);
         R.uniq.emplace_back();
       }
-      Uniq& u = R.uniq[found];
-      u.cnt += 1.0;
-      u.inputIdx.push_back(r);
+      R.uniq[found].cnt += 1.0;
+      uniqOfRead[r] = found;
     }
+    // the input reads of every unique sequence, ascending (a counting sort of the reads by unique id)
+    const uint32_t nUq = uint32_t(R.uniq.size());
+    uint32_t run = 0;
+    uint64_t arenaBytes = 0;
+    for (uint32_t u = 0; u < nUq; ++u) {
+      Uniq& q = R.uniq[u];
+      q.inputBegin = q.inputEnd = run;
+      run += uint32_t(q.cnt);
+      const uint32_t fr = firstRead[u];
+      q.seq = View{bases + offsets[fr], uint32_t(offsets[fr + 1] - offsets[fr])};
+      q.qual = View{quals + offsets[fr], q.seq.n};  // (several reads: replaced by the per-base median below)
+      if (q.cnt > 1.0) arenaBytes += q.seq.n;
+    }
+    R.inputList.resize(run);
+    for (uint32_t r = 0; r < n; ++r)
+      if (uniqOfRead[r] != UINT32_MAX) R.inputList[R.uniq[uniqOfRead[r]].inputEnd++] = r;
+    R.qualArena.resize(arenaBytes);
+    uint64_t at = 0;
+    for (uint32_t u = 0; u < nUq; ++u)
+      if (R.uniq[u].cnt > 1.0) {
+        R.uniq[u].qual = View{R.qualArena.data() + at, R.uniq[u].seq.n};
+        at += R.uniq[u].seq.n;
+      }
   }
   const double tDedupe = nowSec() - tStart;
-  // sequence bytes + per-base median quality over the members (clusterDown.cpp:293-359, qualRep "median")
-  // (abundant sequences come first and cost the most: blocks of 256 uniques are handed out dynamically)
+  // per-base median quality over the reads of a unique sequence (clusterDown.cpp:293-359, qualRep "median"); a
+  // sequence seen once keeps its read's qualities.  (abundant sequences come first and cost the most: blocks of 256
+  // uniques are handed out dynamically)
   parallelForDynamic((R.uniq.size() + 255) / 256, [&](size_t blk) {
     std::vector<uint8_t> col;
     std::vector<uint32_t> hist;
     const size_t lo = blk * 256, hi = std::min(R.uniq.size(), lo + 256);
     for (size_t x = lo; x < hi; ++x) {
       Uniq& u = R.uniq[x];
-      const uint32_t fr = u.inputIdx[0];
-      const size_t len = size_t(offsets[fr + 1] - offsets[fr]), k = u.inputIdx.size();
-      u.seq.assign(reinterpret_cast<const char*>(bases + offsets[fr]), len);
-      u.qual.resize(len);
-      if (k == 1) {
-        std::memcpy(u.qual.data(), quals + offsets[fr], len);
-        continue;
-      }
+      const size_t len = u.seq.size(), k = size_t(u.inputEnd - u.inputBegin);
+      if (k <= 1) continue;
+      const uint32_t* members = R.inputList.data() + u.inputBegin;
+      uint8_t* out = const_cast<uint8_t*>(u.qual.data());  // (its slice of the arena)
       if (k < 16) {
         col.resize(k);
         for (size_t i = 0; i < len; ++i) {
-          for (size_t m = 0; m < k; ++m) col[m] = quals[offsets[u.inputIdx[m]] + i];
+          for (size_t m = 0; m < k; ++m) col[m] = quals[offsets[members[m]] + i];
           std::sort(col.begin(), col.end());
-          u.qual[i] = (k % 2) ? col[k / 2] : uint8_t((uint32_t(col[k / 2 - 1]) + col[k / 2]) / 2);
+          out[i] = (k % 2) ? col[k / 2] : uint8_t((uint32_t(col[k / 2 - 1]) + col[k / 2]) / 2);
         }
         continue;
       }
       // many members: per-column histograms filled member by member (sequential reads), medians read off them
       hist.assign(len * 256, 0);
       for (size_t m = 0; m < k; ++m) {
-        const uint8_t* q = quals + offsets[u.inputIdx[m]];
+        const uint8_t* q = quals + offsets[members[m]];
         for (size_t i = 0; i < len; ++i) ++hist[i * 256 + q[i]];
       }
       const size_t r1 = (k % 2) ? k / 2 : k / 2 - 1, r2 = k / 2;  // order statistics (0-based) the median needs
@@ -1114,7 +1158,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
             break;
           }
         }
-        u.qual[i] = (k % 2) ? uint8_t(v1) : uint8_t((v1 + v2) / 2);
+        out[i] = (k % 2) ? uint8_t(v1) : uint8_t((v1 + v2) / 2);
       }
     }
   }, 8);
@@ -1127,22 +1171,18 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     return SDGPU_OK;
   }
   const double tMedian = nowSec() - tStart;
-  // the unique reads become sequence-store entries 0..nU-1
+  // the unique reads become sequence-store entries 0..nU-1, translated straight from where they lie
   {
-    std::vector<uint64_t> off(size_t(nU) + 1, 0);
+    std::vector<const uint8_t*> sp(nU), qp(nU);
+    std::vector<uint32_t> ln(nU);
     std::vector<double> cn(nU);
     for (uint32_t u = 0; u < nU; ++u) {
-      off[u + 1] = off[u] + R.uniq[u].seq.size();
+      sp[u] = R.uniq[u].seq.data();
+      qp[u] = R.uniq[u].qual.data();
+      ln[u] = R.uniq[u].seq.n;
       cn[u] = R.uniq[u].cnt;
     }
-    std::vector<uint8_t> b(off[nU]), q(off[nU]);
-    parallelFor(nU, [&](size_t lo, size_t hi) {
-      for (size_t u = lo; u < hi; ++u) {
-        std::memcpy(b.data() + off[u], R.uniq[u].seq.data(), R.uniq[u].seq.size());
-        std::memcpy(q.data() + off[u], R.uniq[u].qual.data(), R.uniq[u].qual.size());
-      }
-    });
-    if (sdgpu_upload_seqs(ctx, b.data(), q.data(), off.data(), cn.data(), nU)) return bail(R.fail(SDGPU_E_CUDA));
+    if (sdgpu_upload_seqs_gather(ctx, sp.data(), qp.data(), ln.data(), cn.data(), nU)) return bail(R.fail(SDGPU_E_CUDA));
     R.storeSize = nU;
     if (sdgpu_timer_start(ctx)) return bail(R.fail(SDGPU_E_CUDA));  // inputs are resident from here on
   }
@@ -1164,7 +1204,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     }
   });
   const double tPrep = nowSec() - tStart;
-  if (g_verboseTiming) fprintf(stderr, "[sdq]   prep: dedupe %.3f median %.3f pack+upload %.3f pool %.3f\n", tDedupe, tMedian - tDedupe, tUpload - tMedian, tPrep - tUpload);
+  if (g_verboseTiming) fprintf(stderr, "[sdq]   prep: dedupe %.3f median %.3f upload %.3f pool %.3f\n", tDedupe, tMedian - tDedupe, tUpload - tMedian, tPrep - tUpload);
   R.dropRemovedAndSort(clusters);     // clusterDown.cpp:389
   int rc = R.buildIndex(clusters);    // clusterDown.cpp:412-417
   if (rc) return bail(rc);
@@ -1188,7 +1228,17 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     clusters[c].row.clear();
     clusters[c].cons.reset();
     for (uint32_t u : clusters[c].members)
-      for (uint32_t r : R.uniq[u].inputIdx) res->membership[r] = c;
+      for (uint32_t x = R.uniq[u].inputBegin; x < R.uniq[u].inputEnd; ++x) res->membership[R.inputList[x]] = c;
+    // the result outlives the caller's read buffers and this run's quality arena: every final cluster owns its bytes
+    Clus& cl = clusters[c];
+    if (cl.seq.data() != reinterpret_cast<const uint8_t*>(cl.ownSeq.data())) {
+      cl.ownSeq.assign(reinterpret_cast<const char*>(cl.seq.data()), cl.seq.size());
+      cl.seq = View{reinterpret_cast<const uint8_t*>(cl.ownSeq.data()), uint32_t(cl.ownSeq.size())};
+    }
+    if (cl.qual.data() != cl.ownQual.data()) {
+      cl.ownQual.assign(cl.qual.begin(), cl.qual.end());
+      cl.qual = View{cl.ownQual.data(), uint32_t(cl.ownQual.size())};
+    }
   }
   if (opts->markChimeras && markChimeras(ctx, *opts, clusters, R.st)) return bail(R.fail(SDGPU_E_CUDA));  // :566-577
   uint64_t launches1 = 0, cells1 = 0;

@@ -1,5 +1,6 @@
 // sdgpu_api.cu — the C ABI declared in include/sdgpu.h: context, sequence store, dispatch.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cstring>
@@ -246,11 +247,22 @@ int sdgpu_get_params(sdgpu_ctx* ctx, sdgpu_params* out) {
   return SDGPU_OK;
 }
 
+// Where an upload's sequences come from: packed arrays (bases / quals / offsets) or one pointer per sequence.
+struct SeqSource {
+  const uint8_t* bases = nullptr;
+  const uint8_t* quals = nullptr;
+  const uint64_t* offsets = nullptr;       // packed form: n + 1 entries
+  const uint8_t* const* seqPtrs = nullptr;  // gathered form
+  const uint8_t* const* qualPtrs = nullptr;
+  const uint32_t* lens = nullptr;
+  const uint8_t* seq(uint32_t s) const { return seqPtrs ? seqPtrs[s] : bases + offsets[s]; }
+  const uint8_t* qual(uint32_t s) const { return seqPtrs ? (qualPtrs ? qualPtrs[s] : nullptr) : (quals ? quals + offsets[s] : nullptr); }
+};
+
 // `replace`: the new sequences become the whole store (sdgpu_upload_seqs).  Nothing of the ctx changes
 // before the batch has been validated: a rejected call leaves the previous store and alphabet as they were.
-static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
-                      const double* cnts, uint32_t n, uint32_t* firstIndex, bool replace) {
-  if (!ctx || (n && (!bases || !offsets))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+static int appendImpl(sdgpu_ctx* ctx, const SeqSource& src, const double* cnts, uint32_t n, uint32_t* firstIndex, bool replace) {
+  if (!ctx || (n && !(src.seqPtrs ? src.lens != nullptr : (src.bases && src.offsets)))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint32_t oldN = replace ? 0u : uint32_t(ctx->hOffsets.size() - 1);
   if (firstIndex) *firstIndex = oldN;
@@ -264,46 +276,66 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
     }
     return SDGPU_OK;
   }
-  if (offsets[0] != 0) return sd_fail(ctx, SDGPU_E_ARG, "offsets[0] must be 0");
+  if (!src.seqPtrs && src.offsets[0] != 0) return sd_fail(ctx, SDGPU_E_ARG, "offsets[0] must be 0");
   const uint64_t oldBases = replace ? 0ull : ctx->hOffsets.back();
-  const uint64_t addBases = offsets[n];
-  // alphabet + code translation on the host (one pass; the store is write-once, read-many)
-  int rc = sd_ensure_pinned(ctx, addBases * 2 + 64);
-  if (rc) return rc;
-  uint8_t* hCodes = reinterpret_cast<uint8_t*>(ctx->hPinned);
-  uint8_t* hQuals = hCodes + addBases;
+  // offsets of the new sequences inside the batch
+  std::vector<uint64_t> off(size_t(n) + 1, 0);
   bool newSym = false;
   uint32_t maxLen = replace ? 0u : ctx->maxLen;
   int usedSym = replace ? 0 : ctx->usedSym;
   for (uint32_t s = 0; s < n; ++s) {
-    if (offsets[s + 1] < offsets[s]) return sd_fail(ctx, SDGPU_E_ARG, "offsets must be non-decreasing");
-    const uint64_t len = offsets[s + 1] - offsets[s];
+    uint64_t len;
+    if (src.seqPtrs) {
+      if (!src.seqPtrs[s]) return sd_fail(ctx, SDGPU_E_ARG, "null sequence pointer");
+      len = src.lens[s];
+    } else {
+      if (src.offsets[s + 1] < src.offsets[s]) return sd_fail(ctx, SDGPU_E_ARG, "offsets must be non-decreasing");
+      len = src.offsets[s + 1] - src.offsets[s];
+    }
     if (len == 0) return sd_fail(ctx, SDGPU_E_ARG, "empty sequence");
     if (len > 0x7fffffffu) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "sequence too long");
     maxLen = std::max<uint32_t>(maxLen, uint32_t(len));
+    off[s + 1] = off[s] + len;
   }
+  const uint64_t addBases = off[n];
+  // alphabet + code translation on the host, straight into pinned staging (one pass; the store is write-once, read-many)
+  int rc = sd_ensure_pinned(ctx, addBases * 2 + 64);
+  if (rc) return rc;
+  uint8_t* hCodes = reinterpret_cast<uint8_t*>(ctx->hPinned);
+  uint8_t* hQuals = hCodes + addBases;
   // translate with the alphabet as it stands, a few threads side by side; only if a character without
   // a code turns up (first upload with degenerate bases) the sequential pass below assigns codes
   bool unknown = false;
   {
-    const unsigned hw = std::thread::hardware_concurrency();
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = unsigned(CPU_COUNT(&set));
     const uint64_t T = addBases < (1u << 20) ? 1 : std::min<uint64_t>(hw ? hw : 1, 8);
     std::vector<int> maxCode(T, -1);
     std::vector<uint8_t> sawUnknown(T, 0);
+    std::vector<uint32_t> cut(T + 1, n);  // thread t takes sequences [cut[t], cut[t + 1]): about the same number of bases each
+    cut[0] = 0;
+    for (uint64_t t = 1; t < T; ++t) cut[t] = uint32_t(std::lower_bound(off.begin(), off.end(), addBases * t / T) - off.begin());
     auto work = [&](uint64_t t) {
-      const uint64_t lo = addBases * t / T, hi = addBases * (t + 1) / T;
       int mc = -1;
       bool unk = false;
-      for (uint64_t x = lo; x < hi; ++x) {
-        const int code = ctx->codeOf[bases[x]];
-        unk |= code < 0;
-        mc = std::max(mc, code);
-        hCodes[x] = uint8_t(code);
-      }
-      if (quals) {
-        std::memcpy(hQuals + lo, quals + lo, hi - lo);
-      } else {
-        std::memset(hQuals + lo, 0, hi - lo);
+      for (uint32_t s = cut[t]; s < cut[t + 1]; ++s) {
+        const uint8_t* b = src.seq(s);
+        const uint8_t* q = src.qual(s);
+        const uint64_t len = off[s + 1] - off[s];
+        uint8_t* dst = hCodes + off[s];
+        for (uint64_t x = 0; x < len; ++x) {
+          const int code = ctx->codeOf[b[x]];
+          unk |= code < 0;
+          mc = std::max(mc, code);
+          dst[x] = uint8_t(code);
+        }
+        if (q) {
+          std::memcpy(hQuals + off[s], q, len);
+        } else {
+          std::memset(hQuals + off[s], 0, len);
+        }
       }
       maxCode[t] = mc;
       sawUnknown[t] = unk;
@@ -321,26 +353,31 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
     // which characters are new, and do they fit?  (checked before any of them gets a code)
     bool isNew[256] = {false};
     int nNew = 0;
-    for (uint64_t x = 0; x < addBases; ++x) {
-      const uint8_t ch = bases[x];
-      if (ctx->codeOf[ch] >= 0 || isNew[ch]) continue;
-      if (ch >= 128) return sd_fail(ctx, SDGPU_E_ALPHABET, "base outside 7-bit ASCII");
-      isNew[ch] = true;
-      if (ctx->nSym + ++nNew > SDGPU_MAX_SYMBOLS) return sd_fail(ctx, SDGPU_E_ALPHABET, "more than 16 distinct base characters");
-    }
-    for (uint64_t x = 0; x < addBases; ++x) {
-      const uint8_t ch = bases[x];
-      int code = ctx->codeOf[ch];
-      if (code < 0) {
+    for (uint32_t s = 0; s < n; ++s) {
+      const uint8_t* b = src.seq(s);
+      for (uint64_t x = 0, len = off[s + 1] - off[s]; x < len; ++x) {
+        const uint8_t ch = b[x];
+        if (ctx->codeOf[ch] >= 0 || isNew[ch]) continue;
         if (ch >= 128) return sd_fail(ctx, SDGPU_E_ALPHABET, "base outside 7-bit ASCII");
-        if (ctx->nSym >= SDGPU_MAX_SYMBOLS) return sd_fail(ctx, SDGPU_E_ALPHABET, "more than 16 distinct base characters");
-        code = ctx->nSym;
-        ctx->codeOf[ch] = int16_t(code);
-        ctx->charOf[ctx->nSym++] = ch;
-        newSym = true;
+        isNew[ch] = true;
+        if (ctx->nSym + ++nNew > SDGPU_MAX_SYMBOLS) return sd_fail(ctx, SDGPU_E_ALPHABET, "more than 16 distinct base characters");
       }
-      hCodes[x] = uint8_t(code);
-      if (code + 1 > usedSym) usedSym = code + 1;
+    }
+    for (uint32_t s = 0; s < n; ++s) {
+      const uint8_t* b = src.seq(s);
+      uint8_t* dst = hCodes + off[s];
+      for (uint64_t x = 0, len = off[s + 1] - off[s]; x < len; ++x) {
+        const uint8_t ch = b[x];
+        int code = ctx->codeOf[ch];
+        if (code < 0) {
+          code = ctx->nSym;
+          ctx->codeOf[ch] = int16_t(code);
+          ctx->charOf[ctx->nSym++] = ch;
+          newSym = true;
+        }
+        dst[x] = uint8_t(code);
+        if (code + 1 > usedSym) usedSym = code + 1;
+      }
     }
   }
   if (newSym && (rc = refreshScoring(ctx))) return rc;
@@ -370,7 +407,7 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
   SD_CUDA(ctx, cudaMemsetAsync(ctx->dCodes + oldBases + addBases, 0, 64, ctx->stream));
   SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging is reused below
   ctx->hOffsets.reserve(needSeqs);
-  for (uint32_t s = 1; s <= n; ++s) ctx->hOffsets.push_back(oldBases + offsets[s]);
+  for (uint32_t s = 1; s <= n; ++s) ctx->hOffsets.push_back(oldBases + off[s]);
   SD_CUDA(ctx, cudaMemcpyAsync(ctx->dOffsets + oldN, ctx->hOffsets.data() + oldN, (uint64_t(n) + 1) * 8,
                                cudaMemcpyHostToDevice, ctx->stream));
   double* hC = reinterpret_cast<double*>(ctx->hPinned);
@@ -389,12 +426,24 @@ static int appendImpl(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
 int sdgpu_upload_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
                       const double* cnts, uint32_t n) {
   if (!ctx) return SDGPU_E_ARG;
-  return appendImpl(ctx, bases, quals, offsets, cnts, n, nullptr, true);
+  SeqSource src;
+  src.bases = bases, src.quals = quals, src.offsets = offsets;
+  return appendImpl(ctx, src, cnts, n, nullptr, true);
+}
+
+int sdgpu_upload_seqs_gather(sdgpu_ctx* ctx, const uint8_t* const* seqPtrs, const uint8_t* const* qualPtrs, const uint32_t* lens,
+                             const double* cnts, uint32_t n) {
+  if (!ctx) return SDGPU_E_ARG;
+  SeqSource src;
+  src.seqPtrs = seqPtrs, src.qualPtrs = qualPtrs, src.lens = lens;
+  return appendImpl(ctx, src, cnts, n, nullptr, true);
 }
 
 int sdgpu_append_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets,
                       const double* cnts, uint32_t n, uint32_t* firstIndex) {
-  return appendImpl(ctx, bases, quals, offsets, cnts, n, firstIndex, false);
+  SeqSource src;
+  src.bases = bases, src.quals = quals, src.offsets = offsets;
+  return appendImpl(ctx, src, cnts, n, firstIndex, false);
 }
 
 int sdgpu_num_seqs(sdgpu_ctx* ctx, uint32_t* n) {
