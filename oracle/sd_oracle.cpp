@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <climits>
 #include <cstring>
 #include <map>
 #include <string>
@@ -879,6 +880,213 @@ int sdo_kmer_compare_revcomp(const uint8_t* a, uint32_t lenA, const uint8_t* b, 
   std::vector<uint8_t> rc(lenB);
   for (uint32_t i = 0; i < lenB; ++i) rc[i] = uint8_t(complementBase(char(b[lenB - 1 - i])));
   return sdo_kmer_compare(a, lenA, rc.data(), lenB, kLen, sharedOut, fracOut);
+}
+
+// ---------------------------------------------------------------- paired-end stitching
+// aligner::alignRegGlobalNoInternalGaps (njhseq; UNVERIFIED restatement): the best alignment of the two mates
+// that has no internal gap, i.e. the best shift.  Score of a shift = substitution scores of the overlapping
+// columns minus the end-gap penalties of the overhangs; shifts are tried from r2 furthest left to r2 furthest
+// right and a later shift must score strictly more to replace the best one.
+static void alignNoInternalGaps(const sdgpu_params& P, const uint8_t* A, uint32_t la, const uint8_t* B, uint32_t lb, AlnResult& out) {
+  const sdgpu_gap_pars& g = P.gaps;
+  long best = LONG_MIN;
+  int bestShift = 0;
+  for (int d = -int(lb) + 1; d <= int(la) - 1; ++d) {
+    long s = 0;
+    for (int i = std::max(0, d); i < std::min<int>(la, int(lb) + d); ++i) s += P.scoreMat[size_t(A[i]) * SDGPU_MAT_DIM + B[i - d]];
+    if (d > 0) s -= g.gapLeftQueryOpen + (d - 1) * g.gapLeftQueryExtend;
+    if (d < 0) s -= g.gapLeftRefOpen + (-d - 1) * g.gapLeftRefExtend;
+    const int tail = int(la) - (int(lb) + d);
+    if (tail > 0) s -= g.gapRightQueryOpen + (tail - 1) * g.gapRightQueryExtend;
+    if (tail < 0) s -= g.gapRightRefOpen + (-tail - 1) * g.gapRightRefExtend;
+    if (s > best) best = s, bestShift = d;
+  }
+  out.score = int32_t(best);
+  out.gaps.clear();  // gapInfo(pos, size, gapInA) in descending position order, like the traceback's
+  const int d = bestShift, tail = int(la) - (int(lb) + d);
+  if (tail > 0) out.gaps.push_back(GapRun{lb, uint32_t(tail), false});
+  if (tail < 0) out.gaps.push_back(GapRun{la, uint32_t(-tail), true});
+  if (d > 0) out.gaps.push_back(GapRun{0u, uint32_t(d), false});
+  if (d < 0) out.gaps.push_back(GapRun{0u, uint32_t(-d), true});
+}
+
+struct sdo_stitch_result {
+  std::vector<uint32_t> status;
+  std::vector<sdgpu_overlap> overlaps;
+  std::vector<std::string> seqs;
+  std::vector<std::vector<uint8_t>> quals;
+  uint64_t retried = 0;
+};
+
+// PairedReadProcessor::processPairedEnd (PairedReadProcessor.cpp:287-664), one pair after the other, on strings
+// like the reference: alignObjectA_ / alignObjectB_ are built with '-' and the overhang cases read their ends.
+sdo_stitch_result* sdo_stitch_pairs(const sdgpu_params* Pp, const sdst_params* Sp, const uint8_t* r1Bases, const uint8_t* r1Quals,
+                                    const uint64_t* r1Offsets, const uint8_t* r2Bases, const uint8_t* r2Quals,
+                                    const uint64_t* r2Offsets, uint32_t n) {
+  const sdgpu_params& P = *Pp;
+  const sdst_params& S = *Sp;
+  auto* res = new sdo_stitch_result();
+  res->status.assign(n, SDST_NOOVERLAP);
+  res->overlaps.assign(n, sdgpu_overlap{});
+  res->seqs.resize(n);
+  res->quals.resize(n);
+  const double percentId = 1 - S.errorAllowed;
+  struct Seq {
+    std::string seq;
+    std::vector<uint8_t> qual;
+  };
+  auto align = [&](const Seq& a, const Seq& b, Gapped& ga, Gapped& gb, sdgpu_comparison& c) {
+    AlnResult aln;
+    const uint8_t* A = reinterpret_cast<const uint8_t*>(a.seq.data());
+    const uint8_t* B = reinterpret_cast<const uint8_t*>(b.seq.data());
+    alignNoInternalGaps(P, A, uint32_t(a.seq.size()), B, uint32_t(b.seq.size()), aln);
+    rearrangeGlobal(A, a.qual.data(), uint32_t(a.seq.size()), B, b.qual.data(), uint32_t(b.seq.size()), aln, ga, gb);
+    std::memset(&c, 0, sizeof(c));
+    c.alnScore = aln.score;
+    profileAlignment(P, nullptr, A, a.qual.data(), uint32_t(a.seq.size()), B, b.qual.data(), uint32_t(b.seq.size()), ga, gb,
+                     SDGPU_USING_QUALITY, c);
+  };
+  auto accept = [&](const sdgpu_comparison& c) {
+    return c.eventBasedIdentityHq >= percentId && c.basesInAln >= S.minOverlap && c.hqMismatches + c.lqMismatches <= S.hardMismatchCutOff &&
+           c.hqMismatches <= S.hqMismatchCutOff && c.lqMismatches <= S.lqMismatchCutOff;
+  };
+  for (uint32_t i = 0; i < n; ++i) {
+    Seq r1{std::string(reinterpret_cast<const char*>(r1Bases + r1Offsets[i]), r1Offsets[i + 1] - r1Offsets[i]),
+           std::vector<uint8_t>(r1Quals + r1Offsets[i], r1Quals + r1Offsets[i + 1])};
+    Seq r2{std::string(reinterpret_cast<const char*>(r2Bases + r2Offsets[i]), r2Offsets[i + 1] - r2Offsets[i]),
+           std::vector<uint8_t>(r2Quals + r2Offsets[i], r2Quals + r2Offsets[i + 1])};
+    if (S.r1Trim) {  // trimOffEndBases
+      const size_t keep = r1.seq.size() > S.r1Trim ? r1.seq.size() - S.r1Trim : 0;
+      r1.seq.resize(keep);
+      r1.qual.resize(keep);
+    }
+    if (S.r2Trim) {  // the mate is reverse-complemented: trimOffForwardBases
+      const size_t cut = std::min<size_t>(r2.seq.size(), S.r2Trim);
+      r2.seq.erase(0, cut);
+      r2.qual.erase(r2.qual.begin(), r2.qual.begin() + cut);
+    }
+    Gapped ga, gb;
+    sdgpu_comparison c;
+    align(r1, r2, ga, gb, c);
+    if (S.trimLowQualWindows && !accept(c)) {
+      uint32_t firstMateWindow = UINT32_MAX;
+      if (r1.seq.size() > S.windowSize)
+        for (uint32_t pos = 0; pos < r1.seq.size() - S.windowSize; pos += S.windowStep) {
+          double sum = 0;
+          for (uint32_t q = pos; q < pos + S.windowSize; ++q) sum += r1.qual[q];
+          if (sum / S.windowSize < S.avgQualCutOff) {
+            firstMateWindow = pos;
+            break;
+          }
+        }
+      uint32_t secondMateWindow = 0;
+      const uint32_t end = uint32_t(r2.seq.size());
+      if (end > S.windowSize + 1)
+        for (uint32_t pos = 0; pos < end - S.windowSize - 1; pos += S.windowStep) {
+          const uint32_t truePos = end - S.windowSize - pos - 1;
+          double sum = 0;
+          for (uint32_t q = truePos; q < truePos + S.windowSize; ++q) sum += r2.qual[q];
+          if (sum / S.windowSize < S.avgQualCutOff) {
+            secondMateWindow = truePos;
+            break;
+          }
+        }
+      const bool cut1 = firstMateWindow != UINT32_MAX && firstMateWindow > 1;
+      const bool cut2 = secondMateWindow != 0 && secondMateWindow + S.windowSize + 2 < r2.seq.size();
+      if (cut1 || cut2) {
+        Seq c1 = r1, c2 = r2;
+        if (cut1) {
+          c1.seq = r1.seq.substr(0, firstMateWindow);
+          c1.qual.assign(r1.qual.begin(), r1.qual.begin() + firstMateWindow);
+        }
+        if (cut2) {
+          c2.seq = r2.seq.substr(secondMateWindow + S.windowSize);
+          c2.qual.assign(r2.qual.begin() + secondMateWindow + S.windowSize, r2.qual.end());
+        }
+        if (double(c1.seq.size()) / r1.seq.size() >= S.percentAfterTrimCutOff && double(c2.seq.size()) / r2.seq.size() >= S.percentAfterTrimCutOff) {
+          align(c1, c2, ga, gb, c);
+          r1 = c1;
+          r2 = c2;
+          ++res->retried;
+        }
+      }
+    }
+    sdgpu_overlap& o = res->overlaps[i];
+    o.alnScore = c.alnScore;
+    o.shift = int32_t(gb.seq.find_first_not_of('-')) - int32_t(ga.seq.find_first_not_of('-'));
+    o.basesInAln = c.basesInAln;
+    o.hqMismatches = c.hqMismatches;
+    o.lqMismatches = c.lqMismatches;
+    o.lowKmerMismatches = c.lowKmerMismatches;
+    o.highQualityMatches = c.highQualityMatches;
+    o.lowQualityMatches = c.lowQualityMatches;
+    o.eventBasedIdentity = c.eventBasedIdentity;
+    o.eventBasedIdentityHq = c.eventBasedIdentityHq;
+    if (!accept(c)) continue;
+    const std::string &sa = ga.seq, &sb = gb.seq;
+    enum { NOOVERHANG, R1OVERHANG, R2OVERHANG };
+    const int frontCase = (sa.front() != '-' && sb.front() != '-') ? NOOVERHANG : (sa.front() != '-' ? R1OVERHANG : R2OVERHANG);
+    const int backCase = (sa.back() != '-' && sb.back() != '-') ? NOOVERHANG : (sa.back() != '-' ? R1OVERHANG : R2OVERHANG);
+    std::string cseq;
+    std::vector<uint8_t> cq;
+    auto addToConsensus = [&](size_t pos) {  // PairedReadProcessor.cpp:43-78
+      const char b1 = sa[pos], b2 = sb[pos];
+      const uint8_t q1 = ga.qual[pos], q2 = gb.qual[pos];
+      if (b1 == '-') {
+        if (q2 >= P.primaryQual) cseq.push_back(b2), cq.push_back(q2);
+      } else if (b2 == '-') {
+        if (q1 >= P.primaryQual) cseq.push_back(b1), cq.push_back(q1);
+      } else if (P.scoreMat[size_t(uint8_t(b1)) * SDGPU_MAT_DIM + uint8_t(b2)] > 0) {
+        cseq.push_back(b1);
+        if (islower(b1) || islower(b2)) cseq.back() = char(tolower(cseq.back()));
+        cq.push_back(q1 >= q2 ? q1 : q2);
+      } else {
+        cseq.push_back(q1 >= q2 ? b1 : b2);
+        cq.push_back(q1 >= q2 ? q1 : q2);
+        if (islower(b1) || islower(b2)) cseq.back() = char(tolower(cseq.back()));
+      }
+    };
+    if (frontCase == NOOVERHANG && backCase == NOOVERHANG) {
+      for (size_t pos = 0; pos < sa.size(); ++pos) addToConsensus(pos);
+      res->status[i] = SDST_PERFECTOVERLAP;
+    } else if ((frontCase == NOOVERHANG || frontCase == R1OVERHANG) && (backCase == NOOVERHANG || backCase == R2OVERHANG)) {
+      const size_t r1End = sa.find_last_not_of('-') + 1, r2Start = sb.find_first_not_of('-');
+      if (r2Start != 0) {
+        cseq.append(sa.substr(0, r2Start));
+        cq.insert(cq.end(), ga.qual.begin(), ga.qual.begin() + r2Start);
+      }
+      for (size_t pos = r2Start; pos < r1End; ++pos) addToConsensus(pos);
+      if (sa.size() != r1End) {
+        cseq.append(sb.substr(r1End));
+        cq.insert(cq.end(), gb.qual.begin() + r1End, gb.qual.end());
+      }
+      res->status[i] = SDST_R1ENDSINR2;
+    } else {
+      size_t r1Start = 0, r2End = sb.size();
+      if (frontCase != NOOVERHANG) r1Start = sa.find_first_not_of('-');
+      if (backCase != NOOVERHANG) r2End = sb.find_last_not_of('-') + 1;
+      for (size_t pos = r1Start; pos < r2End; ++pos) addToConsensus(pos);
+      if ((frontCase == NOOVERHANG || frontCase == R2OVERHANG) && (backCase == NOOVERHANG || backCase == R1OVERHANG)) {
+        res->status[i] = SDST_R1BEGINSINR2;
+      } else if (frontCase == R2OVERHANG && backCase == R2OVERHANG) {
+        res->status[i] = SDST_R1ALLINR2;
+      } else {
+        res->status[i] = SDST_R2ALLINR1;
+      }
+    }
+    res->seqs[i] = cseq;
+    res->quals[i] = cq;
+  }
+  return res;
+}
+void sdo_stitch_free(sdo_stitch_result* r) { delete r; }
+uint64_t sdo_stitch_retried(const sdo_stitch_result* r) { return r->retried; }
+uint32_t sdo_stitch_status(const sdo_stitch_result* r, uint32_t i) { return r->status[i]; }
+void sdo_stitch_overlap(const sdo_stitch_result* r, uint32_t i, sdgpu_overlap* out) { *out = r->overlaps[i]; }
+uint32_t sdo_stitch_len(const sdo_stitch_result* r, uint32_t i) { return uint32_t(r->seqs[i].size()); }
+void sdo_stitch_seq(const sdo_stitch_result* r, uint32_t i, uint8_t* seq, uint8_t* qual) {
+  std::memcpy(seq, r->seqs[i].data(), r->seqs[i].size());
+  std::memcpy(qual, r->quals[i].data(), r->quals[i].size());
 }
 
 // qluster body, following clusterDown.cpp:230-563 (dedupe -> quality rep -> sort -> indexKmers

@@ -19,6 +19,7 @@
 #define SD_ORACLE_H_
 #include <stdint.h>
 #include "../include/sdgpu.h"
+#include "../include/sdgpu_stitch.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -60,6 +61,18 @@ int sdo_kmer_compare(const uint8_t* a, uint32_t lenA, const uint8_t* b, uint32_t
 /* kmerInfo(b, kLen, true) + a.compareKmersRevComp(b) (extractorPairedEnd.cpp:819-824) */
 int sdo_kmer_compare_revcomp(const uint8_t* a, uint32_t lenA, const uint8_t* b, uint32_t lenB,
                              uint32_t kLen, uint32_t* sharedOut, double* fracOut);
+
+/* ---- paired-end stitching: PairedReadProcessor::processPairedEnd (PairedReadProcessor.cpp:287-664) ---- */
+typedef struct sdo_stitch_result sdo_stitch_result;
+sdo_stitch_result* sdo_stitch_pairs(const sdgpu_params* p, const sdst_params* s, const uint8_t* r1Bases, const uint8_t* r1Quals,
+                                    const uint64_t* r1Offsets, const uint8_t* r2Bases, const uint8_t* r2Quals,
+                                    const uint64_t* r2Offsets, uint32_t n);
+void sdo_stitch_free(sdo_stitch_result* r);
+uint64_t sdo_stitch_retried(const sdo_stitch_result* r);
+uint32_t sdo_stitch_status(const sdo_stitch_result* r, uint32_t i);
+void sdo_stitch_overlap(const sdo_stitch_result* r, uint32_t i, sdgpu_overlap* out);
+uint32_t sdo_stitch_len(const sdo_stitch_result* r, uint32_t i);
+void sdo_stitch_seq(const sdo_stitch_result* r, uint32_t i, uint8_t* seq, uint8_t* qual);
 
 /* ---- qluster (clusterDown.cpp:205-563 call sequence) ---- */
 typedef struct sdo_iter_par { /* one par-file line, etc/SeekDeepParameterFiles/illumina_lkmer1 */

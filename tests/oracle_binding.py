@@ -70,6 +70,42 @@ class Oracle:
         lib.sdo_chimera_probe_batch.argtypes = [C.POINTER(_abi.Params), v, v, v, v, v, v, C.c_uint32, C.c_uint32,
                                                 C.POINTER(IterParC), C.c_int, v]
 
+    def stitch_pairs(self, params, stitchPars, r1, r2):
+        """PairedReadProcessor::processPairedEnd restated: (status, overlaps, list of (seq bytes, quals)), retried count."""
+        from seekdeep_b200 import stitch as ST
+        lib = self.lib
+        v = C.c_void_p
+        lib.sdo_stitch_pairs.restype = v
+        lib.sdo_stitch_pairs.argtypes = [C.POINTER(_abi.Params), C.POINTER(ST.ProcessParamsC), v, v, v, v, v, v, C.c_uint32]
+        lib.sdo_stitch_free.argtypes = [v]
+        lib.sdo_stitch_retried.restype = C.c_uint64
+        lib.sdo_stitch_retried.argtypes = [v]
+        lib.sdo_stitch_status.restype = C.c_uint32
+        lib.sdo_stitch_status.argtypes = [v, C.c_uint32]
+        lib.sdo_stitch_overlap.argtypes = [v, C.c_uint32, v]
+        lib.sdo_stitch_len.restype = C.c_uint32
+        lib.sdo_stitch_len.argtypes = [v, C.c_uint32]
+        lib.sdo_stitch_seq.argtypes = [v, C.c_uint32, v, v]
+        b1, q1, o1 = (np.ascontiguousarray(a, t) for a, t in zip(r1, (np.uint8, np.uint8, np.uint64)))
+        b2, q2, o2 = (np.ascontiguousarray(a, t) for a, t in zip(r2, (np.uint8, np.uint8, np.uint64)))
+        n = len(o1) - 1
+        sp = stitchPars.to_c()
+        h = lib.sdo_stitch_pairs(C.byref(params), C.byref(sp), _p(b1), _p(q1), _p(o1), _p(b2), _p(q2), _p(o2), n)
+        try:
+            status = np.array([lib.sdo_stitch_status(h, i) for i in range(n)], np.uint32)
+            overlaps = np.zeros(n, ST.OVERLAP_DTYPE)
+            seqs = []
+            for i in range(n):
+                lib.sdo_stitch_overlap(h, i, C.c_void_p(overlaps[i:i + 1].ctypes.data))
+                ln = lib.sdo_stitch_len(h, i)
+                s, q = np.zeros(ln, np.uint8), np.zeros(ln, np.uint8)
+                if ln:
+                    lib.sdo_stitch_seq(h, i, _p(s), _p(q))
+                seqs.append((s.tobytes(), q))
+            return status, overlaps, seqs, lib.sdo_stitch_retried(h)
+        finally:
+            lib.sdo_stitch_free(h)
+
     # one pair, strings in
     def align_global(self, params, a, b, gapCap=64):
         a = a.encode() if isinstance(a, str) else bytes(a)

@@ -16,12 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for hdr in ("sdgpu.h", "sdgpu_qluster.h"):
+    for hdr in ("sdgpu.h", "sdgpu_qluster.h", "sdgpu_stitch.h"):
         path = os.path.join(ROOT, "include", hdr)
         if not os.path.exists(path):
             continue
         txt = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
-        names |= set(re.findall(r"\b(sdgpu_[a-z0-9_]+|sdq_[a-z0-9_]+)\s*\(", txt))
+        names |= set(re.findall(r"\b(sdgpu_[a-z0-9_]+|sdq_[a-z0-9_]+|sdst_[a-z0-9_]+)\s*\(", txt))
     return names
 
 
@@ -71,7 +71,7 @@ def test_headers_compile_as_c99_and_cxx():
     """include/*.h are the drop-in boundary: plain C (no C++-isms) and usable from C++."""
     import subprocess
     inc = os.path.join(ROOT, "include")
-    for hdr in ("sdgpu.h", "sdgpu_qluster.h"):
+    for hdr in ("sdgpu.h", "sdgpu_qluster.h", "sdgpu_stitch.h"):
         for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c"], ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++"]):
             r = subprocess.run(cmd + [os.path.join(inc, hdr)], capture_output=True, text=True)
             assert r.returncode == 0, f"{' '.join(cmd)} {hdr}:\n{r.stderr}"
