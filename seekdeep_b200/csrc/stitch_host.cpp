@@ -233,79 +233,83 @@ int sdst_process_pairs(sdgpu_ctx* ctx, const sdst_params* pars, const uint8_t* r
       res->counts[6] = m;
     }
   }
-  // overhang cases and consensus (:448-628)
-  std::vector<uint32_t> outLen(n, 0);
-  for (uint32_t i = 0; i < n; ++i) {
+  // overhang cases and consensus (:448-628).  The reference walks alignment columns and lets addToConsensus decide; in
+  // two of its cases the walked range reaches past the overlap into columns where one mate is '-' (R1ALLINR2: the
+  // mate's bases behind r1's end; R2ALLINR1: r1's bases in front of the mate's start), and there a base is kept only
+  // if its quality reaches primaryQual_ (:52-62).  emit() produces the combined read of pair i, or just its length.
+  const int32_t* mat = gp.scoreMat;
+  const uint32_t primaryQual = gp.primaryQual;
+  auto emit = [&](size_t i, uint8_t* cs, uint8_t* cq) -> uint32_t {
     const sdgpu_overlap& o = res->overlaps[i];
-    if (!accepted(o, P)) continue;
-    const int d = o.shift, l1 = int(R1[i].len), l2 = int(R2[i].len);
-    // gapped strings: A = '-' x max(0,-d) + r1 + ..., B = '-' x max(0,d) + r2 + ...
-    const int front = d > 0 ? 1 : (d < 0 ? 2 : 0);                    // 0 none, 1 r1 overhangs, 2 r2 overhangs
-    const int tail = l1 - (l2 + d);
-    const int back = tail > 0 ? 1 : (tail < 0 ? 2 : 0);
-    uint32_t st;
-    if (front == 0 && back == 0) {
-      st = SDST_PERFECTOVERLAP;
-      outLen[i] = o.basesInAln;
-    } else if ((front == 0 || front == 1) && (back == 0 || back == 2)) {
-      st = SDST_R1ENDSINR2;
-      outLen[i] = uint32_t(std::max(0, d)) + o.basesInAln + uint32_t(std::max(0, -tail));
-    } else if ((front == 0 || front == 2) && (back == 0 || back == 1)) {
-      st = SDST_R1BEGINSINR2;
-      outLen[i] = o.basesInAln;
-    } else if (front == 2 && back == 2) {
-      st = SDST_R1ALLINR2;
-      outLen[i] = o.basesInAln;
-    } else {
-      st = SDST_R2ALLINR1;
-      outLen[i] = o.basesInAln;
+    const int d = o.shift;
+    const Read &r1 = R1[i], &r2 = R2[i];
+    const int l1 = int(r1.len), l2 = int(r2.len);
+    const uint32_t st = res->status[i];
+    uint32_t w = 0;
+    auto put = [&](uint8_t base, uint8_t q) {
+      if (cs) cs[w] = base, cq[w] = q;
+      ++w;
+    };
+    const int i0 = d > 0 ? d : 0, i1 = std::min(l1, l2 + d);  // r1 positions of the overlap
+    if (st == SDST_R1ENDSINR2)
+      for (int p = 0; p < d; ++p) put(r1.seq[p], r1.qual[p]);  // r1 beginning, as it is
+    if (st == SDST_R2ALLINR1)
+      for (int p = 0; p < d; ++p)                                // gap in r2: r1's base if it is sure enough
+        if (r1.qual[p] >= primaryQual) put(r1.seq[p], r1.qual[p]);
+    for (int p = i0; p < i1; ++p) {  // both mates present
+      const uint8_t b1 = r1.seq[p], b2 = r2.seq[p - d], q1 = r1.qual[p], q2 = r2.qual[p - d];
+      const bool lower = std::islower(b1) || std::islower(b2);
+      uint8_t cb;
+      if (mat[size_t(b1 & 127) * SDGPU_MAT_DIM + (b2 & 127)] > 0) {  // match: r1's base, the higher quality
+        cb = b1;
+      } else {  // mismatch: the base of the higher quality, r1 on ties
+        cb = q1 >= q2 ? b1 : b2;
+      }
+      if (lower) cb = uint8_t(std::tolower(cb));
+      put(cb, q1 >= q2 ? q1 : q2);
     }
-    res->status[i] = st;
-  }
+    if (st == SDST_R1ENDSINR2)
+      for (int p = l1 - d; p < l2; ++p) put(r2.seq[p], r2.qual[p]);  // r2 ending, as it is
+    if (st == SDST_R1ALLINR2)
+      for (int p = l1 - d; p < l2; ++p)                              // gap in r1: the mate's base if it is sure enough
+        if (r2.qual[p] >= primaryQual) put(r2.seq[p], r2.qual[p]);
+    return w;
+  };
+  std::vector<uint32_t> outLen(n, 0);
+  parallelFor(n, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      const sdgpu_overlap& o = res->overlaps[i];
+      if (!accepted(o, P)) continue;
+      const int d = o.shift, l1 = int(R1[i].len), l2 = int(R2[i].len);
+      // alignObjectA_ = '-' x max(0,-d) + r1 + ..., alignObjectB_ = '-' x max(0,d) + r2 + ...: which mate stands alone at each end
+      const int front = d > 0 ? 1 : (d < 0 ? 2 : 0);  // 0 none, 1 r1 overhangs, 2 r2 overhangs
+      const int tail = l1 - (l2 + d);
+      const int back = tail > 0 ? 1 : (tail < 0 ? 2 : 0);
+      uint32_t st;
+      if (front == 0 && back == 0) {
+        st = SDST_PERFECTOVERLAP;
+      } else if ((front == 0 || front == 1) && (back == 0 || back == 2)) {
+        st = SDST_R1ENDSINR2;
+      } else if ((front == 0 || front == 2) && (back == 0 || back == 1)) {
+        st = SDST_R1BEGINSINR2;
+      } else if (front == 2 && back == 2) {
+        st = SDST_R1ALLINR2;
+      } else {
+        st = SDST_R2ALLINR1;
+      }
+      res->status[i] = st;
+      outLen[i] = emit(i, nullptr, nullptr);
+    }
+  });
   for (uint32_t i = 0; i < n; ++i) {
     res->offsets[i + 1] = res->offsets[i] + outLen[i];
     ++res->counts[res->status[i]];
   }
   res->bases.resize(res->offsets[n]);
   res->quals.resize(res->offsets[n]);
-  const int32_t* mat = gp.scoreMat;
   parallelFor(n, [&](size_t lo, size_t hi) {
-    for (size_t i = lo; i < hi; ++i) {
-      if (res->status[i] == SDST_NOOVERLAP) continue;
-      const sdgpu_overlap& o = res->overlaps[i];
-      const int d = o.shift;
-      const Read &r1 = R1[i], &r2 = R2[i];
-      uint8_t* cs = res->bases.data() + res->offsets[i];
-      uint8_t* cq = res->quals.data() + res->offsets[i];
-      uint32_t w = 0;
-      const int i0 = d > 0 ? d : 0, i1 = std::min<int>(int(r1.len), int(r2.len) + d);  // r1 positions of the overlap
-      if (res->status[i] == SDST_R1ENDSINR2 && d > 0) {  // r1 beginning
-        std::memcpy(cs, r1.seq, size_t(d));
-        std::memcpy(cq, r1.qual, size_t(d));
-        w = uint32_t(d);
-      }
-      for (int p = i0; p < i1; ++p) {  // addToConsensus over the overlap (no '-' there)
-        const uint8_t b1 = r1.seq[p], b2 = r2.seq[p - d], q1 = r1.qual[p], q2 = r2.qual[p - d];
-        const bool lower = std::islower(b1) || std::islower(b2);
-        uint8_t cb;
-        if (mat[size_t(b1 & 127) * SDGPU_MAT_DIM + (b2 & 127)] > 0) {  // match: r1's base, the higher quality
-          cb = b1;
-        } else {  // mismatch: the base of the higher quality, r1 on ties
-          cb = q1 >= q2 ? b1 : b2;
-        }
-        if (lower) cb = uint8_t(std::tolower(cb));
-        cs[w] = cb;
-        cq[w] = q1 >= q2 ? q1 : q2;
-        ++w;
-      }
-      if (res->status[i] == SDST_R1ENDSINR2 && int(r2.len) + d > int(r1.len)) {  // r2 ending
-        const int from = int(r1.len) - d;
-        std::memcpy(cs + w, r2.seq + from, size_t(int(r2.len) - from));
-        std::memcpy(cq + w, r2.qual + from, size_t(int(r2.len) - from));
-        w += uint32_t(int(r2.len) - from);
-      }
-      (void)w;
-    }
+    for (size_t i = lo; i < hi; ++i)
+      if (res->status[i] != SDST_NOOVERLAP) emit(i, res->bases.data() + res->offsets[i], res->quals.data() + res->offsets[i]);
   });
   *out = res;
   return SDGPU_OK;
