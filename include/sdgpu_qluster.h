@@ -99,6 +99,21 @@ int sdq_cluster_chimeric(const sdq_result* r, uint32_t c, uint32_t* parents, uin
 /* final cluster index of every input read (UINT32_MAX: dropped as a small read) */
 int sdq_membership(const sdq_result* r, uint32_t* clusterOfRead);
 
+/* Population clustering across samples.  Replaces the collapse inside
+ * sampColl.doPopulationClustering(sampColl.createPopInput(), alignerObj, collapserObj, pars.popIteratorMap)
+ * (src/SeekDeepPrograms/SeekDeepProgram/processClusters/processClusters.cpp:226): the final clusters of every sample
+ * -- each keeping its own count, nothing deduplicated -- go through the par-file iterations once, with k-mer checks
+ * off (collapserObj.opts_.kmerOpts_.checkKmers_ = false, :127), no singlet round, no k-mer re-count, no chimera
+ * marking.  sdq_membership of the result gives, for every input cluster in sample-major order, the population
+ * cluster it ended in; consensus sequences, counts and statistics come back like sdq_run's.  The per-sample steps
+ * around it (replicate merging, the exclusion filters, renaming; :158-196) are bookkeeping left to the caller. */
+int sdq_population_cluster(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* popPars, uint32_t nPars,
+                           const sdq_result* const* samples, uint32_t nSamples, sdq_result** out);
+/* ... with the input clusters packed by the caller (like sdgpu_upload_seqs; cnts may be NULL: all 1) */
+int sdq_population_cluster_packed(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* popPars, uint32_t nPars,
+                                  const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, const double* cnts,
+                                  uint32_t nClusters, sdq_result** out);
+
 /* Many independent samples (one qluster each, like qlusterCmds.txt + runMultipleCommands,
  * SeekDeepUtilsRunner.cpp:294-356) on ONE GPU: nWorkers host threads, each with its own ctx on
  * `device`, pull samples from a shared queue, so one sample's host-only phases overlap another's

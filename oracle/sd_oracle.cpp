@@ -1091,18 +1091,27 @@ void sdo_stitch_seq(const sdo_stitch_result* r, uint32_t i, uint8_t* seq, uint8_
 
 // qluster body, following clusterDown.cpp:230-563 (dedupe -> quality rep -> sort -> indexKmers
 // -> singlet split -> runFullClustering x3 -> final sort).
-sdo_qluster_result* sdo_qluster(const sdgpu_params* p, const sdo_qluster_opts* o, const sdo_iter_par* initPars,
-                                uint32_t nInit, const sdo_iter_par* pars, uint32_t nPars, const uint8_t* bases,
-                                const uint8_t* quals, const uint64_t* offsets, uint32_t n) {
+static sdo_qluster_result* qlusterImpl(const sdgpu_params* p, const sdo_qluster_opts* o, const sdo_iter_par* initPars,
+                                       uint32_t nInit, const sdo_iter_par* pars, uint32_t nPars, const uint8_t* bases,
+                                       const uint8_t* quals, const uint64_t* offsets, uint32_t n, const double* clusterCnts,
+                                       bool clustersIn) {
   Engine E(*p, *o);
   auto* res = new sdo_qluster_result();
   res->membership.assign(n, UINT32_MAX);
-  // exact-sequence dedupe, first-seen order (clusterDown.cpp:272-288)
+  // exact-sequence dedupe, first-seen order (clusterDown.cpp:272-288); population input (processClusters.cpp:226)
+  // arrives as clusters with their counts and is not deduplicated
   std::unordered_map<std::string, uint32_t> seen;
   for (uint32_t r = 0; r < n; ++r) {
     const uint32_t len = uint32_t(offsets[r + 1] - offsets[r]);
     if (len <= o->smallReadSize) continue;  // clusterDown.cpp:269-270
     std::string s(reinterpret_cast<const char*>(bases + offsets[r]), len);
+    if (clustersIn) {
+      E.uniq.emplace_back();
+      E.uniq.back().seq = s;
+      E.uniq.back().cnt = clusterCnts ? clusterCnts[r] : 1.0;
+      E.uniq.back().inputIdx.push_back(r);
+      continue;
+    }
     auto it = seen.find(s);
     if (it == seen.end()) {
       it = seen.emplace(s, uint32_t(E.uniq.size())).first;
@@ -1183,6 +1192,25 @@ sdo_qluster_result* sdo_qluster(const sdgpu_params* p, const sdo_qluster_opts* o
   res->nAlign = E.nAlign;
   res->nCells = E.nCells;
   return res;
+}
+
+sdo_qluster_result* sdo_qluster(const sdgpu_params* p, const sdo_qluster_opts* o, const sdo_iter_par* initPars,
+                                uint32_t nInit, const sdo_iter_par* pars, uint32_t nPars, const uint8_t* bases,
+                                const uint8_t* quals, const uint64_t* offsets, uint32_t n) {
+  return qlusterImpl(p, o, initPars, nInit, pars, nPars, bases, quals, offsets, n, nullptr, false);
+}
+
+// doPopulationClustering's collapse (processClusters.cpp:226; checkKmers off, :127): one runClustering over the
+// samples' clusters with their counts
+sdo_qluster_result* sdo_population_cluster(const sdgpu_params* p, const sdo_qluster_opts* o, const sdo_iter_par* popPars,
+                                           uint32_t nPars, const uint8_t* bases, const uint8_t* quals,
+                                           const uint64_t* offsets, const double* cnts, uint32_t n) {
+  sdo_qluster_opts q = *o;
+  q.checkKmers = 0;
+  q.startWithSingles = 1;
+  q.dontRecalLowFreq = 1;
+  q.markChimeras = 0;
+  return qlusterImpl(p, &q, popPars, nPars, popPars, nPars, bases, quals, offsets, n, cnts, true);
 }
 
 void sdo_qluster_free(sdo_qluster_result* r) { delete r; }

@@ -115,6 +115,10 @@ sdo_qluster_result* sdo_qluster(const sdgpu_params* p, const sdo_qluster_opts* o
                                 const sdo_iter_par* initPars, uint32_t nInit,
                                 const sdo_iter_par* pars, uint32_t nPars, const uint8_t* bases,
                                 const uint8_t* quals, const uint64_t* offsets, uint32_t n);
+/* doPopulationClustering's collapse (processClusters.cpp:226): input = clusters with counts, no dedupe, no k-mer checks */
+sdo_qluster_result* sdo_population_cluster(const sdgpu_params* p, const sdo_qluster_opts* o,
+                                           const sdo_iter_par* popPars, uint32_t nPars, const uint8_t* bases,
+                                           const uint8_t* quals, const uint64_t* offsets, const double* cnts, uint32_t n);
 void sdo_qluster_free(sdo_qluster_result* r);
 uint32_t sdo_qluster_num_clusters(const sdo_qluster_result* r);
 uint32_t sdo_qluster_num_unique(const sdo_qluster_result* r);

@@ -8,4 +8,4 @@ from . import _abi  # noqa: F401
 from .scoring import GapScoringParameters, SubstituteMatrix, make_params  # noqa: F401
 from .iterpars import CollapseIterations, IterPar  # noqa: F401
 from .aligner import GpuAligner, SdgpuError  # noqa: F401
-from .qluster import QlusterPars, qluster, qluster_many, shard_pair_blocks, shard_samples  # noqa: F401
+from .qluster import QlusterPars, population_cluster, qluster, qluster_many, shard_pair_blocks, shard_samples  # noqa: F401

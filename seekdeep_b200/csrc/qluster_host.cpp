@@ -997,13 +997,28 @@ extern "C" {
 
 const char* sdq_last_error(void) { return g_err.c_str(); }
 
-int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, uint32_t nInit, const sdq_iter_par* pars,
-            uint32_t nPars, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, uint32_t n,
-            sdq_result** out) {
-  if (!ctx || !opts || !out || (n && (!bases || !quals || !offsets)) || (nInit && !initPars) || (nPars && !pars)) {
-    g_err = "sdq_run: null argument";
-    return SDGPU_E_ARG;
-  }
+}  // extern "C"
+
+namespace {
+// The collapse's input: packed reads (sdq_run) or one pointer per sequence with a count each (population
+// clustering: the final clusters of many samples, which are not deduplicated).
+struct ReadSrc {
+  const uint8_t* bases = nullptr;
+  const uint8_t* quals = nullptr;
+  const uint64_t* offsets = nullptr;
+  const uint8_t* const* seqPtrs = nullptr;
+  const uint8_t* const* qualPtrs = nullptr;
+  const uint32_t* lens = nullptr;
+  const double* cnts = nullptr;  // with seqPtrs: seqBase_.cnt_ of every input cluster
+  const uint8_t* seq(uint32_t r) const { return seqPtrs ? seqPtrs[r] : bases + offsets[r]; }
+  const uint8_t* qual(uint32_t r) const { return seqPtrs ? qualPtrs[r] : quals + offsets[r]; }
+  uint32_t len(uint32_t r) const { return seqPtrs ? lens[r] : uint32_t(offsets[r + 1] - offsets[r]); }
+};
+}  // namespace
+
+static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, uint32_t nInit, const sdq_iter_par* pars,
+                       uint32_t nPars, const ReadSrc& in, uint32_t n, sdq_result** out) {
+  const bool clustersIn = in.seqPtrs != nullptr;  // every input is a cluster of its own, with its count
   *out = nullptr;
   const double tStart = nowSec();
   Runner R(ctx, *opts);
@@ -1034,8 +1049,8 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     parallelFor(n, [&](size_t lo, size_t hi) {
       uint64_t mine[2] = {0, 0};
       for (size_t r = lo; r < hi; ++r) {
-        const uint32_t len = uint32_t(offsets[r + 1] - offsets[r]);
-        const uint8_t* p = bases + offsets[r];
+        const uint32_t len = in.len(uint32_t(r));
+        const uint8_t* p = in.seq(uint32_t(r));
         uint64_t h = 0x9e3779b97f4a7c15ull ^ len;
         uint32_t i = 0;
         for (; i + 8 <= len; i += 8) {
@@ -1064,16 +1079,23 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     firstRead.reserve(n);
     R.uniq.reserve(n);
     for (uint32_t r = 0; r < n; ++r) {
-      const uint32_t len = uint32_t(offsets[r + 1] - offsets[r]);
+      const uint32_t len = in.len(r);
       if (len <= opts->smallReadSize) continue;
-      const uint8_t* p = bases + offsets[r];
+      if (clustersIn) {  // population input: no dedupe, the cluster brings its count
+        uniqOfRead[r] = uint32_t(R.uniq.size());
+        firstRead.push_back(r);
+        R.uniq.emplace_back();
+        R.uniq.back().cnt = in.cnts ? in.cnts[r] : 1.0;
+        continue;
+      }
+      const uint8_t* p = in.seq(r);
       const uint64_t h = readHash[r];
       size_t slot = size_t(h) & (cap - 1);
       uint32_t found = UINT32_MAX;
       while (table[slot] != UINT32_MAX) {
         const uint32_t u = table[slot];
         const uint32_t fr = firstRead[u];
-        if (readHash[fr] == h && uint32_t(offsets[fr + 1] - offsets[fr]) == len && std::memcmp(bases + offsets[fr], p, len) == 0) {
+        if (readHash[fr] == h && in.len(fr) == len && std::memcmp(in.seq(fr), p, len) == 0) {
           found = u;
           break;
         }
@@ -1095,18 +1117,18 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
     for (uint32_t u = 0; u < nUq; ++u) {
       Uniq& q = R.uniq[u];
       q.inputBegin = q.inputEnd = run;
-      run += uint32_t(q.cnt);
+      run += clustersIn ? 1u : uint32_t(q.cnt);
       const uint32_t fr = firstRead[u];
-      q.seq = View{bases + offsets[fr], uint32_t(offsets[fr + 1] - offsets[fr])};
-      q.qual = View{quals + offsets[fr], q.seq.n};  // (several reads: replaced by the per-base median below)
-      if (q.cnt > 1.0) arenaBytes += q.seq.n;
+      q.seq = View{in.seq(fr), in.len(fr)};
+      q.qual = View{in.qual(fr), q.seq.n};  // (several reads: replaced by the per-base median below)
+      if (!clustersIn && q.cnt > 1.0) arenaBytes += q.seq.n;
     }
     R.inputList.resize(run);
     for (uint32_t r = 0; r < n; ++r)
       if (uniqOfRead[r] != UINT32_MAX) R.inputList[R.uniq[uniqOfRead[r]].inputEnd++] = r;
     R.qualArena.resize(arenaBytes);
     uint64_t at = 0;
-    for (uint32_t u = 0; u < nUq; ++u)
+    for (uint32_t u = 0; u < nUq && !clustersIn; ++u)
       if (R.uniq[u].cnt > 1.0) {
         R.uniq[u].qual = View{R.qualArena.data() + at, R.uniq[u].seq.n};
         at += R.uniq[u].seq.n;
@@ -1129,7 +1151,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
       if (k < 16) {
         col.resize(k);
         for (size_t i = 0; i < len; ++i) {
-          for (size_t m = 0; m < k; ++m) col[m] = quals[offsets[members[m]] + i];
+          for (size_t m = 0; m < k; ++m) col[m] = in.qual(members[m])[i];
           std::sort(col.begin(), col.end());
           out[i] = (k % 2) ? col[k / 2] : uint8_t((uint32_t(col[k / 2 - 1]) + col[k / 2]) / 2);
         }
@@ -1138,7 +1160,7 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
       // many members: per-column histograms filled member by member (sequential reads), medians read off them
       hist.assign(len * 256, 0);
       for (size_t m = 0; m < k; ++m) {
-        const uint8_t* q = quals + offsets[members[m]];
+        const uint8_t* q = in.qual(members[m]);
         for (size_t i = 0; i < len; ++i) ++hist[i * 256 + q[i]];
       }
       const size_t r1 = (k % 2) ? k / 2 : k / 2 - 1, r2 = k / 2;  // order statistics (0-based) the median needs
@@ -1261,6 +1283,81 @@ int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, 
   }
   *out = res;
   return SDGPU_OK;
+}
+
+extern "C" {
+
+int sdq_run(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, uint32_t nInit, const sdq_iter_par* pars,
+            uint32_t nPars, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, uint32_t n,
+            sdq_result** out) {
+  if (!ctx || !opts || !out || (n && (!bases || !quals || !offsets)) || (nInit && !initPars) || (nPars && !pars)) {
+    g_err = "sdq_run: null argument";
+    return SDGPU_E_ARG;
+  }
+  ReadSrc in;
+  in.bases = bases, in.quals = quals, in.offsets = offsets;
+  return runCollapse(ctx, opts, initPars, nInit, pars, nPars, in, n, out);
+}
+
+// sampColl.doPopulationClustering(sampColl.createPopInput(), alignerObj, collapserObj, popIteratorMap)
+// (processClusters.cpp:226): the final clusters of every sample, each with its own count and without any
+// deduplication, go through collapser::runClustering once -- no k-mer checks (collapserObj.opts_.kmerOpts_.checkKmers_
+// = false, :127), no singlet round, no k-mer re-count, no chimera marking.  membership of the result: for every input
+// cluster, sample-major, the population cluster it ended in.
+int sdq_population_cluster(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* popPars, uint32_t nPars,
+                           const sdq_result* const* samples, uint32_t nSamples, sdq_result** out) {
+  if (!ctx || !opts || !out || (nPars && !popPars) || (nSamples && !samples)) {
+    g_err = "sdq_population_cluster: null argument";
+    return SDGPU_E_ARG;
+  }
+  std::vector<const uint8_t*> sp, qp;
+  std::vector<uint32_t> ln;
+  std::vector<double> cn;
+  for (uint32_t s = 0; s < nSamples; ++s) {
+    if (!samples[s]) {
+      g_err = "sdq_population_cluster: null sample result";
+      return SDGPU_E_ARG;
+    }
+    for (const Clus& c : samples[s]->clusters) {
+      sp.push_back(c.seq.data());
+      qp.push_back(c.qual.data());
+      ln.push_back(uint32_t(c.seq.size()));
+      cn.push_back(c.cnt);
+    }
+  }
+  sdq_opts o = *opts;
+  o.checkKmers = 0;
+  o.startWithSingles = 1;
+  o.dontRecalLowFreq = 1;
+  o.markChimeras = 0;
+  ReadSrc in;
+  in.seqPtrs = sp.data(), in.qualPtrs = qp.data(), in.lens = ln.data(), in.cnts = cn.data();
+  return runCollapse(ctx, &o, popPars, nPars, popPars, nPars, in, uint32_t(sp.size()), out);
+}
+
+// the same with the input clusters packed by the caller (bases / quals / offsets like sdgpu_upload_seqs, cnts per cluster)
+int sdq_population_cluster_packed(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* popPars, uint32_t nPars,
+                                  const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, const double* cnts,
+                                  uint32_t nClusters, sdq_result** out) {
+  if (!ctx || !opts || !out || (nPars && !popPars) || (nClusters && (!bases || !quals || !offsets))) {
+    g_err = "sdq_population_cluster_packed: null argument";
+    return SDGPU_E_ARG;
+  }
+  std::vector<const uint8_t*> sp(nClusters), qp(nClusters);
+  std::vector<uint32_t> ln(nClusters);
+  for (uint32_t c = 0; c < nClusters; ++c) {
+    sp[c] = bases + offsets[c];
+    qp[c] = quals + offsets[c];
+    ln[c] = uint32_t(offsets[c + 1] - offsets[c]);
+  }
+  sdq_opts o = *opts;
+  o.checkKmers = 0;
+  o.startWithSingles = 1;
+  o.dontRecalLowFreq = 1;
+  o.markChimeras = 0;
+  ReadSrc in;
+  in.seqPtrs = sp.data(), in.qualPtrs = qp.data(), in.lens = ln.data(), in.cnts = cnts;
+  return runCollapse(ctx, &o, popPars, nPars, popPars, nPars, in, nClusters, out);
 }
 
 void sdq_free(sdq_result* r) { delete r; }

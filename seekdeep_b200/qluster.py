@@ -101,6 +101,8 @@ def _bind(lib):
     lib.sdq_cluster_cnt.argtypes = [v, C.c_uint32]
     lib.sdq_cluster_seq.argtypes = [v, C.c_uint32, v, v]
     lib.sdq_membership.argtypes = [v, v]
+    lib.sdq_population_cluster_packed.restype = C.c_int
+    lib.sdq_population_cluster_packed.argtypes = [v, C.POINTER(QlusterOptsC), v, C.c_uint32, v, v, v, v, C.c_uint32, C.POINTER(v)]
     lib.sdq_clusters_total_len.restype = C.c_uint64
     lib.sdq_clusters_total_len.argtypes = [v]
     lib.sdq_clusters_packed.restype = C.c_int
@@ -199,6 +201,47 @@ def qluster_many(params, samples, device=0, nWorkers=2, pars: QlusterPars = None
         finally:
             lib.sdq_free(out[s])
     return results
+
+
+def population_cluster(aligner: GpuAligner, samples, pars: QlusterPars = None, popIteratorMap: CollapseIterations = None,
+                       want_clusters=True):
+    """sampColl.doPopulationClustering(...) (processClusters.cpp:226): the final clusters of several samples (`samples` =
+    qluster() results, or (bases, quals, offsets, cnts) tuples of packed clusters) collapsed across samples with
+    popIteratorMap, k-mer checks off.  Returns a qluster()-shaped result plus "sampleOfInput" / "clusterOfInput": for
+    every input cluster, in sample-major order, where it came from; result["membership"][i] is its population cluster."""
+    lib = aligner._lib
+    _bind(lib)
+    pars = pars or QlusterPars()
+    popIteratorMap = popIteratorMap or CollapseIterations.gen_illumina_default_pars(100)
+    packs = []
+    for smp in samples:
+        if isinstance(smp, dict):
+            pk = smp["packed"]
+            packs.append((pk["bases"], pk["quals"], pk["offsets"], pk["cnts"]))
+        else:
+            packs.append(smp)
+    bases = np.concatenate([np.asarray(p[0], np.uint8) for p in packs]) if packs else np.zeros(0, np.uint8)
+    quals = np.concatenate([np.asarray(p[1], np.uint8) for p in packs]) if packs else np.zeros(0, np.uint8)
+    cnts = np.concatenate([np.asarray(p[3], np.float64) for p in packs]) if packs else np.zeros(0, np.float64)
+    lens = np.concatenate([np.diff(np.asarray(p[2], np.uint64)) for p in packs]) if packs else np.zeros(0, np.uint64)
+    offsets = np.zeros(len(lens) + 1, np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    n = len(lens)
+    opts = pars.to_c()
+    pp, npp = iter_pars_to_c(popIteratorMap)
+    h = C.c_void_p()
+    rc = lib.sdq_population_cluster_packed(aligner._ctx, C.byref(opts), pp, npp, _ptr(bases), _ptr(quals), _ptr(offsets), _ptr(cnts), n,
+                                           C.byref(h))
+    if rc != _abi.OK:
+        raise SdgpuError(rc, (lib.sdq_last_error() or b"").decode())
+    try:
+        res = _result_to_dict(lib, h, n, want_clusters)
+    finally:
+        lib.sdq_free(h)
+    res["sampleOfInput"] = np.concatenate([np.full(len(p[2]) - 1, s, np.uint32) for s, p in enumerate(packs)]) if packs else np.zeros(0, np.uint32)
+    res["clusterOfInput"] = np.concatenate([np.arange(len(p[2]) - 1, dtype=np.uint32) for p in packs]) if packs else np.zeros(0, np.uint32)
+    res["input"] = (bases, quals, offsets, cnts)
+    return res
 
 
 def shard_samples(nSamples, rank, world):

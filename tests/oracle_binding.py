@@ -182,6 +182,20 @@ class Oracle:
         (self.lib.sdo_kmer_compare_revcomp if revCompB else self.lib.sdo_kmer_compare)(a, len(a), b, len(b), k, C.byref(s), C.byref(f))
         return s.value, f.value
 
+    def population_cluster(self, params, opts, popPars, bases, quals, offsets, cnts):
+        """doPopulationClustering's collapse over packed input clusters (counts per cluster, no dedupe)."""
+        self.lib.sdo_population_cluster.restype = C.c_void_p
+        self.lib.sdo_population_cluster.argtypes = [C.POINTER(_abi.Params), C.POINTER(QlusterOptsC), C.c_void_p, C.c_uint32,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        bases = np.ascontiguousarray(bases, np.uint8)
+        quals = np.ascontiguousarray(quals, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        cnts = np.ascontiguousarray(cnts, np.float64)
+        pp = iter_pars_to_c(list(popPars))
+        n = len(offsets) - 1
+        h = self.lib.sdo_population_cluster(C.byref(params), C.byref(opts), pp, len(pp), _p(bases), _p(quals), _p(offsets), _p(cnts), n)
+        return self._qluster_result(h, n)
+
     def qluster(self, params, opts, initPars, pars, bases, quals, offsets):
         bases = np.ascontiguousarray(bases, np.uint8)
         quals = np.ascontiguousarray(quals, np.uint8)
@@ -190,6 +204,9 @@ class Oracle:
         n = len(offsets) - 1
         h = self.lib.sdo_qluster(C.byref(params), C.byref(opts), ip, len(ip), pp, len(pp), _p(bases), _p(quals),
                                  _p(offsets), n)
+        return self._qluster_result(h, n)
+
+    def _qluster_result(self, h, n):
         try:
             nc = self.lib.sdo_qluster_num_clusters(h)
             res = {"nUnique": self.lib.sdo_qluster_num_unique(h), "nAlign": self.lib.sdo_qluster_num_alignments(h),

@@ -129,6 +129,40 @@ def test_qluster_matches_frozen_oracle_at_baseline_sizes(name, mode):
     assert (prof["bandCells"] > 0) == (mode != "noBand")
 
 
+def test_population_clustering_matches_oracle(oracle):
+    """processClusters' population step (processClusters.cpp:226, sdq_population_cluster): six samples drawn from a
+    shared haplotype pool are collapsed one by one (qluster), then their final clusters are collapsed across samples
+    with an OTU table; input clusters keep their counts and are not deduplicated, k-mer checks are off.  Membership
+    (sample cluster -> population cluster), population consensus sequences / qualities / counts must equal the oracle's."""
+    rng = np.random.default_rng(77)
+    pool = synth.make_haplotypes(rng, 9, 180, 1, 6)
+    params = sd.make_params()
+    iters = CollapseIterations.gen_illumina_default_pars(100)
+    results = []
+    with sd.GpuAligner(params) as al:
+        for s in range(6):
+            haps = [pool[i] for i in rng.choice(len(pool), 4, replace=False)]
+            seqs, quals, _ = synth.fast_reads(rng, haps, 700, 0.004)
+            results.append(sd.qluster(al, *synth.pack(seqs, quals), sd.QlusterPars(), iters, want_clusters=False))
+        popIters = CollapseIterations.gen_illumina_default_pars(100)
+        got = sd.population_cluster(al, results, sd.QlusterPars(), popIters)
+        otu = sd.population_cluster(al, results, sd.QlusterPars(), CollapseIterations.gen_otu_pars(100, 0.99, True))
+    bases, quals, offsets, cnts = got["input"]
+    pars = sd.QlusterPars()
+    want = oracle.population_cluster(params, pars.to_c(), popIters.iters, bases, quals, offsets, cnts)
+    assert_same(got, want)
+    wantOtu = oracle.population_cluster(params, pars.to_c(), CollapseIterations.gen_otu_pars(100, 0.99, True).iters, bases, quals, offsets, cnts)
+    assert_same(otu, wantOtu)
+    n = len(offsets) - 1
+    assert len(got["sampleOfInput"]) == n == sum(len(r["packed"]["cnts"]) for r in results)
+    assert len(got["clusters"]) < n  # the shared haplotypes were merged across samples ...
+    assert sum(c for _, _, c in got["clusters"]) == cnts.sum()  # ... and no read was lost
+    # every abundant pool haplotype that was drawn is a population cluster exactly once
+    popSeqs = [s for s, _, _ in got["clusters"]]
+    assert len(set(popSeqs)) == len(popSeqs)
+    assert sum(h.tobytes().decode() in popSeqs for h in pool) >= 6
+
+
 def test_config1_full_size_properties():
     """BASELINE config 1 at full size (10k reads x 250 bp, 20 haplotypes), without the oracle:
     size-independent properties of the collapse — conservation of reads, determinism, exact recovery
