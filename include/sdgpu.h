@@ -260,7 +260,9 @@ int sdgpu_chimera_probe_pairs(sdgpu_ctx* ctx, const uint32_t* parentIdx, const u
  * GPUs with no exchange (BASELINE config 3).  Replaces the all-by-all loop of
  * clusterDown.cpp:727-805 (alignCacheGlobal + profileAlignment per pair, the same columns) and is
  * the kernel of processClusters' population comparisons (processClusters.cpp:226).  Pair lists are
- * generated on the device; 28 bytes per pair come back. */
+ * generated on the device; 28 bytes per pair come back.  The three indel tallies and the identity of the summary are
+ * the comparison's doubles rounded to float (relative error <= 6e-8, inside the 1e-6 bar of the contract; the
+ * integer fields are exact); a caller that needs the doubles asks sdgpu_align_profile for the pairs it cares about. */
 typedef struct sdgpu_pair_summary {
   int32_t alnScore;
   uint16_t hqMismatches, lqMismatches, lowKmerMismatches, numGaps;

@@ -46,9 +46,18 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/sdgpu_qluster.h"
 
 namespace {
+
+// NVTX range over a host phase of the collapse loop (prep / listing + grids / sequential pass / consensus / sort / index),
+// so that a timeline shows which phases leave the GPU idle
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_err;
 // Pairs per asynchronous alignment chunk (0 = default 1 M).  Workers that share a GPU use small
@@ -432,6 +441,7 @@ class Runner {
       if (!PR[cp].remove && PR[cp].cnt > double(it.smallCutoff)) elig.push_back(cp);
     // ---- speculative batch: the window = first stopCheck(+1: a read skips itself) candidates
     double tt0 = nowSec();
+    std::unique_ptr<NvtxRange> gridRange(new NvtxRange("sdq:list+grids"));
     const uint32_t wn = uint32_t(std::min<uint64_t>(elig.size(), uint64_t(it.stopCheck) + 1));
     std::vector<uint8_t> inWindow(cs.size(), 0);
     {
@@ -470,12 +480,14 @@ class Runner {
       int rc = gridPass(cs, window, fullStore, fullPos);
       if (!rc) rc = gridPass(cs, fresh, incStore, incPos);
       tSpec += nowSec() - tt0;  // listing + GPU + filing
+      gridRange.reset();
       if (g_verboseTiming && nowSec() - tt0 > 0.01)
         fprintf(stderr, "[sdq]   line %d: %zu live, window %u (%zu new), %zu reads x window + %zu x new, spec %.3f s (listing %.3f)\n", line,
                 alive, wn, fresh.size(), fullStore.size(), incStore.size(), nowSec() - tt0, tList);
       if (rc) return rc;
     }
     tt0 = nowSec();
+    NvtxRange passRange("sdq:sequential pass");
     // ---- the sequential pass (smallest cluster first; first passing candidate absorbs it)
     size_t amountAdded = 0;
     bool windowIntact = true;  // no window cluster absorbed yet: every read sees the static window
@@ -545,6 +557,7 @@ class Runner {
 
   // baseCluster::calculateConsensus for every cluster that absorbed reads, one GPU batch.
   int calculateConsensusBatch(ClusVec& cs) {
+    NvtxRange range("sdq:consensus");
     struct Job {
       uint32_t clus;
       size_t firstPair, firstMember;
@@ -820,6 +833,7 @@ class Runner {
     return clusLess(*a.c, *b.c);
   }
   void dropRemovedAndSort(ClusVec& cs) {
+    NvtxRange range("sdq:sort");
     const double t0 = nowSec();
     std::vector<Clus*>& v = cs.ptrs();
     if (posValid && PR.size() == v.size()) {
@@ -886,6 +900,7 @@ class Runner {
   }
 
   int buildIndex(ClusVec& cs) {  // indexKmers over the current clusters
+    NvtxRange range("sdq:indexKmers");
     const double t0 = nowSec();
     struct Tick {
       double& acc;
@@ -1020,6 +1035,7 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
                        uint32_t nPars, const ReadSrc& in, uint32_t n, sdq_result** out) {
   const bool clustersIn = in.seqPtrs != nullptr;  // every input is a cluster of its own, with its count
   *out = nullptr;
+  std::unique_ptr<NvtxRange> prepRange(new NvtxRange("sdq:prep (dedupe, medians, upload)"));
   const double tStart = nowSec();
   Runner R(ctx, *opts);
   auto res = new sdq_result();
@@ -1226,6 +1242,7 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
     }
   });
   const double tPrep = nowSec() - tStart;
+  prepRange.reset();
   if (g_verboseTiming) fprintf(stderr, "[sdq]   prep: dedupe %.3f median %.3f upload %.3f pool %.3f\n", tDedupe, tMedian - tDedupe, tUpload - tMedian, tPrep - tUpload);
   R.dropRemovedAndSort(clusters);     // clusterDown.cpp:389
   int rc = R.buildIndex(clusters);    // clusterDown.cpp:412-417
