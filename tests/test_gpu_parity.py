@@ -169,6 +169,30 @@ def test_kmer_compare_revcomp_matches_oracle(oracle):
         assert ei.value.code == _abi.E_ALPHABET
 
 
+def test_cxx_gapped_strings_from_gap_lists(oracle):
+    """examples/gapped_strings_cabi.cpp (INTEGRATION level 2, compiled): alignObjectA_ / alignObjectB_ rebuilt from the gap
+    lists the C ABI returns must be the oracle's rearrangeGlobal strings -- internal gaps, end gaps, several runs."""
+    import subprocess
+    import __graft_entry__ as g
+    exe = g.build_example("gapped_strings_cabi")
+    rng = np.random.default_rng(12)
+    base = H.rand_seq(rng, 90)
+    pairs = [(base, H.mutate(rng, base, 2, 1, 1)), (base, base[7:]), (base[:-9], base), (H.mutate(rng, base, 0, 2, 2, hp=True), base),
+             (base, np.concatenate([H.rand_seq(rng, 5), base[:40], base[46:]]))]
+    args = []
+    for a, b in pairs:
+        args += [a.tobytes().decode(), b.tobytes().decode()]
+    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [ln.split("\t") for ln in r.stdout.strip().splitlines()]
+    assert len(lines) == len(pairs)
+    params = make_params()
+    for (a, b), (score, alnA, alnB) in zip(pairs, lines):
+        comp, gaps, wa, wb = oracle.align_profile(params, a.tobytes(), np.full(len(a), 30, np.uint8), b.tobytes(), np.full(len(b), 30, np.uint8))
+        assert int(score) == comp.alnScore and alnA == wa and alnB == wb
+    assert any("-" in ln[1] for ln in lines) and any("-" in ln[2] for ln in lines)
+
+
 def test_append_and_errors():
     p = make_params()
     with GpuAligner(p) as al:
