@@ -49,7 +49,7 @@ typedef struct sdq_opts {
   uint32_t chiRunCutOff;         /* candidates with cnt_ <= this are not examined (njhseq default 1) */
   uint32_t chiOverlapSizeCutoff; /* overLapSizeCutoff_: bases a parent must explain (njhseq default 5) */
   uint32_t chiPosSpacing;        /* posSpacing_ (--chiPosSpacing) */
-  uint32_t reserved;
+  uint32_t converge;             /* colOpts_.clusOpts_.converge_ (--converge, clusterDownSetUp.cpp:394): repeat a par line while it merges */
   double chiParentFreqs;         /* parentFreqs_ (--parFreqs, 2) */
   sdq_iter_par chiOverlap;       /* chiOverlap_ (njhseq: oneBaseIndel 2, twoBaseIndel 1, lowKmer 1;
                                     qluster sets largeBaseIndel .99, clusterDown.cpp:572) */

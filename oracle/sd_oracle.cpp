@@ -758,6 +758,15 @@ struct Engine {
       std::sort(cs.begin(), cs.end(), clusLess);
       if (cs.size() < 2) break;
       collapseWithParameters(cs, its[i]);
+      // --converge (clusterDownSetUp.cpp:394, "Keep clustering at each iteration until there is no more collapsing"):
+      // the same line again, on the re-sorted survivors, while it still merges something
+      while (O.converge) {
+        const size_t before = cs.size();
+        cs.erase(std::remove_if(cs.begin(), cs.end(), [](const Clus& c) { return c.remove; }), cs.end());
+        if (cs.size() == before || cs.size() < 2) break;
+        std::sort(cs.begin(), cs.end(), clusLess);
+        collapseWithParameters(cs, its[i]);
+      }
     }
     cs.erase(std::remove_if(cs.begin(), cs.end(), [](const Clus& c) { return c.remove; }), cs.end());
     std::sort(cs.begin(), cs.end(), clusLess);

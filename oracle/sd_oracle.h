@@ -102,7 +102,7 @@ typedef struct sdo_qluster_opts {
   uint32_t chiRunCutOff;         /* candidates with cnt_ <= this are skipped */
   uint32_t chiOverlapSizeCutoff; /* overLapSizeCutoff_ */
   uint32_t chiPosSpacing;        /* posSpacing_ */
-  uint32_t reserved;
+  uint32_t converge;             /* colOpts_.clusOpts_.converge_ (--converge, clusterDownSetUp.cpp:394): repeat a par line while it merges */
   double chiParentFreqs;         /* parentFreqs_ */
   sdo_iter_par chiOverlap;       /* chiOverlap_ */
 } sdo_qluster_opts;

@@ -894,6 +894,13 @@ class Runner {
       if (cs.size() < 2) break;
       int rc = collapseWithParameters(cs, its[i], lineOf(its[i]));
       if (rc) return rc;
+      // --converge: the same line again, on the re-sorted survivors, while it still merges something
+      while (O.converge && orderDirty) {
+        dropRemovedAndSort(cs);
+        orderDirty = false;
+        if (cs.size() < 2) break;
+        if ((rc = collapseWithParameters(cs, its[i], lineOf(its[i])))) return rc;
+      }
     }
     dropRemovedAndSort(cs);
     return 0;

@@ -91,18 +91,33 @@ __global__ void __launch_bounds__(128) screenScanKernel(const SdScreenArgs a) {
             const uint8_t *cA = a.seqs.codes + offA, *cB = a.seqs.codes + offB;
             const uint8_t *fA = a.seqs.flags + offA, *fB = a.seqs.flags + offB;  // per-base SD_FLAG_* bytes
             unsigned hq = 0, lq = 0, lk = 0;
-            for (int p = gl; p < L; p += SCAN_G) {
-              const int ca = cA[p], cb = cB[p];
-              const int s = sTab[ca * SDGPU_MAX_SYMBOLS + cb];
-              sdiag += s;
-              if (s < 0) {  // aligner::profileAlignment: a column whose score is negative is a mismatch
-                const unsigned fa = fA[p], fb = fB[p];
-                if (usingQuality && !(fa & fb & SD_FLAG_QUAL_OK)) {
-                  ++lq;
-                } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
-                  ++lk;
-                } else {
-                  ++hq;
+            // four columns at a time: the two mates' codes as 32-bit words (two aligned loads + a funnel shift each, the
+            // mates start at arbitrary bytes; the store ends in spare bytes).  Equal words are four matches when every
+            // stored symbol scores the same non-negative value against itself; any other word goes column by column.
+            const unsigned shA = unsigned(reinterpret_cast<uintptr_t>(cA) & 3u) * 8u, shB = unsigned(reinterpret_cast<uintptr_t>(cB) & 3u) * 8u;
+            const uint32_t* wA = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(cA) & ~uintptr_t(3));
+            const uint32_t* wB = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(cB) & ~uintptr_t(3));
+            for (int w = gl; 4 * w < L; w += SCAN_G) {
+              const uint32_t va = __funnelshift_r(__ldg(wA + w), __ldg(wA + w + 1), shA);
+              const uint32_t vb = __funnelshift_r(__ldg(wB + w), __ldg(wB + w + 1), shB);
+              const int p0 = 4 * w, nv = min(4, L - p0);
+              if (nv == 4 && va == vb && a.selfScore >= 0) {
+                sdiag += 4 * a.selfScore;
+                continue;
+              }
+              for (int x = 0; x < nv; ++x) {
+                const int ca = (va >> (8 * x)) & 255, cb = (vb >> (8 * x)) & 255, p = p0 + x;
+                const int s = sTab[ca * SDGPU_MAX_SYMBOLS + cb];
+                sdiag += s;
+                if (s < 0) {  // aligner::profileAlignment: a column whose score is negative is a mismatch
+                  const unsigned fa = fA[p], fb = fB[p];
+                  if (usingQuality && !(fa & fb & SD_FLAG_QUAL_OK)) {
+                    ++lq;
+                  } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
+                    ++lk;
+                  } else {
+                    ++hq;
+                  }
                 }
               }
             }
@@ -415,6 +430,11 @@ bool sd_screen_plan(const sdgpu_ctx* ctx, uint32_t maxLenA, uint32_t maxLenB, Sd
   if (K > (1 << 16) || magnitude * uint64_t(K) >= (1ull << 29)) return false;
   out->K = K;
   out->maxSub = maxSub;
+  // the score every stored symbol has against itself, if it is the same non-negative number for all of them (else -1)
+  out->selfScore = s.score[0];
+  for (int x = 0; x < ctx->nSym; ++x)
+    if (s.score[x * SDGPU_MAX_SYMBOLS + x] != out->selfScore) out->selfScore = -1;
+  if (out->selfScore < 0) out->selfScore = -1;
   // band of w diagonals, offsets -w/2 .. w/2 - 1, equal lengths L: a path touching offset w/2 makes >= w/2 right
   // moves above the last row and has at most L - w/2 diagonal moves; a path touching offset -w/2 - 1 makes
   // >= w/2 + 1 down moves left of the last column.  With deficit = maxSub*L - S_diag, S_diag beats both bounds iff

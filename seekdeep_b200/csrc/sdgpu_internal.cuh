@@ -292,6 +292,7 @@ struct SdScreenArgs {
   uint32_t* work;       // ctx->dWork (SD_W_* words)
   int K;                // perturbation scale: a power of two above the move count of any path
   int maxSub;
+  int selfScore;        // score of every stored symbol against itself when they all agree and it is >= 0, else -1
   long long bandSlack[3];  // a pair whose deficit maxSub*L - S_diag is below bandSlack[b] cannot be beaten outside band b
   int screenOn;         // 0: the scan only lists the non-self pairs of a grid launch
 };

@@ -25,7 +25,7 @@ class QlusterOptsC(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("kLen", "runCutOff", "kmersByPosition", "expandKmerPos", "expandKmerSize",
                                           "checkKmers", "startWithSingles", "leaveOutSinglets", "dontRecalLowFreq",
                                           "smallReadSize", "markChimeras", "chiKeepLowQual", "chiRunCutOff",
-                                          "chiOverlapSizeCutoff", "chiPosSpacing", "reserved")] + \
+                                          "chiOverlapSizeCutoff", "chiPosSpacing", "converge")] + \
                [("chiParentFreqs", C.c_double), ("chiOverlap", IterParC)]
 
 
@@ -49,6 +49,7 @@ class QlusterPars:
     startWithSingles: bool = False
     leaveOutSinglets: bool = False
     dontRecalLowFreqMismatchAndReRun: bool = False
+    converge: bool = False  # --converge: keep clustering at each iteration until there is no more collapsing
     smallReadSize: int = 18  # 2 * kLength (clusterDownSetUp.cpp:406)
     # pars_.chiOpts_ (clusterDownSetUp.cpp:372-381): on unless --noMarkChimeras, parentFreqs 2
     markChimeras: bool = True
@@ -66,7 +67,7 @@ class QlusterPars:
                             self.expandKmerSize, int(self.checkKmers), int(self.startWithSingles),
                             int(self.leaveOutSinglets), int(self.dontRecalLowFreqMismatchAndReRun), self.smallReadSize,
                             int(self.markChimeras), int(self.chiKeepLowQaulityMismatches), self.chiRunCutOff,
-                            self.chiOverlapSizeCutoff, self.chiPosSpacing, 0, float(self.parFreqs),
+                            self.chiOverlapSizeCutoff, self.chiPosSpacing, int(self.converge), float(self.parFreqs),
                             IterParC(0, 0, o[0], o[1], o[2], o[3], o[4], o[5], 0, 0, 0.0))
 
 

@@ -62,6 +62,7 @@ def test_qluster_options(oracle):
             (sd.QlusterPars(startWithSingles=True), CollapseIterations.gen_illumina_default_pars(20)),
             (sd.QlusterPars(leaveOutSinglets=True, dontRecalLowFreqMismatchAndReRun=True), CollapseIterations.gen_illumina_default_pars(100)),
             (sd.QlusterPars(checkKmers=False, kmersByPosition=False, runCutOff=3), CollapseIterations.gen_illumina_default_pars(3)),
+            (sd.QlusterPars(converge=True), CollapseIterations.gen_illumina_default_pars(4)),
             (sd.QlusterPars(runCutOff=1), CollapseIterations.gen_otu_pars(100, 0.97, True)),
             (sd.QlusterPars(expandKmerPos=True, expandKmerSize=2), CollapseIterations.gen_otu_pars(100, 0.98, False))):
         got, want = run_pair(oracle, params, pars, iters, bases, q, offsets)
