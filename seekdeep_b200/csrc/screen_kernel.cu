@@ -56,6 +56,9 @@ constexpr int SCR_MIN_LEN = 40;         // shorter pairs are left to the general
 __global__ void __launch_bounds__(128) screenScanKernel(const SdScreenArgs a) {
   __shared__ int sTab[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];
   __shared__ sdgpu_iter_par sLines[SDGPU_MAX_PASS_LINES];
+  __shared__ SdScreenItem sItem[4][256];  // the verdicts of a warp's grab, filed together
+  __shared__ uint8_t sBinOf[4][256];
+  const int wInCta = threadIdx.x >> 5;
   for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS; x += blockDim.x) sTab[x] = a.sc.score[x];
   for (int x = threadIdx.x; x < int(a.nLines); x += blockDim.x) sLines[x] = a.lines[x];
   __syncthreads();
@@ -158,25 +161,45 @@ __global__ void __launch_bounds__(128) screenScanKernel(const SdScreenArgs a) {
           }
         }
       }
-      // file the pair: one atomic per list and warp
-      const bool leader = gl == 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const unsigned votes = __ballot_sync(FULL, leader && bin == b);
-        if (votes == 0) continue;
-        uint32_t first = 0;
-        if (lane == __ffs(votes) - 1) first = atomicAdd(&a.work[SD_W_BIN0 + b], uint32_t(__popc(votes)));
-        first = __shfl_sync(FULL, first, __ffs(votes) - 1);
-        if (leader && bin == b) {
-          const uint32_t slot = first + __popc(votes & ((1u << lane) - 1u));
-          if (b < 3) {
-            a.items[size_t(b) * a.nPairs + slot] = SdScreenItem{pair, sdiag * a.K, mask};
-          } else {
-            a.redo[slot] = pair;
-          }
-        }
+      // park the verdict: the warp files all 256 pairs of its grab at once (below)
+      if (gl == 0) {
+        const uint32_t slot = round * PPW + uint32_t(q);
+        sBinOf[wInCta][slot] = uint8_t(bin);
+        sItem[wInCta][slot] = SdScreenItem{pair, sdiag * a.K, mask};
       }
     }
+    // file the grab: one atomic per list and warp for 256 pairs (the lists' tails are hot addresses for every SM)
+    __syncwarp();
+    const unsigned ltMask = (1u << lane) - 1u;
+    uint32_t cnt[4] = {0, 0, 0, 0}, first[4] = {0, 0, 0, 0}, running[4] = {0, 0, 0, 0};
+    for (int c = 0; c < 8; ++c) {
+      const int bn = sBinOf[wInCta][c * 32 + lane];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) cnt[x] += __popc(__ballot_sync(FULL, bn == x));
+    }
+    const uint32_t myCnt = lane == 0 ? cnt[0] : (lane == 1 ? cnt[1] : (lane == 2 ? cnt[2] : cnt[3]));
+    uint32_t myFirst = 0;
+    if (lane < 4 && myCnt) myFirst = atomicAdd(&a.work[SD_W_BIN0 + lane], myCnt);  // lane x reserves list x's slots
+#pragma unroll
+    for (int x = 0; x < 4; ++x) first[x] = __shfl_sync(FULL, myFirst, x);
+    for (int c = 0; c < 8; ++c) {
+      const int bn = sBinOf[wInCta][c * 32 + lane];
+      const SdScreenItem it = sItem[wInCta][c * 32 + lane];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const unsigned votes = __ballot_sync(FULL, bn == x);
+        if (bn == x) {
+          const uint32_t slot = first[x] + running[x] + __popc(votes & ltMask);
+          if (x < 3) {
+            a.items[size_t(x) * a.nPairs + slot] = it;
+          } else {
+            a.redo[slot] = it.pair;
+          }
+        }
+        running[x] += __popc(votes);
+      }
+    }
+    __syncwarp();
   }
 }
 

@@ -101,7 +101,7 @@ def test_screen_every_certified_pair_is_gapless(oracle):
     want, gaps = oracle.align_profile_batch(params, bases, q, offsets, refIdx, readIdx, _abi.USING_QUALITY, gapCap=4)
     with GpuAligner(params) as al:
         al.upload_seqs(bases, q, offsets)
-        al.set_pass_table([IterPar(100, 0, 9, 9, 9, 999, 999, 999)])
+        al.set_pass_table([IterPar(100, 0, 999, 999, 999, 999, 999, 999)])
         al.profile_enable(True)
         al.profile_read(reset=True)
         masks = al.align_pass(refIdx, readIdx)
