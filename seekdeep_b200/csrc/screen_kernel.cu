@@ -94,18 +94,34 @@ __global__ void __launch_bounds__(128) screenScanKernel(const SdScreenArgs a) {
             const uint8_t *cA = a.seqs.codes + offA, *cB = a.seqs.codes + offB;
             const uint8_t *fA = a.seqs.flags + offA, *fB = a.seqs.flags + offB;  // per-base SD_FLAG_* bytes
             unsigned hq = 0, lq = 0, lk = 0;
-            // four columns at a time: the two mates' codes as 32-bit words (two aligned loads + a funnel shift each, the
-            // mates start at arbitrary bytes; the store ends in spare bytes).  Equal words are four matches when every
-            // stored symbol scores the same non-negative value against itself; any other word goes column by column.
+            // four columns at a time: the two sequences' codes as 32-bit words (two aligned loads + a funnel shift each:
+            // sequences start at arbitrary bytes; the store ends in spare bytes).
             const unsigned shA = unsigned(reinterpret_cast<uintptr_t>(cA) & 3u) * 8u, shB = unsigned(reinterpret_cast<uintptr_t>(cB) & 3u) * 8u;
             const uint32_t* wA = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(cA) & ~uintptr_t(3));
             const uint32_t* wB = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(cB) & ~uintptr_t(3));
+            const unsigned shFA = unsigned(reinterpret_cast<uintptr_t>(fA) & 3u) * 8u, shFB = unsigned(reinterpret_cast<uintptr_t>(fB) & 3u) * 8u;
+            const uint32_t* wFA = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(fA) & ~uintptr_t(3));
+            const uint32_t* wFB = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(fB) & ~uintptr_t(3));
             for (int w = gl; 4 * w < L; w += SCAN_G) {
               const uint32_t va = __funnelshift_r(__ldg(wA + w), __ldg(wA + w + 1), shA);
               const uint32_t vb = __funnelshift_r(__ldg(wB + w), __ldg(wB + w + 1), shB);
               const int p0 = 4 * w, nv = min(4, L - p0);
-              if (nv == 4 && va == vb && a.selfScore >= 0) {
-                sdiag += 4 * a.selfScore;
+              if (a.selfScore >= 0 && a.misScore < 0) {
+                // match / mismatch matrix: no table, no branches.  Codes are < 16, so adding 0x7f to every byte of
+                // the XOR raises bit 7 exactly in the bytes that differ; flag bytes are folded the same way.
+                const uint32_t valid = nv == 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nv)) - 1u));
+                const uint32_t mis = (((va ^ vb) + 0x7f7f7f7fu) & valid);
+                sdiag += nv * a.selfScore - __popc(mis) * (a.selfScore - a.misScore);
+                if (mis) {
+                  const uint32_t fa = __funnelshift_r(__ldg(wFA + w), __ldg(wFA + w + 1), shFA);
+                  const uint32_t fb = __funnelshift_r(__ldg(wFB + w), __ldg(wFB + w + 1), shFB);
+                  const uint32_t good = usingQuality ? (((fa & fb) << 7) & 0x80808080u) : 0x80808080u;       // SD_FLAG_QUAL_OK in both
+                  const uint32_t low = checkKmer ? ((((fa | fb) >> 1) << 7) & 0x80808080u) : 0u;             // SD_FLAG_LOW_KMER in either
+                  const uint32_t isLq = mis & ~good, isLk = mis & good & low;
+                  lq += __popc(isLq);
+                  lk += __popc(isLk);
+                  hq += __popc(mis & good & ~low);
+                }
                 continue;
               }
               for (int x = 0; x < nv; ++x) {
@@ -458,6 +474,12 @@ bool sd_screen_plan(const sdgpu_ctx* ctx, uint32_t maxLenA, uint32_t maxLenB, Sd
   for (int x = 0; x < ctx->nSym; ++x)
     if (s.score[x * SDGPU_MAX_SYMBOLS + x] != out->selfScore) out->selfScore = -1;
   if (out->selfScore < 0) out->selfScore = -1;
+  // ... and the score of every pair of different symbols, if it is the same negative number for all of them (else 0)
+  out->misScore = ctx->nSym > 1 ? s.score[1] : 0;
+  for (int x = 0; x < ctx->nSym; ++x)
+    for (int y = 0; y < ctx->nSym; ++y)
+      if (x != y && s.score[x * SDGPU_MAX_SYMBOLS + y] != out->misScore) out->misScore = 0;
+  if (out->misScore >= 0) out->misScore = 0;
   // band of w diagonals, offsets -w/2 .. w/2 - 1, equal lengths L: a path touching offset w/2 makes >= w/2 right
   // moves above the last row and has at most L - w/2 diagonal moves; a path touching offset -w/2 - 1 makes
   // >= w/2 + 1 down moves left of the last column.  With deficit = maxSub*L - S_diag, S_diag beats both bounds iff

@@ -293,6 +293,7 @@ struct SdScreenArgs {
   int K;                // perturbation scale: a power of two above the move count of any path
   int maxSub;
   int selfScore;        // score of every stored symbol against itself when they all agree and it is >= 0, else -1
+  int misScore;         // score of every pair of different stored symbols when they all agree and it is < 0, else 0
   long long bandSlack[3];  // a pair whose deficit maxSub*L - S_diag is below bandSlack[b] cannot be beaten outside band b
   int screenOn;         // 0: the scan only lists the non-self pairs of a grid launch
 };
