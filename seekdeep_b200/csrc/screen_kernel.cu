@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) screenScanKernel(const SdScreenArgs a) {
   const bool usingQuality = (a.flags & SDGPU_USING_QUALITY) != 0;
   for (;;) {
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&a.work[SD_W_SCAN], 64u * PPW);  // 64 rounds of pairs per grab
+    if (lane == 0) base = atomicAdd(&a.work[SD_W_SCAN], 64u * PPW);  // 64 rounds of pairs (256) per grab
     base = __shfl_sync(FULL, base, 0);
     if (base >= a.nPairs) break;
     for (uint32_t round = 0; round < 64; ++round) {
@@ -102,40 +102,53 @@ __global__ void __launch_bounds__(128) screenScanKernel(const SdScreenArgs a) {
             const unsigned shFA = unsigned(reinterpret_cast<uintptr_t>(fA) & 3u) * 8u, shFB = unsigned(reinterpret_cast<uintptr_t>(fB) & 3u) * 8u;
             const uint32_t* wFA = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(fA) & ~uintptr_t(3));
             const uint32_t* wFB = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(fB) & ~uintptr_t(3));
-            for (int w = gl; 4 * w < L; w += SCAN_G) {
-              const uint32_t va = __funnelshift_r(__ldg(wA + w), __ldg(wA + w + 1), shA);
-              const uint32_t vb = __funnelshift_r(__ldg(wB + w), __ldg(wB + w + 1), shB);
-              const int p0 = 4 * w, nv = min(4, L - p0);
-              if (a.selfScore >= 0 && a.misScore < 0) {
-                // match / mismatch matrix: no table, no branches.  Codes are < 16, so adding 0x7f to every byte of
-                // the XOR raises bit 7 exactly in the bytes that differ; flag bytes are folded the same way.
-                const uint32_t valid = nv == 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nv)) - 1u));
-                const uint32_t mis = (((va ^ vb) + 0x7f7f7f7fu) & valid);
-                sdiag += nv * a.selfScore - __popc(mis) * (a.selfScore - a.misScore);
-                if (mis) {
-                  const uint32_t fa = __funnelshift_r(__ldg(wFA + w), __ldg(wFA + w + 1), shFA);
-                  const uint32_t fb = __funnelshift_r(__ldg(wFB + w), __ldg(wFB + w + 1), shFB);
-                  const uint32_t good = usingQuality ? (((fa & fb) << 7) & 0x80808080u) : 0x80808080u;       // SD_FLAG_QUAL_OK in both
-                  const uint32_t low = checkKmer ? ((((fa | fb) >> 1) << 7) & 0x80808080u) : 0u;             // SD_FLAG_LOW_KMER in either
-                  const uint32_t isLq = mis & ~good, isLk = mis & good & low;
-                  lq += __popc(isLq);
-                  lk += __popc(isLk);
-                  hq += __popc(mis & good & ~low);
-                }
-                continue;
+            // (the kernel is bound by load latency, not by instructions: the words of five iterations are requested
+            //  before the first one is looked at)
+            constexpr int MLP = 5;
+            for (int w0 = gl; 4 * w0 < L; w0 += SCAN_G * MLP) {
+              uint32_t va[MLP], vb[MLP];
+#pragma unroll
+              for (int t = 0; t < MLP; ++t) {
+                const int w = w0 + SCAN_G * t;
+                const bool in = 4 * w < L;
+                va[t] = in ? __funnelshift_r(__ldg(wA + w), __ldg(wA + w + 1), shA) : 0u;
+                vb[t] = in ? __funnelshift_r(__ldg(wB + w), __ldg(wB + w + 1), shB) : 0u;
               }
-              for (int x = 0; x < nv; ++x) {
-                const int ca = (va >> (8 * x)) & 255, cb = (vb >> (8 * x)) & 255, p = p0 + x;
-                const int s = sTab[ca * SDGPU_MAX_SYMBOLS + cb];
-                sdiag += s;
-                if (s < 0) {  // aligner::profileAlignment: a column whose score is negative is a mismatch
-                  const unsigned fa = fA[p], fb = fB[p];
-                  if (usingQuality && !(fa & fb & SD_FLAG_QUAL_OK)) {
-                    ++lq;
-                  } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
-                    ++lk;
-                  } else {
-                    ++hq;
+#pragma unroll
+              for (int t = 0; t < MLP; ++t) {
+                const int w = w0 + SCAN_G * t;
+                const int p0 = 4 * w, nv = min(4, L - p0);
+                if (nv <= 0) continue;
+                if (a.selfScore >= 0 && a.misScore < 0) {
+                  // match / mismatch matrix: no table, no branches.  Codes are < 16, so adding 0x7f to every byte of
+                  // the XOR raises bit 7 exactly in the bytes that differ; flag bytes are folded the same way.
+                  const uint32_t valid = nv == 4 ? 0x80808080u : (0x80808080u & ((1u << (8 * nv)) - 1u));
+                  const uint32_t mis = (((va[t] ^ vb[t]) + 0x7f7f7f7fu) & valid);
+                  sdiag += nv * a.selfScore - __popc(mis) * (a.selfScore - a.misScore);
+                  if (mis) {
+                    const uint32_t fa = __funnelshift_r(__ldg(wFA + w), __ldg(wFA + w + 1), shFA);
+                    const uint32_t fb = __funnelshift_r(__ldg(wFB + w), __ldg(wFB + w + 1), shFB);
+                    const uint32_t good = usingQuality ? (((fa & fb) << 7) & 0x80808080u) : 0x80808080u;       // SD_FLAG_QUAL_OK in both
+                    const uint32_t low = checkKmer ? ((((fa | fb) >> 1) << 7) & 0x80808080u) : 0u;             // SD_FLAG_LOW_KMER in either
+                    lq += __popc(mis & ~good);
+                    lk += __popc(mis & good & low);
+                    hq += __popc(mis & good & ~low);
+                  }
+                  continue;
+                }
+                for (int x = 0; x < nv; ++x) {
+                  const int ca = (va[t] >> (8 * x)) & 255, cb = (vb[t] >> (8 * x)) & 255, p = p0 + x;
+                  const int sc = sTab[ca * SDGPU_MAX_SYMBOLS + cb];
+                  sdiag += sc;
+                  if (sc < 0) {  // aligner::profileAlignment: a column whose score is negative is a mismatch
+                    const unsigned fa = fA[p], fb = fB[p];
+                    if (usingQuality && !(fa & fb & SD_FLAG_QUAL_OK)) {
+                      ++lq;
+                    } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
+                      ++lk;
+                    } else {
+                      ++hq;
+                    }
                   }
                 }
               }
