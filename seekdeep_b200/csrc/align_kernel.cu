@@ -949,13 +949,14 @@ __device__ __forceinline__ void bandCell(BandLane& st, int i, int j, int lane, i
 // into the score table (ref: code * 64 = its row, read: code * 4 = its column), so a cell's score is
 // one LDS at base + row + column.
 constexpr int BAND_STAGE = 2048;
+constexpr int BAND_TABW = 20;  // row stride (words) of the band kernel's score table: the rows of A, C, G, T fall on disjoint banks
 struct BandCodes {
   const uint16_t* rowOff;  // [i-1] -> byte offset of ref base i's row (shared memory, or nullptr)
   const uint8_t* colOff;   // [j-1] -> byte offset of read base j's column
   const uint8_t *cA, *cB;  // global codes (sequences too long to stage)
   const char* tab;         // score table, bytes
   __device__ __forceinline__ int row(int i) const {
-    return rowOff ? int(rowOff[i - 1]) : int(__ldg(cA + i - 1)) * (SDGPU_MAX_SYMBOLS * 4);
+    return rowOff ? int(rowOff[i - 1]) : int(__ldg(cA + i - 1)) * (BAND_TABW * 4);
   }
   __device__ __forceinline__ int col(int j) const { return rowOff ? int(colOff[j - 1]) : int(__ldg(cB + j - 1)) * 4; }
   __device__ __forceinline__ int score(int r, int c) const { return *reinterpret_cast<const int*>(tab + r + c); }
@@ -979,7 +980,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) alignBandKernel(const A
   __shared__ int sTab[SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS];
   __shared__ uint16_t sRow[WARPS_PER_CTA][BAND_STAGE];
   __shared__ uint8_t sCol[WARPS_PER_CTA][BAND_STAGE];
+  __shared__ int sTabW[SDGPU_MAX_SYMBOLS * BAND_TABW];  // the DP's copy of the table (sTab serves the errorProfile stage)
   for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * SDGPU_MAX_SYMBOLS; x += blockDim.x) sTab[x] = a.sc.score[x];
+  for (int x = threadIdx.x; x < SDGPU_MAX_SYMBOLS * BAND_TABW; x += blockDim.x) {
+    const int r = x / BAND_TABW, c = x - r * BAND_TABW;
+    sTabW[x] = c < SDGPU_MAX_SYMBOLS ? int(a.sc.score[r * SDGPU_MAX_SYMBOLS + c]) : 0;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warpInCta = threadIdx.x >> 5;
@@ -1008,10 +1014,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8) alignBandKernel(const A
     const int dlo = (diff - 63) >> 1;        // floor: the band [dlo, dlo + 63] is centred between offsets 0 and diff
     const int aBase = 2 - ((2 - dlo) & 1);   // lanes meet their even offset d0 on anti-diagonals aBase, aBase + 2, ...
     if (diff >= -BAND_MAX_DIFF && diff <= BAND_MAX_DIFF) {
-      BandCodes bc{nullptr, nullptr, pv.cA, pv.cB, reinterpret_cast<const char*>(sTab)};
+      BandCodes bc{nullptr, nullptr, pv.cA, pv.cB, reinterpret_cast<const char*>(sTabW)};
       const bool staged = la <= BAND_STAGE && lb <= BAND_STAGE;
       if (staged) {
-        for (int x = lane; x < la; x += 32) sRow[warpInCta][x] = uint16_t(int(pv.cA[x]) * (SDGPU_MAX_SYMBOLS * 4));
+        for (int x = lane; x < la; x += 32) sRow[warpInCta][x] = uint16_t(int(pv.cA[x]) * (BAND_TABW * 4));
         for (int x = lane; x < lb; x += 32) sCol[warpInCta][x] = uint8_t(int(pv.cB[x]) * 4);
         bc.rowOff = sRow[warpInCta];
         bc.colOff = sCol[warpInCta];

@@ -350,6 +350,7 @@ class Runner {
   std::vector<sdgpu_comparison> cmpBuf;
   std::vector<sdgpu_gap> gapBuf;
   double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0, tIndex = 0, tSubmit = 0;
+  double tConsAlign = 0, tConsCount = 0, tConsBuild = 0, tConsUpload = 0;  // parts of tCons
   uint64_t keptVersions = 0, skippedScans = 0;
   bool orderDirty = true;
   // symbols of the consensus counters (bases + '-'), ASCII order kept for njhseq's tie rule
@@ -432,26 +433,24 @@ class Runner {
   // njhseq collapser::collapseWithParameters + findMatch for one par-file line
   int collapseWithParameters(ClusVec& cs, const sdq_iter_par& it, int line) {
     ++serial;
-    size_t alive = 0;
-    for (const Pos& x : PR) alive += !x.remove;
+    // (the list was compacted and re-sorted after the last iteration that merged anything: nothing in it is removed,
+    //  and counts descend, so the candidate clusters of the smallCutoff rule are a prefix of it)
+    const size_t alive = PR.size();
     if (alive < 2) return 0;
     const uint64_t bit = 1ull << line;
-    std::vector<uint32_t> elig;  // candidate clusters in sorted order (smallCutoff rule)
-    for (uint32_t cp = 0; cp < cs.size(); ++cp)
-      if (!PR[cp].remove && PR[cp].cnt > double(it.smallCutoff)) elig.push_back(cp);
+    const uint32_t eligEnd = uint32_t(std::partition_point(PR.begin(), PR.end(), [&](const Pos& x) { return x.cnt > double(it.smallCutoff); }) -
+                                      PR.begin());
     // ---- speculative batch: the window = first stopCheck(+1: a read skips itself) candidates
     double tt0 = nowSec();
     std::unique_ptr<NvtxRange> gridRange(new NvtxRange("sdq:list+grids"));
-    const uint32_t wn = uint32_t(std::min<uint64_t>(elig.size(), uint64_t(it.stopCheck) + 1));
-    std::vector<uint8_t> inWindow(cs.size(), 0);
+    const uint32_t wn = uint32_t(std::min<uint64_t>(eligEnd, uint64_t(it.stopCheck) + 1));  // the window: positions [0, wn)
     {
       if (inPrevWindow.size() < storeSize) inPrevWindow.resize(storeSize, 0);
       if (lastIn.size() < storeSize) lastIn.resize(storeSize, 0);
       if (onDemandAt.size() < storeSize) onDemandAt.resize(storeSize, 0);
       std::vector<uint32_t> window, fresh;  // store indices: the whole window / its entries the previous one lacked
       for (uint32_t w = 0; w < wn; ++w) {
-        inWindow[elig[w]] = 1;
-        const uint32_t sIdx = PR[elig[w]].store;
+        const uint32_t sIdx = PR[w].store;
         window.push_back(sIdx);
         if (!inPrevWindow[sIdx]) fresh.push_back(sIdx);
       }
@@ -501,8 +500,7 @@ class Runner {
       }
       Clus& read = cs[rp];
       uint32_t count = 0;
-      for (uint32_t e = 0; e < elig.size(); ++e) {
-        const uint32_t cp = elig[e];
+      for (uint32_t cp = 0; cp < eligEnd; ++cp) {
         if (PR[cp].remove) continue;
         if (cp == rp) continue;
         ++count;
@@ -538,7 +536,7 @@ class Runner {
           PR[cp].changed = 1;
           read.row.clear();
           read.cons.reset();
-          if (inWindow[rp]) windowIntact = false;
+          if (rp < wn) windowIntact = false;
           ++amountAdded;
           break;
         }
@@ -601,6 +599,7 @@ class Runner {
       jobs.push_back(j);
     }
     if (jobs.empty()) return 0;
+    double tc0 = nowSec();
     // alignments with gap lists; pairs whose list overflowed are re-run with a larger capacity
     const size_t n = a.size();
     uint32_t gapCap = 8;
@@ -637,6 +636,8 @@ class Runner {
       todo.swap(next);
       gapCap *= 8;
     }
+    tConsAlign += nowSec() - tc0;
+    tc0 = nowSec();
     // column counters -> new consensus (ConsensusHelper::increaseCounters / buildConsensus)
     // (clusters are independent of each other here: a few host threads share the jobs; what must
     //  stay in job order -- the list of new device versions -- is collected afterwards)
@@ -716,6 +717,8 @@ class Runner {
       }
       if (!symOk) jobBad[ch.job] = 1;
     }, 8);
+    tConsCount += nowSec() - tc0;
+    tc0 = nowSec();
     // (b) the new consensus of every cluster, clusters side by side
     parallelForDynamic(jobs.size(), [&](size_t jx) {
       const Job& j = jobs[jx];
@@ -782,6 +785,13 @@ class Runner {
       }
       cl.avgErr = averageErrorRate(cl.qual);
     });
+    tConsBuild += nowSec() - tc0;
+    tc0 = nowSec();
+    struct UploadTick {
+      double& acc;
+      double t0;
+      ~UploadTick() { acc += nowSec() - t0; }
+    } uploadTick{tConsUpload, tc0};
     for (size_t jx = 0; jx < jobs.size(); ++jx) {
       if (outcome[jx] == OUT_BAD_SYMBOL) {
         g_err = "more than 18 distinct symbols in consensus columns";
@@ -1302,6 +1312,8 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
   if (getenv("SDQ_TIMING")) {
     fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f (submit %.3f, %llu batches) spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f sort %.3f index %.3f lines %zu\n",
             res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSubmit, (unsigned long long)R.st.gpuBatches, R.tSpec, R.tInsert, R.tPass, R.tCons, R.tSort, R.tIndex, R.lines.size());
+    fprintf(stderr, "[sdq] consensus: member alignments %.3f counting %.3f rebuild %.3f new versions %.3f\n", R.tConsAlign, R.tConsCount, R.tConsBuild,
+            R.tConsUpload);
     fprintf(stderr, "[sdq] consensus updates kept on the device version: %llu, store entries: %u (unique reads %u), scans skipped %llu\n",
             (unsigned long long)R.keptVersions, R.storeSize, nU, (unsigned long long)R.skippedScans);
   }
