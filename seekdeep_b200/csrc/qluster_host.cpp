@@ -156,9 +156,10 @@ static const bool g_verboseTiming = getenv("SDQ_TIMING") && atoi(getenv("SDQ_TIM
 // Items of very different cost (clusters absorbing 1 .. thousands of members): threads pull indices
 // from a shared counter.
 template <class Fn>
-static void parallelForDynamic(size_t n, Fn fn, size_t maxThreads = 4) {
+static void parallelForDynamic(size_t n, Fn fn, size_t maxThreads = 4, size_t minItemsPerThread = 1) {
   const unsigned hw = allowedCpus();
   size_t T = std::min<size_t>(hw ? hw : 1, maxThreads);
+  T = std::min(T, std::max<size_t>(1, n / minItemsPerThread));  // (starting a thread costs as much as tens of small items)
   if (n < 8) T = 1;
   if (T <= 1) {
     for (size_t i = 0; i < n; ++i) fn(i);
@@ -716,7 +717,7 @@ class Runner {
           }
       }
       if (!symOk) jobBad[ch.job] = 1;
-    }, 8);
+    }, 8, 2);
     tConsCount += nowSec() - tc0;
     tc0 = nowSec();
     // (b) the new consensus of every cluster, clusters side by side
@@ -784,7 +785,7 @@ class Runner {
         }
       }
       cl.avgErr = averageErrorRate(cl.qual);
-    });
+    }, 4, 32);
     tConsBuild += nowSec() - tc0;
     tc0 = nowSec();
     struct UploadTick {
