@@ -161,6 +161,9 @@ int sdgpu_append_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
                       const uint64_t* offsets, const double* cnts, uint32_t n,
                       uint32_t* firstIndex);
 int sdgpu_num_seqs(sdgpu_ctx* ctx, uint32_t* n);
+/* The distinct base characters the ctx has met so far (at most 16; A, C, G, T, N are always listed first): what a
+ * caller sizes per-symbol tables with, e.g. the consensus column counters (njhseq charCounter). */
+int sdgpu_get_alphabet(sdgpu_ctx* ctx, uint8_t chars[16], uint32_t* n);
 /* Overwrites seqBase_.cnt_ of stored sequences (clusters grow as they absorb reads; the k-mer
  * index weights every k-mer by the current count, clusterDown.cpp:505-510). */
 int sdgpu_update_cnts(sdgpu_ctx* ctx, const uint32_t* seqIdx, const double* cnts, uint32_t n);

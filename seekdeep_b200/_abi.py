@@ -80,6 +80,7 @@ SIGNATURES = {
     "sdgpu_upload_seqs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_upload_seqs_gather": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_append_seqs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, _u32p]),
+    "sdgpu_get_alphabet": (C.c_int, [_ctx, C.c_void_p, _u32p]),
     "sdgpu_num_seqs": (C.c_int, [_ctx, _u32p]),
     "sdgpu_update_cnts": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_build_kmer_index": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32]),

@@ -198,6 +198,40 @@ struct Uniq {  // one exact-unique input sequence; its store index is its positi
   uint32_t inputBegin = 0, inputEnd = 0;  // its input reads: Runner::inputList[inputBegin, inputEnd), ascending
 };
 
+// The unique sequences a cluster holds.  Almost every cluster of a run is a singleton that is absorbed or stays alone,
+// so the first member lives in the object and only clusters that absorb others allocate.
+class Members {
+ public:
+  struct Iter {
+    const Members* m;
+    size_t i;
+    uint32_t operator*() const { return (*m)[i]; }
+    Iter& operator++() {
+      ++i;
+      return *this;
+    }
+    bool operator!=(const Iter& o) const { return i != o.i; }
+  };
+  void init(uint32_t u) {
+    first_ = u;
+    has_ = true;
+    more_.clear();
+  }
+  size_t size() const { return has_ ? 1 + more_.size() : 0; }
+  uint32_t operator[](size_t i) const { return i == 0 ? first_ : more_[i - 1]; }
+  void append(const Members& o) {
+    more_.reserve(more_.size() + o.size());
+    for (size_t i = 0; i < o.size(); ++i) more_.push_back(o[i]);
+  }
+  Iter begin() const { return Iter{this, 0}; }
+  Iter end() const { return Iter{this, size()}; }
+
+ private:
+  uint32_t first_ = 0;
+  bool has_ = false;
+  std::vector<uint32_t> more_;
+};
+
 // njhseq charCounter restricted to what consensus building uses, over the few symbols that occur
 constexpr int NSYM = 18;
 struct Col {
@@ -236,7 +270,7 @@ struct alignas(64) Clus {
   View seq, qual;          // current consensus: its seed read until a consensus rebuild changes it, then own storage
   std::string ownSeq;
   std::vector<uint8_t> ownQual;
-  std::vector<uint32_t> members;
+  Members members;
   uint32_t chiParent[2] = {0, 0}, chiPos[2] = {0, 0};
   std::vector<uint8_t> devSig;  // checkQual outcome per base of the device version (empty: exact copy)
   std::unique_ptr<ConsState> cons;
@@ -530,7 +564,7 @@ class Runner {
         if (v && (*v & bit)) {
           Clus& clus = cs[cp];
           clus.cnt += read.cnt;
-          clus.members.insert(clus.members.end(), read.members.begin(), read.members.end());
+          clus.members.append(read.members);
           clus.needCons = true;
           read.remove = true;
           PR[rp].remove = 1;
@@ -1078,10 +1112,7 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
   {
     // 64-bit hash of the bases, all reads in parallel; open addressing, equal hashes confirmed byte for byte
     std::vector<uint64_t> readHash(n);
-    std::mutex seenMu;
-    uint64_t seen[2] = {0, 0};  // 7-bit characters that occur (the consensus counters' symbol slots)
     parallelFor(n, [&](size_t lo, size_t hi) {
-      uint64_t mine[2] = {0, 0};
       for (size_t r = lo; r < hi; ++r) {
         const uint32_t len = in.len(uint32_t(r));
         const uint8_t* p = in.seq(uint32_t(r));
@@ -1095,16 +1126,8 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
         }
         for (; i < len; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
         readHash[r] = h ^ (h >> 29);
-        for (uint32_t x = 0; x < len; ++x) mine[(p[x] >> 6) & 1] |= 1ull << (p[x] & 63);
       }
-      std::lock_guard<std::mutex> lk(seenMu);
-      seen[0] |= mine[0];
-      seen[1] |= mine[1];
     });
-    // every symbol gets its counter slot now, so the threaded consensus rebuild only reads the slot table
-    R.slot('-');
-    for (int c = 0; c < 128; ++c)
-      if ((seen[c >> 6] >> (c & 63)) & 1) R.slot(char(c));
     size_t cap = 1024;
     while (cap < size_t(n) * 2 + 16) cap <<= 1;
     std::vector<uint32_t> table(cap, UINT32_MAX);
@@ -1241,6 +1264,13 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
     if (sdgpu_upload_seqs_gather(ctx, sp.data(), qp.data(), ln.data(), cn.data(), nU)) return bail(R.fail(SDGPU_E_CUDA));
     R.storeSize = nU;
     if (sdgpu_timer_start(ctx)) return bail(R.fail(SDGPU_E_CUDA));  // inputs are resident from here on
+    // every symbol the store knows gets its consensus-counter slot now (the upload has just walked every base), so the
+    // threaded consensus rebuild only reads the slot table
+    uint8_t chars[16];
+    uint32_t nChars = 0;
+    if (sdgpu_get_alphabet(ctx, chars, &nChars)) return bail(R.fail(SDGPU_E_CUDA));
+    R.slot('-');
+    for (uint32_t c = 0; c < nChars; ++c) R.slot(char(chars[c]));
   }
   const double tUpload = nowSec() - tStart;
   res->pool.resize(nU);  // never resized again: ClusVec holds pointers into it
@@ -1255,7 +1285,7 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
       c.cnt = R.uniq[u].cnt;
       c.firstId = u;
       c.storeIdx = u;
-      c.members = {u};
+      c.members.init(u);
       c.avgErr = averageErrorRate(c.qual);
     }
   });

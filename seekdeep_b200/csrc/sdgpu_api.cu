@@ -446,6 +446,13 @@ int sdgpu_append_seqs(sdgpu_ctx* ctx, const uint8_t* bases, const uint8_t* quals
   return appendImpl(ctx, src, cnts, n, firstIndex, false);
 }
 
+int sdgpu_get_alphabet(sdgpu_ctx* ctx, uint8_t chars[16], uint32_t* n) {
+  if (!ctx || !chars || !n) return SDGPU_E_ARG;
+  for (int x = 0; x < ctx->nSym; ++x) chars[x] = ctx->charOf[x];
+  *n = uint32_t(ctx->nSym);
+  return SDGPU_OK;
+}
+
 int sdgpu_num_seqs(sdgpu_ctx* ctx, uint32_t* n) {
   if (!ctx || !n) return SDGPU_E_ARG;
   *n = uint32_t(ctx->hOffsets.size() - 1);
