@@ -220,8 +220,7 @@ class Members {
   size_t size() const { return has_ ? 1 + more_.size() : 0; }
   uint32_t operator[](size_t i) const { return i == 0 ? first_ : more_[i - 1]; }
   void append(const Members& o) {
-    more_.reserve(more_.size() + o.size());
-    for (size_t i = 0; i < o.size(); ++i) more_.push_back(o[i]);
+    for (size_t i = 0; i < o.size(); ++i) more_.push_back(o[i]);  // (push_back grows geometrically; an exact reserve per call would not)
   }
   Iter begin() const { return Iter{this, 0}; }
   Iter end() const { return Iter{this, size()}; }
