@@ -697,18 +697,53 @@ class Runner {
       const Job& j = jobs[ch.job];
       std::string ga, gb;
       std::vector<uint8_t> gq;
+      // Ungapped members differ from the base sequence in a few columns only.  Per chunk: wAll = their total weight,
+      // qAll[i] = sum of quality x weight over ALL of them (one multiply-add sweep per member); the columns where a
+      // member does not carry the base's symbol are tallied symbol by symbol in `local` and remembered in wOff / qOff,
+      // so that the base symbol of column i receives wAll - wOff[i] and qAll[i] - qOff[i].  Integer sums: exact.
       std::vector<Col> local;
+      std::vector<uint32_t> qAll, wOff, qOff;
+      uint32_t wAll = 0;
       bool symOk = true;
       Clus& cl = cs[j.clus];
       ConsState& S = *cl.cons;
       const std::string& base = S.baseSeq;
+      const size_t L = base.size();
       for (size_t m = ch.m0; m < ch.m1; ++m) {
         const Uniq& r = uniq[cl.members[m]];
         const uint32_t w = uint32_t(std::llround(r.cnt));
         const std::vector<sdgpu_gap>& gl = gaps[j.firstPair + (m - j.firstMember)];
-        if (gl.empty() && r.seq.size() == base.size()) {  // ungapped: column i is base position i
-          if (local.empty()) local.assign(base.size(), Col());
-          for (uint32_t i = 0; i < base.size(); ++i) symOk &= add(local[i], r.seq[i], r.qual[i], w);
+        if (gl.empty() && r.seq.size() == L) {  // ungapped: column i is base position i
+          if (local.empty()) {
+            local.assign(L, Col());
+            qAll.assign(L, 0);
+            wOff.assign(L, 0);
+            qOff.assign(L, 0);
+          }
+          wAll += w;
+          const uint8_t* q = r.qual.data();
+          const uint8_t* sq = r.seq.data();
+          uint32_t* qa = qAll.data();
+          for (size_t i = 0; i < L; ++i) qa[i] += uint32_t(q[i]) * w;
+          size_t i = 0;
+          for (; i + 8 <= L; i += 8) {  // eight columns at a time: where does the member leave the base sequence?
+            uint64_t x, y;
+            std::memcpy(&x, sq + i, 8);
+            std::memcpy(&y, base.data() + i, 8);
+            if (x == y) continue;
+            for (size_t k = i; k < i + 8; ++k)
+              if (sq[k] != uint8_t(base[k])) {
+                symOk &= add(local[k], char(sq[k]), q[k], w);
+                wOff[k] += w;
+                qOff[k] += uint32_t(q[k]) * w;
+              }
+          }
+          for (; i < L; ++i)
+            if (sq[i] != uint8_t(base[i])) {
+              symOk &= add(local[i], char(sq[i]), q[i], w);
+              wOff[i] += w;
+              qOff[i] += uint32_t(q[i]) * w;
+            }
           continue;
         }
         std::lock_guard<std::mutex> lk(jobMu[ch.job]);
@@ -743,11 +778,19 @@ class Runner {
       }
       if (!local.empty()) {
         std::lock_guard<std::mutex> lk(jobMu[ch.job]);
-        for (size_t i = 0; i < local.size(); ++i)
+        for (size_t i = 0; i < local.size(); ++i) {
           for (int x = 0; x < NSYM; ++x) {
             S.counters[i].cnt[x] += local[i].cnt[x];
             S.counters[i].qual[x] += local[i].qual[x];
           }
+          const int bs = slot(base[i]);  // (registered: the base sequence is in the store)
+          if (bs < 0) {
+            symOk = false;
+            continue;
+          }
+          S.counters[i].cnt[bs] += wAll - wOff[i];
+          S.counters[i].qual[bs] += qAll[i] - qOff[i];
+        }
       }
       if (!symOk) jobBad[ch.job] = 1;
     }, 8, 2);
