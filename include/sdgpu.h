@@ -197,6 +197,19 @@ int sdgpu_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nRead
                            const uint32_t* clusters, uint32_t nClusters, uint32_t* sharedOut,
                            double* fracOut);
 
+/* k-mer binning in front of the collapse (qluster --useKmerBinning / --kmerCutOff / --kCompareLen,
+ * src/SeekDeepPrograms/SeekDeepProgram/clusterDown/clusterDownSetUp.cpp:352-354; njhseq collapser::runFullClustering
+ * bins its clusters by k-mer similarity to a bin's first read before it aligns anything).
+ * sdgpu_build_kmer_lists replaces kmerInfo(seq, kLen, false) for every stored sequence at any 1 <= kLen <= 16 (the
+ * dense profiles above stop at 16 384 bins): the sequence's own k-mers, sorted, on the device.
+ * sdgpu_kmer_bin_masks replaces seed.compareKmers(read) for every (read, seed) of reads[] x seeds[] (nSeeds <= 64):
+ * bit c of maskOut[r] is set <=> the shared fraction -- the exact double shared / (min(lenSeed, lenRead) - kLen + 1)
+ * -- is > cutOff; only 8 bytes per read return.  sharedOut (may be NULL) receives the shared counts, row-major
+ * [nReads][nSeeds].  Sequences appended after the last sdgpu_build_kmer_lists call are not covered (SDGPU_E_ARG). */
+int sdgpu_build_kmer_lists(sdgpu_ctx* ctx, uint32_t kLen);
+int sdgpu_kmer_bin_masks(sdgpu_ctx* ctx, const uint32_t* seeds, uint32_t nSeeds, const uint32_t* reads, uint32_t nReads,
+                         double cutOff, uint64_t* maskOut, uint32_t* sharedOut);
+
 /* Replaces, per pair i: alignerObj.alignCacheGlobal(seq[refIdx[i]], seq[readIdx[i]]) followed
  * by alignerObj.profileAlignment(ref, read, checkKmer, usingQuality, doingMatchQuality)
  * (clusterDown.cpp:739-741), returning aligner::comp_ in out[i].  If gapsOut != NULL the gap
@@ -206,6 +219,34 @@ int sdgpu_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nRead
 int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx,
                         uint32_t nPairs, uint32_t flags, sdgpu_comparison* out,
                         sdgpu_gap* gapsOut, uint32_t gapCap);
+
+/* Per-event part of aligner::comp_: distances_.mismatches_, distances_.lowKmerMismatches_ and
+ * distances_.alignmentGaps_, the maps qluster's --writeOutFinalAllByAllComparison dumps column by column
+ * (clusterDown.cpp:759-800: refBase, refBasePos, refQual, seqBase, seqBasePos, seqQual, kMerFreqByPos,
+ * highQuality for every mismatch; ref_/size/refPos_ for every gap).  sdgpu_align_events runs alignCacheGlobal +
+ * profileAlignment like sdgpu_align_profile and, from the traced alignment still on the device, lists the events
+ * of pair i in alignment-column order into eventsOut[i*eventCap ...]; nEventsOut[i] = how many the pair has (more
+ * than eventCap: the list is cut).  A gap's gapedSequence_ / qualities_ are the `size` bases and qualities of the
+ * OTHER sequence starting at seqPos (gap in the ref) or refPos (gap in the read). */
+#define SDGPU_EV_MISMATCH_HQ 1u      /* in mismatches_, highQuality(qScorePars_) true */
+#define SDGPU_EV_MISMATCH_LQ 2u      /* in mismatches_, highQuality false */
+#define SDGPU_EV_MISMATCH_LOWKMER 3u /* in lowKmerMismatches_ */
+#define SDGPU_EV_GAP_IN_REF 4u       /* alignmentGaps_ entry with ref_ true ("gap-insertion"): '-' in the ref */
+#define SDGPU_EV_GAP_IN_READ 5u      /* ... ref_ false ("gap-deletion"): '-' in the read */
+#define SDGPU_EV_END_GAP 0x10u       /* or-ed onto a gap kind: an end gap that profileAlignment did not count
+                                        (countEndGaps_ off), hence not in alignmentGaps_ */
+typedef struct sdgpu_event {
+  uint32_t kind;        /* SDGPU_EV_* */
+  uint32_t alnPos;      /* alignment column = key of the map (gap: its first column) */
+  uint32_t refPos;      /* mismatch::refBasePos / gap::refPos_: ref bases in front of the column */
+  uint32_t seqPos;      /* mismatch::seqBasePos / gap::seqPos_ */
+  uint32_t size;        /* gap::size_; 1 for a mismatch */
+  uint32_t kmerFreqRef; /* mismatches under SDGPU_CHECK_KMER: KmerMaps count of the k-mer centred on the ref base ... */
+  uint32_t kmerFreqSeq; /* ... and on the read base (the by-position table when the index is by position); else 0 */
+  uint8_t refBase, seqBase, refQual, seqQual; /* mismatch: both sides; gap: first gapped base / quality on the side that has bases, 0 on the other */
+} sdgpu_event;
+int sdgpu_align_events(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs, uint32_t flags,
+                       sdgpu_comparison* out, sdgpu_event* eventsOut, uint32_t eventCap, uint32_t* nEventsOut);
 
 /* Replaces: iteration.errors_.passErrorProfile(alignerObj.comp_) / the OTU identity test
  * (ControlBencher.hpp:120; clusterDownSetUp.cpp:289-312) for up to 64 par-file lines at once.

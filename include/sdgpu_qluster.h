@@ -53,6 +53,16 @@ typedef struct sdq_opts {
   double chiParentFreqs;         /* parentFreqs_ (--parFreqs, 2) */
   sdq_iter_par chiOverlap;       /* chiOverlap_ (njhseq: oneBaseIndel 2, twoBaseIndel 1, lowKmer 1;
                                     qluster sets largeBaseIndel .99, clusterDown.cpp:572) */
+  /* k-mer binning in front of every clustering run: colOpts_.kmerBinOpts_ (clusterDownSetUp.cpp:352-354).  The clusters
+   * are binned greedily by compareKmers against each bin's first cluster (a cluster joins the first bin whose seed
+   * shares more than kmerCutOff of its k-mers, else it opens a bin), every bin of two or more is collapsed on its own
+   * with binPars (pars.binIteratorMap, clusterDown.cpp:489), and the survivors then go through the run's own
+   * iterations.  The k-mer comparisons run on the GPU (sdgpu_build_kmer_lists / sdgpu_kmer_bin_masks). */
+  double kmerCutOff;             /* kmerCutOff_ (--kmerCutOff) */
+  uint32_t useKmerBinning;       /* useKmerBinning_ (--useKmerBinning) */
+  uint32_t kCompareLen;          /* kCompareLen_ (--kCompareLen), 1..16 */
+  const sdq_iter_par* binPars;   /* pars.binIteratorMap (--binPar); NULL: the iterations of the run itself */
+  uint64_t nBinPars;
 } sdq_opts;
 
 typedef struct sdq_result sdq_result;
@@ -69,6 +79,8 @@ typedef struct sdq_stats {
   uint64_t chimeraPairs;    /* (parent, candidate) probes of markChimeras */
   uint64_t chimericClusters;
   uint64_t passingPairs;    /* computed comparisons whose verdict mask was not zero (the only ones that cross PCIe) */
+  uint64_t kmerPairs;       /* (seed, cluster) k-mer comparisons of --useKmerBinning */
+  uint64_t kmerBins;        /* bins those comparisons formed, summed over the clustering runs */
   double secondsGpu;        /* wall time inside sdgpu_align_profile calls */
   double secondsTotal;
   double msResident;        /* CUDA-event time on the ctx stream from "unique reads resident in HBM" to the end */

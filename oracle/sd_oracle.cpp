@@ -752,7 +752,45 @@ struct Engine {
     }
   }
 
+  // njhseq collapser::runFullClustering with kmerBinOpts_.useKmerBinning_ (clusterDownSetUp.cpp:352-354; restated from
+  // njhseq's published greedyKmerSimCluster / kmerCluster::compareRead, no call site in /root/reference shows it):
+  // in list order, a cluster joins the first bin whose first cluster shares MORE THAN kmerCutOff of its k-mers
+  // (kmerInfo::compareKmers(...).second > cutOff), else it opens a bin; every bin of two or more runs through
+  // binIteratorMap on its own; the survivors, bin after bin, are the list the run's own iterations start from.
   void runFullClustering(std::vector<Clus>& cs, const sdo_iter_par* its, uint32_t nIts) {
+    if (O.useKmerBinning) {
+      std::vector<std::vector<Clus>> bins;
+      for (Clus& c : cs) {
+        if (c.remove) continue;
+        bool placed = false;
+        for (auto& bin : bins) {
+          uint32_t shared;
+          double frac;
+          compareKmers(reinterpret_cast<const uint8_t*>(bin[0].seq.data()), uint32_t(bin[0].seq.size()),
+                       reinterpret_cast<const uint8_t*>(c.seq.data()), uint32_t(c.seq.size()), O.kCompareLen, shared, frac);
+          if (frac > O.kmerCutOff) {
+            bin.push_back(std::move(c));
+            placed = true;
+            break;
+          }
+        }
+        if (!placed) {
+          bins.emplace_back();
+          bins.back().push_back(std::move(c));
+        }
+      }
+      cs.clear();
+      const sdo_iter_par* binIts = O.binPars ? O.binPars : its;
+      const uint32_t nBinIts = O.binPars ? uint32_t(O.nBinPars) : nIts;
+      for (auto& bin : bins) {
+        if (bin.size() > 1) runClustering(bin, binIts, nBinIts);
+        for (Clus& c : bin) cs.push_back(std::move(c));
+      }
+    }
+    runClustering(cs, its, nIts);
+  }
+
+  void runClustering(std::vector<Clus>& cs, const sdo_iter_par* its, uint32_t nIts) {
     for (uint32_t i = 0; i < nIts; ++i) {
       cs.erase(std::remove_if(cs.begin(), cs.end(), [](const Clus& c) { return c.remove; }), cs.end());
       std::sort(cs.begin(), cs.end(), clusLess);

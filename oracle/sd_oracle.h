@@ -105,6 +105,12 @@ typedef struct sdo_qluster_opts {
   uint32_t converge;             /* colOpts_.clusOpts_.converge_ (--converge, clusterDownSetUp.cpp:394): repeat a par line while it merges */
   double chiParentFreqs;         /* parentFreqs_ */
   sdo_iter_par chiOverlap;       /* chiOverlap_ */
+  /* colOpts_.kmerBinOpts_ (clusterDownSetUp.cpp:352-354) + pars.binIteratorMap (clusterDown.cpp:489) */
+  double kmerCutOff;
+  uint32_t useKmerBinning;
+  uint32_t kCompareLen;
+  const sdo_iter_par* binPars;   /* NULL: the iterations of the run itself */
+  uint64_t nBinPars;
 } sdo_qluster_opts;
 
 typedef struct sdo_qluster_result sdo_qluster_result;

@@ -88,6 +88,8 @@ SIGNATURES = {
     "sdgpu_build_kmer_profiles": (C.c_int, [_ctx, C.c_uint32]),
     "sdgpu_kmer_compare": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
     "sdgpu_kmer_compare_all": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sdgpu_build_kmer_lists": (C.c_int, [_ctx, C.c_uint32]),
+    "sdgpu_kmer_bin_masks": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p]),
     "sdgpu_align_profile": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sdgpu_set_pass_table": (C.c_int, [_ctx, C.c_void_p, C.c_uint32]),
     "sdgpu_align_pass": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),

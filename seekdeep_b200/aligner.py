@@ -137,6 +137,21 @@ class GpuAligner:
                                                      _ptr(shared), _ptr(frac)))
         return shared, frac
 
+    def build_kmer_lists(self, kLen):
+        """≙ kmerInfo(seq, kLen, false) for every stored sequence, any kLen <= 16: sorted k-mer lists on the device."""
+        self._check(self._lib.sdgpu_build_kmer_lists(self._ctx, int(kLen)))
+
+    def kmer_bin_masks(self, seeds, reads, cutOff, want_shared=False):
+        """≙ seed.compareKmers(read).second > cutOff for every (read, seed): uint64 mask per read (bit c = seed c);
+        with want_shared also the shared k-mer counts [nReads, nSeeds] (qluster --useKmerBinning)."""
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        reads = np.ascontiguousarray(reads, np.uint32)
+        masks = np.zeros(len(reads), np.uint64)
+        shared = np.zeros((len(reads), len(seeds)), np.uint32) if want_shared else None
+        self._check(self._lib.sdgpu_kmer_bin_masks(self._ctx, _ptr(seeds), len(seeds), _ptr(reads), len(reads), float(cutOff),
+                                                   _ptr(masks), _ptr(shared)))
+        return (masks, shared) if want_shared else masks
+
     # -- alignment + errorProfile
     def align_profile(self, refIdx, readIdx, checkKmer=False, usingQuality=True, doingMatchQuality=False, gapCap=0):
         """≙ for each pair: alignCacheGlobal(ref, read); profileAlignment(ref, read, checkKmer,

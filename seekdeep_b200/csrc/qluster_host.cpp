@@ -385,6 +385,7 @@ class Runner {
   std::vector<sdgpu_gap> gapBuf;
   double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0, tIndex = 0, tSubmit = 0;
   double tConsAlign = 0, tConsCount = 0, tConsBuild = 0, tConsUpload = 0;  // parts of tCons
+  double tBin = 0;  // k-mer binning (lists + masks + settling)
   uint64_t keptVersions = 0, skippedScans = 0;
   bool orderDirty = true;
   // symbols of the consensus counters (bases + '-'), ASCII order kept for njhseq's tie rule
@@ -972,7 +973,79 @@ class Runner {
     tSort += nowSec() - t0;
   }
 
+  // njhseq collapser::runFullClustering: with kmerBinOpts_.useKmerBinning_ (clusterDownSetUp.cpp:352-354) the clusters
+  // are first binned by k-mer similarity and every bin is collapsed on its own with binIteratorMap (clusterDown.cpp:489).
   int runFullClustering(ClusVec& cs, const sdq_iter_par* its, uint32_t nIts) {
+    if (O.useKmerBinning) {
+      int rc = binAndCollapse(cs, its, nIts);
+      if (rc) return rc;
+    }
+    return runClustering(cs, its, nIts);
+  }
+
+  // Greedy k-mer binning (njhseq greedyKmerSimCluster / kmerCluster::compareRead): in list order a cluster joins the
+  // first bin whose seed shares more than kmerCutOff of its k-mers, else it opens a bin.  The order dependence only concerns
+  // which clusters are seeds, so a round hands the GPU the next <= 64 unbinned clusters as candidate seeds against every
+  // unbinned cluster (sdgpu_kmer_bin_masks: one 64-bit word per cluster comes back) and settles it here: candidate j is a
+  // seed iff none of this round's earlier seeds passes it (bins of earlier rounds have already refused everything that is
+  // still unbinned); the others join the earliest seed that passes them or wait for the next round.
+  int binAndCollapse(ClusVec& cs, const sdq_iter_par* its, uint32_t nIts) {
+    NvtxRange range("sdq:k-mer binning");
+    const double t0 = nowSec();
+    int rc = sdgpu_build_kmer_lists(ctx_, O.kCompareLen);
+    if (rc) return fail(rc);
+    std::vector<Clus*>& v = cs.ptrs();
+    v.erase(std::remove_if(v.begin(), v.end(), [](const Clus* c) { return c->remove; }), v.end());
+    std::vector<uint32_t> unb(v.size()), rest, seeds, readStore;
+    for (uint32_t i = 0; i < unb.size(); ++i) unb[i] = i;
+    std::vector<uint64_t> masks;
+    std::vector<std::vector<Clus*>> bins;
+    while (!unb.empty()) {
+      const uint32_t nc = uint32_t(std::min<size_t>(64, unb.size()));
+      seeds.resize(nc);
+      readStore.resize(unb.size());
+      masks.resize(unb.size());
+      for (size_t x = 0; x < unb.size(); ++x) readStore[x] = v[unb[x]]->storeIdx;
+      for (uint32_t j = 0; j < nc; ++j) seeds[j] = readStore[j];
+      rc = sdgpu_kmer_bin_masks(ctx_, seeds.data(), nc, readStore.data(), uint32_t(readStore.size()), O.kmerCutOff, masks.data(), nullptr);
+      if (rc) return fail(rc);
+      st.kmerPairs += uint64_t(nc) * readStore.size();
+      uint64_t actual = 0;  // this round's candidates that became seeds (only bits below x while x is a candidate)
+      uint32_t binOfBit[64];
+      rest.clear();
+      for (size_t x = 0; x < unb.size(); ++x) {
+        const uint64_t m = masks[x] & actual;
+        if (m) {
+          bins[binOfBit[__builtin_ctzll(m)]].push_back(v[unb[x]]);
+        } else if (x < nc) {
+          actual |= 1ull << x;
+          binOfBit[x] = uint32_t(bins.size());
+          bins.emplace_back(1, v[unb[x]]);
+        } else {
+          rest.push_back(unb[x]);
+        }
+      }
+      unb.swap(rest);
+    }
+    st.kmerBins += bins.size();
+    tBin += nowSec() - t0;
+    const sdq_iter_par* binIts = O.binPars ? O.binPars : its;
+    const uint32_t nBinIts = O.binPars ? uint32_t(O.nBinPars) : nIts;
+    std::vector<Clus*> survivors;
+    for (auto& bin : bins) {
+      if (bin.size() > 1) {
+        ClusVec b;
+        b.ptrs().swap(bin);
+        if ((rc = runClustering(b, binIts, nBinIts))) return rc;
+        bin.swap(b.ptrs());
+      }
+      survivors.insert(survivors.end(), bin.begin(), bin.end());
+    }
+    v.swap(survivors);
+    return 0;
+  }
+
+  int runClustering(ClusVec& cs, const sdq_iter_par* its, uint32_t nIts) {
     orderDirty = true;
     posValid = false;  // the list may have been re-composed (singletons joining)
     for (uint32_t i = 0; i < nIts; ++i) {
@@ -1144,6 +1217,17 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
   // every distinct par-file line becomes one bit of the verdict mask
   for (uint32_t i = 0; i < nInit; ++i) R.lineOf(initPars[i]);
   for (uint32_t i = 0; i < nPars; ++i) R.lineOf(pars[i]);
+  if (opts->useKmerBinning) {
+    if (opts->kCompareLen == 0 || opts->kCompareLen > 16) {
+      g_err = "useKmerBinning: kCompareLen must be 1..16";
+      return bail(SDGPU_E_ARG);
+    }
+    if (opts->nBinPars && !opts->binPars) {
+      g_err = "useKmerBinning: nBinPars without binPars";
+      return bail(SDGPU_E_ARG);
+    }
+    for (uint64_t i = 0; opts->binPars && i < opts->nBinPars; ++i) R.lineOf(opts->binPars[i]);
+  }
   if (R.lines.size() > SDGPU_MAX_PASS_LINES) {
     g_err = "more than 64 distinct par-file lines";
     return bail(SDGPU_E_UNSUPPORTED);

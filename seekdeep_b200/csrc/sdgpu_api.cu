@@ -189,6 +189,7 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   cudaFree(ctx->dIdxCnts);
   cudaFree(ctx->dProfiles);
   cudaFree(ctx->dProfilesRev);
+  cudaFree(ctx->dKmerLists);
   cudaFree(ctx->dRcIndex);
   cudaFree(ctx->dScratch);
   cudaFree(ctx->dWork);
@@ -273,6 +274,7 @@ static int appendImpl(sdgpu_ctx* ctx, const SeqSource& src, const double* cnts, 
       ctx->usedSym = 0;
       ctx->haveIndex = false;
       ctx->profSeqs = 0;
+      ctx->listSeqs = 0;
     }
     return SDGPU_OK;
   }
@@ -387,6 +389,7 @@ static int appendImpl(sdgpu_ctx* ctx, const SeqSource& src, const double* cnts, 
     ctx->maxLen = 0;
     ctx->haveIndex = false;
     ctx->profSeqs = 0;
+    ctx->listSeqs = 0;
   }
   // grow device arrays
   uint64_t capB = ctx->capBases, capB2 = ctx->capBases, capB3 = ctx->capBases;
@@ -505,6 +508,19 @@ int sdgpu_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   if (!ctx) return SDGPU_E_ARG;
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
   return sd_build_kmer_profiles(ctx, kLen);
+}
+
+int sdgpu_build_kmer_lists(sdgpu_ctx* ctx, uint32_t kLen) {
+  if (!ctx) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_build_kmer_lists(ctx, kLen);
+}
+
+int sdgpu_kmer_bin_masks(sdgpu_ctx* ctx, const uint32_t* seeds, uint32_t nSeeds, const uint32_t* reads, uint32_t nReads,
+                         double cutOff, uint64_t* maskOut, uint32_t* sharedOut) {
+  if (!ctx || (nSeeds && !seeds) || (nReads && (!reads || !maskOut))) return SDGPU_E_ARG;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sd_kmer_bin_masks(ctx, seeds, nSeeds, reads, nReads, cutOff, maskOut, sharedOut);
 }
 
 int sdgpu_kmer_compare(sdgpu_ctx* ctx, const uint32_t* a, const uint32_t* b, uint32_t nPairs, int revCompB,

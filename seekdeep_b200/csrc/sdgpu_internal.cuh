@@ -80,9 +80,10 @@ struct DevKmerIndex {
   uint32_t nPos;
 };
 
-// KmerMaps::isKmerLowFrequency for the k-mer centred on base p (clamped to the sequence): count <= runCutOff
-__device__ __forceinline__ bool sd_low_freq(const DevKmerIndex& idx, const uint8_t* codes, int len, int p) {
+// KmerMaps count of the k-mer centred on base p (clamped to the sequence); false: the sequence has no such k-mer
+__device__ __forceinline__ bool sd_kmer_count_at(const DevKmerIndex& idx, const uint8_t* codes, int len, int p, uint32_t& cnt) {
   const int k = int(idx.kLen);
+  cnt = 0;
   if (k == 0 || len < k) return false;
   int start = p >= k / 2 ? p - k / 2 : 0;
   if (start + k > len) start = len - k;
@@ -104,7 +105,14 @@ __device__ __forceinline__ bool sd_low_freq(const DevKmerIndex& idx, const uint8
       hi = mid;
     }
   }
-  const uint32_t cnt = (lo < idx.n && __ldg(idx.keys + lo) == key) ? __ldg(idx.counts + lo) : 0u;
+  cnt = (lo < idx.n && __ldg(idx.keys + lo) == key) ? __ldg(idx.counts + lo) : 0u;
+  return true;
+}
+
+// KmerMaps::isKmerLowFrequency for the k-mer centred on base p: count <= runCutOff
+__device__ __forceinline__ bool sd_low_freq(const DevKmerIndex& idx, const uint8_t* codes, int len, int p) {
+  uint32_t cnt;
+  if (!sd_kmer_count_at(idx, codes, len, p, cnt)) return false;
   return cnt <= idx.runCutOff;
 }
 
@@ -156,6 +164,10 @@ struct sdgpu_ctx {
   bool profRevValid = false;
   uint32_t* dRcIndex = nullptr;      // k-mer id -> id of its reverse complement
   uint32_t rcIndexCap = 0;
+  // sorted k-mer lists (kmer_list_kernels.cu): one uint64 key per base slot of the store
+  uint64_t* dKmerLists = nullptr;
+  uint64_t listCapKeys = 0;
+  uint32_t listK = 0, listSeqs = 0;
   // scratch for the alignment kernel (pointer slabs), pair staging, work counter
   uint8_t* dScratch = nullptr;
   uint64_t scratchBytes = 0;
@@ -333,3 +345,11 @@ int sd_kmer_compare_all_dev(sdgpu_ctx* ctx, const uint32_t* dReads, uint32_t nRe
                             uint32_t nClusters, uint32_t* dShared, double* dFrac);
 int sd_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nReads, const uint32_t* clusters,
                         uint32_t nClusters, uint32_t* sharedOut, double* fracOut);
+// events_kernel.cu: the per-event lists of a batch whose gap lists are on the device
+int sd_launch_events(sdgpu_ctx* ctx, const uint32_t* dRef, const uint32_t* dRead, uint32_t nPairs, uint32_t flags,
+                     const sdgpu_comparison* dCmp, const sdgpu_gap* dGaps, uint32_t gapCap, sdgpu_event* dEvents, uint32_t eventCap,
+                     uint32_t* dNEvents);
+// kmer_list_kernels.cu
+int sd_build_kmer_lists(sdgpu_ctx* ctx, uint32_t kLen);
+int sd_kmer_bin_masks(sdgpu_ctx* ctx, const uint32_t* seeds, uint32_t nSeeds, const uint32_t* reads, uint32_t nReads, double cutOff,
+                      uint64_t* maskOut, uint32_t* sharedOut);

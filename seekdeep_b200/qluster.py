@@ -26,13 +26,16 @@ class QlusterOptsC(C.Structure):
                                           "checkKmers", "startWithSingles", "leaveOutSinglets", "dontRecalLowFreq",
                                           "smallReadSize", "markChimeras", "chiKeepLowQual", "chiRunCutOff",
                                           "chiOverlapSizeCutoff", "chiPosSpacing", "converge")] + \
-               [("chiParentFreqs", C.c_double), ("chiOverlap", IterParC)]
+               [("chiParentFreqs", C.c_double), ("chiOverlap", IterParC), ("kmerCutOff", C.c_double),
+                ("useKmerBinning", C.c_uint32), ("kCompareLen", C.c_uint32), ("binPars", C.c_void_p),
+                ("nBinPars", C.c_uint64)]
 
 
 class StatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("inputReads", "uniqueSeqs", "finalClusters", "pairsComputed", "pairsConsumed",
                                           "consensusAligns", "cellUpdates", "gpuBatches", "onDemandPairs",
-                                          "chimeraPairs", "chimericClusters", "passingPairs")] + \
+                                          "chimeraPairs", "chimericClusters", "passingPairs", "kmerPairs",
+                                          "kmerBins")] + \
                [("secondsGpu", C.c_double), ("secondsTotal", C.c_double), ("msResident", C.c_double)]
 
 
@@ -60,9 +63,27 @@ class QlusterPars:
     chiOverlapSizeCutoff: int = 5
     # chiOverlap_: njhseq's ChimeraOpts defaults + `largeBaseIndel_ = .99` (clusterDown.cpp:572)
     chiOverlap: tuple = (2.0, 1.0, 0.99, 0.0, 0.0, 1.0)  # one, two, large indel; hq, lq, lowKmer mismatches
+    # colOpts_.kmerBinOpts_ (clusterDownSetUp.cpp:352-354); 10 / 0.80 are njhseq's defaults as far as memory serves
+    useKmerBinning: bool = False
+    kCompareLen: int = 10
+    kmerCutOff: float = 0.80
 
-    def to_c(self):
+    def to_c(self, binIteratorMap=None):
+        """`binIteratorMap` (pars.binIteratorMap, --binPar) is attached as opts.binPars; the array is kept alive on the
+        returned struct."""
         o = self.chiOverlap
+        c = self._to_c_base(o)
+        c.kmerCutOff = float(self.kmerCutOff)
+        c.useKmerBinning = int(self.useKmerBinning)
+        c.kCompareLen = int(self.kCompareLen)
+        if binIteratorMap is not None:
+            arr, n = iter_pars_to_c(binIteratorMap)
+            c._binKeep = arr
+            c.binPars = C.cast(arr, C.c_void_p)
+            c.nBinPars = n
+        return c
+
+    def _to_c_base(self, o):
         return QlusterOptsC(self.kLength, self.runCutOff, int(self.kmersByPosition), int(self.expandKmerPos),
                             self.expandKmerSize, int(self.checkKmers), int(self.startWithSingles),
                             int(self.leaveOutSinglets), int(self.dontRecalLowFreqMismatchAndReRun), self.smallReadSize,
@@ -114,7 +135,7 @@ def _bind(lib):
 
 
 def qluster(aligner: GpuAligner, bases, quals, offsets, pars: QlusterPars = None, iteratorMap: CollapseIterations = None,
-            intialParameters: CollapseIterations = None, want_clusters=True):
+            intialParameters: CollapseIterations = None, want_clusters=True, binIteratorMap: CollapseIterations = None):
     """Run the collapse of one sample on `aligner`'s GPU.  `iteratorMap` / `intialParameters` are
     the reference's names (clusterDownPars, setUpPars.hpp:126-127); both default to
     genIlluminaDefaultPars(100) like `--illumina`."""
@@ -127,7 +148,7 @@ def qluster(aligner: GpuAligner, bases, quals, offsets, pars: QlusterPars = None
     quals = np.ascontiguousarray(quals, np.uint8)
     offsets = np.ascontiguousarray(offsets, np.uint64)
     n = len(offsets) - 1
-    opts = pars.to_c()
+    opts = pars.to_c(binIteratorMap)
     ip, nip = iter_pars_to_c(intialParameters)
     pp, npp = iter_pars_to_c(iteratorMap)
     h = C.c_void_p()

@@ -357,3 +357,43 @@ def test_compare_kmers_revcomp_micro_cases(oracle):
     a, b = "ACGGTTACGATTACA", "TGTAATCGTAACCGT"                               # b = revcomp(a)
     assert oracle.kmer_compare(a, b, 5, revCompB=True) == oracle.kmer_compare(a, a, 5) == (11, 1.0)
     assert oracle.kmer_compare("ACGRT", "AYCGT", 3, revCompB=True) == oracle.kmer_compare("ACGRT", "ACGRT", 3)  # R <-> Y
+
+
+def test_kmer_binning_control_flow(oracle):
+    """--useKmerBinning as restated (clusterDownSetUp.cpp:352-354; njhseq runFullClustering): clusters are binned by
+    compareKmers against each bin's first cluster (strictly more than kmerCutOff shared), every bin of two or more runs
+    through binIteratorMap on its own, the survivors then go through the run's own iterations."""
+    import seekdeep_b200 as sd
+    from seekdeep_b200.iterpars import CollapseIterations, IterPar
+    rng = np.random.default_rng(23)
+    A = "".join(rng.choice(list("ACGT"), 90))
+    B = "".join(rng.choice(list("ACGT"), 90))
+    A1 = A[:45] + ("A" if A[45] != "A" else "C") + A[46:]  # one high-quality mismatch off A
+    hi = [38] * 90
+    bases, quals, offsets = _pack_reads([(A, hi)] * 5 + [(A1, hi)] * 2 + [(B, hi)] * 3)
+    strict = [IterPar(stopCheck=100, smallCutoff=0, oneBaseIndel=0, twoBaseIndel=0, largeBaseIndel=0, hqMismatches=0,
+                      lqMismatches=0, lowKmerMismatches=0)]
+    loose = CollapseIterations.gen_otu_pars(100, 0.90, False)
+
+    def run(**kw):
+        binIts = kw.pop("binIts", None)
+        pars = sd.QlusterPars(markChimeras=False, checkKmers=False, **kw)
+        r = oracle.qluster(sd.make_params(), pars.to_c(binIts), strict, strict, bases, quals, offsets)
+        return sorted(((c[0], c[2]) for c in r["clusters"]), key=lambda x: -x[1])
+
+    plain = run()
+    assert plain == [(A, 5.0), (B, 3.0), (A1, 2.0)]
+    # A and A1 share 83 of their 87 4-mers (0.95 > 0.5), B is unrelated: bins {A, A1}, {B}; the loose bin iterations merge
+    # A1 into A, the strict iterations of the run then find nothing to do
+    assert run(useKmerBinning=True, kCompareLen=4, kmerCutOff=0.5, binIts=loose) == [(A, 7.0), (B, 3.0)]
+    # no bin iterations given: the bins run the strict lines themselves -> nothing merges
+    assert run(useKmerBinning=True, kCompareLen=4, kmerCutOff=0.5) == plain
+    # strict '>' : a cut-off the fraction cannot exceed puts every cluster in its own bin -> the plain run
+    assert run(useKmerBinning=True, kCompareLen=4, kmerCutOff=1.0, binIts=loose) == plain
+    # the exact fraction of (A, A1) is 83/87 at k = 4: a cut-off equal to it does not bin them, just below does
+    from tests import oracle_binding  # noqa: F401
+    sh, fr = oracle.kmer_compare(A.encode(), A1.encode(), 4)
+    assert run(useKmerBinning=True, kCompareLen=4, kmerCutOff=fr, binIts=loose) == plain
+    assert run(useKmerBinning=True, kCompareLen=4, kmerCutOff=float(np.nextafter(fr, 0)), binIts=loose) == [(A, 7.0), (B, 3.0)]
+    # cut-off below zero: one bin with everything; the loose lines (90 % identity) still keep B apart
+    assert run(useKmerBinning=True, kCompareLen=4, kmerCutOff=-1.0, binIts=loose) == [(A, 7.0), (B, 3.0)]
