@@ -860,6 +860,97 @@ int sdo_align_profile(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8
   return SDGPU_OK;
 }
 
+// The per-event maps of aligner::comp_ after profileAlignment -- distances_.mismatches_, lowKmerMismatches_,
+// alignmentGaps_ (dumped by clusterDown.cpp:759-800) -- listed in alignment-column order.  Walks the gapped strings
+// the way profileAlignment does; returns the number of events (may exceed cap).
+int sdo_align_events(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8_t* a, const uint8_t* qa, uint32_t lenA,
+                     const uint8_t* b, const uint8_t* qb, uint32_t lenB, uint32_t flags, sdgpu_comparison* cmpOut,
+                     sdgpu_event* out, uint32_t cap) {
+  if (!p || !a || !b || lenA == 0 || lenB == 0) return -1;
+  const KMaps* km = kmaps ? kmaps->km : nullptr;
+  std::vector<Cell> mat;
+  AlnResult r;
+  Gapped ga, gb;
+  sdgpu_comparison c;
+  alignProfile(*p, km, a, qa, lenA, b, qb, lenB, flags, mat, r, ga, gb, c);
+  if (cmpOut) *cmpOut = c;
+  const bool checkKmer = flags & SDGPU_CHECK_KMER, usingQuality = flags & SDGPU_USING_QUALITY;
+  const std::string &sa = ga.seq, &sb = gb.seq;
+  const uint32_t len = uint32_t(sa.size());
+  uint32_t n = 0, pa = 0, pb = 0;
+  auto emit = [&](const sdgpu_event& e) {
+    if (n < cap && out) out[n] = e;
+    ++n;
+  };
+  auto kcount = [&](const uint8_t* seq, uint32_t l, uint32_t pos) -> uint32_t {
+    uint32_t start;
+    if (!km || !kmerStartFor(pos, km->kLen, l, start)) return 0;
+    return km->count(std::string(reinterpret_cast<const char*>(seq + start), km->kLen), start);
+  };
+  for (uint32_t i = 0; i < len; ++i) {
+    if (sa[i] == '-' || sb[i] == '-') {
+      const bool inA = sa[i] == '-';
+      const std::string& gs = inA ? sa : sb;
+      uint32_t size = 1;
+      while (i + size < len && gs[i + size] == '-') ++size;
+      const bool endGap = (i + size >= len) || i == 0;
+      sdgpu_event e;
+      std::memset(&e, 0, sizeof(e));
+      e.kind = (inA ? SDGPU_EV_GAP_IN_REF : SDGPU_EV_GAP_IN_READ) | ((endGap && !p->countEndGaps) ? SDGPU_EV_END_GAP : 0u);
+      e.alnPos = i;
+      e.refPos = pa;
+      e.seqPos = pb;
+      e.size = size;
+      if (inA) {
+        e.seqBase = uint8_t(sb[i]);
+        e.seqQual = qb ? qb[pb] : 0;
+        pb += size;
+      } else {
+        e.refBase = uint8_t(sa[i]);
+        e.refQual = qa ? qa[pa] : 0;
+        pa += size;
+      }
+      emit(e);
+      i += size - 1;
+      continue;
+    }
+    if (p->scoreMat[size_t(uint8_t(sa[i]) & 127) * SDGPU_MAT_DIM + (uint8_t(sb[i]) & 127)] < 0) {
+      bool hq = true;
+      std::vector<uint8_t> zA, zB;
+      const uint8_t* QA = qa;
+      const uint8_t* QB = qb;
+      if (!QA) { zA.assign(lenA, 0); QA = zA.data(); }
+      if (!QB) { zB.assign(lenB, 0); QB = zB.data(); }
+      if (usingQuality) hq = checkQual(QA, lenA, pa, *p) && checkQual(QB, lenB, pb, *p);
+      sdgpu_event e;
+      std::memset(&e, 0, sizeof(e));
+      if (!hq) {
+        e.kind = SDGPU_EV_MISMATCH_LQ;
+      } else if (checkKmer && (isLowFreqAt(km, a, lenA, pa) || isLowFreqAt(km, b, lenB, pb))) {
+        e.kind = SDGPU_EV_MISMATCH_LOWKMER;
+      } else {
+        e.kind = SDGPU_EV_MISMATCH_HQ;
+      }
+      e.alnPos = i;
+      e.refPos = pa;
+      e.seqPos = pb;
+      e.size = 1;
+      if (checkKmer) {
+        e.kmerFreqRef = kcount(a, lenA, pa);
+        e.kmerFreqSeq = kcount(b, lenB, pb);
+      }
+      e.refBase = uint8_t(sa[i]);
+      e.seqBase = uint8_t(sb[i]);
+      e.refQual = QA[pa];
+      e.seqQual = QB[pb];
+      emit(e);
+    }
+    ++pa;
+    ++pb;
+  }
+  return int(n);
+}
+
 int sdo_align_profile_batch(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8_t* bases,
                             const uint8_t* quals, const uint64_t* offsets, const uint32_t* refIdx,
                             const uint32_t* readIdx, uint32_t nPairs, uint32_t flags, sdgpu_comparison* out,

@@ -40,6 +40,10 @@ int sdo_align_profile(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8
                       uint32_t gapCap, char* alnA, char* alnB);
 
 /* Batched form over a packed sequence store (same layout as sdgpu_upload_seqs). */
+/* per-event lists of comp_ (mismatches_, lowKmerMismatches_, alignmentGaps_; clusterDown.cpp:759-800) */
+int sdo_align_events(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8_t* a, const uint8_t* qa, uint32_t lenA,
+                     const uint8_t* b, const uint8_t* qb, uint32_t lenB, uint32_t flags, sdgpu_comparison* cmpOut,
+                     sdgpu_event* out, uint32_t cap);
 int sdo_align_profile_batch(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8_t* bases,
                             const uint8_t* quals, const uint64_t* offsets,
                             const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs,

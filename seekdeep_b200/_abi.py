@@ -58,6 +58,11 @@ PAIR_SUMMARY_DTYPE = _np.dtype([("alnScore", "<i4"), ("hqMismatches", "<u2"), ("
 CHIMERA_PROBE_DTYPE = _np.dtype([("alnScore", "<i4")] + [(n, "<u4") for n in (
     "keptMismatches", "numGaps", "firstPos", "lastPos", "firstAlnPos", "lastAlnPos", "flags")])
 CHI_FRONT_PASS, CHI_BACK_PASS = 1, 2
+EVENT_DTYPE = _np.dtype([("kind", "<u4"), ("alnPos", "<u4"), ("refPos", "<u4"), ("seqPos", "<u4"), ("size", "<u4"),
+                         ("kmerFreqRef", "<u4"), ("kmerFreqSeq", "<u4"), ("refBase", "u1"), ("seqBase", "u1"),
+                         ("refQual", "u1"), ("seqQual", "u1")])
+assert EVENT_DTYPE.itemsize == 32
+EV_MISMATCH_HQ, EV_MISMATCH_LQ, EV_MISMATCH_LOWKMER, EV_GAP_IN_REF, EV_GAP_IN_READ, EV_END_GAP = 1, 2, 3, 4, 5, 0x10
 GRID_HIT_DTYPE = _np.dtype([("read", "<u4"), ("cluster", "<u4"), ("mask", "<u8")])
 assert GRID_HIT_DTYPE.itemsize == 16
 assert CHIMERA_PROBE_DTYPE.itemsize == 32
@@ -91,6 +96,7 @@ SIGNATURES = {
     "sdgpu_build_kmer_lists": (C.c_int, [_ctx, C.c_uint32]),
     "sdgpu_kmer_bin_masks": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p]),
     "sdgpu_align_profile": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sdgpu_align_events": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "sdgpu_set_pass_table": (C.c_int, [_ctx, C.c_void_p, C.c_uint32]),
     "sdgpu_align_pass": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sdgpu_align_pass_grid": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), _u64p]),

@@ -168,6 +168,24 @@ class GpuAligner:
                                                   _ptr(gaps), gapCap))
         return (out, gaps) if gapCap else out
 
+    def align_events(self, refIdx, readIdx, checkKmer=False, usingQuality=True, doingMatchQuality=False, eventCap=64):
+        """≙ alignCacheGlobal + profileAlignment, then comp_.distances_.mismatches_ / lowKmerMismatches_ /
+        alignmentGaps_ as event lists (clusterDown.cpp:759-800).  Returns (comparisons, [events of pair i])."""
+        refIdx = np.ascontiguousarray(refIdx, np.uint32)
+        readIdx = np.ascontiguousarray(readIdx, np.uint32)
+        n = len(refIdx)
+        flags = (_abi.CHECK_KMER if checkKmer else 0) | (_abi.USING_QUALITY if usingQuality else 0) | \
+                (_abi.MATCH_QUALITY if doingMatchQuality else 0)
+        out = np.zeros(n, _abi.COMPARISON_DTYPE)
+        nEv = np.zeros(n, np.uint32)
+        while True:
+            ev = np.zeros((n, eventCap), _abi.EVENT_DTYPE)
+            self._check(self._lib.sdgpu_align_events(self._ctx, _ptr(refIdx), _ptr(readIdx), n, flags, _ptr(out), _ptr(ev),
+                                                     eventCap, _ptr(nEv)))
+            if n == 0 or nEv.max() <= eventCap:
+                return out, [ev[i, :nEv[i]] for i in range(n)]
+            eventCap = int(nEv.max())
+
     # -- device-resident benchmarking helpers
     def dev_alloc(self, nbytes):
         p = C.c_void_p()

@@ -107,6 +107,11 @@ class Row {
   }
   uint32_t size() const { return n_; }
   uint64_t orMask() const { return or_; }  // superset of every verdict bit held in the row
+  template <class F>
+  void forEach(F f) const {
+    for (uint32_t i = 0; i < n_ && i < INLINE; ++i) f(keys_[i], vals_[i]);
+    for (const auto& e : more_) f(e.first, e.second);
+  }
 
  private:
   static constexpr uint32_t INLINE = 2;
@@ -363,6 +368,7 @@ class Runner {
   uint64_t serial = 0;                // iteration counter across the three clustering runs
   std::vector<uint32_t> prevWindow;   // store indices of the previous iteration's window
   std::vector<uint8_t> inPrevWindow;  // by store index
+  std::vector<uint32_t> winPos;       // by store index: position + 1 in the current iteration's window, 0 = not in it
   uint64_t lastListSerial = 0;        // serial of the latest iteration that listed (judged) every live read
   // Compact copies, by position in the sorted cluster list, of what the per-iteration loops look at for EVERY
   // cluster: rebuilt whenever the list is re-sorted, updated in place at the few points an iteration changes
@@ -506,9 +512,12 @@ class Runner {
       lastListSerial = serial;
       for (uint32_t s : prevWindow) inPrevWindow[s] = 0;
       prevWindow = window;
-      for (uint32_t s : window) {
+      if (winPos.size() < storeSize) winPos.resize(storeSize, 0);
+      for (uint32_t w = 0; w < wn; ++w) {
+        const uint32_t s = window[w];
         inPrevWindow[s] = 1;
         lastIn[s] = serial;
+        winPos[s] = w + 1;
       }
       const double tList = nowSec() - tt0;
       int rc = gridPass(cs, window, fullStore, fullPos);
@@ -534,6 +543,33 @@ class Runner {
         continue;
       }
       Clus& read = cs[rp];
+      if (windowIntact) {
+        // While no window cluster has been absorbed, the candidates a read looks at are window positions -- all alive,
+        // all judged -- so the first passing candidate is the smallest window position among the read's own (few)
+        // non-zero verdicts, provided it lies within the first stopCheck candidates the read counts (itself skipped).
+        uint32_t best = UINT32_MAX;
+        read.row.forEach([&](uint32_t k, uint64_t v) {
+          if (!(v & bit) || k >= winPos.size()) return;
+          const uint32_t wp = winPos[k];
+          if (wp != 0 && wp - 1 != rp && wp - 1 < best) best = wp - 1;
+        });
+        const uint32_t looked = best == UINT32_MAX ? std::min<uint32_t>(wn - (rp < wn ? 1u : 0u), it.stopCheck) : best + 1 - (rp < best ? 1u : 0u);
+        if (best != UINT32_MAX && looked > it.stopCheck) best = UINT32_MAX;  // beyond the read's stopCheck-th candidate
+        st.pairsConsumed += std::min<uint32_t>(looked, it.stopCheck);
+        if (best == UINT32_MAX) continue;
+        Clus& clus = cs[best];
+        clus.cnt += read.cnt;
+        clus.members.append(read.members);
+        clus.needCons = true;
+        read.remove = true;
+        PR[rp].remove = 1;
+        PR[best].changed = 1;
+        read.row.clear();
+        read.cons.reset();
+        if (rp < wn) windowIntact = false;
+        ++amountAdded;
+        continue;
+      }
       uint32_t count = 0;
       for (uint32_t cp = 0; cp < eligEnd; ++cp) {
         if (PR[cp].remove) continue;
@@ -577,6 +613,7 @@ class Runner {
         }
       }
     }
+    for (uint32_t s : prevWindow) winPos[s] = 0;  // (prevWindow is this iteration's window by now)
     tPass += nowSec() - tt0;
     if (amountAdded > 0) {
       orderDirty = true;
@@ -696,8 +733,13 @@ class Runner {
     parallelForDynamic(chunks.size(), [&](size_t cx) {
       const Chunk& ch = chunks[cx];
       const Job& j = jobs[ch.job];
-      std::string ga, gb;
-      std::vector<uint8_t> gq;
+      struct InsRec {
+        uint32_t pos, offset;  // in front of base position `pos`, the offset-th inserted base (1-based)
+        uint8_t sym, qual;
+        uint32_t w;
+        uint8_t leading;       // part of a gap at the very start of the alignment (ConsensusHelper's beginningGap)
+      };
+      std::vector<InsRec> ins;
       // Ungapped members differ from the base sequence in a few columns only.  Per chunk: wAll = their total weight,
       // qAll[i] = sum of quality x weight over ALL of them (one multiply-add sweep per member); the columns where a
       // member does not carry the base's symbol are tallied symbol by symbol in `local` and remembered in wOff / qOff,
@@ -747,38 +789,48 @@ class Runner {
             }
           continue;
         }
-        std::lock_guard<std::mutex> lk(jobMu[ch.job]);
-        ga = base;
-        gb.assign(reinterpret_cast<const char*>(r.seq.data()), r.seq.size());
-        gq.assign(r.qual.begin(), r.qual.end());
-        for (const sdgpu_gap& g : gl) {  // descending positions
-          if (g.gapInA) {
-            ga.insert(g.pos, g.size, '-');
-          } else {
-            gb.insert(g.pos, g.size, '-');
-            gq.insert(gq.begin() + g.pos, g.size, uint8_t(0));
+        // gapped member: walk the alignment its gap list spells (the list is in traceback order: last entry = first
+        // gap).  Columns that carry a base of the base sequence are tallied in `local` like the mismatches above (a '-'
+        // of the member counts as symbol '-' with quality 0); bases the member inserts between two base positions go to
+        // the cluster's insertion maps, collected here and filed under the cluster's lock when the chunk is done.
+        if (local.empty()) {
+          local.assign(L, Col());
+          qAll.assign(L, 0);
+          wOff.assign(L, 0);
+          qOff.assign(L, 0);
+        }
+        const uint8_t* q = r.qual.data();
+        const uint8_t* sq = r.seq.data();
+        const uint32_t lr = uint32_t(r.seq.size());
+        uint32_t pa = 0, pb = 0;
+        auto diagonal = [&](uint32_t upto, bool inA) {
+          while ((inA ? pa : pb) < upto && pa < L && pb < lr) {
+            symOk &= add(local[pa], char(sq[pb]), q[pb], w);
+            ++pa;
+            ++pb;
+          }
+        };
+        for (size_t g = gl.size(); g-- > 0;) {
+          const sdgpu_gap& gp = gl[g];
+          diagonal(gp.pos, gp.gapInA != 0);
+          if (gp.gapInA) {  // '-' in the base sequence: the member inserts gp.size bases in front of base position pa
+            for (uint32_t x = 0; x < gp.size && pb < lr; ++x, ++pb)
+              ins.push_back(InsRec{pa, x + 1, sq[pb], q[pb], w, uint8_t(pa == 0 && pb == x)});
+          } else {          // '-' in the member
+            for (uint32_t x = 0; x < gp.size && pa < L; ++x, ++pa) symOk &= add(local[pa], '-', 0, w);
           }
         }
-        uint32_t offSet = 0, currentOffset = 1, start = 0;
-        const uint32_t len = uint32_t(ga.size());
-        if (len && ga[0] == '-') {
-          while (start < len && ga[start] == '-') ++start;
-          for (uint32_t i = 0; i < start; ++i) symOk &= add(S.beginningGap[i], gb[i], gq[i], w);
-          offSet = start;
-        }
-        for (uint32_t i = start; i < len; ++i) {
-          if (ga[i] == '-') {
-            symOk &= add(S.insertions[i - offSet][currentOffset], gb[i], gq[i], w);
-            ++currentOffset;
-            ++offSet;
-            continue;
-          }
-          currentOffset = 1;
-          symOk &= add(S.counters[i - offSet], gb[i], gq[i], w);
-        }
+        diagonal(uint32_t(L), true);
       }
-      if (!local.empty()) {
+      if (!local.empty() || !ins.empty()) {
         std::lock_guard<std::mutex> lk(jobMu[ch.job]);
+        for (const InsRec& x : ins) {
+          if (x.leading) {
+            symOk &= add(S.beginningGap[x.offset - 1], char(x.sym), x.qual, x.w);
+          } else {
+            symOk &= add(S.insertions[x.pos][x.offset], char(x.sym), x.qual, x.w);
+          }
+        }
         for (size_t i = 0; i < local.size(); ++i) {
           for (int x = 0; x < NSYM; ++x) {
             S.counters[i].cnt[x] += local[i].cnt[x];
@@ -950,7 +1002,11 @@ class Runner {
       v.erase(std::remove_if(v.begin(), v.end(), [](const Clus* c) { return c->remove; }), v.end());
       PR.resize(v.size());
       for (size_t i = 0; i < v.size(); ++i) PR[i] = Pos{v[i]->cnt, v[i]->avgErr, v[i], 0, v[i]->row.orMask(), v[i]->storeIdx, 0, 0};
-      if (!std::is_sorted(PR.begin(), PR.end(), posLess)) {
+      // (the singletons joining the survivors of the first run: two sorted runs back to back -> one merge)
+      const auto firstDescent = std::is_sorted_until(PR.begin(), PR.end(), posLess);
+      if (firstDescent != PR.end() && std::is_sorted(firstDescent, PR.end(), posLess)) {
+        std::inplace_merge(PR.begin(), firstDescent, PR.end(), posLess);
+      } else if (firstDescent != PR.end()) {
         const size_t n = PR.size();
         const size_t T = n >= (1u << 15) ? std::min<size_t>(allowedCpus(), 4) : 1;
         if (T > 1) {
@@ -1206,7 +1262,15 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
   const double tStart = nowSec();
   Runner R(ctx, *opts);
   auto res = new sdq_result();
+  std::thread poolThread;  // constructs res->pool while the main thread goes on (see below)
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if (t.joinable()) t.join();
+    }
+  } poolJoiner{poolThread};
   auto bail = [&](int rc) {
+    if (poolThread.joinable()) poolThread.join();
     delete res;
     return rc;
   };
@@ -1318,6 +1382,9 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
       }
   }
   const double tDedupe = nowSec() - tStart;
+  // the cluster objects (one per unique sequence, never resized again: ClusVec holds pointers into the pool) are
+  // constructed on a helper thread while this one computes medians and uploads
+  poolThread = std::thread([res, nPool = R.uniq.size()] { res->pool.resize(nPool); });
   // per-base median quality over the reads of a unique sequence (clusterDown.cpp:293-359, qualRep "median"); a
   // sequence seen once keeps its read's qualities.  (abundant sequences come first and cost the most: blocks of 256
   // uniques are handed out dynamically)
@@ -1399,7 +1466,7 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
     for (uint32_t c = 0; c < nChars; ++c) R.slot(char(chars[c]));
   }
   const double tUpload = nowSec() - tStart;
-  res->pool.resize(nU);  // never resized again: ClusVec holds pointers into it
+  poolThread.join();
   ClusVec clusters;
   for (uint32_t u = 0; u < nU; ++u) clusters.push_back(&res->pool[u]);
   parallelFor(nU, [&](size_t lo, size_t hi) {

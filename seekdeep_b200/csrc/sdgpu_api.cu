@@ -190,6 +190,7 @@ void sdgpu_destroy(sdgpu_ctx* ctx) {
   cudaFree(ctx->dProfiles);
   cudaFree(ctx->dProfilesRev);
   cudaFree(ctx->dKmerLists);
+  cudaFree(ctx->dCharOf);
   cudaFree(ctx->dRcIndex);
   cudaFree(ctx->dScratch);
   cudaFree(ctx->dWork);
@@ -578,6 +579,67 @@ int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* 
   ctx->h2dBytes += 2 * bytesIdx;
   ctx->d2hBytes += bytesOut + bytesGaps;
   return SDGPU_OK;
+}
+
+int sdgpu_align_events(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs, uint32_t flags,
+                       sdgpu_comparison* out, sdgpu_event* eventsOut, uint32_t eventCap, uint32_t* nEventsOut) {
+  if (!ctx || (nPairs && (!refIdx || !readIdx || !nEventsOut || (eventCap && !eventsOut)))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  if (nPairs == 0) return SDGPU_OK;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  uint32_t maxA = 0, maxB = 0;
+  for (uint32_t x = 0; x < nPairs; ++x) {
+    if (refIdx[x] >= nSeqs || readIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "pair index out of range");
+    maxA = std::max<uint32_t>(maxA, uint32_t(ctx->hOffsets[refIdx[x] + 1] - ctx->hOffsets[refIdx[x]]));
+    maxB = std::max<uint32_t>(maxB, uint32_t(ctx->hOffsets[readIdx[x] + 1] - ctx->hOffsets[readIdx[x]]));
+  }
+  std::vector<sdgpu_comparison> localOut;
+  if (!out) {
+    localOut.resize(nPairs);
+    out = localOut.data();
+  }
+  const uint64_t bytesIdx = uint64_t(nPairs) * 4;
+  const uint64_t bytesOut = uint64_t(nPairs) * sizeof(sdgpu_comparison);
+  const uint64_t bytesEv = (uint64_t(nPairs) * eventCap * sizeof(sdgpu_event) + 15) & ~15ull;
+  uint32_t gapCap = 16;
+  for (int attempt = 0;; ++attempt) {  // a second round only when some pair has more gap runs than the first one had room for
+    const uint64_t bytesGaps = (uint64_t(nPairs) * gapCap * sizeof(sdgpu_gap) + 15) & ~15ull;
+    int rc = sd_ensure_stage(ctx, bytesOut + bytesGaps + bytesEv + 3 * bytesIdx + 256);
+    if (rc) return rc;
+    uint8_t* base = reinterpret_cast<uint8_t*>(ctx->dStage);
+    sdgpu_comparison* dOut = reinterpret_cast<sdgpu_comparison*>(base);
+    sdgpu_gap* dGaps = reinterpret_cast<sdgpu_gap*>(base + bytesOut);
+    sdgpu_event* dEvents = reinterpret_cast<sdgpu_event*>(base + bytesOut + bytesGaps);
+    uint32_t* dN = reinterpret_cast<uint32_t*>(base + bytesOut + bytesGaps + bytesEv);
+    uint32_t* dRef = dN + nPairs;
+    uint32_t* dRead = dRef + nPairs;
+    SD_CUDA(ctx, cudaMemcpyAsync(dRef, refIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(dRead, readIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemsetAsync(dGaps, 0, bytesGaps, ctx->stream));
+    rc = sd_launch_align(ctx, dRef, dRead, nPairs, flags, dOut, dGaps, gapCap, maxA, maxB);
+    if (rc) return rc;
+    rc = sd_launch_events(ctx, dRef, dRead, nPairs, flags, dOut, dGaps, gapCap, dEvents, eventCap, dN);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, dOut, bytesOut, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(nEventsOut, dN, bytesIdx, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->h2dBytes += 2 * bytesIdx;
+    ctx->d2hBytes += bytesOut + bytesIdx;
+    uint32_t need = 0;
+    for (uint32_t x = 0; x < nPairs; ++x)
+      if (nEventsOut[x] == 0xFFFFFFFFu) need = std::max(need, out[x].nGapRuns);
+    if (need == 0) {
+      if (eventCap) {
+        SD_CUDA(ctx, cudaMemcpyAsync(eventsOut, dEvents, uint64_t(nPairs) * eventCap * sizeof(sdgpu_event), cudaMemcpyDeviceToHost, ctx->stream));
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->d2hBytes += uint64_t(nPairs) * eventCap * sizeof(sdgpu_event);
+      }
+      for (uint32_t x = 0; x < nPairs; ++x) out[x].status &= ~SDGPU_ST_GAPLIST_TRUNCATED;  // (no gap list is returned here)
+      return SDGPU_OK;
+    }
+    if (attempt > 0) return sd_fail(ctx, SDGPU_E_OVERFLOW, "gap list still truncated after resizing");
+    gapCap = need;
+  }
 }
 
 int sdgpu_set_pass_table(sdgpu_ctx* ctx, const sdgpu_iter_par* lines, uint32_t nLines) {

@@ -168,6 +168,7 @@ struct sdgpu_ctx {
   uint64_t* dKmerLists = nullptr;
   uint64_t listCapKeys = 0;
   uint32_t listK = 0, listSeqs = 0;
+  uint8_t* dCharOf = nullptr;  // code -> character, for the event lists (events_kernel.cu)
   // scratch for the alignment kernel (pointer slabs), pair staging, work counter
   uint8_t* dScratch = nullptr;
   uint64_t scratchBytes = 0;

@@ -145,6 +145,23 @@ class Oracle:
         assert rc == 0
         return (out, gaps) if gapCap else out
 
+    def align_events(self, params, a, qa, b, qb, flags=_abi.USING_QUALITY, kmaps=None):
+        """(comparison, events) of one pair: comp_'s mismatches_ / lowKmerMismatches_ / alignmentGaps_ in column order."""
+        self.lib.sdo_align_events.restype = C.c_int
+        self.lib.sdo_align_events.argtypes = [C.POINTER(_abi.Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                              C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        qa = None if qa is None else np.ascontiguousarray(qa, np.uint8)
+        qb = None if qb is None else np.ascontiguousarray(qb, np.uint8)
+        cmp_ = np.zeros(1, _abi.COMPARISON_DTYPE)
+        cap = len(a) + len(b) + 2
+        ev = np.zeros(cap, _abi.EVENT_DTYPE)
+        n = self.lib.sdo_align_events(C.byref(params), kmaps, _p(a), _p(qa), len(a), _p(b), _p(qb), len(b), flags, _p(cmp_),
+                                      _p(ev), cap)
+        assert 0 <= n <= cap
+        return cmp_[0], ev[:n]
+
     def chimera_probe_batch(self, params, bases, quals, offsets, parentIdx, candIdx, chiOverlap, keepLowQual=False,
                             flags=_abi.USING_QUALITY, kmaps=None):
         bases = np.ascontiguousarray(bases, np.uint8)

@@ -1,0 +1,68 @@
+"""sdgpu_align_events: comp_.distances_.mismatches_ / lowKmerMismatches_ / alignmentGaps_ (the maps qluster's
+--writeOutFinalAllByAllComparison dumps, clusterDown.cpp:759-800) as event lists, identical to the oracle's walk over
+the gapped strings: kinds, columns, positions, bases, qualities, k-mer counts."""
+import numpy as np
+import pytest
+
+from seekdeep_b200 import _abi
+from seekdeep_b200.aligner import GpuAligner
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(oracle, params, seqs, quals, bases, q, offsets, cnts, refIdx, readIdx, flags, kIndex):
+    km = None
+    with GpuAligner(params) as al:
+        al.upload_seqs(bases, q, offsets, cnts)
+        if kIndex:
+            al.index_kmers(*kIndex)
+            km = oracle.index_kmers(bases, offsets, cnts, *kIndex)
+        try:
+            got, events = al.align_events(refIdx, readIdx, checkKmer=bool(flags & 1), usingQuality=bool(flags & 2),
+                                          doingMatchQuality=bool(flags & 4), eventCap=6)  # small: the wrapper has to grow it
+            plain = al.align_profile(refIdx, readIdx, checkKmer=bool(flags & 1), usingQuality=bool(flags & 2),
+                                     doingMatchQuality=bool(flags & 4))
+            assert np.array_equal(got, plain)  # the scalar part is sdgpu_align_profile's
+            nGapEv = 0
+            for i, (a, b) in enumerate(zip(refIdx, readIdx)):
+                wc, wev = oracle.align_events(params, seqs[a], quals[a], seqs[b], quals[b], flags, kmaps=km)
+                assert len(events[i]) == len(wev), (i, len(events[i]), len(wev))
+                assert np.array_equal(events[i], wev), (i, events[i], wev)
+                for name in _abi.INT_FIELDS:
+                    assert got[name][i] == wc[name], (name, i)
+                nGapEv += int((wev["kind"] >= _abi.EV_GAP_IN_REF).sum())
+        finally:
+            if km:
+                oracle.free_kmaps(km)
+    return nGapEv
+
+
+@pytest.mark.parametrize("pname", ["qluster", "asym", "countEnds"])
+def test_align_events_match_oracle(oracle, pname):
+    rng = np.random.default_rng(len(pname) * 7 + 1)
+    params = H.params_for(pname)
+    bases, q, offsets, cnts, seqs, quals = H.make_store(rng, 40, 180)
+    n = 300
+    refIdx = rng.integers(0, 40, n).astype(np.uint32)
+    readIdx = rng.integers(0, 40, n).astype(np.uint32)
+    nGaps = _check(oracle, params, seqs, quals, bases, q, offsets, cnts, refIdx, readIdx, _abi.USING_QUALITY | _abi.CHECK_KMER, (9, 1, True))
+    assert nGaps > 0
+    _check(oracle, params, seqs, quals, bases, q, offsets, cnts, refIdx[:100], readIdx[:100], _abi.USING_QUALITY, None)
+    _check(oracle, params, seqs, quals, bases, q, offsets, cnts, refIdx[:100], readIdx[:100], _abi.CHECK_KMER, (7, 2, False))
+
+
+def test_align_events_unrelated_and_ragged(oracle):
+    """Unrelated sequences of very different lengths: dozens of gap runs per pair (the first, 16-run gap list is too
+    small and the call sizes a second one), end gaps on both sides, sequences of one and two bases."""
+    rng = np.random.default_rng(3)
+    seqs = [H.rand_seq(rng, int(n)) for n in rng.integers(1, 260, 32)]
+    seqs[0] = H.rand_seq(rng, 1)
+    seqs[1] = H.rand_seq(rng, 2)
+    quals = [H.rand_quals(rng, len(s)) for s in seqs]
+    bases, q, offsets = np.concatenate(seqs), np.concatenate(quals), np.zeros(33, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    refIdx, readIdx = np.meshgrid(np.arange(32, dtype=np.uint32), np.arange(32, dtype=np.uint32))
+    nGaps = _check(oracle, H.params_for("qluster"), seqs, quals, bases, q, offsets, None, refIdx.ravel(), readIdx.ravel(),
+                   _abi.USING_QUALITY, None)
+    assert nGaps > 16 * 32

@@ -397,3 +397,47 @@ def test_kmer_binning_control_flow(oracle):
     assert run(useKmerBinning=True, kCompareLen=4, kmerCutOff=float(np.nextafter(fr, 0)), binIts=loose) == [(A, 7.0), (B, 3.0)]
     # cut-off below zero: one bin with everything; the loose lines (90 % identity) still keep B apart
     assert run(useKmerBinning=True, kCompareLen=4, kmerCutOff=-1.0, binIts=loose) == [(A, 7.0), (B, 3.0)]
+
+
+def test_align_events_micro_case(oracle):
+    """comp_'s per-event maps as restated (clusterDown.cpp:759-800 dumps them): one high-quality mismatch, one
+    low-quality mismatch, an internal 2-base deletion in the read, a free right end gap -- positions, bases, qualities
+    and kinds spelled out by hand."""
+    import seekdeep_b200 as sd
+    from seekdeep_b200 import _abi
+    ref = "ACGTTGCAAGGCTTAACCGGATCGTTAGCAATCCGATTGACCATGCATGC"
+    read = list(ref)
+    read[5] = "A"    # G -> A, high quality
+    read[20] = "C"   # A -> C, low quality
+    del read[30:32]  # 2-base deletion in the read
+    read = "".join(read)[:-3]  # the read ends 3 bases early: right end gap, free under qluster's gaps
+    qa = np.full(len(ref), 38, np.uint8)
+    qb = np.full(len(read), 38, np.uint8)
+    qb[20] = 9
+    params = sd.make_params()
+    cmp_, ev = oracle.align_events(params, np.frombuffer(ref.encode(), np.uint8), qa, np.frombuffer(read.encode(), np.uint8), qb)
+    kinds = [int(e["kind"]) for e in ev]
+    assert kinds == [_abi.EV_MISMATCH_HQ, _abi.EV_MISMATCH_LQ, _abi.EV_GAP_IN_READ, _abi.EV_GAP_IN_READ | _abi.EV_END_GAP]
+    e0, e1, e2, e3 = ev
+    assert (e0["alnPos"], e0["refPos"], e0["seqPos"], chr(e0["refBase"]), chr(e0["seqBase"]), e0["refQual"], e0["seqQual"]) == (5, 5, 5, "G", "A", 38, 38)
+    assert (e1["alnPos"], e1["refPos"], e1["seqPos"], chr(e1["refBase"]), chr(e1["seqBase"]), e1["seqQual"]) == (20, 20, 20, "A", "C", 9)
+    assert e2["size"] == 2 and e2["refPos"] in (29, 30, 31) and e2["seqPos"] == e2["refPos"] and e2["alnPos"] == e2["refPos"]
+    assert ref[e2["refPos"]] == chr(e2["refBase"])
+    assert (e3["size"], e3["refPos"], e3["seqPos"], e3["alnPos"]) == (3, len(ref) - 3, len(read), len(ref) - 3)
+    assert cmp_["hqMismatches"] == 1 and cmp_["lqMismatches"] == 1 and cmp_["numGaps"] == 1 and cmp_["twoBaseIndel"] == 1.0
+    # counts of the events agree with the scalar comparison on random related pairs
+    from tests import helpers as H
+    rng = np.random.default_rng(5)
+    bases, quals, offsets, cnts, seqs, qs = H.make_store(rng, 24, 140)
+    km = oracle.index_kmers(bases, offsets, cnts, 9, 1, True)
+    for i in range(1, 24):
+        c, ev = oracle.align_events(params, seqs[0], qs[0], seqs[i], qs[i], _abi.USING_QUALITY | _abi.CHECK_KMER, kmaps=km)
+        k = ev["kind"]
+        assert (k == _abi.EV_MISMATCH_HQ).sum() == c["hqMismatches"] and (k == _abi.EV_MISMATCH_LQ).sum() == c["lqMismatches"]
+        assert (k == _abi.EV_MISMATCH_LOWKMER).sum() == c["lowKmerMismatches"]
+        assert ((k == _abi.EV_GAP_IN_REF) | (k == _abi.EV_GAP_IN_READ)).sum() == c["numGaps"]
+        assert (k >= _abi.EV_GAP_IN_REF).sum() == c["nGapRuns"]
+        assert np.all(np.diff(ev["alnPos"].astype(np.int64)) > 0)
+        low = ev[k == _abi.EV_MISMATCH_LOWKMER]
+        assert np.all((low["kmerFreqRef"] <= 1) | (low["kmerFreqSeq"] <= 1))  # runCutOff 1
+    oracle.free_kmaps(km)
