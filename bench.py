@@ -225,6 +225,28 @@ def kmer_roofline(al, bases, quals, offsets, peaks):
                       "algorithmic_bytes": algoc,
                       "note": "cluster tile in shared memory, each read profile fetched from HBM once: HBM traffic is the compulsory "
                               "bytes, the kernel is bound by min/add SIMD on the ALU pipe + LDS, not by HBM"}
+    # qluster --useKmerBinning on the same sample: sorted k-mer lists (k = 10) of every read, then one round of the binning
+    # comparison (64 candidate seeds x every read, 8 bytes per read back)
+    al.build_kmer_lists(10)
+    al.sync()
+    bestl = 1e9
+    for _ in range(3):
+        al.timer_start()
+        al.build_kmer_lists(10)
+        bestl = min(bestl, al.timer_stop())
+    algol = float(lens.sum() + len(lens) * 16 + np.maximum(lens - 9, 0).sum() * 8)  # codes + offsets in, one uint64 key per k-mer out
+    seeds = np.arange(min(64, len(lens)), dtype=np.uint32)
+    reads = np.arange(len(lens), dtype=np.uint32)
+    al.kmer_bin_masks(seeds, reads, 0.8)
+    t0 = time.perf_counter()
+    al.kmer_bin_masks(seeds, reads, 0.8)
+    dtm = time.perf_counter() - t0
+    out["binning"] = {"kernel": "kmerListKernel(k=10) + kmerBinKernel(64 seeds x reads)", "list_ms": bestl,
+                      "list_achieved": algol / (bestl * 1e-3) / 1e9, "list_frac": algol / (bestl * 1e-3) / 1e9 / peak, "unit": "GB/s",
+                      "list_algorithmic_bytes": algol, "masks_ms_host_call": dtm * 1e3, "mask_pairs_per_s": len(seeds) * len(reads) / dtm,
+                      "note": "lists: per-sequence bitonic sort in shared memory, HBM traffic = codes in + 8 B per k-mer out; masks: one "
+                              "binary search per read k-mer against seed lists staged in shared memory (LDS-bound), timed through the host "
+                              "call (index lists up, 8 bytes per read back)"}
     return out
 
 

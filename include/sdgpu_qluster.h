@@ -111,6 +111,24 @@ int sdq_cluster_chimeric(const sdq_result* r, uint32_t c, uint32_t* parents, uin
 /* final cluster index of every input read (UINT32_MAX: dropped as a small read) */
 int sdq_membership(const sdq_result* r, uint32_t* clusterOfRead);
 
+/* FASTQ ingest in front of the collapse (the reference reads through njhseq's SeqInput::readNextRead,
+ * clusterDown.cpp:207-232).  sdq_read_fastq parses a plain or gzip FASTQ file (four-line records, Phred+33) into the
+ * packed (bases, quals, offsets) form sdq_run takes -- lower-case bases upper-cased, qualities as numbers -- and
+ * sdq_run_fastq feeds it to sdq_run.  Malformed input (multi-line records, length mismatch, characters outside
+ * Phred+33) is refused with SDGPU_E_UNSUPPORTED and a message naming the record (sdq_fastq_last_error).  Per-read
+ * trimming and the Illumina sample-number filter (clusterDown.cpp:83-181, :233-270) stay with the caller. */
+typedef struct sdq_reads sdq_reads;
+int sdq_read_fastq(const char* path, sdq_reads** out);
+void sdq_reads_free(sdq_reads* r);
+uint32_t sdq_reads_count(const sdq_reads* r);
+const uint8_t* sdq_reads_bases(const sdq_reads* r);
+const uint8_t* sdq_reads_quals(const sdq_reads* r);
+const uint64_t* sdq_reads_offsets(const sdq_reads* r); /* count + 1 entries */
+const char* sdq_reads_name(const sdq_reads* r, uint32_t i); /* without the '@'; NULL when out of range */
+const char* sdq_fastq_last_error(void);
+int sdq_run_fastq(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par* initPars, uint32_t nInit,
+                  const sdq_iter_par* pars, uint32_t nPars, const char* fastqPath, sdq_result** out);
+
 /* Population clustering across samples.  Replaces the collapse inside
  * sampColl.doPopulationClustering(sampColl.createPopInput(), alignerObj, collapserObj, pars.popIteratorMap)
  * (src/SeekDeepPrograms/SeekDeepProgram/processClusters/processClusters.cpp:226): the final clusters of every sample

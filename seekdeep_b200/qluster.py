@@ -279,3 +279,64 @@ def shard_pair_blocks(totalPairs, rank, world):
     base, extra = divmod(int(totalPairs), int(world))
     first = rank * base + min(rank, extra)
     return first, base + (1 if rank < extra else 0)
+
+
+def read_fastq(path):
+    """sdq_read_fastq: a plain or gzip FASTQ file as packed (bases, quals, offsets, names) -- what qluster() takes."""
+    lib = _abi.load()
+    v = C.c_void_p
+    lib.sdq_read_fastq.restype = C.c_int
+    lib.sdq_read_fastq.argtypes = [C.c_char_p, C.POINTER(v)]
+    lib.sdq_reads_free.argtypes = [v]
+    lib.sdq_reads_count.restype = C.c_uint32
+    lib.sdq_reads_count.argtypes = [v]
+    for f in ("bases", "quals", "offsets"):
+        getattr(lib, "sdq_reads_" + f).restype = v
+        getattr(lib, "sdq_reads_" + f).argtypes = [v]
+    lib.sdq_reads_name.restype = C.c_char_p
+    lib.sdq_reads_name.argtypes = [v, C.c_uint32]
+    lib.sdq_fastq_last_error.restype = C.c_char_p
+    h = v()
+    rc = lib.sdq_read_fastq(str(path).encode(), C.byref(h))
+    if rc != _abi.OK:
+        raise SdgpuError(rc, (lib.sdq_fastq_last_error() or b"").decode())
+    try:
+        n = lib.sdq_reads_count(h)
+        offsets = np.ctypeslib.as_array(C.cast(lib.sdq_reads_offsets(h), C.POINTER(C.c_uint64)), (n + 1,)).copy()
+        tot = int(offsets[-1])
+        if tot:
+            bases = np.ctypeslib.as_array(C.cast(lib.sdq_reads_bases(h), C.POINTER(C.c_uint8)), (tot,)).copy()
+            quals = np.ctypeslib.as_array(C.cast(lib.sdq_reads_quals(h), C.POINTER(C.c_uint8)), (tot,)).copy()
+        else:
+            bases, quals = np.zeros(0, np.uint8), np.zeros(0, np.uint8)
+        names = [lib.sdq_reads_name(h, i).decode() for i in range(n)]
+    finally:
+        lib.sdq_reads_free(h)
+    return bases, quals, offsets, names
+
+
+def qluster_fastq(aligner: GpuAligner, path, pars: QlusterPars = None, iteratorMap: CollapseIterations = None,
+                  intialParameters: CollapseIterations = None, want_clusters=True):
+    """`SeekDeep qluster --fastq path`: sdq_run_fastq = sdq_read_fastq + sdq_run, everything behind the C ABI."""
+    lib = aligner._lib
+    _bind(lib)
+    v = C.c_void_p
+    lib.sdq_run_fastq.restype = C.c_int
+    lib.sdq_run_fastq.argtypes = [v, C.POINTER(QlusterOptsC), v, C.c_uint32, v, C.c_uint32, C.c_char_p, C.POINTER(v)]
+    lib.sdq_fastq_last_error.restype = C.c_char_p
+    pars = pars or QlusterPars()
+    iteratorMap = iteratorMap or CollapseIterations.gen_illumina_default_pars(100)
+    intialParameters = intialParameters or iteratorMap
+    opts = pars.to_c()
+    ip, nip = iter_pars_to_c(intialParameters)
+    pp, npp = iter_pars_to_c(iteratorMap)
+    h = v()
+    rc = lib.sdq_run_fastq(aligner._ctx, C.byref(opts), ip, nip, pp, npp, str(path).encode(), C.byref(h))
+    if rc != _abi.OK:
+        raise SdgpuError(rc, (lib.sdq_fastq_last_error() or lib.sdq_last_error() or b"").decode())
+    try:
+        st = StatsC()
+        lib.sdq_get_stats(h, C.byref(st))
+        return _result_to_dict(lib, h, int(st.inputReads), want_clusters)
+    finally:
+        lib.sdq_free(h)

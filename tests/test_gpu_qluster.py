@@ -281,3 +281,25 @@ def test_stop_check_small_cutoff_and_consensus_micro_cases(oracle):
     got, want = run_pair(oracle, sd.make_params(), sd.QlusterPars(markChimeras=False), its, bases, quals, offsets)
     assert_same(got, want)
     assert len(got["clusters"]) == 1 and got["clusters"][0][1][p] == 22 and got["clusters"][0][2] == 5.0
+
+
+def test_qluster_from_fastq_file(oracle, tmp_path):
+    """sdq_run_fastq (FASTQ ingest + collapse behind the C ABI) == the collapse of the same reads handed over packed."""
+    import gzip
+    from seekdeep_b200.qluster import qluster_fastq
+    rng = np.random.default_rng(41)
+    haps = synth.make_haplotypes(rng, 5, 130, 1, 5)
+    seqs, quals, _ = synth.fast_reads(rng, haps, 900, 0.005)
+    bases, q, offsets = synth.pack(seqs, quals)
+    path = tmp_path / "sample.fastq.gz"
+    with gzip.open(path, "wt") as f:
+        for i, (s, ql) in enumerate(zip(seqs, quals)):
+            f.write(f"@r{i}\n{s.tobytes().decode()}\n+\n{''.join(chr(33 + int(x)) for x in ql)}\n")
+    params = sd.make_params()
+    iters = CollapseIterations.gen_illumina_default_pars(100)
+    with sd.GpuAligner(params) as al:
+        got = qluster_fastq(al, path, sd.QlusterPars(), iters)
+        packed = sd.qluster(al, bases, q, offsets, sd.QlusterPars(), iters)
+    assert_same(got, packed)
+    want = oracle.qluster(params, oracle_opts(sd.QlusterPars()), iters.iters, iters.iters, bases, q, offsets)
+    assert_same(got, want)
