@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) kmerProfileKernel(DevSeqs seqs, uint32_t 
 // funnel shifts and squeezes each word's four codes into one byte (first base most significant),
 // so every k-mer id is a 2*kLen-bit field of one 64-bit register: per sequence the LSU sees
 // W + 3 word loads per lane instead of two byte loads per position.
-template <int W, bool WIDE>
+template <int W>
 __device__ __forceinline__ void profileLane4(const uint32_t* codeWords, uint64_t off, uint32_t base, uint32_t len,
                                              uint32_t nk, uint32_t kLen, uint32_t mask, uint32_t lane, uint32_t* mine) {
   const uint32_t p0 = base + lane * 4 * W;
@@ -194,36 +194,21 @@ __device__ __forceinline__ void profileLane4(const uint32_t* codeWords, uint64_t
     bits = (bits << 8) | ((r * 0x40100401u) >> 24);  // c0<<6 | c1<<4 | c2<<2 | c3
   }
   constexpr int T = 4 * (W + 2);  // codes held in `bits`; code i sits at bit 2*(T-1-i)
-  // one variable shift puts the lane's last k-mer at bit 0; k-mer i then sits at the compile-time offset 2 * (4W - 1 - i)
-  const uint64_t aligned = bits >> (2 * (T - (4 * W - 1) - int(kLen)));  // (T - (4W - 1) = 9 codes >= kLen + 1)
-  auto count = [&](int i) {
-    const uint32_t id = uint32_t(aligned >> (2 * (4 * W - 1 - i))) & mask;
-    if (WIDE) {
-      atomicAdd(&mine[id], 1u);  // one 32-bit counter per bin while counting (packed to uint16 on the way out)
-    } else {
+#pragma unroll
+  for (int i = 0; i < 4 * W; ++i) {
+    if (p0 + i < nk) {
+      const uint32_t id = uint32_t(bits >> (2 * (T - i - int(kLen)))) & mask;
       atomicAdd(&mine[id >> 1], 1u << (16 * (id & 1)));
     }
-  };
-  if (nk - p0 >= 4u * W) {  // every start position of this lane exists (all lanes but the last active one): no per-k-mer guard
-#pragma unroll
-    for (int i = 0; i < 4 * W; ++i) count(i);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4 * W; ++i)
-      if (p0 + i < nk) count(i);
   }
 }
 
-// WIDE (profiles of at most 1024 bins, k <= 5): the warp's histogram has one 32-bit counter per bin, so counting a k-mer
-// is shift + mask + one shared-memory add instead of also splitting the id into word and half; the counters are packed
-// to uint16 while they are written out.  At k = 5 the kernel is bound by these per-k-mer instructions, not by HBM.
-template <bool STREAM, bool WIDE>
 __global__ void __launch_bounds__(256, 6) kmerProfileKernel4(DevSeqs seqs, uint32_t kLen, uint32_t profSize,
                                                              uint16_t* profiles) {
   extern __shared__ uint4 sProfVec[];
   const uint32_t warpInCta = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t warpsPerCta = blockDim.x >> 5;
-  const uint32_t vecs = WIDE ? profSize / 4 : profSize / 8;  // uint4 per warp histogram
+  const uint32_t vecs = profSize / 8;
   uint4* mineVec = sProfVec + warpInCta * vecs;
   uint32_t* mine = reinterpret_cast<uint32_t*>(mineVec);
   const uint32_t* codeWords = reinterpret_cast<const uint32_t*>(seqs.codes);  // cudaMalloc'd: aligned
@@ -238,40 +223,20 @@ __global__ void __launch_bounds__(256, 6) kmerProfileKernel4(DevSeqs seqs, uint3
       for (uint32_t base = 0; base < nk; base += 512) {
         const uint32_t rem = nk - base;
         if (rem <= 128) {
-          profileLane4<1, WIDE>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
+          profileLane4<1>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
         } else if (rem <= 256) {
-          profileLane4<2, WIDE>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
+          profileLane4<2>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
         } else if (rem <= 384) {
-          profileLane4<3, WIDE>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
+          profileLane4<3>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
         } else {
-          profileLane4<4, WIDE>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
+          profileLane4<4>(codeWords, off, base, len, nk, kLen, mask, lane, mine);
         }
       }
     }
     __syncwarp();
     uint4* dst = reinterpret_cast<uint4*>(profiles + size_t(s) * profSize);
-    if (WIDE) {
-      for (uint32_t x = lane; x < vecs / 2; x += 32) {  // eight 32-bit counters -> eight uint16 (a sequence has < 65536 bases)
-        const uint4 a = mineVec[2 * x], b = mineVec[2 * x + 1];
-        const uint4 o = make_uint4(__byte_perm(a.x, a.y, 0x5410), __byte_perm(a.z, a.w, 0x5410), __byte_perm(b.x, b.y, 0x5410),
-                                   __byte_perm(b.z, b.w, 0x5410));
-        if (STREAM) {
-          __stcs(dst + x, o);
-        } else {
-          dst[x] = o;
-        }
-        mineVec[2 * x] = make_uint4(0, 0, 0, 0);
-        mineVec[2 * x + 1] = make_uint4(0, 0, 0, 0);
-      }
-      __syncwarp();
-      continue;
-    }
     for (uint32_t x = lane; x < vecs; x += 32) {  // write out and leave the histogram zeroed for the next sequence
-      if (STREAM) {
-        __stcs(dst + x, mineVec[x]);  // written once, read by a later kernel: do not let 2 KB per sequence push the codes out of L2
-      } else {
-        dst[x] = mineVec[x];
-      }
+      dst[x] = mineVec[x];
       mineVec[x] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
@@ -521,29 +486,16 @@ int sd_build_kmer_profiles(sdgpu_ctx* ctx, uint32_t kLen) {
   uint32_t warpsPerCta = uint32_t((200u << 10) / (size_t(profSize) * 2));  // stay under the 227 KB shared-memory limit
   warpsPerCta = warpsPerCta < 1 ? 1 : (warpsPerCta > 8 ? 8 : warpsPerCta);
   const bool acgtOnly = sigma <= 4 && kLen <= 8 && profSize == (1u << (2 * kLen));  // codes 0..3: 2-bit fast path
-  static const int tuneStore = getenv("SD_PROF_STORE") ? atoi(getenv("SD_PROF_STORE")) : 1;   // tuning knobs (scripts/kmer_profile_sweep.py)
-  static const int tuneCtas = getenv("SD_PROF_CTAS") ? atoi(getenv("SD_PROF_CTAS")) : 32;
-  static const int tuneWarps = getenv("SD_PROF_WARPS") ? atoi(getenv("SD_PROF_WARPS")) : 0;
-  static const int tuneWide = getenv("SD_PROF_WIDE") ? atoi(getenv("SD_PROF_WIDE")) : 1;
-  if (tuneWarps > 0 && uint32_t(tuneWarps) < warpsPerCta) warpsPerCta = uint32_t(tuneWarps);
-  const bool wide = acgtOnly && tuneWide && profSize <= 1024;  // 32-bit counters while counting: 4 KB per warp at most
-  const size_t smemT = size_t(warpsPerCta) * profSize * (wide ? 4 : 2);
-  const void* fn = !acgtOnly ? (const void*)kmerProfileKernel
-                   : wide    ? (tuneStore ? (const void*)kmerProfileKernel4<true, true> : (const void*)kmerProfileKernel4<false, true>)
-                             : (tuneStore ? (const void*)kmerProfileKernel4<true, false> : (const void*)kmerProfileKernel4<false, false>);
-  SD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemT)));
+  const size_t smem = size_t(warpsPerCta) * profSize * 2;
+  SD_CUDA(ctx, cudaFuncSetAttribute(acgtOnly ? (const void*)kmerProfileKernel4 : (const void*)kmerProfileKernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   uint32_t grid = (nSeqs + warpsPerCta - 1) / warpsPerCta;
-  const uint32_t maxGrid = uint32_t(ctx->numSMs) * uint32_t(tuneCtas);  // (swept 6..1000 CTAs per SM on B200: 32-64 is best, 6 costs 5 %)
+  const uint32_t maxGrid = uint32_t(ctx->numSMs) * 32;  // (swept 6..1000 CTAs per SM on B200: 32-64 is best, 6 costs 5 %)
   if (grid > maxGrid) grid = maxGrid;
   if (acgtOnly) {
-    const DevSeqs ds = sd_dev_seqs(ctx);
-    const uint32_t threads = warpsPerCta * 32;
-    if (wide && tuneStore) kmerProfileKernel4<true, true><<<grid, threads, smemT, ctx->stream>>>(ds, kLen, profSize, ctx->dProfiles);
-    else if (wide) kmerProfileKernel4<false, true><<<grid, threads, smemT, ctx->stream>>>(ds, kLen, profSize, ctx->dProfiles);
-    else if (tuneStore) kmerProfileKernel4<true, false><<<grid, threads, smemT, ctx->stream>>>(ds, kLen, profSize, ctx->dProfiles);
-    else kmerProfileKernel4<false, false><<<grid, threads, smemT, ctx->stream>>>(ds, kLen, profSize, ctx->dProfiles);
+    kmerProfileKernel4<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, profSize, ctx->dProfiles);
   } else {
-    kmerProfileKernel<<<grid, warpsPerCta * 32, smemT, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, top, profSize, ctx->dProfiles);
+    kmerProfileKernel<<<grid, warpsPerCta * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, sigma, top, profSize, ctx->dProfiles);
   }
   SD_CUDA(ctx, cudaGetLastError());
   ++ctx->launches;
