@@ -273,6 +273,16 @@ typedef struct sdgpu_grid_hit {
 } sdgpu_grid_hit;
 int sdgpu_align_pass_grid(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uint32_t nClusters, const uint32_t* readIdx,
                           uint32_t nReads, uint32_t flags, const sdgpu_grid_hit** hits, uint64_t* nHits);
+/* Streaming form: the grid runs in chunks of whole reads (about 2 M pairs each, double-buffered); onChunk is called on the
+ * calling thread, in read order, as soon as a chunk has finished -- with that chunk's records and readsDone, the number of
+ * leading entries of readIdx[] whose pairs are now all judged -- while the GPU already works on the next chunk.  The
+ * collapse loop files verdicts and runs its sequential pass over the finished reads inside the callback
+ * (collapser::findMatch consumes a read's comparisons in list order, clusterDown.cpp:488-518).  The records are only
+ * valid during the call; the callback must not call into ctx.  onChunk == NULL: records are kept for
+ * sdgpu_align_pass_grid. */
+typedef void (*sdgpu_grid_chunk_fn)(void* user, const sdgpu_grid_hit* hits, uint64_t nHits, uint32_t readsDone);
+int sdgpu_align_pass_grid_stream(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uint32_t nClusters, const uint32_t* readIdx,
+                                 uint32_t nReads, uint32_t flags, sdgpu_grid_chunk_fn onChunk, void* user);
 
 /* Chimera probe: the per-(parent, candidate) part of collapser::markChimeras
  * (clusterDown.cpp:566-577; options clusterDownSetUp.cpp:372-381).  Per pair i the call runs

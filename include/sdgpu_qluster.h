@@ -81,6 +81,7 @@ typedef struct sdq_stats {
   uint64_t passingPairs;    /* computed comparisons whose verdict mask was not zero (the only ones that cross PCIe) */
   uint64_t kmerPairs;       /* (seed, cluster) k-mer comparisons of --useKmerBinning */
   uint64_t kmerBins;        /* bins those comparisons formed, summed over the clustering runs */
+  uint64_t streamedGrids;   /* (read x window) grids whose chunks were consumed by the sequential pass while the GPU worked on the next */
   double secondsGpu;        /* wall time inside sdgpu_align_profile calls */
   double secondsTotal;
   double msResident;        /* CUDA-event time on the ctx stream from "unique reads resident in HBM" to the end */

@@ -100,6 +100,7 @@ SIGNATURES = {
     "sdgpu_set_pass_table": (C.c_int, [_ctx, C.c_void_p, C.c_uint32]),
     "sdgpu_align_pass": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sdgpu_align_pass_grid": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), _u64p]),
+    "sdgpu_align_pass_grid_stream": (C.c_int, [_ctx, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "sdgpu_set_screen": (C.c_int, [_ctx, C.c_int]),
     "sdgpu_align_no_internal_gaps": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "sdgpu_chimera_probe_pairs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]),

@@ -38,6 +38,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -392,6 +393,8 @@ class Runner {
   double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0, tIndex = 0, tSubmit = 0;
   double tConsAlign = 0, tConsCount = 0, tConsBuild = 0, tConsUpload = 0;  // parts of tCons
   double tBin = 0;  // k-mer binning (lists + masks + settling)
+  uint64_t streamMinPairs = getenv("SDQ_STREAM_MIN_PAIRS") ? uint64_t(atoll(getenv("SDQ_STREAM_MIN_PAIRS"))) : (3ull << 21);  // (test hook)
+  uint64_t streamedGrids = 0;
   uint64_t keptVersions = 0, skippedScans = 0;
   bool orderDirty = true;
   // symbols of the consensus counters (bases + '-'), ASCII order kept for njhseq's tie rule
@@ -471,6 +474,39 @@ class Runner {
     return (coverStart != 0 && lastIn[s] >= coverStart) || onDemandAt[s] == serial;
   }
 
+  // what the streaming grid call hands back to the collapse loop, chunk by chunk (sdgpu_grid_chunk_fn)
+  struct StreamCtx {
+    Runner* R;
+    ClusVec* cs;
+    const std::vector<uint32_t>* window;   // store indices of the grid's clusters
+    const std::vector<uint32_t>* readPos;  // list position of every read of the grid, in pass order
+    std::function<void(size_t)>* fastStep;
+    bool* windowIntact;
+    size_t* streamed;
+    uint64_t nHits;
+    static void onChunk(void* user, const sdgpu_grid_hit* hits, uint64_t n, uint32_t readsDone) {
+      StreamCtx& S = *static_cast<StreamCtx*>(user);
+      Runner& R = *S.R;
+      double t0 = nowSec();
+      for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t rp = (*S.readPos)[hits[i].read];
+        (*S.cs)[rp].row.insert((*S.window)[hits[i].cluster], hits[i].mask);
+        R.PR[rp].orMask |= hits[i].mask;
+      }
+      S.nHits += n;
+      double t1 = nowSec();
+      R.tInsert += t1 - t0;
+      // the reads of the finished chunks take their turn, as long as the window is intact (once a window cluster has
+      // been absorbed a read may need a candidate judged on demand: that is the pass proper's business)
+      while (*S.streamed < readsDone && *S.windowIntact) {
+        const uint32_t rp = (*S.readPos)[*S.streamed];
+        if (!R.PR[rp].remove) (*S.fastStep)(rp);
+        ++*S.streamed;
+      }
+      R.tPass += nowSec() - t1;
+    }
+  };
+
   // njhseq collapser::collapseWithParameters + findMatch for one par-file line
   int collapseWithParameters(ClusVec& cs, const sdq_iter_par& it, int line) {
     ++serial;
@@ -485,6 +521,41 @@ class Runner {
     double tt0 = nowSec();
     std::unique_ptr<NvtxRange> gridRange(new NvtxRange("sdq:list+grids"));
     const uint32_t wn = uint32_t(std::min<uint64_t>(eligEnd, uint64_t(it.stopCheck) + 1));  // the window: positions [0, wn)
+    size_t amountAdded = 0;
+    bool windowIntact = true;   // no window cluster absorbed yet: every read sees the static window
+    size_t streamed = 0;        // leading entries of the whole-window read list the streaming callback has dealt with
+    size_t resumeAt = cs.size();  // the pass proper starts below this position
+    // One read's turn while the window is intact: the candidates it looks at are window positions -- all alive, all
+    // judged -- so its first passing candidate is the smallest window position among its own (few) non-zero verdicts,
+    // provided it lies within the first stopCheck candidates the read counts (itself skipped).
+    std::function<void(size_t)> fastStep = [&](size_t rp) {
+      if (!(PR[rp].orMask & bit)) {  // judged against every window cluster, no verdict has this line's bit
+        ++skippedScans;
+        return;
+      }
+      Clus& read = cs[rp];
+      uint32_t best = UINT32_MAX;
+      read.row.forEach([&](uint32_t k, uint64_t v) {
+        if (!(v & bit) || k >= winPos.size()) return;
+        const uint32_t wp = winPos[k];
+        if (wp != 0 && wp - 1 != rp && wp - 1 < best) best = wp - 1;
+      });
+      const uint32_t looked = best == UINT32_MAX ? std::min<uint32_t>(wn - (rp < wn ? 1u : 0u), it.stopCheck) : best + 1 - (rp < best ? 1u : 0u);
+      if (best != UINT32_MAX && looked > it.stopCheck) best = UINT32_MAX;  // beyond the read's stopCheck-th candidate
+      st.pairsConsumed += std::min<uint32_t>(looked, it.stopCheck);
+      if (best == UINT32_MAX) return;
+      Clus& clus = cs[best];
+      clus.cnt += read.cnt;
+      clus.members.append(read.members);
+      clus.needCons = true;
+      read.remove = true;
+      PR[rp].remove = 1;
+      PR[best].changed = 1;
+      read.row.clear();
+      read.cons.reset();
+      if (rp < wn) windowIntact = false;
+      ++amountAdded;
+    };
     {
       if (inPrevWindow.size() < storeSize) inPrevWindow.resize(storeSize, 0);
       if (lastIn.size() < storeSize) lastIn.resize(storeSize, 0);
@@ -520,56 +591,46 @@ class Runner {
         winPos[s] = w + 1;
       }
       const double tList = nowSec() - tt0;
-      int rc = gridPass(cs, window, fullStore, fullPos);
-      if (!rc) rc = gridPass(cs, fresh, incStore, incPos);
-      tSpec += nowSec() - tt0;  // listing + GPU + filing
+      // A large grid of whole-window reads (the iteration in which the singletons meet the clusters) is consumed chunk by
+      // chunk: verdicts are filed and the pass below runs over the finished reads -- in list order, which is the pass's
+      // order -- while the GPU works on the next chunk.
+      int rc = 0;
+      const bool stream = incStore.empty() && uint64_t(fullStore.size()) * window.size() >= streamMinPairs;
+      if (stream) {
+        StreamCtx sc{this, &cs, &window, &fullPos, &fastStep, &windowIntact, &streamed, 0};
+        const double t0 = nowSec();
+        rc = sdgpu_align_pass_grid_stream(ctx_, window.data(), uint32_t(window.size()), fullStore.data(), uint32_t(fullStore.size()), flags(),
+                                          &StreamCtx::onChunk, &sc);
+        st.secondsGpu += nowSec() - t0;
+        if (rc) return fail(rc);
+        ++st.gpuBatches;
+        st.pairsComputed += uint64_t(window.size()) * fullStore.size();
+        st.passingPairs += sc.nHits;
+        if (streamed > 0) resumeAt = fullPos[streamed - 1];  // every live read above this position has had its turn
+        ++streamedGrids;
+        ++st.streamedGrids;
+      } else {
+        rc = gridPass(cs, window, fullStore, fullPos);
+        if (!rc) rc = gridPass(cs, fresh, incStore, incPos);
+      }
+      tSpec += nowSec() - tt0;  // listing + GPU + filing (+ the streamed part of the pass)
       gridRange.reset();
       if (g_verboseTiming && nowSec() - tt0 > 0.01)
-        fprintf(stderr, "[sdq]   line %d: %zu live, window %u (%zu new), %zu reads x window + %zu x new, spec %.3f s (listing %.3f)\n", line,
-                alive, wn, fresh.size(), fullStore.size(), incStore.size(), nowSec() - tt0, tList);
+        fprintf(stderr, "[sdq]   line %d: %zu live, window %u (%zu new), %zu reads x window + %zu x new, spec %.3f s (listing %.3f)%s\n", line,
+                alive, wn, fresh.size(), fullStore.size(), incStore.size(), nowSec() - tt0, tList, stream ? " streamed" : "");
       if (rc) return rc;
     }
     tt0 = nowSec();
     NvtxRange passRange("sdq:sequential pass");
     // ---- the sequential pass (smallest cluster first; first passing candidate absorbs it)
-    size_t amountAdded = 0;
-    bool windowIntact = true;  // no window cluster absorbed yet: every read sees the static window
     std::vector<uint32_t> odClus(1), odStore, odPos;
-    for (size_t rp = cs.size(); rp-- > 0;) {
+    for (size_t rp = resumeAt; rp-- > 0;) {
       if (PR[rp].remove) continue;
-      // it has been judged against every window cluster; if no verdict has this line's bit there is nothing to find
-      if (windowIntact && !(PR[rp].orMask & bit)) {
-        ++skippedScans;
+      if (windowIntact) {
+        fastStep(rp);
         continue;
       }
       Clus& read = cs[rp];
-      if (windowIntact) {
-        // While no window cluster has been absorbed, the candidates a read looks at are window positions -- all alive,
-        // all judged -- so the first passing candidate is the smallest window position among the read's own (few)
-        // non-zero verdicts, provided it lies within the first stopCheck candidates the read counts (itself skipped).
-        uint32_t best = UINT32_MAX;
-        read.row.forEach([&](uint32_t k, uint64_t v) {
-          if (!(v & bit) || k >= winPos.size()) return;
-          const uint32_t wp = winPos[k];
-          if (wp != 0 && wp - 1 != rp && wp - 1 < best) best = wp - 1;
-        });
-        const uint32_t looked = best == UINT32_MAX ? std::min<uint32_t>(wn - (rp < wn ? 1u : 0u), it.stopCheck) : best + 1 - (rp < best ? 1u : 0u);
-        if (best != UINT32_MAX && looked > it.stopCheck) best = UINT32_MAX;  // beyond the read's stopCheck-th candidate
-        st.pairsConsumed += std::min<uint32_t>(looked, it.stopCheck);
-        if (best == UINT32_MAX) continue;
-        Clus& clus = cs[best];
-        clus.cnt += read.cnt;
-        clus.members.append(read.members);
-        clus.needCons = true;
-        read.remove = true;
-        PR[rp].remove = 1;
-        PR[best].changed = 1;
-        read.row.clear();
-        read.cons.reset();
-        if (rp < wn) windowIntact = false;
-        ++amountAdded;
-        continue;
-      }
       uint32_t count = 0;
       for (uint32_t cp = 0; cp < eligEnd; ++cp) {
         if (PR[cp].remove) continue;
@@ -1538,8 +1599,8 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
             res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSubmit, (unsigned long long)R.st.gpuBatches, R.tSpec, R.tInsert, R.tPass, R.tCons, R.tSort, R.tIndex, R.lines.size());
     fprintf(stderr, "[sdq] consensus: member alignments %.3f counting %.3f rebuild %.3f new versions %.3f\n", R.tConsAlign, R.tConsCount, R.tConsBuild,
             R.tConsUpload);
-    fprintf(stderr, "[sdq] consensus updates kept on the device version: %llu, store entries: %u (unique reads %u), scans skipped %llu\n",
-            (unsigned long long)R.keptVersions, R.storeSize, nU, (unsigned long long)R.skippedScans);
+    fprintf(stderr, "[sdq] consensus updates kept on the device version: %llu, store entries: %u (unique reads %u), scans skipped %llu, streamed grids %llu\n",
+            (unsigned long long)R.keptVersions, R.storeSize, nU, (unsigned long long)R.skippedScans, (unsigned long long)R.streamedGrids);
   }
   *out = res;
   return SDGPU_OK;

@@ -3,6 +3,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -797,9 +798,19 @@ int sdgpu_set_screen(sdgpu_ctx* ctx, int mode) {
 // of two mapped pinned buffers, which the host empties while the next chunk runs.
 int sdgpu_align_pass_grid(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uint32_t nClusters, const uint32_t* readIdx,
                           uint32_t nReads, uint32_t flags, const sdgpu_grid_hit** hits, uint64_t* nHits) {
-  if (!ctx || !hits || !nHits || (nClusters && !clusterIdx) || (nReads && !readIdx)) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  if (!ctx || !hits || !nHits) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
   *hits = nullptr;
   *nHits = 0;
+  const int rc = sdgpu_align_pass_grid_stream(ctx, clusterIdx, nClusters, readIdx, nReads, flags, nullptr, nullptr);
+  if (rc) return rc;
+  *hits = ctx->gridHits.data();
+  *nHits = ctx->gridHits.size();
+  return SDGPU_OK;
+}
+
+int sdgpu_align_pass_grid_stream(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uint32_t nClusters, const uint32_t* readIdx,
+                                 uint32_t nReads, uint32_t flags, sdgpu_grid_chunk_fn onChunk, void* user) {
+  if (!ctx || (nClusters && !clusterIdx) || (nReads && !readIdx)) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
   ctx->gridHits.clear();
   if (nClusters == 0 || nReads == 0) return SDGPU_OK;
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -833,15 +844,23 @@ int sdgpu_align_pass_grid(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uint32_t n
   std::memcpy(hIdx + nClusters, readIdx, size_t(nReads) * 4);
   SD_CUDA(ctx, cudaMemcpyAsync(ctx->dGridIdx, hIdx, nIdx * 4, cudaMemcpyHostToDevice, ctx->stream));
   ctx->h2dBytes += nIdx * 4;
-  const uint64_t chunkPairs = 1ull << 21;
+  uint64_t chunkPairs = 1ull << 21;
+  if (const char* e = getenv("SDGPU_GRID_CHUNK_PAIRS")) {  // test hook: many small chunks
+    const long long v = atoll(e);
+    if (v > 0) chunkPairs = uint64_t(v);
+  }
   const uint32_t readsPerChunk = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(nReads, chunkPairs / nClusters)));
   if (uint64_t(readsPerChunk) * nClusters >= (1ull << 32)) return sd_fail(ctx, SDGPU_E_UNSUPPORTED, "more than 2^32 clusters in one grid call");
   auto drain = [&](sdgpu_ctx::GridSlot& G) -> int {
     SD_CUDA(ctx, cudaEventSynchronize(G.done));
     G.busy = false;
     const uint32_t n = *G.hCount;
-    ctx->gridHits.insert(ctx->gridHits.end(), G.hHits, G.hHits + n);
     ctx->d2hBytes += uint64_t(n) * sizeof(sdgpu_grid_hit) + 4;
+    if (onChunk) {  // the caller consumes the chunk while the GPU works on the next one
+      onChunk(user, G.hHits, n, G.readsDone);
+    } else {
+      ctx->gridHits.insert(ctx->gridHits.end(), G.hHits, G.hHits + n);
+    }
     return SDGPU_OK;
   };
   uint32_t k = 0;
@@ -879,14 +898,13 @@ int sdgpu_align_pass_grid(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uint32_t n
     SD_CUDA(ctx, cudaMemcpyAsync(G.hCount, ctx->dWork + SD_W_HITS + slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SD_CUDA(ctx, cudaEventRecord(G.done, ctx->stream));
     G.busy = true;
+    G.readsDone = r0 + nr;
   }
   // the older slot first
   for (uint32_t x = 0; x < 2; ++x) {
     sdgpu_ctx::GridSlot& G = ctx->gridSlots[(k + x) & 1];
     if (G.busy && (rc = drain(G))) return rc;
   }
-  *hits = ctx->gridHits.data();
-  *nHits = ctx->gridHits.size();
   return SDGPU_OK;
 }
 

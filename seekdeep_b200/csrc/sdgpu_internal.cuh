@@ -226,6 +226,7 @@ struct sdgpu_ctx {
     uint64_t cap = 0;
     cudaEvent_t done = nullptr;
     bool busy = false;
+    uint32_t readsDone = 0;           // reads of the caller's list finished once this slot's chunk is
   } gridSlots[2];
   std::vector<sdgpu_grid_hit> gridHits;
   uint64_t bandCells = 0, bandCertCells = 0, bandRedo = 0, bandPairs = 0;  // read-back baselines for profile_read

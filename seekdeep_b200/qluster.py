@@ -35,7 +35,7 @@ class StatsC(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("inputReads", "uniqueSeqs", "finalClusters", "pairsComputed", "pairsConsumed",
                                           "consensusAligns", "cellUpdates", "gpuBatches", "onDemandPairs",
                                           "chimeraPairs", "chimericClusters", "passingPairs", "kmerPairs",
-                                          "kmerBins")] + \
+                                          "kmerBins", "streamedGrids")] + \
                [("secondsGpu", C.c_double), ("secondsTotal", C.c_double), ("msResident", C.c_double)]
 
 

@@ -101,7 +101,7 @@ int main(void) {
   O(sdgpu_comparison, oneBaseIndel); O(sdgpu_comparison, queryCoverage); O(sdgpu_iter_par, perId);
   O(sdq_opts, markChimeras); O(sdq_opts, chiParentFreqs); O(sdq_opts, chiOverlap);
   O(sdq_opts, kmerCutOff); O(sdq_opts, useKmerBinning); O(sdq_opts, kCompareLen); O(sdq_opts, binPars); O(sdq_opts, nBinPars);
-  O(sdq_stats, kmerPairs); O(sdq_stats, kmerBins);
+  O(sdq_stats, kmerPairs); O(sdq_stats, kmerBins); O(sdq_stats, streamedGrids);
   O(sdq_stats, chimeraPairs); O(sdq_stats, secondsGpu); O(sdq_stats, msResident);
   O(sdgpu_chimera_probe, flags); O(sdgpu_profile, evaluatedCells); O(sdgpu_profile, bandKernelMs); O(sdgpu_profile, screenCertCells);
   O(sdgpu_grid_hit, mask); O(sdq_stats, passingPairs);
@@ -125,7 +125,7 @@ int main(void) {
     for f in ("markChimeras", "chiParentFreqs", "chiOverlap", "kmerCutOff", "useKmerBinning", "kCompareLen", "binPars", "nBinPars"):
         assert c["sdq_opts." + f] == getattr(Q.QlusterOptsC, f).offset, f
     assert c["sdq_stats"] == C.sizeof(Q.StatsC)
-    for f in ("chimeraPairs", "secondsGpu", "msResident", "kmerPairs", "kmerBins"):
+    for f in ("chimeraPairs", "secondsGpu", "msResident", "kmerPairs", "kmerBins", "streamedGrids"):
         assert c["sdq_stats." + f] == getattr(Q.StatsC, f).offset, f
     # sdgpu_profile is mirrored inside GpuAligner.profile_read: 16 x 8 bytes
     assert c["sdgpu_profile"] == 128 and c["sdgpu_profile.evaluatedCells"] == 48 and c["sdgpu_profile.bandKernelMs"] == 72
