@@ -220,6 +220,15 @@ int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* 
                         uint32_t nPairs, uint32_t flags, sdgpu_comparison* out,
                         sdgpu_gap* gapsOut, uint32_t gapCap);
 
+/* Gap lists only, packed: what baseCluster::calculateConsensus needs of alignCacheGlobal(consensus, member) -- the
+ * alignment, i.e. alnInfoGlobal::gapInfos_ -- for nPairs pairs.  Members of a cluster mostly align to its consensus
+ * without a gap, so only the pairs that have gap runs come back, as records of 32-bit words in no particular order:
+ * [pair index, nRuns | 0x80000000 if the list was cut at gapCap, then (pos, size, gapInA) for each of the
+ * min(nRuns, gapCap) runs, in traceback order].  A pair without a record aligned gaplessly.  *recs stays valid until
+ * the next call on ctx. */
+int sdgpu_align_gap_lists(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs, uint32_t gapCap,
+                          const uint32_t** recs, uint64_t* nWords);
+
 /* Per-event part of aligner::comp_: distances_.mismatches_, distances_.lowKmerMismatches_ and
  * distances_.alignmentGaps_, the maps qluster's --writeOutFinalAllByAllComparison dumps column by column
  * (clusterDown.cpp:759-800: refBase, refBasePos, refQual, seqBase, seqBasePos, seqQual, kMerFreqByPos,

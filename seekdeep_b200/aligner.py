@@ -168,6 +168,28 @@ class GpuAligner:
                                                   _ptr(gaps), gapCap))
         return (out, gaps) if gapCap else out
 
+    def align_gap_lists(self, refIdx, readIdx, gapCap=8):
+        """≙ alignCacheGlobal per pair, alnInfoGlobal::gapInfos_ only, packed (sdgpu_align_gap_lists): {pair: (nRuns, gaps)}
+        for the pairs whose alignment has gap runs; gaps is GAP_DTYPE[min(nRuns, gapCap)] in traceback order."""
+        refIdx = np.ascontiguousarray(refIdx, np.uint32)
+        readIdx = np.ascontiguousarray(readIdx, np.uint32)
+        recs, nWords = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.sdgpu_align_gap_lists(self._ctx, _ptr(refIdx), _ptr(readIdx), len(refIdx), gapCap, C.byref(recs),
+                                                    C.byref(nWords)))
+        out = {}
+        if nWords.value:
+            w = np.ctypeslib.as_array(C.cast(recs, C.POINTER(C.c_uint32)), (nWords.value,)).copy()
+            i = 0
+            while i < len(w):
+                n = int(w[i + 1] & 0x7fffffff)
+                kept = min(n, gapCap)
+                g = np.zeros(kept, _abi.GAP_DTYPE)
+                body = w[i + 2:i + 2 + 3 * kept].reshape(kept, 3)
+                g["pos"], g["size"], g["gapInA"] = body[:, 0], body[:, 1], body[:, 2]
+                out[int(w[i])] = (n, g)
+                i += 2 + 3 * kept
+        return out
+
     def align_events(self, refIdx, readIdx, checkKmer=False, usingQuality=True, doingMatchQuality=False, eventCap=64):
         """≙ alignCacheGlobal + profileAlignment, then comp_.distances_.mismatches_ / lowKmerMismatches_ /
         alignmentGaps_ as event lists (clusterDown.cpp:759-800).  Returns (comparisons, [events of pair i])."""

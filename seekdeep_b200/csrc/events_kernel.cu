@@ -101,7 +101,36 @@ __global__ void __launch_bounds__(128) alignEventsKernel(DevScoring sc, DevSeqs 
   nEvents[p] = n;
 }
 
+// Packed gap lists of a batch: only the pairs whose alignment has gap runs leave a record -- [pair, nRuns (bit 31: the
+// list was cut at gapCap), then (pos, size, gapInA) per kept run] -- at a slot reserved with one atomic.
+__global__ void __launch_bounds__(256) packGapListsKernel(const sdgpu_comparison* cmp, const sdgpu_gap* gaps, uint32_t gapCap, uint32_t nPairs,
+                                                           uint32_t* packed, unsigned long long* nWords) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nPairs) return;
+  const uint32_t n = cmp[p].nGapRuns;
+  if (n == 0) return;
+  const uint32_t m = n < gapCap ? n : gapCap;
+  const unsigned long long at = atomicAdd(nWords, 2ull + 3ull * m);
+  packed[at] = p;
+  packed[at + 1] = n | (n > gapCap ? 0x80000000u : 0u);
+  const sdgpu_gap* gl = gaps + size_t(p) * gapCap;
+  for (uint32_t g = 0; g < m; ++g) {
+    packed[at + 2 + 3 * g] = gl[g].pos;
+    packed[at + 3 + 3 * g] = gl[g].size;
+    packed[at + 4 + 3 * g] = gl[g].gapInA;
+  }
+}
+
 }  // namespace
+
+int sd_launch_pack_gaps(sdgpu_ctx* ctx, const sdgpu_comparison* dCmp, const sdgpu_gap* dGaps, uint32_t gapCap, uint32_t nPairs,
+                        uint32_t* dPacked, unsigned long long* dNWords) {
+  if (nPairs == 0) return SDGPU_OK;
+  packGapListsKernel<<<(nPairs + 255) / 256, 256, 0, ctx->stream>>>(dCmp, dGaps, gapCap, nPairs, dPacked, dNWords);
+  SD_CUDA(ctx, cudaGetLastError());
+  ++ctx->launches;
+  return SDGPU_OK;
+}
 
 int sd_launch_events(sdgpu_ctx* ctx, const uint32_t* dRef, const uint32_t* dRead, uint32_t nPairs, uint32_t flags,
                      const sdgpu_comparison* dCmp, const sdgpu_gap* dGaps, uint32_t gapCap, sdgpu_event* dEvents, uint32_t eventCap,

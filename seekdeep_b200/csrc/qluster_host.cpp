@@ -394,7 +394,8 @@ class Runner {
   double tConsAlign = 0, tConsCount = 0, tConsBuild = 0, tConsUpload = 0;  // parts of tCons
   double tBin = 0;  // k-mer binning (lists + masks + settling)
   uint64_t streamMinPairs = getenv("SDQ_STREAM_MIN_PAIRS") ? uint64_t(atoll(getenv("SDQ_STREAM_MIN_PAIRS"))) : (3ull << 21);  // (test hook)
-  uint64_t streamedGrids = 0;
+  uint64_t streamedGrids = 0, nStreamCb = 0, streamedReads = 0;
+  double tStreamCb = 0;  // time inside the streaming callbacks (filing + the streamed part of the pass)
   uint64_t keptVersions = 0, skippedScans = 0;
   bool orderDirty = true;
   // symbols of the consensus counters (bases + '-'), ASCII order kept for njhseq's tie rule
@@ -504,6 +505,8 @@ class Runner {
         ++*S.streamed;
       }
       R.tPass += nowSec() - t1;
+      R.tStreamCb += nowSec() - t0;
+      ++R.nStreamCb;
     }
   };
 
@@ -608,6 +611,7 @@ class Runner {
         st.passingPairs += sc.nHits;
         if (streamed > 0) resumeAt = fullPos[streamed - 1];  // every live read above this position has had its turn
         ++streamedGrids;
+        streamedReads += streamed;
         ++st.streamedGrids;
       } else {
         rc = gridPass(cs, window, fullStore, fullPos);
@@ -749,21 +753,25 @@ class Runner {
           pa[i] = a[todo[off + i]];
           pb[i] = b[todo[off + i]];
         }
-        if (cmpBuf.size() < m) cmpBuf.resize(m);
-        if (gapBuf.size() < size_t(m) * gapCap) gapBuf.resize(size_t(m) * gapCap);
+        const uint32_t* recs = nullptr;
+        uint64_t nWords = 0;
         const double t0 = nowSec();
-        int rc = sdgpu_align_profile(ctx_, pa.data(), pb.data(), m, 0u, cmpBuf.data(), gapBuf.data(), gapCap);
+        int rc = sdgpu_align_gap_lists(ctx_, pa.data(), pb.data(), m, gapCap, &recs, &nWords);  // only pairs with gap runs come back
         st.secondsGpu += nowSec() - t0;
         if (rc) return fail(rc);
         ++st.gpuBatches;
         st.consensusAligns += m;
-        for (uint32_t i = 0; i < m; ++i) {
-          if (cmpBuf[i].status & SDGPU_ST_GAPLIST_TRUNCATED) {
+        for (uint64_t w = 0; w < nWords;) {
+          const uint32_t i = recs[w], nRuns = recs[w + 1] & 0x7fffffffu;
+          const uint32_t kept = std::min(nRuns, gapCap);
+          if (recs[w + 1] >> 31) {
             next.push_back(todo[off + i]);
           } else {
-            gaps[todo[off + i]].assign(gapBuf.begin() + size_t(i) * gapCap,
-                                       gapBuf.begin() + size_t(i) * gapCap + cmpBuf[i].nGapRuns);
+            std::vector<sdgpu_gap>& g = gaps[todo[off + i]];
+            g.resize(kept);
+            for (uint32_t k = 0; k < kept; ++k) g[k] = sdgpu_gap{recs[w + 2 + 3 * k], recs[w + 3 + 3 * k], recs[w + 4 + 3 * k]};
           }
+          w += 2 + 3ull * kept;
         }
       }
       todo.swap(next);
@@ -1564,23 +1572,26 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
     if ((rc = R.buildIndex(clusters))) return bail(rc);
     if ((rc = R.runFullClustering(clusters, pars, nPars))) return bail(rc);
   }
+  const double tTail0 = nowSec();
   R.dropRemovedAndSort(clusters);  // :560
-  for (uint32_t c = 0; c < clusters.size(); ++c) {
-    clusters[c].row.clear();
-    clusters[c].cons.reset();
-    for (uint32_t u : clusters[c].members)
-      for (uint32_t x = R.uniq[u].inputBegin; x < R.uniq[u].inputEnd; ++x) res->membership[R.inputList[x]] = c;
-    // the result outlives the caller's read buffers and this run's quality arena: every final cluster owns its bytes
-    Clus& cl = clusters[c];
-    if (cl.seq.data() != reinterpret_cast<const uint8_t*>(cl.ownSeq.data())) {
-      cl.ownSeq.assign(reinterpret_cast<const char*>(cl.seq.data()), cl.seq.size());
-      cl.seq = View{reinterpret_cast<const uint8_t*>(cl.ownSeq.data()), uint32_t(cl.ownSeq.size())};
+  parallelFor(clusters.size(), [&](size_t lo, size_t hi) {  // clusters are independent here; their reads are disjoint
+    for (size_t c = lo; c < hi; ++c) {
+      Clus& cl = clusters[c];
+      cl.row.clear();
+      cl.cons.reset();
+      for (uint32_t u : cl.members)
+        for (uint32_t x = R.uniq[u].inputBegin; x < R.uniq[u].inputEnd; ++x) res->membership[R.inputList[x]] = uint32_t(c);
+      // the result outlives the caller's read buffers and this run's quality arena: every final cluster owns its bytes
+      if (cl.seq.data() != reinterpret_cast<const uint8_t*>(cl.ownSeq.data())) {
+        cl.ownSeq.assign(reinterpret_cast<const char*>(cl.seq.data()), cl.seq.size());
+        cl.seq = View{reinterpret_cast<const uint8_t*>(cl.ownSeq.data()), uint32_t(cl.ownSeq.size())};
+      }
+      if (cl.qual.data() != cl.ownQual.data()) {
+        cl.ownQual.assign(cl.qual.begin(), cl.qual.end());
+        cl.qual = View{cl.ownQual.data(), uint32_t(cl.ownQual.size())};
+      }
     }
-    if (cl.qual.data() != cl.ownQual.data()) {
-      cl.ownQual.assign(cl.qual.begin(), cl.qual.end());
-      cl.qual = View{cl.ownQual.data(), uint32_t(cl.ownQual.size())};
-    }
-  }
+  }, 1024);
   if (opts->markChimeras && markChimeras(ctx, *opts, clusters, R.st)) return bail(R.fail(SDGPU_E_CUDA));  // :566-577
   uint64_t launches1 = 0, cells1 = 0;
   float msResident = 0;
@@ -1597,10 +1608,12 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
   if (getenv("SDQ_TIMING")) {
     fprintf(stderr, "[sdq] total %.3f prep %.3f gpu %.3f (submit %.3f, %llu batches) spec %.3f insert %.3f pass %.3f cons(incl gpu) %.3f sort %.3f index %.3f lines %zu\n",
             res->stats.secondsTotal, tPrep, R.st.secondsGpu, R.tSubmit, (unsigned long long)R.st.gpuBatches, R.tSpec, R.tInsert, R.tPass, R.tCons, R.tSort, R.tIndex, R.lines.size());
+    fprintf(stderr, "[sdq] tail (final sort, membership, chimeras) %.3f\n", nowSec() - tTail0);
     fprintf(stderr, "[sdq] consensus: member alignments %.3f counting %.3f rebuild %.3f new versions %.3f\n", R.tConsAlign, R.tConsCount, R.tConsBuild,
             R.tConsUpload);
-    fprintf(stderr, "[sdq] consensus updates kept on the device version: %llu, store entries: %u (unique reads %u), scans skipped %llu, streamed grids %llu\n",
-            (unsigned long long)R.keptVersions, R.storeSize, nU, (unsigned long long)R.skippedScans, (unsigned long long)R.streamedGrids);
+    fprintf(stderr, "[sdq] consensus updates kept on the device version: %llu, store entries: %u (unique reads %u), scans skipped %llu, streamed grids %llu (%llu callbacks, %.3f s inside, %llu reads passed there)\n",
+            (unsigned long long)R.keptVersions, R.storeSize, nU, (unsigned long long)R.skippedScans, (unsigned long long)R.streamedGrids,
+            (unsigned long long)R.nStreamCb, R.tStreamCb, (unsigned long long)R.streamedReads);
   }
   *out = res;
   return SDGPU_OK;

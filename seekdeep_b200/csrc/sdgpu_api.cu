@@ -582,6 +582,56 @@ int sdgpu_align_profile(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* 
   return SDGPU_OK;
 }
 
+int sdgpu_align_gap_lists(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs, uint32_t gapCap,
+                          const uint32_t** recsOut, uint64_t* nWordsOut) {
+  if (!ctx || !recsOut || !nWordsOut || (nPairs && (!refIdx || !readIdx)) || gapCap == 0) return sd_fail(ctx, SDGPU_E_ARG, "null argument");
+  *recsOut = nullptr;
+  *nWordsOut = 0;
+  ctx->gapRecs.clear();
+  if (nPairs == 0) return SDGPU_OK;
+  SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
+  uint32_t maxA = 0, maxB = 0;
+  for (uint32_t x = 0; x < nPairs; ++x) {
+    if (refIdx[x] >= nSeqs || readIdx[x] >= nSeqs) return sd_fail(ctx, SDGPU_E_ARG, "pair index out of range");
+    maxA = std::max<uint32_t>(maxA, uint32_t(ctx->hOffsets[refIdx[x] + 1] - ctx->hOffsets[refIdx[x]]));
+    maxB = std::max<uint32_t>(maxB, uint32_t(ctx->hOffsets[readIdx[x] + 1] - ctx->hOffsets[readIdx[x]]));
+  }
+  const uint64_t bytesIdx = uint64_t(nPairs) * 4;
+  const uint64_t bytesOut = uint64_t(nPairs) * sizeof(sdgpu_comparison);
+  const uint64_t bytesGaps = (uint64_t(nPairs) * gapCap * sizeof(sdgpu_gap) + 15) & ~15ull;
+  const uint64_t bytesPacked = (uint64_t(nPairs) * (2 + 3ull * gapCap) * 4 + 15) & ~15ull;
+  int rc = sd_ensure_stage(ctx, bytesOut + bytesGaps + bytesPacked + 2 * bytesIdx + 256);
+  if (rc) return rc;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->dStage);
+  sdgpu_comparison* dOut = reinterpret_cast<sdgpu_comparison*>(base);
+  sdgpu_gap* dGaps = reinterpret_cast<sdgpu_gap*>(base + bytesOut);
+  uint32_t* dPacked = reinterpret_cast<uint32_t*>(base + bytesOut + bytesGaps);
+  unsigned long long* dNWords = reinterpret_cast<unsigned long long*>(base + bytesOut + bytesGaps + bytesPacked);
+  uint32_t* dRef = reinterpret_cast<uint32_t*>(dNWords + 2);
+  uint32_t* dRead = dRef + nPairs;
+  SD_CUDA(ctx, cudaMemcpyAsync(dRef, refIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemcpyAsync(dRead, readIdx, bytesIdx, cudaMemcpyHostToDevice, ctx->stream));
+  SD_CUDA(ctx, cudaMemsetAsync(dGaps, 0, bytesGaps, ctx->stream));
+  SD_CUDA(ctx, cudaMemsetAsync(dNWords, 0, 16, ctx->stream));
+  rc = sd_launch_align(ctx, dRef, dRead, nPairs, 0u, dOut, dGaps, gapCap, maxA, maxB);
+  if (rc) return rc;
+  if ((rc = sd_launch_pack_gaps(ctx, dOut, dGaps, gapCap, nPairs, dPacked, dNWords))) return rc;
+  unsigned long long nWords = 0;
+  SD_CUDA(ctx, cudaMemcpyAsync(&nWords, dNWords, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->gapRecs.resize(nWords);
+  if (nWords) {
+    SD_CUDA(ctx, cudaMemcpyAsync(ctx->gapRecs.data(), dPacked, nWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->h2dBytes += 2 * bytesIdx;
+  ctx->d2hBytes += 8 + nWords * 4;
+  *recsOut = ctx->gapRecs.data();
+  *nWordsOut = nWords;
+  return SDGPU_OK;
+}
+
 int sdgpu_align_events(sdgpu_ctx* ctx, const uint32_t* refIdx, const uint32_t* readIdx, uint32_t nPairs, uint32_t flags,
                        sdgpu_comparison* out, sdgpu_event* eventsOut, uint32_t eventCap, uint32_t* nEventsOut) {
   if (!ctx || (nPairs && (!refIdx || !readIdx || !nEventsOut || (eventCap && !eventsOut)))) return sd_fail(ctx, SDGPU_E_ARG, "null argument");

@@ -169,6 +169,7 @@ struct sdgpu_ctx {
   uint64_t listCapKeys = 0;
   uint32_t listK = 0, listSeqs = 0;
   uint8_t* dCharOf = nullptr;  // code -> character, for the event lists (events_kernel.cu)
+  std::vector<uint32_t> gapRecs;  // packed gap lists of the last sdgpu_align_gap_lists call
   // scratch for the alignment kernel (pointer slabs), pair staging, work counter
   uint8_t* dScratch = nullptr;
   uint64_t scratchBytes = 0;
@@ -351,6 +352,8 @@ int sd_kmer_compare_all(sdgpu_ctx* ctx, const uint32_t* reads, uint32_t nReads, 
 int sd_launch_events(sdgpu_ctx* ctx, const uint32_t* dRef, const uint32_t* dRead, uint32_t nPairs, uint32_t flags,
                      const sdgpu_comparison* dCmp, const sdgpu_gap* dGaps, uint32_t gapCap, sdgpu_event* dEvents, uint32_t eventCap,
                      uint32_t* dNEvents);
+int sd_launch_pack_gaps(sdgpu_ctx* ctx, const sdgpu_comparison* dCmp, const sdgpu_gap* dGaps, uint32_t gapCap, uint32_t nPairs,
+                        uint32_t* dPacked, unsigned long long* dNWords);
 // kmer_list_kernels.cu
 int sd_build_kmer_lists(sdgpu_ctx* ctx, uint32_t kLen);
 int sd_kmer_bin_masks(sdgpu_ctx* ctx, const uint32_t* seeds, uint32_t nSeeds, const uint32_t* reads, uint32_t nReads, double cutOff,

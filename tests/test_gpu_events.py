@@ -66,3 +66,25 @@ def test_align_events_unrelated_and_ragged(oracle):
     nGaps = _check(oracle, H.params_for("qluster"), seqs, quals, bases, q, offsets, None, refIdx.ravel(), readIdx.ravel(),
                    _abi.USING_QUALITY, None)
     assert nGaps > 16 * 32
+
+
+def test_align_gap_lists_match_align_profile(oracle):
+    """sdgpu_align_gap_lists (what the consensus rebuild asks for): packed records only for the pairs with gap runs, equal
+    to the gap lists sdgpu_align_profile returns densely; lists longer than gapCap are flagged by their full run count."""
+    rng = np.random.default_rng(19)
+    bases, q, offsets, cnts, seqs, quals = H.make_store(rng, 60, 200)
+    n = 3000
+    refIdx = rng.integers(0, 60, n).astype(np.uint32)
+    readIdx = rng.integers(0, 60, n).astype(np.uint32)
+    with GpuAligner(H.params_for("qluster")) as al:
+        al.upload_seqs(bases, q, offsets, cnts)
+        for gapCap in (2, 8):
+            dense, gaps = al.align_profile(refIdx, readIdx, usingQuality=False, gapCap=gapCap)
+            packed = al.align_gap_lists(refIdx, readIdx, gapCap=gapCap)
+            assert set(packed) == set(np.nonzero(dense["nGapRuns"])[0].tolist())
+            for p, (nRuns, g) in packed.items():
+                assert nRuns == dense["nGapRuns"][p]
+                assert np.array_equal(g, gaps[p, :min(nRuns, gapCap)])
+            if gapCap == 2:
+                assert any(nRuns > 2 for nRuns, _ in packed.values())
+        assert al.align_gap_lists(refIdx[:0], readIdx[:0]) == {}
