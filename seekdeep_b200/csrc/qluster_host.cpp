@@ -267,6 +267,7 @@ struct ConsState {  // column counters of one cluster against one base sequence
 struct alignas(64) Clus {
   double cnt = 0;
   double avgErr = 0;
+  double sumLenCnt = 0;    // sum over the members of length x count (integers: exact in any order), for the average member length
   uint32_t storeIdx = 0;   // device sequence-store entry (verdict-equivalent to (seq, qual))
   uint32_t firstId = 0;    // cluster::firstReadName_ stand-in (tie-break of the sort)
   bool remove = false, needCons = false;
@@ -549,6 +550,7 @@ class Runner {
       if (best == UINT32_MAX) return;
       Clus& clus = cs[best];
       clus.cnt += read.cnt;
+      clus.sumLenCnt += read.sumLenCnt;
       clus.members.append(read.members);
       clus.needCons = true;
       read.remove = true;
@@ -629,6 +631,10 @@ class Runner {
     // ---- the sequential pass (smallest cluster first; first passing candidate absorbs it)
     std::vector<uint32_t> odClus(1), odStore, odPos;
     for (size_t rp = resumeAt; rp-- > 0;) {
+      if (rp >= 12 && (PR[rp - 12].orMask & bit)) {  // the cluster object a coming turn will touch (its row spans two lines)
+        __builtin_prefetch(PR[rp - 12].c);
+        __builtin_prefetch(reinterpret_cast<const char*>(PR[rp - 12].c) + 64);
+      }
       if (PR[rp].remove) continue;
       if (windowIntact) {
         fastStep(rp);
@@ -665,6 +671,7 @@ class Runner {
         if (v && (*v & bit)) {
           Clus& clus = cs[cp];
           clus.cnt += read.cnt;
+          clus.sumLenCnt += read.sumLenCnt;
           clus.members.append(read.members);
           clus.needCons = true;
           read.remove = true;
@@ -680,6 +687,9 @@ class Runner {
     }
     for (uint32_t s : prevWindow) winPos[s] = 0;  // (prevWindow is this iteration's window by now)
     tPass += nowSec() - tt0;
+    if (g_verboseTiming && nowSec() - tt0 > 0.001)
+      fprintf(stderr, "[sdq]   line %d: pass %.4f s over %zu positions (from %zu), %zu absorbed, window intact %d, on-demand pairs so far %llu\n", line,
+              nowSec() - tt0, PR.size(), resumeAt, amountAdded, int(windowIntact), (unsigned long long)st.onDemandPairs);
     if (amountAdded > 0) {
       orderDirty = true;
       tt0 = nowSec();
@@ -705,12 +715,9 @@ class Runner {
       if (!cl.needCons) continue;
       cl.needCons = false;
       if (cl.members.size() <= 1) continue;
-      double totalLen = 0, totalCnt = 0;
-      for (uint32_t u : cl.members) {
-        totalLen += uniq[u].seq.size() * uniq[u].cnt;
-        totalCnt += uniq[u].cnt;
-      }
-      const double avgLen = totalLen / totalCnt;
+      // (the members' counts add up to the cluster's; both sums are sums of integers, so keeping them up to date at
+      //  every absorption gives the very doubles a walk over the members would)
+      const double avgLen = cl.sumLenCnt / cl.cnt;
       uint32_t baseStore = cl.storeIdx;
       View baseSeq = cl.seq;
       if (std::fabs(double(cl.seq.size()) - avgLen) > 0.1 * avgLen) {  // restart from the longest member
@@ -1070,7 +1077,9 @@ class Runner {
     } else {  // a new list (start of a clustering run): build the records from the clusters and sort them all
       v.erase(std::remove_if(v.begin(), v.end(), [](const Clus* c) { return c->remove; }), v.end());
       PR.resize(v.size());
-      for (size_t i = 0; i < v.size(); ++i) PR[i] = Pos{v[i]->cnt, v[i]->avgErr, v[i], 0, v[i]->row.orMask(), v[i]->storeIdx, 0, 0};
+      parallelFor(v.size(), [&](size_t lo, size_t hi) {  // (one cache miss per cluster object: worth a few threads at 178 k clusters)
+        for (size_t i = lo; i < hi; ++i) PR[i] = Pos{v[i]->cnt, v[i]->avgErr, v[i], 0, v[i]->row.orMask(), v[i]->storeIdx, 0, 0};
+      }, 4096);
       // (the singletons joining the survivors of the first run: two sorted runs back to back -> one merge)
       const auto firstDescent = std::is_sorted_until(PR.begin(), PR.end(), posLess);
       if (firstDescent != PR.end() && std::is_sorted(firstDescent, PR.end(), posLess)) {
@@ -1545,6 +1554,7 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
       c.seq = R.uniq[u].seq;
       c.qual = R.uniq[u].qual;
       c.cnt = R.uniq[u].cnt;
+      c.sumLenCnt = double(R.uniq[u].seq.size()) * R.uniq[u].cnt;
       c.firstId = u;
       c.storeIdx = u;
       c.members.init(u);
