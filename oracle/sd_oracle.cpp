@@ -271,15 +271,14 @@ static void compareKmers(const uint8_t* a, uint32_t la, const uint8_t* b, uint32
 // qualThresWindow strictly above secondaryQual.  The trailing window reproduces njhseq's
 // bound (the last base of the read is not inspected when the window reaches the end).
 static bool checkQual(const uint8_t* q, uint32_t len, uint32_t pos, const sdgpu_params& P) {
-  if (q[pos] <= P.primaryQual) return false;
+  if (!SDGPU_QUAL_ABOVE(q[pos], P.primaryQual)) return false;
   const uint32_t out = P.qualThresWindow;
   const uint32_t lower = pos > out ? pos - out : 0;
   for (uint32_t i = lower; i < pos; ++i)
-    if (q[i] <= P.secondaryQual) return false;
-  uint32_t higher = len - 1;
-  if (pos + out + 1 < len) higher = pos + out + 1;
+    if (!SDGPU_QUAL_ABOVE(q[i], P.secondaryQual)) return false;
+  const uint32_t higher = SDGPU_QUAL_WINDOW_END(pos, out, len);
   for (uint32_t i = pos + 1; i < higher; ++i)
-    if (q[i] <= P.secondaryQual) return false;
+    if (!SDGPU_QUAL_ABOVE(q[i], P.secondaryQual)) return false;
   return true;
 }
 
@@ -380,7 +379,7 @@ static void profileAlignment(const sdgpu_params& P, const KMaps* km, const uint8
       if (!hq) {
         ++c.lqMismatches;
         cls = 2;
-      } else if (checkKmer && (isLowFreqAt(km, A, la, pa) || isLowFreqAt(km, B, lb, pb))) {
+      } else if (checkKmer && ((SDGPU_POLICY_LOWKMER_EITHER_SIDE && isLowFreqAt(km, A, la, pa)) || isLowFreqAt(km, B, lb, pb))) {
         ++c.lowKmerMismatches;
         cls = 3;
       } else {
@@ -768,7 +767,7 @@ struct Engine {
           double frac;
           compareKmers(reinterpret_cast<const uint8_t*>(bin[0].seq.data()), uint32_t(bin[0].seq.size()),
                        reinterpret_cast<const uint8_t*>(c.seq.data()), uint32_t(c.seq.size()), O.kCompareLen, shared, frac);
-          if (frac > O.kmerCutOff) {
+          if (SDGPU_KMER_BIN_PASSES(frac, O.kmerCutOff)) {
             bin.push_back(std::move(c));
             placed = true;
             break;
@@ -926,7 +925,7 @@ int sdo_align_events(const sdgpu_params* p, const sdo_kmaps* kmaps, const uint8_
       std::memset(&e, 0, sizeof(e));
       if (!hq) {
         e.kind = SDGPU_EV_MISMATCH_LQ;
-      } else if (checkKmer && (isLowFreqAt(km, a, lenA, pa) || isLowFreqAt(km, b, lenB, pb))) {
+      } else if (checkKmer && ((SDGPU_POLICY_LOWKMER_EITHER_SIDE && isLowFreqAt(km, a, lenA, pa)) || isLowFreqAt(km, b, lenB, pb))) {
         e.kind = SDGPU_EV_MISMATCH_LOWKMER;
       } else {
         e.kind = SDGPU_EV_MISMATCH_HQ;

@@ -18,6 +18,8 @@
 #ifndef SD_ORACLE_H_
 #define SD_ORACLE_H_
 #include <stdint.h>
+
+#include "../include/sdgpu_policy.h" /* the unverifiable rules, one name each, shared with the product */
 #include "../include/sdgpu.h"
 #include "../include/sdgpu_stitch.h"
 

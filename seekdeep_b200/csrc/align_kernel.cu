@@ -212,7 +212,7 @@ __device__ __forceinline__ void chimeraProbeDev(const ChiArgs& a, const PairView
       const bool good = !usingQuality || (fa & fb & SD_FLAG_QUAL_OK);
       if (!good) {
         cls = 2;
-      } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
+      } else if (checkKmer && (SDGPU_LOWKMER_FLAGS(fa, fb) & SD_FLAG_LOW_KMER)) {
         cls = 3;
       } else {
         cls = 1;
@@ -424,7 +424,7 @@ __device__ void finishPair(const AlignArgs& a, const Bits& bits, const PairView&
       const bool good = !usingQuality || (fa & fb & SD_FLAG_QUAL_OK);
       if (!good) {
         cls = 2;
-      } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
+      } else if (checkKmer && (SDGPU_LOWKMER_FLAGS(fa, fb) & SD_FLAG_LOW_KMER)) {
         cls = 3;
       } else {
         cls = 1;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128) alignEventsKernel(DevScoring sc, DevSeqs 
         const bool good = !usingQuality || (fa & fb & SD_FLAG_QUAL_OK);
         if (!good) {
           e.kind = SDGPU_EV_MISMATCH_LQ;
-        } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
+        } else if (checkKmer && (SDGPU_LOWKMER_FLAGS(fa, fb) & SD_FLAG_LOW_KMER)) {
           e.kind = SDGPU_EV_MISMATCH_LOWKMER;
         } else {
           e.kind = SDGPU_EV_MISMATCH_HQ;

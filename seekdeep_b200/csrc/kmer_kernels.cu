@@ -103,12 +103,11 @@ __global__ void __launch_bounds__(256) qualFlagKernel(DevSeqs seqs, uint32_t fir
   const int len = int(seqs.offsets[s + 1] - off);
   const uint8_t* q = seqs.quals + off;
   for (int pos = int(lane); pos < len; pos += 32) {
-    bool ok = int(q[pos]) > primaryQual;
+    bool ok = SDGPU_QUAL_ABOVE(int(q[pos]), primaryQual);
     const int lower = pos > window ? pos - window : 0;
-    for (int i = lower; ok && i < pos; ++i) ok = int(q[i]) > secondaryQual;
-    int higher = len - 1;
-    if (pos + window + 1 < len) higher = pos + window + 1;
-    for (int i = pos + 1; ok && i < higher; ++i) ok = int(q[i]) > secondaryQual;
+    for (int i = lower; ok && i < pos; ++i) ok = SDGPU_QUAL_ABOVE(int(q[i]), secondaryQual);
+    const int higher = SDGPU_QUAL_WINDOW_END(pos, window, len);
+    for (int i = pos + 1; ok && i < higher; ++i) ok = SDGPU_QUAL_ABOVE(int(q[i]), secondaryQual);
     flags[off + pos] = ok ? uint8_t(SD_FLAG_QUAL_OK) : uint8_t(0);
   }
 }

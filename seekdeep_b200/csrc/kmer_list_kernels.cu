@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(512) kmerBinKernel(DevSeqs seqs, const uint64_
         if (lane == 0) {
           const uint32_t minLen = lenR < sLen[c] ? lenR : sLen[c];
           const double frac = (minLen >= kLen) ? double(cnt) / double(minLen - kLen + 1) : 0.0;
-          if (frac > cutOff) mask |= 1ull << (s0 + c);
+          if (SDGPU_KMER_BIN_PASSES(frac, cutOff)) mask |= 1ull << (s0 + c);
           if (sharedOut) sharedOut[size_t(r) * nSeeds + s0 + c] = cnt;
         }
       }

@@ -50,6 +50,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "../../include/sdgpu_qluster.h"
+#include "../../include/sdgpu_policy.h"
 
 namespace {
 
@@ -289,12 +290,11 @@ void qualSignature(const Q& q, const sdgpu_params& P, std::vector<uint8_t>& sig)
   const int len = int(q.size()), out = int(P.qualThresWindow);
   sig.assign(q.size(), 0);
   for (int pos = 0; pos < len; ++pos) {
-    bool ok = q[pos] > P.primaryQual;
+    bool ok = SDGPU_QUAL_ABOVE(q[pos], P.primaryQual);
     const int lower = pos > out ? pos - out : 0;
-    for (int i = lower; ok && i < pos; ++i) ok = q[i] > P.secondaryQual;
-    int higher = len - 1;
-    if (pos + out + 1 < len) higher = pos + out + 1;
-    for (int i = pos + 1; ok && i < higher; ++i) ok = q[i] > P.secondaryQual;
+    for (int i = lower; ok && i < pos; ++i) ok = SDGPU_QUAL_ABOVE(q[i], P.secondaryQual);
+    const int higher = SDGPU_QUAL_WINDOW_END(pos, out, len);
+    for (int i = pos + 1; ok && i < higher; ++i) ok = SDGPU_QUAL_ABOVE(q[i], P.secondaryQual);
     sig[pos] = ok ? 1 : 0;
   }
 }

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) screenScanKernel(const SdScreenArgs a) {
                     const uint32_t fa = __funnelshift_r(__ldg(wFA + w), __ldg(wFA + w + 1), shFA);
                     const uint32_t fb = __funnelshift_r(__ldg(wFB + w), __ldg(wFB + w + 1), shFB);
                     const uint32_t good = usingQuality ? (((fa & fb) << 7) & 0x80808080u) : 0x80808080u;       // SD_FLAG_QUAL_OK in both
-                    const uint32_t low = checkKmer ? ((((fa | fb) >> 1) << 7) & 0x80808080u) : 0u;             // SD_FLAG_LOW_KMER in either
+                    const uint32_t low = checkKmer ? (((SDGPU_LOWKMER_FLAGS(fa, fb) >> 1) << 7) & 0x80808080u) : 0u;             // SD_FLAG_LOW_KMER in either
                     lq += __popc(mis & ~good);
                     lk += __popc(mis & good & low);
                     hq += __popc(mis & good & ~low);
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(128) screenScanKernel(const SdScreenArgs a) {
                     const unsigned fa = fA[p], fb = fB[p];
                     if (usingQuality && !(fa & fb & SD_FLAG_QUAL_OK)) {
                       ++lq;
-                    } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
+                    } else if (checkKmer && (SDGPU_LOWKMER_FLAGS(fa, fb) & SD_FLAG_LOW_KMER)) {
                       ++lk;
                     } else {
                       ++hq;

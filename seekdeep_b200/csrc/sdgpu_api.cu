@@ -11,6 +11,9 @@
 
 #include "sdgpu_internal.cuh"
 
+// host_translate.cpp
+extern "C" void sd_translate_bases(const uint8_t* src, uint8_t* dst, uint64_t len, const int16_t* codeOf, int* maxCode, bool* unknown);
+
 static thread_local std::string g_createErr;
 
 int sd_fail(sdgpu_ctx* ctx, int code, const std::string& msg) {
@@ -328,13 +331,7 @@ static int appendImpl(sdgpu_ctx* ctx, const SeqSource& src, const double* cnts, 
         const uint8_t* b = src.seq(s);
         const uint8_t* q = src.qual(s);
         const uint64_t len = off[s + 1] - off[s];
-        uint8_t* dst = hCodes + off[s];
-        for (uint64_t x = 0; x < len; ++x) {
-          const int code = ctx->codeOf[b[x]];
-          unk |= code < 0;
-          mc = std::max(mc, code);
-          dst[x] = uint8_t(code);
-        }
+        sd_translate_bases(b, hCodes + off[s], len, ctx->codeOf, &mc, &unk);
         if (q) {
           std::memcpy(hQuals + off[s], q, len);
         } else {

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/sdgpu.h"
+#include "../../include/sdgpu_policy.h"
 
 #define SDGPU_MAX_SYMBOLS 16  // distinct base characters per ctx (dynamic alphabet)
 #define SDGPU_GAP_CODE 0xFF   // '-' in the device-side gapped strings

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) overlapKernel(const StitchArgs 
       if (s < 0) {
         if (usingQuality && !good) {
           ++lq;
-        } else if (checkKmer && ((fa | fb) & SD_FLAG_LOW_KMER)) {
+        } else if (checkKmer && (SDGPU_LOWKMER_FLAGS(fa, fb) & SD_FLAG_LOW_KMER)) {
           ++lk;
         } else {
           ++hq;

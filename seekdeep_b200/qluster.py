@@ -5,6 +5,9 @@ sequence) and clusterDownSetUp.cpp:254-312 (technology defaults).  Sharding of m
 GPUs follows the reference's own model: one independent qluster per sample
 (SeekDeepUtilsRunner_setUpTarAmpAnalysis.cpp:998-1001, runMultipleCommands)."""
 import ctypes as C
+import os
+import sys
+import time
 from dataclasses import dataclass
 
 import numpy as np
@@ -152,13 +155,19 @@ def qluster(aligner: GpuAligner, bases, quals, offsets, pars: QlusterPars = None
     ip, nip = iter_pars_to_c(intialParameters)
     pp, npp = iter_pars_to_c(iteratorMap)
     h = C.c_void_p()
+    t0 = time.perf_counter()
     rc = lib.sdq_run(aligner._ctx, C.byref(opts), ip, nip, pp, npp, _ptr(bases), _ptr(quals), _ptr(offsets), n, C.byref(h))
     if rc != _abi.OK:
         raise SdgpuError(rc, (lib.sdq_last_error() or b"").decode())
+    t1 = time.perf_counter()
     try:
-        return _result_to_dict(lib, h, n, want_clusters)
+        res = _result_to_dict(lib, h, n, want_clusters)
     finally:
+        t2 = time.perf_counter()
         lib.sdq_free(h)
+    if os.environ.get("SDQ_TIMING"):
+        print(f"[sdq] python: sdq_run {t1 - t0:.3f} fetch {t2 - t1:.3f} free {time.perf_counter() - t2:.3f}", file=sys.stderr)
+    return res
 
 
 def _result_to_dict(lib, h, n, want_clusters):

@@ -75,3 +75,37 @@ def test_reference_arm_prints_the_contract_line():
     r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=600)
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_host_base_translation_matches_table_lookup():
+    """sd_translate_bases (the upload's inner loop: 32 bases per step through two byte shuffles when a block holds only
+    A, C, G, T, N, the code table byte by byte otherwise) against a plain table look-up: every length around the block
+    size, blocks with degenerate / lower-case / unknown characters at every position."""
+    import ctypes as C
+    import numpy as np
+    from seekdeep_b200 import _abi
+    lib = _abi.load()
+    fn = lib.sd_translate_bases
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_bool)]
+    codeOf = np.full(256, -1, np.int16)
+    for i, ch in enumerate(b"ACGTNRYa"):
+        codeOf[ch] = i
+    rng = np.random.default_rng(8)
+    for trial in range(300):
+        n = int(rng.integers(0, 200))
+        src = np.frombuffer(b"ACGTN", np.uint8)[rng.integers(0, 5, n)].copy()
+        kind = trial % 4
+        if n and kind:  # sprinkle other characters: coded ones (R, Y, a) and, every fourth trial, one without a code
+            for p in rng.integers(0, n, int(rng.integers(1, 4))):
+                src[p] = rng.choice(np.frombuffer(b"RYa", np.uint8))
+            if kind == 3:
+                src[int(rng.integers(0, n))] = ord("x")
+        dst = np.zeros(n + 1, np.uint8)
+        dst[n] = 0xAB  # guard
+        mc, unk = C.c_int(-1), C.c_bool(False)
+        fn(src.ctypes.data, dst.ctypes.data, n, codeOf.ctypes.data, C.byref(mc), C.byref(unk))
+        want = codeOf[src]
+        assert np.array_equal(dst[:n], want.astype(np.uint8)) and dst[n] == 0xAB
+        assert mc.value == (int(want.max()) if n else -1)
+        assert unk.value == bool((want < 0).any())
