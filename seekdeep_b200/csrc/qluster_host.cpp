@@ -829,6 +829,13 @@ class Runner {
       const std::string& base = S.baseSeq;
       const size_t L = base.size();
       for (size_t m = ch.m0; m < ch.m1; ++m) {
+        if (m + 3 < ch.m1) {  // members lie all over the caller's read buffers: have a later one's bytes on their way
+          const Uniq& nx = uniq[cl.members[m + 3]];
+          for (uint32_t o = 0; o < nx.seq.n; o += 64) {
+            __builtin_prefetch(nx.seq.data() + o);
+            __builtin_prefetch(nx.qual.data() + o);
+          }
+        }
         const Uniq& r = uniq[cl.members[m]];
         const uint32_t w = uint32_t(std::llround(r.cnt));
         const std::vector<sdgpu_gap>& gl = gaps[j.firstPair + (m - j.firstMember)];
@@ -1413,6 +1420,7 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
         R.uniq.back().cnt = in.cnts ? in.cnts[r] : 1.0;
         continue;
       }
+      if (r + 8 < n) __builtin_prefetch(&table[size_t(readHash[r + 8]) & (cap - 1)]);
       const uint8_t* p = in.seq(r);
       const uint64_t h = readHash[r];
       size_t slot = size_t(h) & (cap - 1);
@@ -1476,6 +1484,29 @@ static int runCollapse(sdgpu_ctx* ctx, const sdq_opts* opts, const sdq_iter_par*
       if (k <= 1) continue;
       const uint32_t* members = R.inputList.data() + u.inputBegin;
       uint8_t* out = const_cast<uint8_t*>(u.qual.data());  // (its slice of the arena)
+      // two, three or four reads (most of the multi-read sequences): the median row by row, no per-column sort
+      if (k == 2) {
+        const uint8_t *a = in.qual(members[0]), *b = in.qual(members[1]);
+        for (size_t i = 0; i < len; ++i) out[i] = uint8_t((uint32_t(a[i]) + b[i]) / 2);
+        continue;
+      }
+      if (k == 3) {
+        const uint8_t *a = in.qual(members[0]), *b = in.qual(members[1]), *c = in.qual(members[2]);
+        for (size_t i = 0; i < len; ++i) {
+          const uint8_t lo = std::min(a[i], b[i]), hi = std::max(a[i], b[i]);
+          out[i] = std::max(lo, std::min(hi, c[i]));
+        }
+        continue;
+      }
+      if (k == 4) {  // mean of the two middle values = (sum - smallest - largest) / 2
+        const uint8_t *a = in.qual(members[0]), *b = in.qual(members[1]), *c = in.qual(members[2]), *d = in.qual(members[3]);
+        for (size_t i = 0; i < len; ++i) {
+          const uint32_t lo = std::min(std::min(a[i], b[i]), std::min(c[i], d[i]));
+          const uint32_t hi = std::max(std::max(a[i], b[i]), std::max(c[i], d[i]));
+          out[i] = uint8_t((uint32_t(a[i]) + b[i] + c[i] + d[i] - lo - hi) / 2);
+        }
+        continue;
+      }
       if (k < 16) {
         col.resize(k);
         for (size_t i = 0; i < len; ++i) {
