@@ -62,10 +62,6 @@ struct NvtxRange {
 };
 
 thread_local std::string g_err;
-// Pairs per asynchronous alignment chunk (0 = default 1 M).  Workers that share a GPU use small
-// chunks: kernels are persistent (they hold every SM until their chunk is done), so another
-// worker's latency-sensitive small batches can only slip in at chunk boundaries.
-thread_local uint32_t g_chunkPairs = 0;
 
 double nowSec() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -389,8 +385,6 @@ class Runner {
   std::vector<uint64_t> lastIn;       // by store index: latest iteration serial whose window held this version
   std::vector<uint64_t> onDemandAt;   // by store index: iteration serial in which it was judged on demand
   static constexpr uint32_t BATCH = 1u << 21;
-  std::vector<sdgpu_comparison> cmpBuf;
-  std::vector<sdgpu_gap> gapBuf;
   double tSpec = 0, tPass = 0, tCons = 0, tInsert = 0, tSort = 0, tIndex = 0, tSubmit = 0;
   double tConsAlign = 0, tConsCount = 0, tConsBuild = 0, tConsUpload = 0;  // parts of tCons
   double tBin = 0;  // k-mer binning (lists + masks + settling)
@@ -1813,7 +1807,6 @@ int sdq_run_many(int device, const sdgpu_params* params, const sdq_opts* opts, c
   std::mutex errMutex;
   std::string firstErr;
   auto worker = [&]() {
-    g_chunkPairs = nWorkers > 1 ? (getenv("SDQ_WORKER_CHUNK") ? uint32_t(atoi(getenv("SDQ_WORKER_CHUNK"))) : (1u << 18)) : 0u;
     sdgpu_ctx* ctx = nullptr;
     int rc = sdgpu_create(device, params, &ctx);
     if (rc) {
