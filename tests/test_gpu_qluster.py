@@ -321,3 +321,35 @@ def test_qluster_from_fastq_file(oracle, tmp_path):
     assert_same(got, packed)
     want = oracle.qluster(params, oracle_opts(sd.QlusterPars()), iters.iters, iters.iters, bases, q, offsets)
     assert_same(got, want)
+
+
+def test_c2_full_size_paths_agree(monkeypatch):
+    """BASELINE config 2 at its full size (200 000 reads x 300 bp: the benchmarked sample; hours for the oracle): the
+    result must not depend on which exact path produced the verdicts or on how the host loop consumed them -- big grid
+    streamed into the sequential pass (the default at this size) vs. consumed after the fact, screen pass on vs. off
+    (certified band + full-matrix kernels instead).  The paths agree with the oracle at 20 000 reads
+    (test_qluster_matches_frozen_oracle_at_baseline_sizes); here they have to agree with each other where the big
+    iteration's grid has nine chunks and 178 799 live clusters."""
+    haps, seqs, quals, _ = synth.config2_fast(nReads=200000)
+    bases, q, offsets = synth.pack(seqs, quals)
+    params = sd.make_params()
+    iters = CollapseIterations.gen_illumina_default_pars(100)
+
+    def run(screen=True):
+        with sd.GpuAligner(params) as al:
+            if not screen:
+                al.set_screen(1)
+            return sd.qluster(al, bases, q, offsets, sd.QlusterPars(), iters, want_clusters=False)
+
+    streamed = run()
+    assert streamed["stats"]["streamedGrids"] >= 1
+    monkeypatch.setenv("SDQ_STREAM_MIN_PAIRS", str(1 << 62))
+    plain = run()
+    assert plain["stats"]["streamedGrids"] == 0
+    noScreen = run(screen=False)
+    for other in (plain, noScreen):
+        assert np.array_equal(streamed["membership"], other["membership"])
+        for k in ("bases", "quals", "offsets", "cnts"):
+            assert np.array_equal(streamed["packed"][k], other["packed"][k]), k
+        assert streamed["chimeras"] == other["chimeras"]
+    assert streamed["stats"]["finalClusters"] == plain["stats"]["finalClusters"] > 1000
