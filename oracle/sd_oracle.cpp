@@ -756,19 +756,44 @@ struct Engine {
   // in list order, a cluster joins the first bin whose first cluster shares MORE THAN kmerCutOff of its k-mers
   // (kmerInfo::compareKmers(...).second > cutOff), else it opens a bin; every bin of two or more runs through
   // binIteratorMap on its own; the survivors, bin after bin, are the list the run's own iterations start from.
+  // kmerInfo of one sequence as a sorted list of its k-mers (with repeats): two such lists share
+  // sum over k-mers of min(count in a, count in b) entries -- compareKmers' first value -- by one merge.
+  static std::vector<std::string> kmerList(const std::string& seq, uint32_t k) {
+    std::vector<std::string> v;
+    for (uint32_t i = 0; i + k <= seq.size(); ++i) v.emplace_back(seq, i, k);
+    std::sort(v.begin(), v.end());
+    return v;
+  }
+  static double sharedKmerFraction(const std::vector<std::string>& a, size_t lenA, const std::vector<std::string>& b, size_t lenB, uint32_t k) {
+    uint32_t shared = 0;
+    for (size_t i = 0, j = 0; i < a.size() && j < b.size();) {
+      const int c = a[i].compare(b[j]);
+      if (c == 0) {
+        ++shared;
+        ++i;
+        ++j;
+      } else if (c < 0) {
+        ++i;
+      } else {
+        ++j;
+      }
+    }
+    const size_t minLen = std::min(lenA, lenB);
+    return minLen >= k ? shared / static_cast<double>(minLen - k + 1) : 0.0;  // compareKmers' second value
+  }
+
   void runFullClustering(std::vector<Clus>& cs, const sdo_iter_par* its, uint32_t nIts) {
     if (O.useKmerBinning) {
       std::vector<std::vector<Clus>> bins;
+      std::vector<std::vector<std::string>> seedKmers;  // kmerInfo of every bin's first cluster
       for (Clus& c : cs) {
         if (c.remove) continue;
+        const std::vector<std::string> mine = kmerList(c.seq, O.kCompareLen);
         bool placed = false;
-        for (auto& bin : bins) {
-          uint32_t shared;
-          double frac;
-          compareKmers(reinterpret_cast<const uint8_t*>(bin[0].seq.data()), uint32_t(bin[0].seq.size()),
-                       reinterpret_cast<const uint8_t*>(c.seq.data()), uint32_t(c.seq.size()), O.kCompareLen, shared, frac);
+        for (size_t bx = 0; bx < bins.size(); ++bx) {
+          const double frac = sharedKmerFraction(seedKmers[bx], bins[bx][0].seq.size(), mine, c.seq.size(), O.kCompareLen);
           if (SDGPU_KMER_BIN_PASSES(frac, O.kmerCutOff)) {
-            bin.push_back(std::move(c));
+            bins[bx].push_back(std::move(c));
             placed = true;
             break;
           }
@@ -776,6 +801,7 @@ struct Engine {
         if (!placed) {
           bins.emplace_back();
           bins.back().push_back(std::move(c));
+          seedKmers.push_back(mine);
         }
       }
       cs.clear();

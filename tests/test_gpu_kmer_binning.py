@@ -88,7 +88,7 @@ def _multi_family_sample(rng, nFam, nReads, length, err=0.004):
     """Reads from several unrelated haplotype families (k-mer bins), each family a root + close variants."""
     seqs, quals = [], []
     for f in range(nFam):
-        haps = synth.make_haplotypes(rng, 4, length + 7 * f, 1, 4)
+        haps = synth.make_haplotypes(rng, 4, length + 7 * (f % 6), 1, 4)
         s, q, _ = synth.fast_reads(rng, haps, nReads // nFam, err)
         seqs += s
         quals += q
@@ -99,7 +99,9 @@ def _multi_family_sample(rng, nFam, nReads, length, err=0.004):
 @pytest.mark.parametrize("seed,nFam,k,cut", [(5, 3, 10, 0.80), (6, 5, 6, 0.55), (7, 2, 12, 0.95), (8, 70, 10, 0.80)])
 def test_qluster_kmer_binning_matches_oracle(oracle, seed, nFam, k, cut):
     rng = np.random.default_rng(seed)
-    bases, q, offsets = _multi_family_sample(rng, nFam, 1400 if nFam < 10 else 2100, 110)
+    # (70 families: more bins than one round's 64 candidate seeds; kept small, the oracle aligns every read against up
+    #  to 100 unrelated clusters once the bins are merged back)
+    bases, q, offsets = _multi_family_sample(rng, nFam, 1400 if nFam < 10 else 560, 110 if nFam < 10 else 90)
     params = sd.make_params()
     iters = CollapseIterations.gen_illumina_default_pars(100)
     pars = sd.QlusterPars(useKmerBinning=True, kCompareLen=k, kmerCutOff=cut)
