@@ -14,30 +14,33 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// One CTA sorts the k-mers of one sequence at a time in shared memory (bitonic network over the next power of two).
-__global__ void __launch_bounds__(256) kmerListKernel(DevSeqs seqs, uint32_t kLen, uint64_t* lists) {
-  extern __shared__ uint64_t sKeys[];
-  for (uint32_t s = blockIdx.x; s < seqs.n; s += gridDim.x) {
+// One warp sorts the k-mers of one sequence at a time in its slice of shared memory (bitonic network over the next power
+// of two, a lane takes every 32nd compare-exchange of a stage): the warps of a CTA work on different sequences and never
+// wait for each other -- a stage ends with a warp barrier, not a CTA barrier.
+__global__ void __launch_bounds__(256) kmerListKernel(DevSeqs seqs, uint32_t kLen, uint32_t slotKeys, uint64_t* lists) {
+  extern __shared__ uint64_t sKeysAll[];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  uint64_t* sKeys = sKeysAll + size_t(warp) * slotKeys;
+  for (uint32_t s = blockIdx.x * warps + warp; s < seqs.n; s += gridDim.x * warps) {
     const uint64_t off = seqs.offsets[s];
     const uint32_t len = uint32_t(seqs.offsets[s + 1] - off);
-    if (len < kLen) continue;  // (uniform over the CTA)
+    if (len < kLen) continue;  // (uniform over the warp)
     const uint32_t nk = len - kLen + 1;
     uint32_t n2 = 2;
     while (n2 < nk) n2 <<= 1;
     const uint8_t* codes = seqs.codes + off;
-    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
-      uint64_t key = ~0ull;  // padding sorts behind every real key (a real key of 16 bases never has all bits set: codes < 16 but
-                             // code 15 sixteen times would; such a sequence still sorts correctly, padding being never written back)
+    for (uint32_t i = lane; i < n2; i += 32) {
+      uint64_t key = ~0ull;  // padding: never below a real key, never written back
       if (i < nk) {
         key = 0;
         for (uint32_t x = 0; x < kLen; ++x) key = (key << 4) | codes[i + x];
       }
       sKeys[i] = key;
     }
-    __syncthreads();
+    __syncwarp();
     for (uint32_t size = 2; size <= n2; size <<= 1) {
       for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-        for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        for (uint32_t t = lane; t < (n2 >> 1); t += 32) {
           const uint32_t lo = 2 * t - (t & (stride - 1));
           const uint32_t hi = lo + stride;
           const bool asc = (lo & size) == 0;
@@ -47,12 +50,11 @@ __global__ void __launch_bounds__(256) kmerListKernel(DevSeqs seqs, uint32_t kLe
             sKeys[hi] = a;
           }
         }
-        __syncthreads();
+        __syncwarp();
       }
     }
-    // a sequence made of code 15 only and k = 16 has keys equal to the padding: equal keys, any order is sorted
-    for (uint32_t i = threadIdx.x; i < nk; i += blockDim.x) lists[off + i] = sKeys[i];
-    __syncthreads();
+    for (uint32_t i = lane; i < nk; i += 32) lists[off + i] = sKeys[i];
+    __syncwarp();
   }
 }
 
@@ -180,11 +182,13 @@ int sd_build_kmer_lists(sdgpu_ctx* ctx, uint32_t kLen) {
   }
   uint32_t n2 = 2;
   while (n2 < ctx->maxLen) n2 <<= 1;
-  const size_t smem = size_t(n2) * 8;
+  uint32_t warps = uint32_t((160u << 10) / (size_t(n2) * 8));  // one slot of n2 keys per warp
+  warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
+  const size_t smem = size_t(warps) * n2 * 8;
   SD_CUDA(ctx, cudaFuncSetAttribute(kmerListKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   uint32_t grid = uint32_t(ctx->numSMs) * 8;
-  if (grid > nSeqs) grid = nSeqs;
-  kmerListKernel<<<grid, 256, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, ctx->dKmerLists);
+  if (grid > (nSeqs + warps - 1) / warps) grid = (nSeqs + warps - 1) / warps;
+  kmerListKernel<<<grid, warps * 32, smem, ctx->stream>>>(sd_dev_seqs(ctx), kLen, n2, ctx->dKmerLists);
   SD_CUDA(ctx, cudaGetLastError());
   ++ctx->launches;
   return SDGPU_OK;
