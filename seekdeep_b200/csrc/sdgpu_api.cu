@@ -861,6 +861,11 @@ int sdgpu_align_pass_grid_stream(sdgpu_ctx* ctx, const uint32_t* clusterIdx, uin
   ctx->gridHits.clear();
   if (nClusters == 0 || nReads == 0) return SDGPU_OK;
   SD_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (sdgpu_ctx::GridSlot& G : ctx->gridSlots)  // a slot still marked busy belongs to a call that failed half-way: its records are not ours
+    if (G.busy) {
+      cudaEventSynchronize(G.done);
+      G.busy = false;
+    }
   if (ctx->nLines == 0) return sd_fail(ctx, SDGPU_E_STATE, "sdgpu_set_pass_table has not been called");
   const uint32_t nSeqs = uint32_t(ctx->hOffsets.size() - 1);
   uint32_t maxA = 0, maxB = 0;
