@@ -50,14 +50,14 @@ DP_KERNEL_DRAM_SOURCE = "profiles/r2_screen_dp_kernel_ncu_full.csv"
 
 
 def make_sample(seed, nReads):
-    from seekdeep_b200 import synth
+    from tests import synth
     haps, seqs, quals, _ = synth.config2_fast(seed=seed, nReads=nReads)
     return synth.pack(seqs, quals)
 
 
 def make_c5_sample(seed, nReads=50_000):
     """One sample of BASELINE configs[4]: the C1 generator (20 haplotypes x 250 bp, 0.5 % substitutions) at 50k reads."""
-    from seekdeep_b200 import synth
+    from tests import synth
     rng = np.random.default_rng(seed)
     haps = synth.make_haplotypes(rng, 20, 250, 1, 6)
     seqs, quals, _ = synth.fast_reads(rng, haps, nReads, 0.005)

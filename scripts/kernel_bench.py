@@ -6,7 +6,8 @@ import time
 import numpy as np
 
 import seekdeep_b200 as sd
-from seekdeep_b200 import _abi, synth
+from seekdeep_b200 import _abi
+from tests import synth
 
 nReads = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 onlyMode = int(sys.argv[2]) if len(sys.argv) > 2 else 0

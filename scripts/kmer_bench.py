@@ -2,7 +2,7 @@
 import sys
 import numpy as np
 import seekdeep_b200 as sd
-from seekdeep_b200 import synth
+from tests import synth
 
 nReads = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 haps, seqs, quals, _ = synth.config2_fast(nReads=nReads)

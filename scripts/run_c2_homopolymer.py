@@ -7,7 +7,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import seekdeep_b200 as sd  # noqa: E402
-from seekdeep_b200 import synth  # noqa: E402
+from tests import synth  # noqa: E402
 
 nReads = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 haps, seqs, quals, which = synth.config2_fast(nReads=nReads)

@@ -12,7 +12,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import seekdeep_b200 as sd  # noqa: E402
-from seekdeep_b200 import synth  # noqa: E402
+from tests import synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -13,7 +13,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import seekdeep_b200 as sd  # noqa: E402
-from seekdeep_b200 import synth  # noqa: E402
+from tests import synth  # noqa: E402
 from seekdeep_b200.qluster import qluster_many  # noqa: E402
 
 perGpu = int(sys.argv[1]) if len(sys.argv) > 1 else 48

@@ -4,7 +4,7 @@ import sys
 import time
 
 import seekdeep_b200 as sd
-from seekdeep_b200 import synth
+from tests import synth
 from seekdeep_b200.qluster import qluster_many
 
 nS = int(sys.argv[1]) if len(sys.argv) > 1 else 4

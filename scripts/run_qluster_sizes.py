@@ -6,7 +6,7 @@ import time
 import numpy as np
 
 import seekdeep_b200 as sd
-from seekdeep_b200 import synth
+from tests import synth
 
 sizes = [int(x) for x in sys.argv[1:]] or [10000]
 for n in sizes:

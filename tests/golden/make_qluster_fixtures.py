@@ -20,7 +20,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 import seekdeep_b200 as sd  # noqa: E402
-from seekdeep_b200 import synth  # noqa: E402
+from tests import synth  # noqa: E402
 from seekdeep_b200.iterpars import CollapseIterations  # noqa: E402
 from tests import oracle_binding  # noqa: E402
 

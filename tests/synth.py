@@ -1,4 +1,4 @@
-"""Seeded synthetic amplicon reads for the BASELINE.json configs (C1..C5).
+"""Seeded synthetic amplicon reads for the BASELINE.json configs (C1..C5): test and bench data, not product code.
 No datasets ship with the reference and there is no network, so every workload is generated."""
 import numpy as np
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import seekdeep_b200 as sd
-from seekdeep_b200 import synth
+from tests import synth
 from seekdeep_b200.aligner import GpuAligner, pack_seqs
 from seekdeep_b200.iterpars import CollapseIterations
 from seekdeep_b200.scoring import make_params

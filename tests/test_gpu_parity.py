@@ -319,7 +319,7 @@ def test_align_pass_matches_pass_error_profile(oracle):
 def test_all_vs_all_matches_oracle(oracle):
     """Config-3 shaped case at oracle-checkable size: every unordered pair of 70 related 400-mers,
     computed as two disjoint pair blocks (the multi-GPU pair-block sharding) + a seqIdx subset."""
-    from seekdeep_b200 import synth
+    from tests import synth
     seqs, quals = synth.config3(seed=3, n=70, length=400, nRoots=4)
     bases, q, offsets = synth.pack(seqs, quals)
     n = len(seqs)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import seekdeep_b200 as sd
-from seekdeep_b200 import synth
+from tests import synth
 from seekdeep_b200.iterpars import CollapseIterations
 from tests import oracle_binding
 
