@@ -88,3 +88,4 @@ def test_align_gap_lists_match_align_profile(oracle):
             if gapCap == 2:
                 assert any(nRuns > 2 for nRuns, _ in packed.values())
         assert al.align_gap_lists(refIdx[:0], readIdx[:0]) == {}
+
