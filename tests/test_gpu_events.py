@@ -89,3 +89,52 @@ def test_align_gap_lists_match_align_profile(oracle):
                 assert any(nRuns > 2 for nRuns, _ in packed.values())
         assert al.align_gap_lists(refIdx[:0], readIdx[:0]) == {}
 
+
+
+def test_cxx_all_by_all_example_matches_python_api():
+    """examples/all_by_all_cabi.cpp (the --writeOutFinalAllByAllComparison tables of clusterDown.cpp:727-805 from one
+    sdgpu_align_events call, C++ straight onto the C ABI) prints what the Python wrapper returns for the same clusters."""
+    import subprocess
+    import __graft_entry__ as g
+    exe = g.build_example("all_by_all_cabi")
+    rng = np.random.default_rng(12)
+    root = H.rand_seq(rng, 150)
+    seqs = [root]
+    for i in range(5):
+        s = H.mutate(rng, root, int(rng.integers(1, 5)), int(i % 2), int((i + 1) % 2), hp=False)
+        seqs.append(s)
+    names = [f"clus{i}" for i in range(len(seqs))]
+    args = []
+    for nme, s in zip(names, seqs):
+        args += [nme, s.tobytes().decode()]
+    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    counts, events = r.stdout.split("--\n")
+    counts = [l.split("\t") for l in counts.strip().splitlines()[1:]]
+    events = [l.split("\t") for l in events.rstrip("\n").splitlines()[1:]]
+    # the same store through the Python wrapper
+    n = len(seqs)
+    quals = [np.where(np.arange(len(s)) % 7 == 3, 12, 35).astype(np.uint8) for s in seqs]
+    offsets = np.zeros(n + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(s) for s in seqs])
+    cnts = np.array([10.0 * (n - i) for i in range(n)])
+    refIdx, readIdx = [], []
+    for s in range(n - 1, -1, -1):
+        for o in range(s):
+            refIdx.append(o)
+            readIdx.append(s)
+    with GpuAligner(H.params_for("qluster")) as al:
+        al.upload_seqs(np.concatenate(seqs), np.concatenate(quals), offsets, cnts)
+        al.index_kmers(9, 1, True)
+        comp, evs = al.align_events(refIdx, readIdx, checkKmer=True, usingQuality=True)
+    assert len(counts) == len(refIdx)
+    for p, row in enumerate(counts):
+        assert row[0] == names[refIdx[p]] and row[1] == names[readIdx[p]] and int(row[2]) == comp["alnScore"][p]
+        assert float(row[3]) == comp["eventBasedIdentity"][p] and float(row[4]) == comp["eventBasedIdentityHq"][p]
+        assert float(row[5]) == comp["oneBaseIndel"][p] and float(row[6]) == comp["twoBaseIndel"][p]
+        assert [int(x) for x in row[8:11]] == [comp["lqMismatches"][p], comp["hqMismatches"][p], comp["lowKmerMismatches"][p]]
+    nMis = sum(int(((e["kind"] >= 1) & (e["kind"] <= 3)).sum()) for e in evs)
+    nGap = sum(int(((e["kind"] == _abi.EV_GAP_IN_REF) | (e["kind"] == _abi.EV_GAP_IN_READ)).sum()) for e in evs)
+    assert sum(1 for e in events if e[2] in ("mismatch", "lowKmerMismatch")) == nMis > 0
+    assert sum(1 for e in events if e[2].startswith("gap-")) == nGap > 0
+    assert all(len(e) == 11 for e in events)
