@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SDGPU_ABI_VERSION 2
+#define SDGPU_ABI_VERSION 3 /* 3: sdq_opts gained the k-mer binning fields, sdq_stats three counters; new entry points only add */
 #define SDGPU_MAT_DIM 128 /* substitution matrix is indexed by 7-bit ASCII, like njhseq's mat_[127][127] */
 
 /* return codes */

@@ -42,7 +42,7 @@ def test_pod_layouts():
     assert C.sizeof(_abi.GapPars) == 40
     assert C.sizeof(_abi.Params) == 40 + 4 * 128 * 128 + 24
     assert C.sizeof(_abi.Comparison) == 104 and C.sizeof(_abi.Gap) == 12
-    assert _abi.load().sdgpu_abi_version() == 2
+    assert _abi.load().sdgpu_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device():
